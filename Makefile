@@ -1,0 +1,49 @@
+# Build: product library (CUDA sm_100a + host C++), CPU oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
+CC        := $(shell test -x /usr/bin/gcc && echo /usr/bin/gcc || echo gcc)
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -ccbin $(CXX) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Ixmimsim_b200/csrc -Xcompiler -fPIC,-fopenmp,-O3 -Xptxas -v
+CXXFLAGS  := -O3 -fPIC -fopenmp -std=c++17 -Iinclude -Ixmimsim_b200/csrc -Wall -Wno-unknown-pragmas
+CFLAGS    := -O3 -fPIC -fopenmp -std=gnu99 -Iinclude -Ixmimsim_b200/csrc -Wall
+SRC       := xmimsim_b200/csrc
+OBJ       := build/obj
+LIB       := xmimsim_b200/lib/libxmimsim_b200.so
+CU_SRCS   := $(wildcard $(SRC)/*.cu)
+CPP_SRCS  := $(wildcard $(SRC)/*.cpp)
+C_SRCS    := $(wildcard $(SRC)/*.c)
+OBJS      := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(OBJ)/%.cpp.o,$(CPP_SRCS)) $(patsubst $(SRC)/%.c,$(OBJ)/%.c.o,$(C_SRCS))
+HDRS      := $(wildcard include/*.h) $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.cuh)
+
+ORC_SRCS  := $(wildcard oracle/*.c)
+ORC_LIB   := oracle/_build/liborc.so
+
+all: $(LIB) $(ORC_LIB)
+lib: $(LIB)
+oracle: $(ORC_LIB)
+
+$(OBJ)/%.cu.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+	@grep -E "registers|spill|error|warning" $(OBJ)/$*.ptxas.log | grep -v "^$$" | sed 's/^/  [ptxas $*] /' | grep -E "Used|spill" | head -40 || true
+
+$(OBJ)/%.cpp.o: $(SRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJ)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(OBJ)/%.c.o: $(SRC)/%.c $(HDRS)
+	@mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p xmimsim_b200/lib
+	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(OBJS) -Xcompiler -fopenmp -lgomp -cudart static
+
+# The oracle links the surrogate provider object (third-party stand-in), never the engine.
+$(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h $(SRC)/xrl_surrogate.c
+	@mkdir -p oracle/_build
+	$(CC) $(CFLAGS) -Ioracle -shared -o $@ $(ORC_SRCS) $(SRC)/xrl_surrogate.c -lm
+
+clean:
+	rm -rf build xmimsim_b200/lib oracle/_build
+.PHONY: all lib oracle clean

@@ -1,0 +1,404 @@
+/* xmimsim_b200.h -- C ABI of the B200-native XMI-MSIM photon-transport engine.
+ *
+ * Plain C, plain pointers and sizes: this is the drop-in boundary.  Every entry
+ * point cites the reference interface (file:line under the reference tree) it replaces.  The
+ * struct layouts of the input tree, the options, the solid-angle grid and the escape ratios are
+ * identical to the reference's C structs so that a reference-side caller can hand its own
+ * objects over without conversion.
+ *
+ * Nothing in here is torch; device memory, streams and (optional) NCCL are private to the .so.
+ */
+#ifndef XMIMSIM_B200_H
+#define XMIMSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Input tree -- same field order/types as include/xmi_data_structs.h:40-329 (reference).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct xmb_general {          /* reference: struct _xmi_general, xmi_data_structs.h:40-47 */
+	float version;
+	char *outputfile;
+	long n_photons_interval;
+	long n_photons_line;
+	int n_interactions_trajectory;
+	char *comments;
+} xmb_general;
+
+typedef struct xmb_layer {            /* struct _xmi_layer, xmi_data_structs.h:66-72 */
+	int n_elements;
+	int *Z;
+	double *weight;
+	double density;
+	double thickness;
+} xmb_layer;
+
+typedef struct xmb_composition {      /* struct _xmi_composition, :91-95 */
+	int n_layers;
+	xmb_layer *layers;
+	int reference_layer;              /* 1-based */
+} xmb_composition;
+
+typedef struct xmb_geometry {         /* struct _xmi_geometry, :119-130 */
+	double d_sample_source;
+	double n_sample_orientation[3];
+	double p_detector_window[3];
+	double n_detector_orientation[3];
+	double area_detector;
+	double collimator_height;
+	double collimator_diameter;
+	double d_source_slit;
+	double slit_size_x;
+	double slit_size_y;
+} xmb_geometry;
+
+typedef enum {                        /* XmiEnergyDiscreteDistribution, :145-149 */
+	XMB_DISCRETE_MONOCHROMATIC = 0,
+	XMB_DISCRETE_GAUSSIAN = 1,
+	XMB_DISCRETE_LORENTZIAN = 2
+} xmb_discrete_distribution;
+
+typedef struct xmb_energy_discrete {  /* struct _xmi_energy_discrete, :167-177 */
+	double energy;
+	double horizontal_intensity;
+	double vertical_intensity;
+	double sigma_x;
+	double sigma_xp;
+	double sigma_y;
+	double sigma_yp;
+	int distribution_type;            /* xmb_discrete_distribution */
+	double scale_parameter;
+} xmb_energy_discrete;
+
+typedef struct xmb_energy_continuous {/* struct _xmi_energy_continuous, :197-205 */
+	double energy;
+	double horizontal_intensity;
+	double vertical_intensity;
+	double sigma_x;
+	double sigma_xp;
+	double sigma_y;
+	double sigma_yp;
+} xmb_energy_continuous;
+
+typedef struct xmb_excitation {       /* struct _xmi_excitation, :223-228 */
+	int n_discrete;
+	xmb_energy_discrete *discrete;
+	int n_continuous;
+	xmb_energy_continuous *continuous;
+} xmb_excitation;
+
+typedef struct xmb_absorbers {        /* struct _xmi_absorbers, :249-254 */
+	int n_exc_layers;
+	xmb_layer *exc_layers;
+	int n_det_layers;
+	xmb_layer *det_layers;
+} xmb_absorbers;
+
+typedef enum {                        /* XmiDetectorConvolutionProfile, :273-277 */
+	XMB_DETECTOR_SILI = 0,
+	XMB_DETECTOR_GE = 1,
+	XMB_DETECTOR_SI_SDD = 2
+} xmb_detector_profile;
+
+typedef struct xmb_detector {         /* struct _xmi_detector, :296-307 */
+	int detector_type;                /* xmb_detector_profile */
+	double live_time;
+	double pulse_width;
+	double gain;
+	double zero;
+	double fano;
+	double noise;
+	int nchannels;
+	int n_crystal_layers;
+	xmb_layer *crystal_layers;
+} xmb_detector;
+
+typedef struct xmb_input {            /* struct _xmi_input, :329-336 */
+	xmb_general *general;
+	xmb_composition *composition;
+	xmb_geometry *geometry;
+	xmb_excitation *excitation;
+	xmb_absorbers *absorbers;
+	xmb_detector *detector;
+} xmb_input;
+
+typedef struct xmb_main_options {     /* struct _xmi_main_options, xmi_data_structs.h:479-495 */
+	int use_M_lines;                  /* default 1 */
+	int use_cascade_auger;            /* default 1 */
+	int use_cascade_radiative;        /* default 1 */
+	int use_variance_reduction;       /* default 1 */
+	int use_sum_peaks;                /* default 0 */
+	int use_escape_peaks;             /* default 1 */
+	int escape_ratios_mode;           /* default 0 */
+	int verbose;                      /* default 0 */
+	int use_poisson;                  /* default 0 */
+	int use_gpu;                      /* default 1 */
+	int omp_num_threads;              /* default: all */
+	int extra_verbose;                /* default 0 */
+	char *custom_detector_response;   /* default NULL */
+	int use_advanced_compton;         /* default 0 */
+	int use_default_seeds;            /* default 0 */
+} xmb_main_options;
+
+typedef struct xmb_solid_angle {      /* struct _xmi_solid_angle, include/xmi_solid_angle.h:28-35 */
+	double *solid_angles;             /* [grid_dims_theta_n][grid_dims_r_n], r fastest */
+	long int grid_dims_r_n;
+	long int grid_dims_theta_n;
+	double *grid_dims_r_vals;
+	double *grid_dims_theta_vals;
+	char *xmi_input_string;
+} xmb_solid_angle;
+
+typedef struct xmb_escape_ratios {    /* struct _xmi_escape_ratios, include/xmi_detector.h:28-40 */
+	int n_elements;
+	int n_fluo_input_energies;
+	int n_compton_input_energies;
+	int n_compton_output_energies;
+	int *Z;
+	double *fluo_escape_ratios;       /* Fortran (n_elements, 109, n_fluo_input_energies): element fastest */
+	double *fluo_escape_input_energies;
+	double *compton_escape_ratios;    /* Fortran (n_compton_input_energies, n_compton_output_energies) */
+	double *compton_escape_input_energies;
+	double *compton_escape_output_energies;
+	char *xmi_input_string;
+} xmb_escape_ratios;
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-section provider: the xraylib calls the reference makes (SURVEY.md 8c lists the call
+ * sites).  Fill it with libxrl's functions to run on real data; xmb_xrl_surrogate() returns the
+ * analytic stand-in shipped with this repo (xraylib is not available offline).
+ * Shell codes K=0..M5=8 (..Q3=30); lines are xraylib's negative macros (KL1=-1 ... P3P5=-383);
+ * Coster-Kronig transitions use XMB_F* below.
+ * ------------------------------------------------------------------------------------------ */
+enum { XMB_FL12 = 0, XMB_FL13, XMB_FL23, XMB_FM12, XMB_FM13, XMB_FM14, XMB_FM15, XMB_FM23,
+       XMB_FM24, XMB_FM25, XMB_FM34, XMB_FM35, XMB_FM45, XMB_N_CK };
+
+typedef struct xmb_xrl_provider {
+	const char *name;
+	double (*AtomicWeight)(int Z);
+	double (*EdgeEnergy)(int Z, int shell);
+	double (*LineEnergy)(int Z, int line);
+	double (*FluorYield)(int Z, int shell);
+	double (*RadRate)(int Z, int line);
+	double (*CosKronTransProb)(int Z, int trans);
+	double (*JumpFactor)(int Z, int shell);
+	double (*CS_Total_Kissel)(int Z, double E);
+	double (*CS_Photo_Total)(int Z, double E);
+	double (*CS_Photo_Partial)(int Z, int shell, double E);
+	double (*CS_Rayl)(int Z, double E);
+	double (*CS_Compt)(int Z, double E);
+	double (*FF_Rayl)(int Z, double q);
+	double (*SF_Compt)(int Z, double q);
+	double (*ComptonProfile)(int Z, double pz);
+	/* vacancy-production cross section of `shell` under cascade mode (1 none, 2 non-radiative,
+	 * 3 radiative, 4 full: src/xmi_aux_f.F90:662-665), given the already-evaluated P[] of the
+	 * deeper shells (P[0]=PK ...).  Restates xraylib's P{L1..M5}_{pure,auger,rad,full}_kissel. */
+	double (*VacancyCS)(int Z, int shell, double E, int cascade, const double *P);
+} xmb_xrl_provider;
+
+const xmb_xrl_provider *xmb_xrl_surrogate(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Opaque handles replacing xmi_inputFPtr / xmi_hdf5FPtr (pointers to Fortran derived types in
+ * the reference, include/xmi_data_structs.h:511, include/xmi_data.h).
+ * ------------------------------------------------------------------------------------------ */
+typedef void *xmb_inputFPtr;
+typedef void *xmb_hdf5FPtr;
+
+/* Geometry derived by xmb_init_input (fields the reference stores inside its Fortran xmi_input:
+ * src/xmi_main.F90:1741-1918). */
+typedef struct xmb_derived {
+	double n_sample_orientation[3];       /* normalised, z >= 0 */
+	double n_detector_orientation[3];     /* normalised */
+	double detector_radius;
+	int collimator_present;
+	double collimator_radius;
+	double collimator_height;
+	double half_apex;
+	double vertex[3];
+	double ndo_new[9];                    /* row-major 3x3, columns = new x,y,z axes in lab coords */
+	double ndo_inv[9];                    /* row-major inverse */
+	double detector_solid_angle;
+	double n_sample_orientation_det[3];
+	int n_layers;
+	const double *thickness_along_Z;      /* [n_layers] */
+	const double *Z_coord_begin;
+	const double *Z_coord_end;
+} xmb_derived;
+
+/* Reference-shaped physics tables for the unique elements of one input (the contents of
+ * xmimsimdata.h5 + what the reference fetches from xraylib inside the loop, pre-tabulated on the
+ * common energy-node grid).  All arrays row-major, last index fastest.  Read-only view owned by
+ * the hdf5 handle; the CPU oracle consumes exactly this view. */
+typedef struct xmb_tables_host {
+	int nZ;
+	const int *Z;                  /* [nZ] ascending */
+	const int *uniqZ;              /* [95]: Z -> index or -1 */
+	const double *atomic_weight;   /* [nZ] */
+	/* energy nodes (uniform grid + edge doublets, sorted) with O(1) bucket index */
+	int n_nodes;
+	const double *node_E;          /* [n_nodes] */
+	double bucket_E0, bucket_inv_dE;
+	int n_buckets;
+	const int *bucket_start;       /* [n_buckets+1]: first node with E >= bucket lower bound */
+	const double *cs_total;        /* [nZ][n_nodes]  CS_Total_Kissel */
+	const double *cs_photo_total;  /* [nZ][n_nodes] */
+	const double *p_rayl;          /* [nZ][n_nodes]  CS_Rayl/CS_Total */
+	const double *p_rayl_compt;    /* [nZ][n_nodes]  (CS_Rayl+CS_Compt)/CS_Total */
+	const double *cs_photo_partial;/* [nZ][9][n_nodes] */
+	const double *cs_vacancy;      /* [4][nZ][9][n_nodes] cascade mode 1..4 -> index mode-1 */
+	/* scattering-angle inverse CDFs (xmimsimdata.h5 shapes: src/xmi_data.c:150-152) */
+	int n_icdf_E, n_icdf_R;
+	const double *icdf_E;          /* [n_icdf_E] uniform */
+	const double *icdf_R;          /* [n_icdf_R] uniform 0..1 */
+	const double *rayl_theta_icdf; /* [nZ][n_icdf_E][n_icdf_R] */
+	const double *compt_theta_icdf;/* [nZ][n_icdf_E][n_icdf_R] */
+	int n_phi_T;                   /* phi table: parameter axis 0..0.5 */
+	const double *phi_T;           /* [n_phi_T] */
+	const double *phi_icdf;        /* [n_phi_T][n_icdf_R] */
+	int n_cp;                      /* Compton profile ICDF points (10001) */
+	const double *cp_R;            /* [n_cp] uniform 0..1 */
+	const double *cp_icdf;         /* [nZ][n_cp] */
+	/* form factor / scattering function on a uniform q grid (for DCSP_Rayl / DCSP_Compt) */
+	int n_q;
+	double q_max;
+	const double *ff;              /* [nZ][n_q] F(Z,q) */
+	const double *sf;              /* [nZ][n_q] S(Z,q) */
+	/* atomic constants */
+	const double *fluor_yield;     /* [nZ][9] */
+	const double *fluor_yield_corr;/* [nZ][9] */
+	const double *cos_kron;        /* [nZ][XMB_N_CK] */
+	const double *rad_rate;        /* [nZ][384] by |line| */
+	const double *line_energy;     /* [nZ][384] */
+	const double *edge_energy;     /* [nZ][9] */
+	/* precalculated at fluorescence-line energies */
+	const double *precalc_xrf_cs;  /* [4][nZ][9][nZ'][220]  (mode, absorber, shell, emitter, |line|) */
+	int n_layers;
+	const double *precalc_mu_cs;   /* [n_layers][nZ][220]  mu_layer(E_line(Z,|line|)) */
+	const double *precalc_cs_total;/* [nZ][nZ'][220] CS_Total_Kissel(Z, E_line(Z',line)) */
+	const double *precalc_p_rayl;  /* [nZ][nZ'][220] interaction probs at line energies */
+	const double *precalc_p_rayl_compt;
+	const double *precalc_cs_photo_total;   /* [nZ][nZ'][220] */
+	const double *precalc_cs_photo_partial; /* [nZ][9][nZ'][220] */
+} xmb_tables_host;
+
+/* ------------------------------------------------------------------------------------------
+ * Entry points
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces xmi_input_C2F (src/xmi_aux_f.F90:782-1025): deep copy, layer weights renormalised to
+ * sum 1 (:857).  Returns 1 on success, 0 on failure. */
+int xmb_input_C2F(const xmb_input *input, xmb_inputFPtr *out);
+/* Replaces xmi_input_F2C (src/xmi_aux_f.F90:766-776): borrowed pointer to the handle's C tree. */
+const xmb_input *xmb_input_F2C(xmb_inputFPtr inputF);
+/* Replaces xmi_free_input_F. */
+void xmb_free_input_F(xmb_inputFPtr *inputF);
+/* Replaces xmi_init_input (src/xmi_main.F90:1741-1918).  Returns 1 / 0 (non-conical collimator
+ * is reported as 0 instead of the reference's exit(1), :1785-1789). */
+int xmb_init_input(xmb_inputFPtr *inputF);
+/* Read-only view of what xmb_init_input derived.  NULL before xmb_init_input. */
+const xmb_derived *xmb_get_derived(xmb_inputFPtr inputF);
+
+/* Replaces xmi_init_from_hdf5 + xmi_update_input_from_hdf5 (include/xmi_data.h:45-50;
+ * src/xmi_data_f.F90:98-848) and the table generator xmi_db (src/xmi_data.c:149-487,
+ * src/xmi_data_f.F90:880-1551): builds the table bundle for the elements of `inputF` from a
+ * cross-section provider.  `quality` scales the integration resolution of the inverse CDFs
+ * (1 = reference's 1e5 theta steps / 1e7 pz steps; 0 = fast setting for tests).
+ * Returns 1 / 0. */
+int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality,
+                           xmb_hdf5FPtr *out);
+const xmb_tables_host *xmb_get_tables(xmb_hdf5FPtr hdf5F);
+void xmb_free_hdf5_F(xmb_hdf5FPtr *hdf5F);
+
+/* Replaces xmi_solid_angle_inputs_f (src/xmi_solid_angle_f.F90:62-301): allocates the grid
+ * struct (malloc; free with xmb_free_solid_angle) and fills the r/theta axes.  Needs the tables
+ * for mu(E) of the layers.  Returns 1 / 0. */
+int xmb_solid_angle_inputs(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, xmb_solid_angle **out);
+/* Replaces xmi_solid_angle_calculation_cl (src/xmi_solid_angle_cl.c:118-439; typedef
+ * XmiSolidAngleCalculation src/xmi_solid_angle.c:51): computes the whole grid on the GPU.
+ * input_string is stored (not copied) in (*solid_angle)->xmi_input_string, as the reference does.
+ * Returns 1 on success, 0 = "fall through to next backend".  hits_per_single is the reference's
+ * global (src/xmi_solid_angle_f.F90:43); seed selects the Philox key. */
+int xmb_solid_angle_calculation(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
+                                xmb_solid_angle **solid_angle, char *input_string,
+                                const xmb_main_options *options, long hits_per_single,
+                                uint64_t seed);
+/* The grid kernel on caller-given axes (any n_r x n_theta): solid_angles[theta][r] and, if non-NULL,
+ * the raw hit counts.  xmb_solid_angle_calculation = xmb_solid_angle_inputs + this.  Returns 1 / 0. */
+int xmb_solid_angle_grid(xmb_inputFPtr inputF, const double *r_vals, long n_r, const double *theta_vals,
+                         long n_theta, long hits_per_single, uint64_t seed, int verbose,
+                         double *solid_angles, int32_t *hits);
+/* Device time (ms, CUDA events) of the last grid computed. */
+double xmb_solid_angle_last_ms(void);
+/* Raw hit counts of the last grid computed by xmb_solid_angle_calculation on this thread's
+ * device (int32 [theta][r]); for parity tests.  Returns number of points copied. */
+long xmb_solid_angle_last_hits(int32_t *hits, long capacity);
+void xmb_free_solid_angle(xmb_solid_angle *sa);   /* xmi_free_solid_angle, src/xmi_solid_angle.c:792-800 */
+
+/* Replaces xmi_main_msim (include/xmi_main.h:29; src/xmi_main.F90:66-954).
+ * channels:        malloc'ed double[(n_int+1)][nchannels], rows cumulative over interaction order, x live_time
+ * brute_history:   malloc'ed double[100][385][n_int]  (all zero with variance reduction on)
+ * var_red_history: malloc'ed double[100][385][n_int]  (NULL if variance reduction off)
+ * n_mpi_hosts/rank semantic: this rank simulates photon ids [rank*N/n, (rank+1)*N/n) of every
+ * source line; outputs are *partial sums* to be summed over ranks (see xmb_main_msim_ex).
+ * Returns 1 / 0. */
+int xmb_main_msim(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, int n_mpi_hosts, double **channels,
+                  const xmb_main_options *options, double **brute_history,
+                  double **var_red_history, const xmb_solid_angle *solid_angles);
+
+/* Extended driver used by the multi-GPU harness: photon-id sharding and raw fixed-point output
+ * so that the cross-rank sum is order-independent and bit-exact at any GPU count. */
+typedef struct xmb_msim_ex {
+	int rank, n_ranks;             /* shard [rank*N/n_ranks, (rank+1)*N/n_ranks) of every line/interval */
+	uint64_t seed;                 /* Philox key; 0 -> default 0x584D494D53494D */
+	int device;                    /* CUDA device ordinal, -1 = current */
+	int keep_on_device;            /* 1: leave accumulators resident (read with xmb_msim_accum_*) */
+	/* outputs */
+	uint64_t n_histories;          /* histories simulated by this rank */
+	double kernel_ms;              /* device time of the history kernel(s), CUDA events */
+	uint64_t n_launches;           /* kernels launched */
+	uint64_t n_interactions;       /* total interactions simulated (for bytes/history) */
+} xmb_msim_ex;
+
+/* Runs the history kernels and leaves the exact fixed-point accumulators in a host buffer of
+ * uint64 limbs: accum[2*i], accum[2*i+1] = low / high 48-bit-split words of slot i.
+ * Slot layout: channels [n_int][nch] (row k = deposits made at interaction k+1, NOT cumulative),
+ * then history [n_int][n_hist_slots].  *n_slots receives the slot count.  The buffer is malloc'ed. */
+int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                      const xmb_solid_angle *solid_angles, xmb_msim_ex *ex,
+                      uint64_t **accum, size_t *n_slots);
+/* Converts (summed) raw accumulators to the reference's three output arrays. */
+int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                         const uint64_t *accum, size_t n_slots, double **channels,
+                         double **brute_history, double **var_red_history);
+
+/* Replaces xmi_detector_convolute_all / the plugin symbol xmi_detector_convolute_all_custom
+ * (include/xmi_main.h:35-37; src/xmi_detector_f.F90:219-289).  channels_conv[i] are malloc'ed. */
+void xmb_detector_convolute_all(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double **channels_noconv,
+                                double **channels_conv, double *brute_history,
+                                double *var_red_history, const xmb_main_options *options,
+                                const xmb_escape_ratios *escape_ratios, int n_interactions_all,
+                                int zero_interaction);
+/* Replaces xmi_detector_convolute_spectrum (include/xmi_main.h:31; src/xmi_detector_f.F90:339-580). */
+void xmb_detector_convolute_spectrum(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
+                                     const double *channels_noconv, double **channels_conv,
+                                     const xmb_main_options *options,
+                                     const xmb_escape_ratios *escape_ratios, int n_interactions);
+
+/* xmi_main_options_new defaults (src/xmi_data_structs.c:2531-2565). */
+void xmb_main_options_defaults(xmb_main_options *options);
+
+/* Library / device info. */
+const char *xmb_version(void);
+int xmb_cuda_device_count(void);
+const char *xmb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+/* oracle.h -- CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * import, link or execute anything under oracle/.  The product (xmimsim_b200/) never does.
+ *
+ * Each function follows the reference file:line cited at its definition.  fp64 throughout, as the
+ * Fortran reference.  Random numbers: the reference uses one MT19937 per OpenMP thread; the oracle
+ * uses the same per-history / per-grid-point Philox4x32-10 counter streams as the GPU engine so
+ * that results are comparable history-by-history (the reference itself is only statistically
+ * reproducible across thread counts).
+ *
+ * PARITY STATUS: the Fortran reference cannot be built here (no Fortran compiler, no xraylib, no
+ * HDF5/GLib), so the oracle is pinned by: the Random123 Philox known-answer vectors,
+ * the reference's quadratic-solver test cases (tests/test-poly-solve-quadratic.F90), analytic
+ * solid angles, and the golden convoluted spectra in examples/.xmso for the detector response.
+ * Spectra parity against examples/.xmso is "parity unpinned": it needs xraylib data.
+ */
+#ifndef XMB_ORACLE_H
+#define XMB_ORACLE_H
+#include <stdint.h>
+#include "xmimsim_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Philox4x32-10 (Random123; Salmon et al. SC'11).  out[4] = philox(ctr[4], key[2]). */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* xmi_poly_solve_quadratic  (src/xmi_aux_f.F90:1872-1905).  Returns number of roots (0,1,2). */
+int orc_poly_solve_quadratic(double a, double b, double c, double *rv1, double *rv2);
+
+/* derived geometry, restating xmi_init_input (src/xmi_main.F90:1741-1918).  input is modified:
+ * normals normalised, sample normal flipped to +z.  Layer arrays are malloc'ed into *d. */
+typedef struct orc_derived {
+	double detector_radius, collimator_radius, collimator_height, half_apex, vertex[3];
+	int collimator_present;
+	double ndo_new[9], ndo_inv[9];   /* row-major */
+	double detector_solid_angle, n_sample_orientation_det[3];
+	int n_layers;
+	double *thickness_along_Z, *Z_coord_begin, *Z_coord_end;
+} orc_derived;
+int orc_init_input(xmb_input *input, orc_derived *d);
+void orc_free_derived(orc_derived *d);
+
+/* xmi_single_solid_angle_calculation (src/xmi_solid_angle_f.F90:432-710) for grid point index
+ * `point_id` (= theta_index * n_r + r_index), Philox stream (seed, point_id).  Returns the solid
+ * angle; *hits receives the number of rays that reached the detector. */
+double orc_single_solid_angle(const orc_derived *d, double r1, double theta1, long hits_per_single,
+                              uint64_t seed, uint64_t point_id, long *hits);
+/* xmi_solid_angle_calculation_f grid loop (src/xmi_solid_angle_f.F90:303-429) over a caller-given
+ * sub-grid: solid_angles[it*n_r + ir], hits likewise.  point ids use the FULL grid width
+ * full_n_r so that a sub-grid reproduces the same streams: id = theta_idx[it]*full_n_r + r_idx[ir]. */
+void orc_solid_angle_grid(const orc_derived *d, const double *r_vals, const int *r_idx, int n_r,
+                          const double *theta_vals, const int *theta_idx, int n_theta, long full_n_r,
+                          long hits_per_single, uint64_t seed, double *solid_angles, int32_t *hits,
+                          int n_threads);
+/* xmi_solid_angle_inputs_f (src/xmi_solid_angle_f.F90:62-301): grid axes from penetration depths;
+ * mu of the layers supplied by the provider.  r_vals/theta_vals: caller arrays of 1024. */
+int orc_solid_angle_axes(const xmb_input *input, const orc_derived *d, const xmb_xrl_provider *xrl,
+                         double *r_vals, double *theta_vals, long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

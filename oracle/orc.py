@@ -1,0 +1,76 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liborc.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liborc.so")
+_lib = None
+
+
+class OrcDerived(C.Structure):
+    _fields_ = [("detector_radius", C.c_double), ("collimator_radius", C.c_double), ("collimator_height", C.c_double),
+                ("half_apex", C.c_double), ("vertex", C.c_double * 3), ("collimator_present", C.c_int),
+                ("ndo_new", C.c_double * 9), ("ndo_inv", C.c_double * 9), ("detector_solid_angle", C.c_double),
+                ("n_sample_orientation_det", C.c_double * 3), ("n_layers", C.c_int),
+                ("thickness_along_Z", C.POINTER(C.c_double)), ("Z_coord_begin", C.POINTER(C.c_double)),
+                ("Z_coord_end", C.POINTER(C.c_double))]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("oracle library missing: run `make oracle`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_poly_solve_quadratic.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)] * 2
+        _lib.orc_poly_solve_quadratic.restype = C.c_int
+        _lib.orc_init_input.argtypes = [C.c_void_p, C.POINTER(OrcDerived)]
+        _lib.orc_init_input.restype = C.c_int
+        _lib.orc_single_solid_angle.argtypes = [C.POINTER(OrcDerived), C.c_double, C.c_double, C.c_long, C.c_uint64,
+                                                C.c_uint64, C.POINTER(C.c_long)]
+        _lib.orc_single_solid_angle.restype = C.c_double
+        _lib.orc_solid_angle_grid.argtypes = [C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_uint64, C.c_void_p,
+                                              C.c_void_p, C.c_int]
+        _lib.orc_solid_angle_grid.restype = None
+        _lib.orc_solid_angle_axes.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        _lib.orc_solid_angle_axes.restype = C.c_int
+        _lib.xmb_xrl_surrogate.restype = C.c_void_p
+    return _lib
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def init_input(cinput_ptr):
+    """orc_init_input on a ctypes xmb_input (modified in place: normals normalised)."""
+    d = OrcDerived()
+    if not lib().orc_init_input(C.cast(cinput_ptr, C.c_void_p), C.byref(d)):
+        raise RuntimeError("orc_init_input failed")
+    return d
+
+
+def solid_angle_grid(d, r_vals, r_idx, theta_vals, theta_idx, full_n_r, hits_per_single, seed, n_threads=8):
+    r = np.ascontiguousarray(r_vals, np.float64); t = np.ascontiguousarray(theta_vals, np.float64)
+    ri = np.ascontiguousarray(r_idx, np.int32); ti = np.ascontiguousarray(theta_idx, np.int32)
+    sa = np.zeros((t.size, r.size)); hits = np.zeros((t.size, r.size), np.int32)
+    lib().orc_solid_angle_grid(C.byref(d), r.ctypes.data, ri.ctypes.data, r.size, t.ctypes.data, ti.ctypes.data, t.size,
+                               full_n_r, hits_per_single, seed, sa.ctypes.data, hits.ctypes.data, n_threads)
+    return sa, hits
+
+
+def solid_angle_axes(cinput_ptr, d, n=1024):
+    r = np.zeros(n); t = np.zeros(n)
+    ok = lib().orc_solid_angle_axes(C.cast(cinput_ptr, C.c_void_p), C.byref(d), lib().xmb_xrl_surrogate(), r.ctypes.data,
+                                    t.ctypes.data, n)
+    if not ok:
+        raise RuntimeError("orc_solid_angle_axes failed")
+    return r, t

@@ -1,0 +1,145 @@
+"""CPU tests of the host side: library loads and exports the declared ABI, input handling, init_input
+against the oracle's independent restatement, table sanity."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import orc
+import xmimsim_b200 as x
+from xmimsim_b200 import abi
+from inputs import example, caso4, no_collimator
+
+
+def test_library_exports_every_declared_symbol():
+    L = abi.lib()
+    names = abi.declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_reference_sizes():
+    # LP64 sizes of the reference structs (include/xmi_data_structs.h) -- a layout drift breaks the drop-in
+    assert C.sizeof(abi.General) == 48
+    assert C.sizeof(abi.Layer) == 40
+    assert C.sizeof(abi.Geometry) == 128
+    assert C.sizeof(abi.EnergyDiscrete) == 72
+    assert C.sizeof(abi.EnergyContinuous) == 56
+    assert C.sizeof(abi.Detector) == 72
+    assert C.sizeof(abi.MainOptions) == 64
+    assert C.sizeof(abi.SolidAngle) == 48
+    assert C.sizeof(abi.EscapeRatios) == 72
+
+
+def test_main_options_defaults():
+    o = x.main_options()
+    assert (o.use_M_lines, o.use_cascade_auger, o.use_cascade_radiative, o.use_variance_reduction) == (1, 1, 1, 1)
+    assert (o.use_sum_peaks, o.use_escape_peaks, o.use_poisson, o.use_advanced_compton) == (0, 1, 0, 0)
+
+
+@pytest.mark.parametrize("name", ["srm1155", "srm1412", "srm1132", "In"])
+def test_init_input_matches_oracle(name):
+    inp = example(name)
+    sim = x.Simulation(inp, quality=0)
+    ci = x.CInput(inp)
+    od = orc.init_input(C.pointer(ci.input))
+    d = sim.derived
+    assert d.detector_radius == od.detector_radius
+    assert d.collimator_present == od.collimator_present
+    assert d.collimator_radius == od.collimator_radius
+    assert d.half_apex == od.half_apex
+    assert list(d.ndo_new) == list(od.ndo_new)
+    assert list(d.ndo_inv) == list(od.ndo_inv)
+    assert d.detector_solid_angle == od.detector_solid_angle
+    assert list(d.n_sample_orientation_det) == list(od.n_sample_orientation_det)
+    for i in range(d.n_layers):
+        assert d.Z_coord_begin[i] == od.Z_coord_begin[i]
+        assert d.Z_coord_end[i] == od.Z_coord_end[i]
+    # frame sanity: inverse * new = identity, x' = detector normal
+    A = np.array(list(d.ndo_new)).reshape(3, 3)
+    B = np.array(list(d.ndo_inv)).reshape(3, 3)
+    assert np.allclose(B @ A, np.eye(3), atol=1e-14)
+    assert np.allclose(A[:, 0], list(d.n_detector_orientation))
+    sim.close()
+
+
+def test_xmsi_reader_conventions(srm1155):
+    # elements sorted by Z, weights normalised (src/xmi_xml.c:1209-1263), lines sorted (:966)
+    for l in srm1155.layers:
+        assert l.Z == sorted(l.Z)
+        assert abs(sum(l.weight) - 1.0) < 1e-12
+    es = [d.energy for d in srm1155.discrete]
+    assert es == sorted(es) and len(es) == 26
+    assert srm1155.n_photons_line == 150000 and srm1155.n_interactions_trajectory == 4
+    assert srm1155.detector_type == 2 and srm1155.nchannels == 2048
+
+
+def test_input_validation():
+    inp = caso4()
+    inp.layers[0].Z = [120]
+    with pytest.raises(RuntimeError):
+        x.Simulation(inp)
+    inp = caso4()
+    inp.collimator_height = 1.0
+    inp.collimator_diameter = 5.0      # wider than the detector: the reference exits, we return 0
+    with pytest.raises(RuntimeError, match="Non conical"):
+        x.Simulation(inp)
+
+
+def test_solid_angle_axes_match_oracle():
+    inp = example("srm1155")
+    sim = x.Simulation(inp, quality=0)
+    r, t = sim.solid_angle_inputs()
+    ci = x.CInput(inp)
+    od = orc.init_input(C.pointer(ci.input))
+    ro, to = orc.solid_angle_axes(C.pointer(ci.input), od)
+    assert np.array_equal(r, ro) and np.array_equal(t, to)
+    assert r.size == 1024 and t.size == 1024 and t[0] == 1e-5 and abs(t[-1] - math.pi / 2) < 1e-15
+    assert abs(r[0] - r[-1] / 1024) < 1e-15
+    sim.close()
+
+
+def test_tables_sanity():
+    inp = example("srm1155")
+    sim = x.Simulation(inp, quality=0)
+    T = sim.tables
+    P = sim.provider.contents
+    nZ, nN = T.nZ, T.n_nodes
+    Z = [T.Z[i] for i in range(nZ)]
+    assert Z == sorted(set(z for l in inp.layers for z in l.Z))
+    E = np.ctypeslib.as_array(T.node_E, shape=(nN,))
+    assert np.all(np.diff(E) > 0) and E[0] == 0.1 and E[-1] >= max(d.energy for d in inp.discrete)
+    cs = np.ctypeslib.as_array(T.cs_total, shape=(nZ, nN))
+    pr = np.ctypeslib.as_array(T.p_rayl, shape=(nZ, nN))
+    prc = np.ctypeslib.as_array(T.p_rayl_compt, shape=(nZ, nN))
+    assert np.all(cs > 0) and np.all(pr > 0) and np.all(prc > pr) and np.all(prc < 1)
+    # tabulation error of linear interpolation between nodes vs the provider, away from edges
+    rng = np.random.default_rng(1)
+    iz = Z.index(26)
+    for e in rng.uniform(1.0, 16.0, 200):
+        k = np.searchsorted(E, e) - 1
+        f = (e - E[k]) / (E[k + 1] - E[k])
+        lin = cs[iz, k] * (1 - f) + cs[iz, k + 1] * f
+        assert abs(lin - P.CS_Total_Kissel(26, e)) / lin < 5e-4
+    # inverse CDFs: monotone in R, end points pinned (src/xmi_data_f.F90:1036-1037)
+    ric = np.ctypeslib.as_array(T.rayl_theta_icdf, shape=(nZ, T.n_icdf_E, T.n_icdf_R))
+    cic = np.ctypeslib.as_array(T.compt_theta_icdf, shape=(nZ, T.n_icdf_E, T.n_icdf_R))
+    for a in (ric, cic):
+        assert np.all(a[:, :, 0] == 0.0) and np.all(np.abs(a[:, :, -1] - math.pi) < 1e-12)
+        assert np.all(np.diff(a, axis=2) >= 0)
+    phi = np.ctypeslib.as_array(T.phi_icdf, shape=(T.n_phi_T, T.n_icdf_R))
+    assert np.all(np.diff(phi, axis=1) >= 0) and np.allclose(phi[0], np.linspace(0, 2 * math.pi, T.n_icdf_R), atol=2e-3)
+    # corrected yields (src/xmi_data_f.F90:1244-1251): L1 = w1 + f12 w2 + (f13 + f12 f23) w3
+    fy = np.ctypeslib.as_array(T.fluor_yield, shape=(nZ, 9))
+    fyc = np.ctypeslib.as_array(T.fluor_yield_corr, shape=(nZ, 9))
+    ck = np.ctypeslib.as_array(T.cos_kron, shape=(nZ, 13))
+    i82 = Z.index(82)
+    exp_l1 = fy[i82, 1] + ck[i82, 0] * fy[i82, 2] + (ck[i82, 1] + ck[i82, 0] * ck[i82, 2]) * fy[i82, 3]
+    assert abs(fyc[i82, 1] - exp_l1) < 1e-15
+    assert fyc[i82, 0] == fy[i82, 0] and fyc[i82, 3] == fy[i82, 3]
+    # radiative rates of a shell's line range sum to one (assumed at src/xmi_main.F90:5422-5426)
+    rr = np.ctypeslib.as_array(T.rad_rate, shape=(nZ, 384))
+    assert abs(rr[i82, 1:30].sum() - 1.0) < 1e-12 and abs(rr[i82, 86:114].sum() - 1.0) < 1e-12
+    sim.close()

@@ -1,0 +1,190 @@
+"""ctypes mirror of include/xmimsim_b200.h and loader of the product library.
+
+The structures have the reference's C layouts (include/xmi_data_structs.h:40-336, :479-495;
+include/xmi_solid_angle.h:28-35; include/xmi_detector.h:28-40).  The product library is mandatory:
+there is no Python or CPU fallback for any compute entry point.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libxmimsim_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class General(C.Structure):
+    _fields_ = [("version", C.c_float), ("outputfile", C.c_char_p), ("n_photons_interval", C.c_long),
+                ("n_photons_line", C.c_long), ("n_interactions_trajectory", C.c_int), ("comments", C.c_char_p)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("n_elements", C.c_int), ("Z", c_int_p), ("weight", c_double_p), ("density", C.c_double),
+                ("thickness", C.c_double)]
+
+
+class Composition(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("layers", C.POINTER(Layer)), ("reference_layer", C.c_int)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("d_sample_source", C.c_double), ("n_sample_orientation", C.c_double * 3),
+                ("p_detector_window", C.c_double * 3), ("n_detector_orientation", C.c_double * 3),
+                ("area_detector", C.c_double), ("collimator_height", C.c_double), ("collimator_diameter", C.c_double),
+                ("d_source_slit", C.c_double), ("slit_size_x", C.c_double), ("slit_size_y", C.c_double)]
+
+
+class EnergyDiscrete(C.Structure):
+    _fields_ = [("energy", C.c_double), ("horizontal_intensity", C.c_double), ("vertical_intensity", C.c_double),
+                ("sigma_x", C.c_double), ("sigma_xp", C.c_double), ("sigma_y", C.c_double), ("sigma_yp", C.c_double),
+                ("distribution_type", C.c_int), ("scale_parameter", C.c_double)]
+
+
+class EnergyContinuous(C.Structure):
+    _fields_ = [("energy", C.c_double), ("horizontal_intensity", C.c_double), ("vertical_intensity", C.c_double),
+                ("sigma_x", C.c_double), ("sigma_xp", C.c_double), ("sigma_y", C.c_double), ("sigma_yp", C.c_double)]
+
+
+class Excitation(C.Structure):
+    _fields_ = [("n_discrete", C.c_int), ("discrete", C.POINTER(EnergyDiscrete)), ("n_continuous", C.c_int),
+                ("continuous", C.POINTER(EnergyContinuous))]
+
+
+class Absorbers(C.Structure):
+    _fields_ = [("n_exc_layers", C.c_int), ("exc_layers", C.POINTER(Layer)), ("n_det_layers", C.c_int),
+                ("det_layers", C.POINTER(Layer))]
+
+
+class Detector(C.Structure):
+    _fields_ = [("detector_type", C.c_int), ("live_time", C.c_double), ("pulse_width", C.c_double),
+                ("gain", C.c_double), ("zero", C.c_double), ("fano", C.c_double), ("noise", C.c_double),
+                ("nchannels", C.c_int), ("n_crystal_layers", C.c_int), ("crystal_layers", C.POINTER(Layer))]
+
+
+class Input(C.Structure):
+    _fields_ = [("general", C.POINTER(General)), ("composition", C.POINTER(Composition)),
+                ("geometry", C.POINTER(Geometry)), ("excitation", C.POINTER(Excitation)),
+                ("absorbers", C.POINTER(Absorbers)), ("detector", C.POINTER(Detector))]
+
+
+class MainOptions(C.Structure):
+    _fields_ = [("use_M_lines", C.c_int), ("use_cascade_auger", C.c_int), ("use_cascade_radiative", C.c_int),
+                ("use_variance_reduction", C.c_int), ("use_sum_peaks", C.c_int), ("use_escape_peaks", C.c_int),
+                ("escape_ratios_mode", C.c_int), ("verbose", C.c_int), ("use_poisson", C.c_int), ("use_gpu", C.c_int),
+                ("omp_num_threads", C.c_int), ("extra_verbose", C.c_int), ("custom_detector_response", C.c_char_p),
+                ("use_advanced_compton", C.c_int), ("use_default_seeds", C.c_int)]
+
+
+class SolidAngle(C.Structure):
+    _fields_ = [("solid_angles", c_double_p), ("grid_dims_r_n", C.c_long), ("grid_dims_theta_n", C.c_long),
+                ("grid_dims_r_vals", c_double_p), ("grid_dims_theta_vals", c_double_p),
+                ("xmi_input_string", C.c_void_p)]
+
+
+class EscapeRatios(C.Structure):
+    _fields_ = [("n_elements", C.c_int), ("n_fluo_input_energies", C.c_int), ("n_compton_input_energies", C.c_int),
+                ("n_compton_output_energies", C.c_int), ("Z", c_int_p), ("fluo_escape_ratios", c_double_p),
+                ("fluo_escape_input_energies", c_double_p), ("compton_escape_ratios", c_double_p),
+                ("compton_escape_input_energies", c_double_p), ("compton_escape_output_energies", c_double_p),
+                ("xmi_input_string", C.c_void_p)]
+
+
+class Derived(C.Structure):
+    _fields_ = [("n_sample_orientation", C.c_double * 3), ("n_detector_orientation", C.c_double * 3),
+                ("detector_radius", C.c_double), ("collimator_present", C.c_int), ("collimator_radius", C.c_double),
+                ("collimator_height", C.c_double), ("half_apex", C.c_double), ("vertex", C.c_double * 3),
+                ("ndo_new", C.c_double * 9), ("ndo_inv", C.c_double * 9), ("detector_solid_angle", C.c_double),
+                ("n_sample_orientation_det", C.c_double * 3), ("n_layers", C.c_int),
+                ("thickness_along_Z", c_double_p), ("Z_coord_begin", c_double_p), ("Z_coord_end", c_double_p)]
+
+
+class TablesHost(C.Structure):
+    _fields_ = [("nZ", C.c_int), ("Z", c_int_p), ("uniqZ", c_int_p), ("atomic_weight", c_double_p),
+                ("n_nodes", C.c_int), ("node_E", c_double_p), ("bucket_E0", C.c_double), ("bucket_inv_dE", C.c_double),
+                ("n_buckets", C.c_int), ("bucket_start", c_int_p),
+                ("cs_total", c_double_p), ("cs_photo_total", c_double_p), ("p_rayl", c_double_p),
+                ("p_rayl_compt", c_double_p), ("cs_photo_partial", c_double_p), ("cs_vacancy", c_double_p),
+                ("n_icdf_E", C.c_int), ("n_icdf_R", C.c_int), ("icdf_E", c_double_p), ("icdf_R", c_double_p),
+                ("rayl_theta_icdf", c_double_p), ("compt_theta_icdf", c_double_p),
+                ("n_phi_T", C.c_int), ("phi_T", c_double_p), ("phi_icdf", c_double_p),
+                ("n_cp", C.c_int), ("cp_R", c_double_p), ("cp_icdf", c_double_p),
+                ("n_q", C.c_int), ("q_max", C.c_double), ("ff", c_double_p), ("sf", c_double_p),
+                ("fluor_yield", c_double_p), ("fluor_yield_corr", c_double_p), ("cos_kron", c_double_p),
+                ("rad_rate", c_double_p), ("line_energy", c_double_p), ("edge_energy", c_double_p),
+                ("precalc_xrf_cs", c_double_p), ("n_layers", C.c_int), ("precalc_mu_cs", c_double_p),
+                ("precalc_cs_total", c_double_p), ("precalc_p_rayl", c_double_p), ("precalc_p_rayl_compt", c_double_p),
+                ("precalc_cs_photo_total", c_double_p), ("precalc_cs_photo_partial", c_double_p)]
+
+
+class XrlProvider(C.Structure):
+    _D, _I = C.c_double, C.c_int
+    _fields_ = [("name", C.c_char_p),
+                ("AtomicWeight", C.CFUNCTYPE(_D, _I)), ("EdgeEnergy", C.CFUNCTYPE(_D, _I, _I)),
+                ("LineEnergy", C.CFUNCTYPE(_D, _I, _I)), ("FluorYield", C.CFUNCTYPE(_D, _I, _I)),
+                ("RadRate", C.CFUNCTYPE(_D, _I, _I)), ("CosKronTransProb", C.CFUNCTYPE(_D, _I, _I)),
+                ("JumpFactor", C.CFUNCTYPE(_D, _I, _I)), ("CS_Total_Kissel", C.CFUNCTYPE(_D, _I, _D)),
+                ("CS_Photo_Total", C.CFUNCTYPE(_D, _I, _D)), ("CS_Photo_Partial", C.CFUNCTYPE(_D, _I, _I, _D)),
+                ("CS_Rayl", C.CFUNCTYPE(_D, _I, _D)), ("CS_Compt", C.CFUNCTYPE(_D, _I, _D)),
+                ("FF_Rayl", C.CFUNCTYPE(_D, _I, _D)), ("SF_Compt", C.CFUNCTYPE(_D, _I, _D)),
+                ("ComptonProfile", C.CFUNCTYPE(_D, _I, _D)),
+                ("VacancyCS", C.CFUNCTYPE(_D, _I, _I, _D, _I, c_double_p))]
+
+
+class MsimEx(C.Structure):
+    _fields_ = [("rank", C.c_int), ("n_ranks", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
+                ("keep_on_device", C.c_int), ("n_histories", C.c_uint64), ("kernel_ms", C.c_double),
+                ("n_launches", C.c_uint64), ("n_interactions", C.c_uint64)]
+
+
+_lib = None
+
+
+def declared_symbols():
+    """Names declared in include/xmimsim_b200.h (parsed from the header itself)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "xmimsim_b200.h")
+    txt = open(hdr).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(xmb_[a-z0-9_A-Z]+)\s*\(", txt)) - {"xmb_discrete_distribution"})
+
+
+def lib():
+    """Load libxmimsim_b200.so (built by `make lib` / __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("xmimsim_b200: %s is missing -- run `make lib` (or __graft_entry__.build()); "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    L.xmb_xrl_surrogate.restype = C.POINTER(XrlProvider)
+    L.xmb_input_C2F.argtypes = [C.POINTER(Input), vpp]; L.xmb_input_C2F.restype = C.c_int
+    L.xmb_input_F2C.argtypes = [vp]; L.xmb_input_F2C.restype = C.POINTER(Input)
+    L.xmb_free_input_F.argtypes = [vpp]; L.xmb_free_input_F.restype = None
+    L.xmb_init_input.argtypes = [vpp]; L.xmb_init_input.restype = C.c_int
+    L.xmb_get_derived.argtypes = [vp]; L.xmb_get_derived.restype = C.POINTER(Derived)
+    L.xmb_init_from_provider.argtypes = [C.POINTER(XrlProvider), vp, C.c_int, vpp]; L.xmb_init_from_provider.restype = C.c_int
+    L.xmb_get_tables.argtypes = [vp]; L.xmb_get_tables.restype = C.POINTER(TablesHost)
+    L.xmb_free_hdf5_F.argtypes = [vpp]; L.xmb_free_hdf5_F.restype = None
+    L.xmb_solid_angle_inputs.argtypes = [vp, vp, C.POINTER(C.POINTER(SolidAngle))]; L.xmb_solid_angle_inputs.restype = C.c_int
+    L.xmb_solid_angle_calculation.argtypes = [vp, vp, C.POINTER(C.POINTER(SolidAngle)), C.c_void_p,
+                                              C.POINTER(MainOptions), C.c_long, C.c_uint64]
+    L.xmb_solid_angle_calculation.restype = C.c_int
+    L.xmb_solid_angle_grid.argtypes = [vp, c_double_p, C.c_long, c_double_p, C.c_long, C.c_long, C.c_uint64, C.c_int,
+                                       c_double_p, C.POINTER(C.c_int32)]
+    L.xmb_solid_angle_grid.restype = C.c_int
+    L.xmb_solid_angle_last_hits.argtypes = [C.POINTER(C.c_int32), C.c_long]; L.xmb_solid_angle_last_hits.restype = C.c_long
+    L.xmb_solid_angle_last_ms.restype = C.c_double
+    L.xmb_free_solid_angle.argtypes = [C.POINTER(SolidAngle)]; L.xmb_free_solid_angle.restype = None
+    L.xmb_main_options_defaults.argtypes = [C.POINTER(MainOptions)]; L.xmb_main_options_defaults.restype = None
+    L.xmb_version.restype = C.c_char_p
+    L.xmb_last_error.restype = C.c_char_p
+    L.xmb_cuda_device_count.restype = C.c_int
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().xmb_last_error().decode()

@@ -1,0 +1,114 @@
+"""Host-side mirror of the reference's call sequence around the hot path (bin/xmimsim.c:262-526):
+
+    xmi_input_C2F -> xmi_init_input -> xmi_init_from_hdf5/xmi_update_input_from_hdf5
+    -> xmi_solid_angle_calculation -> xmi_main_msim -> xmi_detector_convolute_all
+
+Every method is a thin ctypes call into libxmimsim_b200.so with the reference's argument meaning.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .xmsi import CInput, InputD
+
+
+def main_options(**kw):
+    """xmi_main_options_new defaults (src/xmi_data_structs.c:2531-2565) with overrides."""
+    o = abi.MainOptions()
+    abi.lib().xmb_main_options_defaults(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _np_from_ptr(ptr, shape, dtype=np.float64):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, dtype)
+    buf = np.ctypeslib.as_array(ptr, shape=(n,))
+    return buf.reshape(shape)
+
+
+class Simulation:
+    """Owns the two opaque handles (input + tables) of one simulation."""
+
+    def __init__(self, inp: InputD, quality: int = 0, provider=None):
+        L = abi.lib()
+        self.L = L
+        self.inp = inp
+        self.cinput = CInput(inp)
+        self.inputF = C.c_void_p()
+        if not L.xmb_input_C2F(C.byref(self.cinput.input), C.byref(self.inputF)):
+            raise RuntimeError("xmb_input_C2F: " + abi.last_error())
+        if not L.xmb_init_input(C.byref(self.inputF)):
+            raise RuntimeError("xmb_init_input: " + abi.last_error())
+        self.provider = provider if provider is not None else L.xmb_xrl_surrogate()
+        self.hdf5F = C.c_void_p()
+        if not L.xmb_init_from_provider(self.provider, self.inputF, quality, C.byref(self.hdf5F)):
+            raise RuntimeError("xmb_init_from_provider: " + abi.last_error())
+        self._sa = None
+
+    # -- views ---------------------------------------------------------------------------------
+    @property
+    def derived(self):
+        return self.L.xmb_get_derived(self.inputF).contents
+
+    @property
+    def tables(self):
+        return self.L.xmb_get_tables(self.hdf5F).contents
+
+    def c_input(self):
+        """The handle's own (normalised) C tree, as xmi_input_F2C would return it."""
+        return self.L.xmb_input_F2C(self.inputF)
+
+    # -- solid angle -----------------------------------------------------------------------------
+    def solid_angle_inputs(self):
+        sa = C.POINTER(abi.SolidAngle)()
+        if not self.L.xmb_solid_angle_inputs(self.inputF, self.hdf5F, C.byref(sa)):
+            raise RuntimeError("xmb_solid_angle_inputs: " + abi.last_error())
+        r = _np_from_ptr(sa.contents.grid_dims_r_vals, (sa.contents.grid_dims_r_n,)).copy()
+        t = _np_from_ptr(sa.contents.grid_dims_theta_vals, (sa.contents.grid_dims_theta_n,)).copy()
+        self.L.xmb_free_solid_angle(sa)
+        return r, t
+
+    def solid_angle_calculation(self, options=None, hits_per_single=5000, seed=0):
+        """xmi_solid_angle_calculation (GPU backend).  Returns (grid[theta][r], r_vals, theta_vals)."""
+        options = options or main_options()
+        sa = C.POINTER(abi.SolidAngle)()
+        if not self.L.xmb_solid_angle_calculation(self.inputF, self.hdf5F, C.byref(sa), None, C.byref(options),
+                                                  hits_per_single, seed):
+            raise RuntimeError("xmb_solid_angle_calculation: " + abi.last_error())
+        if self._sa is not None:
+            self.L.xmb_free_solid_angle(self._sa)
+        self._sa = sa
+        s = sa.contents
+        grid = _np_from_ptr(s.solid_angles, (s.grid_dims_theta_n, s.grid_dims_r_n))
+        return grid, _np_from_ptr(s.grid_dims_r_vals, (s.grid_dims_r_n,)), _np_from_ptr(s.grid_dims_theta_vals, (s.grid_dims_theta_n,))
+
+    def solid_angle_grid(self, r_vals, theta_vals, hits_per_single=5000, seed=0, verbose=0):
+        """Grid over caller-given axes.  Returns (solid_angles[theta][r], hits[theta][r])."""
+        r = np.ascontiguousarray(r_vals, dtype=np.float64)
+        t = np.ascontiguousarray(theta_vals, dtype=np.float64)
+        out = np.zeros((t.size, r.size), dtype=np.float64)
+        hits = np.zeros((t.size, r.size), dtype=np.int32)
+        ok = self.L.xmb_solid_angle_grid(self.inputF, r.ctypes.data_as(abi.c_double_p), r.size,
+                                         t.ctypes.data_as(abi.c_double_p), t.size, hits_per_single, seed, verbose,
+                                         out.ctypes.data_as(abi.c_double_p), hits.ctypes.data_as(C.POINTER(C.c_int32)))
+        if not ok:
+            raise RuntimeError("xmb_solid_angle_grid: " + abi.last_error())
+        return out, hits
+
+    def solid_angle_struct(self):
+        return self._sa
+
+    def close(self):
+        if self._sa is not None:
+            self.L.xmb_free_solid_angle(self._sa)
+            self._sa = None
+        if self.hdf5F:
+            self.L.xmb_free_hdf5_F(C.byref(self.hdf5F))
+        if self.inputF:
+            self.L.xmb_free_input_F(C.byref(self.inputF))

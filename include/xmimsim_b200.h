@@ -251,7 +251,8 @@ typedef struct xmb_tables_host {
 	const double *p_rayl;          /* [nZ][n_nodes]  CS_Rayl/CS_Total */
 	const double *p_rayl_compt;    /* [nZ][n_nodes]  (CS_Rayl+CS_Compt)/CS_Total */
 	const double *cs_photo_partial;/* [nZ][9][n_nodes] */
-	const double *cs_vacancy;      /* [4][nZ][9][n_nodes] cascade mode 1..4 -> index mode-1 */
+	const double *cs_vacancy;      /* [4][nZ][9][n_nodes] cascade mode 1..4 -> index mode-1
+	                                  (xraylib's P{K..M5}_{pure,auger,rad,full}_kissel) */
 	/* scattering-angle inverse CDFs (xmimsimdata.h5 shapes: src/xmi_data.c:150-152) */
 	int n_icdf_E, n_icdf_R;
 	const double *icdf_E;          /* [n_icdf_E] uniform */
@@ -276,15 +277,14 @@ typedef struct xmb_tables_host {
 	const double *rad_rate;        /* [nZ][384] by |line| */
 	const double *line_energy;     /* [nZ][384] */
 	const double *edge_energy;     /* [nZ][9] */
-	/* precalculated at fluorescence-line energies */
-	const double *precalc_xrf_cs;  /* [4][nZ][9][nZ'][220]  (mode, absorber, shell, emitter, |line|) */
+	/* Per-layer tables on the nodes.  Every fluorescence-line energy (|line| <= 219, E >= 0.1 keV) of
+	 * every element present and every monochromatic source-line energy IS a node, so a lookup at such
+	 * an energy returns the provider's value exactly: this is how the reference's precalc_mu_cs
+	 * (src/xmi_main.F90:227-237), precalc_xrf_cs (src/xmi_data_f.F90:1307-1476) and initial_mus
+	 * (:597) are represented. */
 	int n_layers;
-	const double *precalc_mu_cs;   /* [n_layers][nZ][220]  mu_layer(E_line(Z,|line|)) */
-	const double *precalc_cs_total;/* [nZ][nZ'][220] CS_Total_Kissel(Z, E_line(Z',line)) */
-	const double *precalc_p_rayl;  /* [nZ][nZ'][220] interaction probs at line energies */
-	const double *precalc_p_rayl_compt;
-	const double *precalc_cs_photo_total;   /* [nZ][nZ'][220] */
-	const double *precalc_cs_photo_partial; /* [nZ][9][nZ'][220] */
+	const double *mu_layer;        /* [n_layers][n_nodes]  sum_i w_i CS_Total_Kissel(Z_i, E) */
+	const double *exc_murhod;      /* [n_nodes] sum over excitation-path absorbers of mu*rho*t */
 } xmb_tables_host;
 
 /* ------------------------------------------------------------------------------------------

@@ -60,6 +60,18 @@ void orc_solid_angle_grid(const orc_derived *d, const double *r_vals, const int 
 int orc_solid_angle_axes(const xmb_input *input, const orc_derived *d, const xmb_xrl_provider *xrl,
                          double *r_vals, double *theta_vals, long n);
 
+/* Photon histories with forced detection: xmi_main_msim (src/xmi_main.F90:66-954) restricted to the
+ * global photon ids [g_begin, g_end) (ids enumerate valid continuous intervals, then discrete lines,
+ * photon-minor).  RAW sums, no live_time:
+ *   channels[(n_int+1)][nch]  cumulative over interaction order (reference's channels(0:n_int,:))
+ *   var_red[n_int][385][100]  = Fortran var_red_history(Z, slot, k)
+ * counters[0] = solid-angle lookups that fell off the grid, counters[1] = interactions simulated. */
+uint64_t orc_total_histories(const xmb_input *in);
+uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T,
+                             const xmb_main_options *opt, const xmb_solid_angle *sa, uint64_t seed,
+                             uint64_t g_begin, uint64_t g_end, int n_threads, double *channels,
+                             double *var_red, uint64_t *counters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,12 @@ def lib():
         _lib.orc_solid_angle_axes.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         _lib.orc_solid_angle_axes.restype = C.c_int
         _lib.xmb_xrl_surrogate.restype = C.c_void_p
+        _lib.orc_total_histories.argtypes = [C.c_void_p]
+        _lib.orc_total_histories.restype = C.c_uint64
+        _lib.orc_main_msim_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+        _lib.orc_main_msim_range.restype = C.c_uint64
     return _lib
 
 
@@ -74,3 +80,15 @@ def solid_angle_axes(cinput_ptr, d, n=1024):
     if not ok:
         raise RuntimeError("orc_solid_angle_axes failed")
     return r, t
+
+
+def main_msim_range(cinput_ptr, d, tables_ptr, options, sa_struct, seed, g_begin, g_end, n_int, nch, n_threads=8):
+    """Oracle histories for global photon ids [g_begin, g_end).  Returns (channels[(n_int+1)][nch] cumulative,
+    var_red[100][385][n_int] in the reference's exported C order, counters) -- RAW, without live_time."""
+    ch = np.zeros((n_int + 1, nch))
+    vr = np.zeros((n_int, 385, 100))
+    cnt = np.zeros(2, np.uint64)
+    lib().orc_main_msim_range(C.cast(cinput_ptr, C.c_void_p), C.byref(d), C.cast(tables_ptr, C.c_void_p),
+                              C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
+                              g_begin, g_end, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
+    return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt

@@ -1,0 +1,158 @@
+"""GPU parity of the photon-history engine against the CPU oracle on identical inputs, tables and
+Philox streams (tier T0 of SURVEY.md 8c), plus size-independent properties at larger sizes."""
+import copy
+
+import numpy as np
+import pytest
+
+import xmimsim_b200 as x
+from helpers import Pair, assert_spectra_close
+from inputs import example, caso4, synthetic_layers, ebel_like
+
+pytestmark = pytest.mark.gpu
+
+# Tolerance: both sides are fp64 and consume the same tables and random numbers.  Differences come from
+# (a) summation order (oracle: per-thread double sums; GPU: exact integers), (b) fused multiply-adds and
+# CUDA-vs-glibc transcendentals (a few ulp per history), (c) the rare history whose discrete decision
+# (layer / element / channel) flips on such an ulp.  (c) bounds the test: one flipped history changes a
+# channel by ~1/N of its content, so spectra must agree to 1e-6 of their maximum at N ~ 5e4 histories.
+RTOL = 2e-6
+
+
+def run_both(inp, options=None, seed=11, grid_n=None, hits=400):
+    options = options or x.main_options()
+    P = Pair(inp)
+    sa = P.grid(hits_per_single=hits, n=grid_n)
+    ch, br, vr = P.sim.main_msim(options, sa)
+    ch_o, vr_o, cnt = P.oracle(options, sa, 0)   # seed 0 -> default key on both sides
+    P.close()
+    return ch, br, vr, ch_o, vr_o, cnt
+
+
+@pytest.mark.parametrize("name,n_line", [("srm1155", 1500), ("srm1412", 1500), ("srm1132", 1500), ("In", 1500)])
+def test_examples_match_oracle(name, n_line):
+    inp = example(name)
+    inp.n_photons_line = n_line
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp)
+    assert ch.shape == (inp.n_interactions_trajectory + 1, inp.nchannels)
+    assert np.all(ch[0] == 0) and np.all(br == 0)            # no zero-interaction / brute-force content with VR
+    assert ch_o[1:].sum() > 0
+    assert_spectra_close(ch, ch_o, RTOL, name + " channels")
+    assert_spectra_close(vr, vr_o, RTOL, name + " var_red_history")
+    # strongest lines agree to 1e-6 relative individually
+    idx = np.argsort(vr_o.sum(axis=2).ravel())[-8:]
+    a = vr.sum(axis=2).ravel()[idx]; b = vr_o.sum(axis=2).ravel()[idx]
+    assert np.all(np.abs(a - b) <= 1e-6 * b)
+    # rows are cumulative over interaction order
+    assert np.all(np.diff(ch, axis=0) >= 0)
+
+
+def test_caso4_single_interaction():
+    inp = caso4()
+    inp.n_photons_line = 20000
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert_spectra_close(ch, ch_o, RTOL, "caso4 channels")
+    assert_spectra_close(vr, vr_o, RTOL, "caso4 history")
+    assert vr[19, 2, 0] > 0                                   # Ca-KL3, first order
+    assert cnt[1] <= inp.n_photons_line
+
+
+@pytest.mark.parametrize("opts", [dict(use_M_lines=0), dict(use_cascade_auger=0), dict(use_cascade_radiative=0),
+                                   dict(use_cascade_auger=0, use_cascade_radiative=0)])
+def test_option_variants(opts):
+    inp = example("srm1412")
+    inp.n_photons_line = 800
+    o = x.main_options(**opts)
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, options=o, grid_n=128)
+    assert_spectra_close(ch, ch_o, RTOL, "channels %r" % opts)
+    assert_spectra_close(vr, vr_o, RTOL, "history %r" % opts)
+
+
+def test_synthetic_ten_layers_eight_interactions():
+    inp = synthetic_layers(n_photons=30000, n_int=8)
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert ch.shape == (9, inp.nchannels)
+    assert_spectra_close(ch, ch_o, RTOL, "synthetic channels")
+    assert_spectra_close(vr, vr_o, RTOL, "synthetic history")
+
+
+def test_continuous_and_broadened_sources():
+    inp = ebel_like(n_intervals=40, n_photons_interval=600, n_photons_line=1500)
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert_spectra_close(ch, ch_o, RTOL, "continuous channels")
+    assert_spectra_close(vr, vr_o, RTOL, "continuous history")
+
+
+def test_gaussian_source_and_excitation_absorber():
+    inp = example("srm1412")       # has an Al excitation-path absorber
+    inp.n_photons_line = 600
+    for d in inp.discrete:
+        d.sigma_x, d.sigma_y, d.sigma_xp, d.sigma_yp = 0.01, 0.02, 1e-4, 2e-4
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert_spectra_close(ch, ch_o, RTOL, "gaussian-source channels")
+
+
+def test_bit_exact_across_rank_counts():
+    """Photon-id shards summed in uint64 must reproduce the single-rank accumulators bit for bit, for any
+    shard count, and so must a repeat run (atomics order does not matter)."""
+    inp = example("srm1155")
+    inp.n_photons_line = 1111            # not a multiple of 32 nor of the rank counts
+    P = Pair(inp)
+    sa = P.grid(n=128)
+    o = x.main_options()
+    ref, ex = P.sim.main_msim_raw(o, sa)
+    assert ex.n_histories == P.n_total and ex.n_launches == 1
+    again, _ = P.sim.main_msim_raw(o, sa)
+    assert np.array_equal(ref, again)
+    for n_ranks in (2, 3, 8):
+        tot = np.zeros_like(ref)
+        nh = 0
+        for r in range(n_ranks):
+            limbs, ex = P.sim.main_msim_raw(o, sa, rank=r, n_ranks=n_ranks)
+            tot += limbs
+            nh += ex.n_histories
+        assert nh == P.n_total
+        # limbs are 48-bit split words: normalise carries before comparing
+        def norm(v):
+            v = v.reshape(-1, 2).astype(object)
+            return [int(a) + (int(b) << 48) for a, b in v]
+        assert norm(tot) == norm(ref), n_ranks
+    ch1 = P.sim.main_msim_finish(ref, o)[0]
+    ch2 = P.sim.main_msim(o, sa)[0]
+    assert np.array_equal(ch1, ch2)
+    other, _ = P.sim.main_msim_raw(o, sa, seed=12345)
+    assert not np.array_equal(ref, other)
+    P.close()
+
+
+def test_linearity_and_weight_bounds_at_larger_size():
+    """Size-independent properties: the spectrum per unit photon converges (two sizes agree within the
+    statistical error), order-1 content dominates, all deposits non-negative."""
+    inp = example("srm1155")
+    res = []
+    for n in (20000, 80000):
+        d = copy.deepcopy(inp)
+        d.n_photons_line = n
+        P = Pair(d)
+        sa = P.grid(n=256, hits_per_single=1000, seed=5)
+        ch, br, vr = P.sim.main_msim(x.main_options(), sa)
+        P.close()
+        res.append((ch, vr))
+    (c1, v1), (c2, v2) = res
+    assert np.all(c1 >= 0) and np.all(c2 >= 0)
+    t1, t2 = c1[-1].sum(), c2[-1].sum()
+    assert abs(t1 / t2 - 1.0) < 5e-3
+    fe1, fe2 = v1[25, 2].sum(), v2[25, 2].sum()
+    assert abs(fe1 / fe2 - 1.0) < 5e-3
+    assert c2[1].sum() > 0.8 * c2[-1].sum()
+
+
+def test_unsupported_modes_fail_loudly():
+    inp = caso4()
+    inp.n_photons_line = 100
+    P = Pair(inp)
+    sa = P.grid(n=64)
+    for kw in (dict(use_variance_reduction=0), dict(use_advanced_compton=1)):
+        with pytest.raises(RuntimeError, match="not implemented"):
+            P.sim.main_msim(x.main_options(**kw), sa)
+    P.close()

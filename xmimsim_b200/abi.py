@@ -112,9 +112,7 @@ class TablesHost(C.Structure):
                 ("n_q", C.c_int), ("q_max", C.c_double), ("ff", c_double_p), ("sf", c_double_p),
                 ("fluor_yield", c_double_p), ("fluor_yield_corr", c_double_p), ("cos_kron", c_double_p),
                 ("rad_rate", c_double_p), ("line_energy", c_double_p), ("edge_energy", c_double_p),
-                ("precalc_xrf_cs", c_double_p), ("n_layers", C.c_int), ("precalc_mu_cs", c_double_p),
-                ("precalc_cs_total", c_double_p), ("precalc_p_rayl", c_double_p), ("precalc_p_rayl_compt", c_double_p),
-                ("precalc_cs_photo_total", c_double_p), ("precalc_cs_photo_partial", c_double_p)]
+                ("n_layers", C.c_int), ("mu_layer", c_double_p), ("exc_murhod", c_double_p)]
 
 
 class XrlProvider(C.Structure):
@@ -179,6 +177,15 @@ def lib():
     L.xmb_solid_angle_last_ms.restype = C.c_double
     L.xmb_free_solid_angle.argtypes = [C.POINTER(SolidAngle)]; L.xmb_free_solid_angle.restype = None
     L.xmb_main_options_defaults.argtypes = [C.POINTER(MainOptions)]; L.xmb_main_options_defaults.restype = None
+    L.xmb_main_msim.argtypes = [vp, vp, C.c_int, C.POINTER(c_double_p), C.POINTER(MainOptions), C.POINTER(c_double_p),
+                                C.POINTER(c_double_p), C.POINTER(SolidAngle)]
+    L.xmb_main_msim.restype = C.c_int
+    L.xmb_main_msim_raw.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(SolidAngle), C.POINTER(MsimEx),
+                                    C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_size_t)]
+    L.xmb_main_msim_raw.restype = C.c_int
+    L.xmb_main_msim_finish.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(C.c_uint64), C.c_size_t,
+                                       C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p)]
+    L.xmb_main_msim_finish.restype = C.c_int
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

@@ -1,0 +1,998 @@
+// history.cu -- photon histories with forced detection on the GPU (north_star items 1 and 2).
+//
+// Replaces the OpenMP photon loops of xmi_main_msim (src/xmi_main.F90:280-867) and everything they
+// call per photon: source sampling (:957-1186), xmi_simulate_photon's variance-reduction branch
+// (:1188-1685), Rayleigh / Compton / photo-electric interactions with Coster-Kronig and line selection
+// (:1986-2411, :4985-5437) and the forced-detection scoring xmi_variance_reduction
+// (src/xmi_variance_reduction.F90:29-1101) with the solid-angle lookup (src/xmi_solid_angle_f.F90:712-801).
+//
+// Mapping: one thread = one history; a warp owns 32 consecutive global photon ids and walks
+// the interaction orders in lock step (with forced interactions every live photon interacts exactly once
+// per iteration, so the interaction order is warp-uniform).  The forced-detection loops over layers,
+// elements, shells and line records are warp-uniform; lanes that are dead or sit in another layer
+// contribute zero.  Every deposit is converted to 2^-56 fixed point per lane, summed exactly across the
+// warp with integer shuffles and added with ONE 128-bit (lo/hi + carry) atomic: the totals are
+// independent of scheduling, launch shape and GPU count, bit for bit.
+// XRF deposits only touch the per-line history slot; the channel spectrum is rebuilt from those slots in
+// the epilogue (a line's channel is a constant), which halves the atomics of the inner loop.
+// Random numbers: Philox4x32-10, stream = global photon id, consumed sequentially.
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include "cuda_util.cuh"
+#include "history.cuh"
+#include "xmb_lines.h"
+
+#define ENERGY_THRESHOLD 1.0
+#define ENERGY_MAX 200.0
+#define XMI_MEC2 (9.10938188e-31 * 2.99792458e8 * 2.99792458e8 / 1.602176487e-19 / 1000.0)
+#define KEV2ANGST 12.39841930
+#define AVOGNUM 0.602252
+#define RE2 0.07940775
+#define HIST_THREADS 128
+
+__constant__ short d_shell_line_first[9] = {1, 30, 59, 86, 118, 140, 161, 182, 201};   // = xmb_shell_line_first
+__constant__ short d_shell_line_last[9] = {29, 58, 85, 113, 136, 158, 180, 200, 219};    // = xmb_shell_line_last
+
+struct NodePos { int pos; double f; };
+
+__device__ __forceinline__ NodePos node_find(const XmbHistParams &P, double E) {
+	int b = (int)floor((E - P.bucket_E0) * P.bucket_inv_dE);
+	b = max(0, min(b, P.n_buckets - 1));
+	int i = P.bucket_start[b];
+	while (i > 0 && P.node_E[i] > E) i--;
+	while (i + 1 < P.n_nodes - 1 && P.node_E[i + 1] <= E) i++;
+	i = min(i, P.n_nodes - 2);
+	NodePos p;
+	p.pos = i;
+	const double e0 = P.node_E[i], e1 = P.node_E[i + 1];
+	p.f = (E - e0) / (e1 - e0);
+	return p;
+}
+__device__ __forceinline__ double row_lerp(const XmbHistParams &P, NodePos np, int off) {
+	const double *r0 = P.rows + (size_t)np.pos * P.row_stride + off;
+	const double a = r0[0], b = r0[P.row_stride];
+	return a + (b - a) * np.f;
+}
+
+// findpos on a uniform axis with the reference's interval convention axis(i) < x <= axis(i+1)
+// (src/xmi_aux_f.F90:1305-1335)
+__device__ __forceinline__ int findpos_uniform(const double *ax, int n, double x) {
+	const double x0 = ax[0], dx = ax[1] - ax[0];
+	if (fabs(x - x0) < 1e-10) return 0;
+	int i = (int)ceil((x - x0) / dx) - 1;
+	i = max(0, min(i, n - 2));
+	while (i > 0 && x <= x0 + dx * i) i--;
+	while (i < n - 2 && x > x0 + dx * (i + 1)) i++;
+	return i;
+}
+// bilinear_interpolation (src/xmi_aux_f.F90:1337-1428); a[i1][i2], i2 fastest
+__device__ __forceinline__ double bilinear(const double *a, int n2, const double *ax1, int n1, const double *ax2, double x1, double x2) {
+	const int p1 = findpos_uniform(ax1, n1, x1), p2 = findpos_uniform(ax2, n2, x2);
+	const double a1l = ax1[p1], a1h = ax1[p1 + 1], a2l = ax2[p2], a2h = ax2[p2 + 1];
+	const double denom = (a1h - a1l) * (a2h - a2l);
+	const double c1 = (a1h - x1) * (a2h - x2) / denom, c2 = (x1 - a1l) * (a2h - x2) / denom;
+	const double c3 = (a1h - x1) * (x2 - a2l) / denom, c4 = (x1 - a1l) * (x2 - a2l) / denom;
+	const double *q = a + (size_t)p1 * n2 + p2;
+	return c1 * q[0] + c2 * q[n2] + c3 * q[1] + c4 * q[n2 + 1];
+}
+
+// ---- exact accumulation ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long to_fixed(double w, unsigned long long *counters) {
+	// w >= 0 relative weight; 2^56 fixed point.  Out-of-range values are counted, never wrapped.
+	const double s = w * 72057594037927936.0;
+	if (!(s < 9.2e18)) { if (s == s) atomicAdd(&counters[2], 1ULL); return 0ULL; }
+	return __double2ull_rn(s);
+}
+__device__ __forceinline__ void add128(unsigned long long *acc, size_t slot, unsigned long long v) {
+	if (v == 0ULL) return;
+	const unsigned long long old = atomicAdd(&acc[2 * slot], v);
+	if (old + v < old) atomicAdd(&acc[2 * slot + 1], 1ULL);
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+// all 32 lanes call; slot is warp-uniform
+__device__ __forceinline__ void deposit_uniform(unsigned long long *acc, size_t slot, unsigned long long v, int lane) {
+	v = warp_sum_u64(v);
+	if (lane == 0) add128(acc, slot, v);
+}
+// all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
+__device__ __forceinline__ void deposit_varying(unsigned long long *acc, long slot, unsigned long long v, int lane) {
+	const long s0 = __shfl_sync(0xffffffffu, slot, 0);
+	if (__all_sync(0xffffffffu, slot == s0)) {
+		if (s0 >= 0) deposit_uniform(acc, (size_t)s0, v, lane);
+	} else if (slot >= 0) add128(acc, (size_t)slot, v);
+}
+
+struct Photon {
+	double cx, cy, cz, dx, dy, dz, ex, ey, ez;
+	double energy, weight, theta, phi;
+	int layer;
+	int n_interactions;
+	bool alive;
+};
+
+__device__ __forceinline__ void normalize3(double &x, double &y, double &z) {
+	const double n = sqrt(x * x + y * y + z * z);
+	x /= n; y /= n; z /= n;
+}
+
+// xmi_update_photon_dirv (src/xmi_main.F90:5071-5148)
+__device__ __forceinline__ void update_dirv(Photon &p, double theta_i, double phi_i) {
+	double phi_new = phi_i;
+	if (phi_i > 2.0 * M_PI) phi_new = phi_i - 2.0 * M_PI;
+	else if (phi_i < 0.0) phi_new = phi_i + 2.0 * M_PI;
+	double sph, cph, sth, cth, sti, cti, spn, cpn;
+	sincos(p.phi, &sph, &cph);
+	sincos(p.theta, &sth, &cth);
+	sincos(theta_i, &sti, &cti);
+	sincos(phi_new, &spn, &cpn);
+	const double v0 = sti * cpn, v1 = sti * spn, v2 = cti;
+	p.dx = cth * cph * v0 + (-sph) * v1 + sth * cph * v2;
+	p.dy = cth * sph * v0 + cph * v1 + sth * sph * v2;
+	p.dz = (-sth) * v0 + 0.0 * v1 + cth * v2;
+	normalize3(p.dx, p.dy, p.dz);
+	p.theta = acos(p.dz);
+	p.phi = atan2(p.dy, p.dx);
+	if (p.phi > 2.0 * M_PI) p.phi -= 2.0 * M_PI;
+	else if (p.phi < 0.0) p.phi += 2.0 * M_PI;
+}
+// xmi_update_photon_elecv (:5150-5182)
+__device__ __forceinline__ void update_elecv(Photon &p) {
+	const double cosalfa = p.dx * p.ex + p.dy * p.ey + p.dz * p.ez;
+	const double sinalfa = sin(acos(cosalfa));
+	const double c_ae = 1.0 / sinalfa, c_be = -c_ae * cosalfa;
+	p.ex = c_ae * p.ex + c_be * p.dx;
+	p.ey = c_ae * p.ey + c_be * p.dy;
+	p.ez = c_ae * p.ez + c_be * p.dz;
+	normalize3(p.ex, p.ey, p.ez);
+}
+// phi0 of the electric vector in the photon frame (:2055-2066)
+__device__ __forceinline__ double elec_phi0(const Photon &p) {
+	double sph, cph, sth, cth;
+	sincos(p.phi, &sph, &cph);
+	sincos(p.theta, &sth, &cth);
+	double cosphi0 = p.ex * (cph * cth) + p.ey * (cth * sph) + p.ez * (-sth);
+	const double sinphi0 = p.ex * sph + p.ey * (-cph) + p.ez * 0.0;
+	if (fabs(cosphi0) > 1.0) cosphi0 = cosphi0 > 0 ? 1.0 : -1.0;
+	double phi0 = acos(cosphi0);
+	if (sinphi0 > 0.0) phi0 = -phi0;
+	return phi0;
+}
+
+// Doppler-broadened Compton energy (src/xmi_main.F90:4985-5067; forced-detection variant
+// src/xmi_variance_reduction.F90:1010-1101)
+__device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi, double E0, double theta_i, XmbRng &rng, bool varred) {
+	const double cc = 1.2399E-6, c0 = 4.85E-12, c1 = 1.456E-2;
+	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp;
+	const double c_lamb0 = cc / (E0 * 1000.0);
+	const double sth2 = sin(theta_i / 2.0);
+	double energy;
+	int tries = 0;
+	for (;;) {
+		const double r = rng.uniform();
+		int pos = (int)(r / P.cp_dR);
+		if (varred && pos == P.n_cp - 2) continue;
+		pos = min(pos, P.n_cp - 2);
+		const double r0 = P.cp_R[pos], r1 = P.cp_R[pos + 1];
+		double pz = icdf[pos] + (icdf[pos + 1] - icdf[pos]) * (r - r0) / (r1 - r0);
+		if (rng.uniform() < 0.5) pz = -pz;
+		const double dlamb = c0 * sth2 * sth2 - c1 * c_lamb0 * sth2 * pz;
+		const double c_lamb = c_lamb0 + dlamb;
+		energy = cc / c_lamb / 1000.0;
+		if (energy <= E0) break;
+		if (varred && tries == 100) break;
+		tries++;
+	}
+	return energy;
+}
+
+// xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801); off-grid points are counted and score zero
+__device__ __forceinline__ double get_solid_angle(const XmbHistParams &P, const Photon &p) {
+	double vx = p.cx - P.p_window[0], vy = p.cy - P.p_window[1], vz = p.cz - P.p_window[2];
+	const double r = sqrt(vx * vx + vy * vy + vz * vz);
+	normalize3(vx, vy, vz);
+	double temp_theta = acos(vx * P.n_detector[0] + vy * P.n_detector[1] + vz * P.n_detector[2]);
+	if (temp_theta > M_PI / 2.0) temp_theta = M_PI - temp_theta;
+	const double theta = (M_PI / 2.0) - temp_theta;
+	const double *R = P.sa_r_vals, *Th = P.sa_t_vals;
+	if (theta < Th[0]) return 0.0;
+	if (r > R[P.sa_nr - 1] || r < R[0] - 1e-10 || theta > Th[P.sa_nt - 1]) { atomicAdd(&P.counters[0], 1ULL); return 0.0; }
+	const int p1 = findpos_uniform(R, P.sa_nr, r), p2 = findpos_uniform(Th, P.sa_nt, theta);
+	const double rl = R[p1], rh = R[p1 + 1], tl = Th[p2], th = Th[p2 + 1];
+	const double denom = (rh - rl) * (th - tl);
+	const double c1 = (rh - r) * (th - theta) / denom, c2 = (r - rl) * (th - theta) / denom;
+	const double c3 = (rh - r) * (theta - tl) / denom, c4 = (r - rl) * (theta - tl) / denom;
+	const double *A = P.sa_grid + (size_t)p2 * P.sa_nr + p1;
+	return c1 * A[0] + c2 * A[1] + c3 * A[P.sa_nr] + c4 * A[P.sa_nr + 1];
+}
+
+__device__ __forceinline__ double ran_gaussian(XmbRng &rng, double sigma) {
+	const double u1 = rng.uniform(), u2 = rng.uniform();
+	return sigma * sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * M_PI * u2);
+}
+
+// ---- source sampling (src/xmi_main.F90:319-438, :579-724, :957-1186) -----------------------------------
+__device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uint64_t g, double *mus /* [nL] stride T */, int T) {
+	int s;
+	uint64_t j;
+	const uint64_t n_cont = P.n_cont_seg * P.n_per_interval;
+	if (g < n_cont) { s = (int)(g / P.n_per_interval); j = g - (uint64_t)s * P.n_per_interval; }
+	else { const uint64_t k = (g - n_cont) / P.n_per_line; s = (int)(P.n_cont_seg + k); j = g - n_cont - k * P.n_per_line; }
+	const XmbSegDev &S = P.segs[s];
+	p.alive = true;
+	p.n_interactions = 0;
+	double hor_ver_ratio;
+	if (S.is_cont) {
+		// xmi_ran_trap (src/xmi_aux_f.F90:1841-1941)
+		const double m = (S.y2 - S.y1) / (S.x2 - S.x1);
+		const double denom = (S.x2 - S.x1) * (S.y1 - S.x1 * m) + m * (S.x2 * S.x2 - S.x1 * S.x1) / 2.0;
+		const double a = m / 2.0, b = S.y1 - S.x1 * m, c = -S.x1 * S.y1 + m * S.x1 * S.x1 / 2.0 - denom * rng.uniform();
+		double rv1, rv2;
+		if (a == 0.0) { rv1 = -1.0 * c / b; rv2 = rv1; }
+		else {
+			const double delta = b * b - 4.0 * a * c;
+			if (delta <= 0.0) { rv1 = -b / 2.0 / a; rv2 = rv1; }
+			else { const double sq = sqrt(delta), t1 = (-b + sq) / 2.0 / a, t2 = (-b - sq) / 2.0 / a; rv1 = fmin(t1, t2); rv2 = fmax(t1, t2); }
+		}
+		p.energy = (S.x1 <= rv1 && rv1 <= S.x2) ? rv1 : rv2;
+		const double hi = S.h1 + (S.h2 - S.h1) * (p.energy - S.x1) / (S.x2 - S.x1);
+		const double ti = S.y1 + (S.y2 - S.y1) * (p.energy - S.x1) / (S.x2 - S.x1);
+		hor_ver_ratio = hi / ti;
+		const NodePos np = node_find(P, p.energy);
+		p.weight = S.total_rel * exp(-row_lerp(P, np, P.off_exc));
+		for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, np, i);
+	} else {
+		hor_ver_ratio = S.hor_ver_ratio;
+		p.weight = S.weight_rel;
+		if (S.distribution_type == XMB_DISCRETE_GAUSSIAN) p.energy = ran_gaussian(rng, S.scale_parameter) + S.energy;
+		else if (S.distribution_type == XMB_DISCRETE_LORENTZIAN) p.energy = S.scale_parameter * tan(M_PI * rng.uniform()) + S.energy;
+		else p.energy = S.energy;
+		if (p.energy <= ENERGY_THRESHOLD || p.energy > ENERGY_MAX) { p.alive = false; return; }
+		const NodePos np = node_find(P, p.energy);
+		for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, np, i);
+	}
+	double x1, y1;
+	if (fabs(S.sigma_x * S.sigma_y) < 1.0E-20) {
+		x1 = P.slit_x1_max * (-1.0 + 2.0 * rng.uniform());
+		y1 = P.slit_y1_max * (-1.0 + 2.0 * rng.uniform());
+		p.cx = p.cy = p.cz = 0.0;
+	} else {
+		x1 = ran_gaussian(rng, S.sigma_xp);
+		y1 = ran_gaussian(rng, S.sigma_yp);
+		p.cx = ran_gaussian(rng, S.sigma_x) - P.d_source_slit * sin(x1);
+		p.cy = ran_gaussian(rng, S.sigma_y) - P.d_source_slit * sin(y1);
+		p.cz = 0.0;
+	}
+	p.dx = tan(x1); p.dy = tan(y1); p.dz = 1.0;
+	normalize3(p.dx, p.dy, p.dz);
+	p.theta = acos(p.dz);
+	p.phi = atan2(p.dy, p.dx);
+	bool horizontal;
+	if (S.is_cont) horizontal = rng.uniform() <= hor_ver_ratio;
+	else horizontal = (double)(j + 1) <= hor_ver_ratio;
+	if (horizontal) { p.ex = 0.0; p.ey = 1.0; p.ez = 0.0; } else { p.ex = 1.0; p.ey = 0.0; p.ez = 0.0; }
+	const double cosalfa = p.ex * p.dx + p.ey * p.dy + p.ez * p.dz;
+	const double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+	p.ex = c_ae * p.ex + c_be * p.dx; p.ey = c_ae * p.ey + c_be * p.dy; p.ez = c_ae * p.ez + c_be * p.dz;
+	// xmi_photon_shift_first_layer (:1140-1186)
+	p.layer = -1;
+	if (p.cz >= P.layers[0].Z_begin) {
+		for (int i = 0; i < P.nL; i++) if (p.cz < P.layers[i].Z_end) { p.layer = i; break; }
+		if (p.layer < 0) { p.alive = false; return; }
+	} else {
+		const double ItimesN = p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2];
+		if (ItimesN == 0.0) { p.alive = false; return; }
+		const double d = ((0.0 - p.cx) * P.n_sample[0] + (0.0 - p.cy) * P.n_sample[1] + (P.layers[0].Z_begin - p.cz) * P.n_sample[2]) / ItimesN;
+		p.cx = d * p.dx + p.cx; p.cy = d * p.dy + p.cy; p.cz = d * p.dz + p.cz;
+		p.layer = 0;
+	}
+}
+
+// distance along (dx,dy,dz) from (x,y,z) to the plane through (0,0,zp) with the sample normal; also moves the point
+__device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x, double &y, double &z, double dx, double dy, double dz,
+                                              double zp, double &dist) {
+	const double ItimesN = dx * P.n_sample[0] + dy * P.n_sample[1] + dz * P.n_sample[2];
+	if (ItimesN == 0.0) return false;
+	const double d = ((0.0 - x) * P.n_sample[0] + (0.0 - y) * P.n_sample[1] + (zp - z) * P.n_sample[2]) / ItimesN;
+	const double nx = d * dx + x, ny = d * dy + y, nz = d * dz + z;
+	dist = sqrt((x - nx) * (x - nx) + (y - ny) * (y - ny) + (z - nz) * (z - nz));
+	x = nx; y = ny; z = nz;
+	return true;
+}
+
+__global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
+	extern __shared__ double smem[];
+	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
+	double *rd = smem + (size_t)P.nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
+	const uint64_t n_total = P.g_end - P.g_begin;
+	const uint64_t n_warps = (n_total + 31) / 32;
+	const uint64_t warps_per_grid = (uint64_t)gridDim.x * (T >> 5);
+	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
+	unsigned long long n_inter_local = 0;
+
+	for (uint64_t w = (uint64_t)blockIdx.x * (T >> 5) + (tid >> 5); w < n_warps; w += warps_per_grid) {
+		const uint64_t g = P.g_begin + w * 32 + lane;
+		Photon p;
+		XmbRng rng;
+		p.alive = g < P.g_end;
+		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
+		if (p.alive) {
+			rng.init(P.seed, g, XMB_TAG_HISTORY);
+			start_photon(P, p, rng, g, mus, T);
+		}
+		for (int it = 0; it < P.n_int; it++) {
+			// ---- forced interaction (src/xmi_main.F90:1229-1518) ------------------------------------
+			if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
+			double interactionR = 0.0;
+			int step_max = 0, step_dir = 1;
+			if (p.alive) {
+				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = P.nL - 1; step_dir = 1; }
+				else { step_max = 0; step_dir = -1; }
+				interactionR = rng.uniform();
+				double lx = p.cx, ly = p.cy, lz = p.cz;
+				double Pabs = 0.0;
+				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+					double dist;
+					if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { p.alive = false; break; }
+					rd[i * T] = dist;
+					Pabs += mus[i * T] * P.layers[i].density * dist;
+				}
+				if (p.alive) {
+					const double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
+					p.weight *= Pabs2;
+					const double l1p = log1p(-1.0 * interactionR * Pabs2);
+					const double negln = -1.0 * l1p;
+					int my_index = p.layer;
+					double my_sum = 0.0;
+					for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+						my_sum += mus[i * T] * P.layers[i].density * rd[i * T];
+						if (my_sum > negln) { my_index = i; break; }
+					}
+					const double murho_idx = mus[my_index * T] * P.layers[my_index].density;
+					double temp_sum = 0.0;
+					for (int i = p.layer; step_dir > 0 ? i <= my_index : i >= my_index; i += step_dir)
+						temp_sum += (1.0 - (mus[i * T] * P.layers[i].density / murho_idx)) * rd[i * T];
+					temp_sum = temp_sum - 1.0 * l1p / murho_idx;
+					p.cx += temp_sum * p.dx; p.cy += temp_sum * p.dy; p.cz += temp_sum * p.dz;
+					p.layer = my_index;
+					p.n_interactions++;
+					n_inter_local++;
+				}
+			}
+			if (!__any_sync(0xffffffffu, p.alive)) break;
+			const int n_ia = it + 1;   // == p.n_interactions for every live lane
+			unsigned long long *acc_k = P.acc + 2 * (size_t)(n_ia - 1) * acc_row;
+
+			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
+			bool vr = p.alive && p.energy > ENERGY_THRESHOLD;
+			double theta = 0.0, phi = 0.0, Pesc_rayl = 0.0, omega = 0.0;
+			NodePos np;
+			np.pos = 0; np.f = 0.0;
+			if (vr) {
+				const double radius = sqrt(rng.uniform()) * P.detector_radius;
+				const double th = 2.0 * M_PI * rng.uniform();
+				double sdp, cdp;
+				sincos(th, &sdp, &cdp);
+				const double dp0 = 0.0, dp1 = cdp * radius, dp2 = sdp * radius;
+				const double rx = p.cx - P.p_window[0], ry = p.cy - P.p_window[1], rz = p.cz - P.p_window[2];
+				const double *B = P.ndo_inv, *A = P.ndo_new;
+				const double lp0 = B[0] * rx + B[1] * ry + B[2] * rz, lp1 = B[3] * rx + B[4] * ry + B[5] * rz, lp2 = B[6] * rx + B[7] * ry + B[8] * rz;
+				double d0 = B[0] * p.dx + B[1] * p.dy + B[2] * p.dz, d1 = B[3] * p.dx + B[4] * p.dy + B[5] * p.dz, d2 = B[6] * p.dx + B[7] * p.dy + B[8] * p.dz;
+				double l0 = dp0 - lp0, l1 = dp1 - lp1, l2 = dp2 - lp2;
+				if (l0 >= 0.0) vr = false;
+				else {
+					double total_distance = sqrt((dp0 - lp0) * (dp0 - lp0) + (dp1 - lp1) * (dp1 - lp1) + (dp2 - lp2) * (dp2 - lp2));
+					normalize3(d0, d1, d2);
+					normalize3(l0, l1, l2);
+					const double n0 = A[0] * l0 + A[1] * l1 + A[2] * l2, n1 = A[3] * l0 + A[4] * l1 + A[5] * l2, n2 = A[6] * l0 + A[7] * l1 + A[8] * l2;
+					double dotprod = d0 * l0 + d1 * l1 + d2 * l2;
+					dotprod = fmin(1.0, fmax(-1.0, dotprod));
+					theta = acos(dotprod);
+					const double dpp = n0 * p.dx + n1 * p.dy + n2 * p.dz;
+					double q0 = n0 - dpp * p.dx, q1 = n1 - dpp * p.dy, q2 = n2 - dpp * p.dz;
+					normalize3(q0, q1, q2);
+					const double en = sqrt(p.ex * p.ex + p.ey * p.ey + p.ez * p.ez);
+					dotprod = q0 * (p.ex / en) + q1 * (p.ey / en) + q2 * (p.ez / en);
+					dotprod = fmin(1.0, fmax(-1.0, dotprod));
+					phi = acos(dotprod);
+					int vmax, vdir;
+					if (n0 * P.n_sample[0] + n1 * P.n_sample[1] + n2 * P.n_sample[2] > 0.0) { vmax = P.nL - 1; vdir = 1; } else { vmax = 0; vdir = -1; }
+					for (int i = 0; i < P.nL; i++) rd[i * T] = 0.0;
+					double tx = p.cx, ty = p.cy, tz = p.cz;
+					double temp_murhod = 0.0;
+					for (int i = p.layer; vdir > 0 ? i <= vmax : i >= vmax; i += vdir) {
+						double dist;
+						if (!step_to_plane(P, tx, ty, tz, n0, n1, n2, vdir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { vr = false; break; }
+						bool last = false;
+						if (dist > total_distance) { dist = total_distance; last = true; }
+						rd[i * T] = P.layers[i].density * dist;
+						temp_murhod += mus[i * T] * P.layers[i].density * dist;
+						if (last) break;
+						total_distance -= dist;
+					}
+					Pesc_rayl = exp(-temp_murhod);
+					omega = get_solid_angle(P, p);
+					np = node_find(P, p.energy);
+				}
+			}
+			// warp-uniform loops over layers / elements / shells / line records
+			for (int L = 0; L < P.nL; L++) {
+				const bool mine = vr && p.layer == L;
+				if (!__any_sync(0xffffffffu, mine)) continue;
+				const XmbLayerDev lay = P.layers[L];
+				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
+				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0;
+				int qi = 0;
+				long ch_rayl = -1;
+				if (mine) {
+					const double q = p.energy / KEV2ANGST * sin(theta / 2.0);
+					const double qx = q / P.q_max * (P.n_q - 1);
+					qi = min((int)qx, P.n_q - 2);
+					qf = qx - qi;
+					double st, ct, cp = cos(phi);
+					sincos(theta, &st, &ct);
+					sin2cos2 = st * st * cp * cp;
+					k0k = 1.0 / (1.0 + (1.0 - ct) * p.energy / 510.998928);
+					const int ch = (int)((p.energy - P.zero) / P.gain);
+					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
+				}
+				for (int e = 0; e < lay.n_elements; e++) {
+					const int zi = P.elem_zi[lay.elem_begin + e];
+					const double wfrac = P.elem_w[lay.elem_begin + e];
+					const size_t hbase = (size_t)P.nch + P.hist_base[zi];
+					const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
+					// Rayleigh (:342-369)
+					unsigned long long fx = 0ULL;
+					double Pconv = 0.0;
+					if (mine) {
+						Pconv = wfrac / mus[L * T];
+						const double F = P.ff[(size_t)zi * P.n_q + qi] * (1.0 - qf) + P.ff[(size_t)zi * P.n_q + qi + 1] * qf;
+						const double dcsp = AVOGNUM / P.atomic_weight[zi] * F * F * RE2 * (1.0 - sin2cos2);
+						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
+					}
+					deposit_uniform(acc_k, hbase + 0, fx, lane);
+					deposit_varying(acc_k, ch_rayl, fx, lane);
+					// Compton (xmi_compton_varred2, :949-1008)
+					fx = 0ULL;
+					long ch_c = -1;
+					if (mine) {
+						const double e_c = compton_energy(P, zi, p.energy, theta, rng, true);
+						const NodePos cp = node_find(P, e_c);
+						double tm = 0.0;
+						for (int j = 0; j < P.nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+						const double S = P.sf[(size_t)zi * P.n_q + qi] * (1.0 - qf) + P.sf[(size_t)zi * P.n_q + qi + 1] * qf;
+						const double dcsp_kn = RE2 / 2.0 * k0k * k0k * (k0k + 1.0 / k0k - 2.0 * sin2cos2);
+						const double Pdir = omega * AVOGNUM / P.atomic_weight[zi] * S * dcsp_kn;
+						fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight, P.counters);
+						const int ch = (int)((e_c - P.zero) / P.gain);
+						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
+					}
+					deposit_uniform(acc_k, hbase + 1, fx, lane);
+					deposit_varying(acc_k, ch_c, fx, lane);
+					// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy
+					const double common = mine ? wfrac * inv_mu * (omega / 4.0 / M_PI) * p.weight : 0.0;   // Pconv/P_shell * Pdir_fluo * weight
+					const bool aboveK = mine && p.energy >= P.edge_K[zi];
+					const int n_sh = P.use_M_lines ? 9 : 4;
+					for (int s = 0; s < n_sh; s++) {
+						const int r0 = P.rec_begin[zi * 10 + s], r1 = P.rec_begin[zi * 10 + s + 1];
+						if (r0 == r1) continue;
+						double Ps = 0.0;
+						if (mine && (s > 0 || aboveK)) Ps = row_lerp(P, np, eoff + XMB_EO_VACANCY + s);
+						if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
+						const double pre = common * Ps;
+						for (int r = r0; r < r1; r++) {
+							const double *mu = P.rec_mu + (size_t)r * P.nL;
+							double tm = 0.0;
+							for (int j = 0; j < P.nL; j++) tm += mu[j] * rd[j * T];
+							const double tw = pre * P.rec_yr[r] * exp(-tm);
+							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed(tw, P.counters) : 0ULL, lane);
+						}
+					}
+				}
+			}
+
+			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
+			if (p.alive) {
+				const XmbLayerDev lay = P.layers[p.layer];
+				const NodePos ep = node_find(P, p.energy);
+				double R2 = rng.uniform();
+				double thr = 0.0;
+				int zi = 0;
+				const double mu_cur = mus[p.layer * T];
+				for (int i = 0; i < lay.n_elements; i++) {
+					zi = P.elem_zi[lay.elem_begin + i];
+					thr += P.elem_w[lay.elem_begin + i] * row_lerp(P, ep, P.off_elem + zi * XMB_ELEM_STRIDE + XMB_EO_CS_TOTAL) / mu_cur;
+					if (R2 < thr) break;
+				}
+				const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
+				R2 = rng.uniform();
+				const double pr = row_lerp(P, ep, eoff + XMB_EO_P_RAYL), prc = row_lerp(P, ep, eoff + XMB_EO_P_RAYL_COMPT);
+				if (R2 < pr) {
+					// Rayleigh (:1986-2101)
+					const double r = rng.uniform();
+					const double theta_i = bilinear(P.rayl_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, r);
+					double tt = sin(theta_i) * sin(theta_i);
+					tt = tt / (4.0 - 2.0 * tt);
+					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, rng.uniform());
+					const double phi0 = elec_phi0(p);
+					update_dirv(p, theta_i, phi0 + phi_i);
+					update_elecv(p);
+				} else if (R2 < prc) {
+					// Compton (:2103-2229)
+					const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, rng.uniform());
+					const double K0K = 1.0 + p.energy * (1.0 - cos(theta_i)) / XMI_MEC2;
+					double tt = sin(theta_i) * sin(theta_i);
+					tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
+					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, rng.uniform());
+					const double phi0 = elec_phi0(p);
+					p.energy = compton_energy(P, zi, p.energy, theta_i, rng, false);
+					{
+						const NodePos cp = node_find(P, p.energy);
+						for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, cp, i);
+					}
+					if (p.energy != 0.0) {
+						update_dirv(p, theta_i, phi_i + phi0);
+						update_elecv(p);
+						const double cti = cos(theta_i), cpi = cos(phi_i), spi = sin(phi_i);
+						double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
+						const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
+						const double rk = rat - 2.0 + 1.0 / rat;
+						pp = pp / (rk + pp);
+						const double r = rng.uniform();
+						const double w_h = (1.0 + pp) / 2.0;
+						if (r > w_h) {
+							const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
+							p.ex = tx; p.ey = ty; p.ez = tz;
+						}
+					}
+				} else {
+					// photo-electric effect with fluorescence (:2231-2411)
+					const double photo_total = row_lerp(P, ep, eoff + XMB_EO_PHOTO_TOTAL);
+					double sumz = 0.0;
+					const double r = rng.uniform();
+					const int max_shell = P.use_M_lines ? 8 : 3;
+					int shell = -1;
+					for (int s = 0; s <= max_shell; s++) {
+						sumz += row_lerp(P, ep, eoff + XMB_EO_PHOTO_PARTIAL + s) / photo_total;
+						if (r < sumz) { shell = s; break; }
+					}
+					if (shell < 0) { p.energy = 0.0; }
+					else {
+						(void)rng.uniform();   // drawn and unused by the reference (xmi_variance_reduction.F90:737)
+						p.weight *= P.fluor_yield_corr[zi * 9 + shell];
+						// Coster-Kronig (:5184-5323)
+						const double *ck = P.cos_kron + zi * XMB_N_CK;
+						while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
+							const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
+							const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
+							const double rr = rng.uniform();
+							double sz = 0.0;
+							int found = -1;
+							for (int t = 0; t < ntr; t++) { sz += ck[first + t]; if (rr < sz) { found = t; break; } }
+							if (found < 0) break;
+							shell = shell + 1 + found;
+						}
+						// line (:5352-5437)
+						const double rl = rng.uniform();
+						double sl = 0.0;
+						int line = 0;
+						const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
+						for (int l = lf; l <= ll; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
+						if (!line) p.energy = 0.0;
+						else {
+							p.energy = P.line_energy[(size_t)zi * 384 + line];
+							const NodePos lp = node_find(P, p.energy);
+							for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, lp, i);
+							const double theta_i = acos(-2.0 * rng.uniform() + 1.0);
+							const double phi_i = 2.0 * M_PI * rng.uniform();
+							update_dirv(p, theta_i, phi_i);
+							update_elecv(p);
+						}
+					}
+				}
+			}
+		}
+	}
+	n_inter_local = warp_sum_u64(n_inter_local);
+	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
+}
+
+// =====================================================================================================
+// Host side: device layouts, launch, exact reduction epilogue.
+// =====================================================================================================
+struct XmbDeviceTables {
+	int cascade = 0, use_M_lines = -1, device = -1;
+	std::vector<void *> allocs;
+	XmbHistParams P{};
+	// host metadata for the epilogue
+	std::vector<int> rec_slot, rec_channel, rec_line, rec_zi, hist_base;
+	int n_rec = 0, n_hist_slots = 0;
+	double W_max = 0.0;
+	uint64_t n_total = 0;
+	// solid-angle grid + accumulators (re-used across calls)
+	double *sa_grid = nullptr, *sa_r = nullptr, *sa_t = nullptr;
+	size_t sa_cap = 0;
+	unsigned long long *acc = nullptr, *limbs = nullptr, *counters = nullptr;
+	size_t acc_slots = 0;
+	~XmbDeviceTables() {
+		for (void *p : allocs) cudaFree(p);
+		cudaFree(sa_grid); cudaFree(sa_r); cudaFree(sa_t); cudaFree(acc); cudaFree(limbs); cudaFree(counters);
+	}
+};
+
+void xmb_free_device_tables(XmbDeviceTables *dev) { delete dev; }
+
+template <typename T>
+static T *upload(XmbDeviceTables *D, const T *src, size_t n, bool &ok) {
+	T *d = nullptr;
+	if (n == 0) n = 1;
+	if (cudaMalloc(&d, sizeof(T) * n) != cudaSuccess) { ok = false; return nullptr; }
+	D->allocs.push_back(d);
+	if (src && cudaMemcpy(d, src, sizeof(T) * n, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+	return d;
+}
+
+// VR line -> shell classification (src/xmi_variance_reduction.F90:587-654)
+static int vr_shell_of_line(int l) {
+	if (l >= 1 && l <= 29) return 0;
+	if (l >= XMB_L1M1 && l <= 58) return 1;
+	if (l >= XMB_L2M1 && l <= 85) return 2;
+	if (l >= 86 && l <= 113) return 3;
+	if (l >= 118 && l <= 136) return 4;
+	if (l >= 140 && l <= 158) return 5;
+	if (l >= 161 && l <= 180) return 6;
+	if (l >= 182 && l <= 200) return 7;
+	if (l >= 201 && l <= 219) return 8;
+	return -1;
+}
+
+static int cascade_mode(const xmb_main_options *o) {   // src/xmi_main.F90:141-153
+	return 1 + (o->use_cascade_auger ? 1 : 0) + (o->use_cascade_radiative ? 2 : 0);
+}
+
+static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt) {
+	const xmb_tables_host &T = h->view;
+	const xmb_input &I = in->in;
+	const int nL = I.composition->n_layers, nZ = T.nZ, nN = T.n_nodes;
+	if (nL > XMB_MAX_LAYERS) { xmb_set_error("more than %d layers", XMB_MAX_LAYERS); return nullptr; }
+	XmbDeviceTables *D = new XmbDeviceTables();
+	D->cascade = cascade_mode(opt);
+	D->use_M_lines = opt->use_M_lines ? 1 : 0;
+	cudaGetDevice(&D->device);
+	XmbHistParams &P = D->P;
+	bool ok = true;
+	// ---- node rows -----------------------------------------------------------------------------------
+	P.nL = nL; P.nZ = nZ;
+	P.off_exc = nL;
+	P.off_elem = nL + 1;
+	P.row_stride = (nL + 1 + nZ * XMB_ELEM_STRIDE + 1) & ~1;
+	std::vector<double> rows((size_t)nN * P.row_stride, 0.0);
+	for (int n = 0; n < nN; n++) {
+		double *r = &rows[(size_t)n * P.row_stride];
+		for (int k = 0; k < nL; k++) r[k] = T.mu_layer[(size_t)k * nN + n];
+		r[P.off_exc] = T.exc_murhod[n];
+		for (int z = 0; z < nZ; z++) {
+			double *e = r + P.off_elem + z * XMB_ELEM_STRIDE;
+			e[XMB_EO_CS_TOTAL] = T.cs_total[(size_t)z * nN + n];
+			e[XMB_EO_P_RAYL] = T.p_rayl[(size_t)z * nN + n];
+			e[XMB_EO_P_RAYL_COMPT] = T.p_rayl_compt[(size_t)z * nN + n];
+			e[XMB_EO_PHOTO_TOTAL] = T.cs_photo_total[(size_t)z * nN + n];
+			for (int s = 0; s < 9; s++) {
+				e[XMB_EO_PHOTO_PARTIAL + s] = T.cs_photo_partial[((size_t)z * 9 + s) * nN + n];
+				e[XMB_EO_VACANCY + s] = T.cs_vacancy[(((size_t)(D->cascade - 1) * nZ + z) * 9 + s) * nN + n];
+			}
+		}
+	}
+	P.rows = upload(D, rows.data(), rows.size(), ok);
+	P.n_nodes = nN; P.n_buckets = T.n_buckets; P.bucket_E0 = T.bucket_E0; P.bucket_inv_dE = T.bucket_inv_dE;
+	P.node_E = upload(D, T.node_E, nN, ok);
+	P.bucket_start = upload(D, T.bucket_start, T.n_buckets + 1, ok);
+	// ---- inverse CDFs, form factors ---------------------------------------------------------------------
+	P.n_icdf_E = T.n_icdf_E; P.n_icdf_R = T.n_icdf_R; P.n_phi_T = T.n_phi_T; P.n_cp = T.n_cp; P.n_q = T.n_q;
+	P.q_max = T.q_max; P.cp_dR = T.cp_R[1] - T.cp_R[0];
+	P.icdf_E = upload(D, T.icdf_E, T.n_icdf_E, ok);
+	P.icdf_R = upload(D, T.icdf_R, T.n_icdf_R, ok);
+	P.phi_T = upload(D, T.phi_T, T.n_phi_T, ok);
+	P.cp_R = upload(D, T.cp_R, T.n_cp, ok);
+	P.rayl_icdf = upload(D, T.rayl_theta_icdf, (size_t)nZ * T.n_icdf_E * T.n_icdf_R, ok);
+	P.compt_icdf = upload(D, T.compt_theta_icdf, (size_t)nZ * T.n_icdf_E * T.n_icdf_R, ok);
+	P.phi_icdf = upload(D, T.phi_icdf, (size_t)T.n_phi_T * T.n_icdf_R, ok);
+	P.cp_icdf = upload(D, T.cp_icdf, (size_t)nZ * T.n_cp, ok);
+	P.ff = upload(D, T.ff, (size_t)nZ * T.n_q, ok);
+	P.sf = upload(D, T.sf, (size_t)nZ * T.n_q, ok);
+	// ---- per-element constants ----------------------------------------------------------------------------
+	P.atomic_weight = upload(D, T.atomic_weight, nZ, ok);
+	std::vector<double> edgeK(nZ);
+	for (int z = 0; z < nZ; z++) edgeK[z] = T.edge_energy[z * 9 + 0];
+	P.edge_K = upload(D, edgeK.data(), nZ, ok);
+	P.fluor_yield_corr = upload(D, T.fluor_yield_corr, (size_t)nZ * 9, ok);
+	P.cos_kron = upload(D, T.cos_kron, (size_t)nZ * XMB_N_CK, ok);
+	P.rad_rate = upload(D, T.rad_rate, (size_t)nZ * 384, ok);
+	P.line_energy = upload(D, T.line_energy, (size_t)nZ * 384, ok);
+	// ---- layers ---------------------------------------------------------------------------------------------
+	std::vector<XmbLayerDev> layers(nL);
+	std::vector<int> elem_zi;
+	std::vector<double> elem_w;
+	for (int k = 0; k < nL; k++) {
+		const xmb_layer &l = I.composition->layers[k];
+		layers[k].n_elements = l.n_elements;
+		layers[k].elem_begin = (int)elem_zi.size();
+		layers[k].density = l.density;
+		layers[k].Z_begin = in->Z_coord_begin[k];
+		layers[k].Z_end = in->Z_coord_end[k];
+		for (int e = 0; e < l.n_elements; e++) { elem_zi.push_back(T.uniqZ[l.Z[e]]); elem_w.push_back(l.weight[e]); }
+	}
+	P.layers = upload(D, layers.data(), nL, ok);
+	P.elem_zi = upload(D, elem_zi.data(), elem_zi.size(), ok);
+	P.elem_w = upload(D, elem_w.data(), elem_w.size(), ok);
+	// ---- forced-detection line records (active lines only) and history slots --------------------------------
+	const int line_last = opt->use_M_lines ? XMB_M5P5 : XMB_L3Q1;
+	const xmb_detector &det = *I.detector;
+	std::vector<int> rec_begin((size_t)nZ * 10, 0);
+	std::vector<double> rec_yr, rec_mu;
+	D->hist_base.assign(nZ, 0);
+	int slot = 0;
+	for (int z = 0; z < nZ; z++) {
+		D->hist_base[z] = slot;
+		slot += 2;   // +0 Rayleigh (history slot 384), +1 Compton (385)
+		for (int s = 0; s < 9; s++) {
+			rec_begin[z * 10 + s] = (int)rec_yr.size();
+			for (int l = 1; l <= line_last; l++) {
+				if (vr_shell_of_line(l) != s) continue;
+				const double E = T.line_energy[(size_t)z * 384 + l];
+				if (E < ENERGY_THRESHOLD) continue;                      // :579
+				const double yr = T.fluor_yield[z * 9 + s] * T.rad_rate[(size_t)z * 384 + l];
+				if (yr <= 0.0) continue;
+				rec_yr.push_back(yr);
+				// mu of every layer at the line energy: exact node lookup (precalc_mu_cs, src/xmi_main.F90:227-237)
+				const double *ne = std::lower_bound(T.node_E, T.node_E + nN, E);
+				const int node = (int)(ne - T.node_E);
+				if (node >= nN || T.node_E[node] != E) { xmb_set_error("line energy is not a table node"); delete D; return nullptr; }
+				for (int k = 0; k < nL; k++) rec_mu.push_back(T.mu_layer[(size_t)k * nN + node]);
+				D->rec_slot.push_back(slot++);
+				int ch = -1;
+				if (E >= ENERGY_THRESHOLD) { ch = (int)((E - det.zero) / det.gain); if (ch < 0 || ch > det.nchannels - 1) ch = -1; }
+				D->rec_channel.push_back(ch);
+				D->rec_line.push_back(l);
+				D->rec_zi.push_back(z);
+			}
+		}
+		rec_begin[z * 10 + 9] = (int)rec_yr.size();
+	}
+	D->n_rec = (int)rec_yr.size();
+	D->n_hist_slots = slot;
+	P.n_hist_slots = slot;
+	P.rec_begin = upload(D, rec_begin.data(), rec_begin.size(), ok);
+	P.rec_yr = upload(D, rec_yr.data(), rec_yr.size(), ok);
+	P.rec_mu = upload(D, rec_mu.data(), rec_mu.size(), ok);
+	P.rec_slot = upload(D, D->rec_slot.data(), D->rec_slot.size(), ok);
+	P.hist_base = upload(D, D->hist_base.data(), nZ, ok);
+	// ---- source segments (src/xmi_main.F90:319-338, :579-601) --------------------------------------------------
+	const xmb_excitation &exc = *I.excitation;
+	const xmb_general &gen = *I.general;
+	std::vector<XmbSegDev> segs;
+	double Wmax = 0.0;
+	for (int i = 0; i + 1 < exc.n_continuous; i++) {
+		const xmb_energy_continuous &a = exc.continuous[i], &b = exc.continuous[i + 1];
+		const double y1 = a.vertical_intensity + a.horizontal_intensity, y2 = b.vertical_intensity + b.horizontal_intensity;
+		const double total = (y1 + y2) * (b.energy - a.energy) / 2.0;
+		if (total == 0.0) continue;
+		XmbSegDev s{};
+		s.is_cont = 1; s.x1 = a.energy; s.x2 = b.energy; s.y1 = y1; s.y2 = y2; s.h1 = a.horizontal_intensity; s.h2 = b.horizontal_intensity;
+		s.total_rel = total / (double)gen.n_photons_interval;
+		s.sigma_x = a.sigma_x; s.sigma_y = a.sigma_y; s.sigma_xp = a.sigma_xp; s.sigma_yp = a.sigma_yp;
+		Wmax = std::max(Wmax, s.total_rel);
+		segs.push_back(s);
+	}
+	const uint64_t n_cont_seg = segs.size();
+	auto exc_corr = [&](double E) {
+		double s = 0.0;
+		for (int k = 0; k < I.absorbers->n_exc_layers; k++)
+			s += I.absorbers->exc_layers[k].density * I.absorbers->exc_layers[k].thickness * xmb_host_mu_layer(h->xrl, &I.absorbers->exc_layers[k], E);
+		return std::exp(-s);
+	};
+	for (int i = 0; i < exc.n_discrete; i++) {
+		const xmb_energy_discrete &e = exc.discrete[i];
+		const double total = e.vertical_intensity + e.horizontal_intensity;
+		XmbSegDev s{};
+		s.is_cont = 0; s.distribution_type = e.distribution_type; s.energy = e.energy; s.scale_parameter = e.scale_parameter;
+		s.weight_rel = total * exc_corr(e.energy) / (double)gen.n_photons_line;
+		s.hor_ver_ratio = e.horizontal_intensity * (double)gen.n_photons_line / total;
+		s.sigma_x = e.sigma_x; s.sigma_y = e.sigma_y; s.sigma_xp = e.sigma_xp; s.sigma_yp = e.sigma_yp;
+		Wmax = std::max(Wmax, s.weight_rel);
+		segs.push_back(s);
+	}
+	if (segs.empty() || Wmax <= 0.0) { xmb_set_error("no excitation"); delete D; return nullptr; }
+	for (auto &s : segs) { s.weight_rel /= Wmax; s.total_rel /= Wmax; }
+	D->W_max = Wmax;
+	P.segs = upload(D, segs.data(), segs.size(), ok);
+	P.n_seg = (int)segs.size();
+	P.n_cont_seg = n_cont_seg;
+	P.n_per_interval = (uint64_t)gen.n_photons_interval;
+	P.n_per_line = (uint64_t)gen.n_photons_line;
+	D->n_total = n_cont_seg * P.n_per_interval + (uint64_t)exc.n_discrete * P.n_per_line;
+	// ---- geometry, detector ---------------------------------------------------------------------------------------
+	const xmb_geometry &g = *I.geometry;
+	for (int i = 0; i < 3; i++) { P.n_sample[i] = g.n_sample_orientation[i]; P.p_window[i] = g.p_detector_window[i]; P.n_detector[i] = g.n_detector_orientation[i]; }
+	for (int i = 0; i < 9; i++) { P.ndo_new[i] = in->der.ndo_new[i]; P.ndo_inv[i] = in->der.ndo_inv[i]; }
+	P.detector_radius = in->der.detector_radius;
+	P.slit_x1_max = std::atan(g.slit_size_x / g.d_source_slit / 2.0);
+	P.slit_y1_max = std::atan(g.slit_size_y / g.d_source_slit / 2.0);
+	P.d_source_slit = g.d_source_slit;
+	P.n_int = gen.n_interactions_trajectory;
+	P.nch = det.nchannels; P.zero = det.zero; P.gain = det.gain;
+	P.use_M_lines = D->use_M_lines;
+	if (!ok) { xmb_set_error("device table upload failed: %s", cudaGetErrorString(cudaGetLastError())); delete D; return nullptr; }
+	return D;
+}
+
+extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                                 const xmb_solid_angle *sa, xmb_msim_ex *ex, uint64_t **accum, size_t *n_slots) {
+	XmbInputF *in = xmb_as_input(inputF);
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!in || !h || !in->inited || !options || !ex || !accum || !n_slots) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
+	if (!options->use_variance_reduction) { xmb_set_error("brute-force mode (use_variance_reduction=0) is not implemented on the GPU path"); return 0; }
+	if (options->use_advanced_compton) { xmb_set_error("use_advanced_compton is not implemented on the GPU path"); return 0; }
+	if (options->escape_ratios_mode) { xmb_set_error("escape_ratios_mode is not implemented on the GPU path"); return 0; }
+	if (!sa || !sa->solid_angles) { xmb_set_error("variance reduction needs a solid-angle grid"); return 0; }
+	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: xmb_main_msim has no CPU fallback"); return 0; }
+	if (ex->device >= 0) XMB_CUDA_OK(cudaSetDevice(ex->device));
+	int dev = 0;
+	cudaGetDevice(&dev);
+	XmbDeviceTables *D = h->dev;
+	if (!D || D->cascade != cascade_mode(options) || D->use_M_lines != (options->use_M_lines ? 1 : 0) || D->device != dev) {
+		if (D) delete D;
+		h->dev = D = build_device_tables(in, h, options);
+		if (!D) return 0;
+	}
+	XmbHistParams P = D->P;
+	// solid-angle grid: an argument of the call -> copied host->device every call
+	const size_t nsa = (size_t)sa->grid_dims_r_n * sa->grid_dims_theta_n;
+	if (D->sa_cap < nsa || !D->sa_grid) {
+		cudaFree(D->sa_grid); cudaFree(D->sa_r); cudaFree(D->sa_t);
+		XMB_CUDA_OK(cudaMalloc(&D->sa_grid, sizeof(double) * nsa));
+		XMB_CUDA_OK(cudaMalloc(&D->sa_r, sizeof(double) * sa->grid_dims_r_n));
+		XMB_CUDA_OK(cudaMalloc(&D->sa_t, sizeof(double) * sa->grid_dims_theta_n));
+		D->sa_cap = nsa;
+	}
+	XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
+	XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * sa->grid_dims_r_n, cudaMemcpyHostToDevice));
+	XMB_CUDA_OK(cudaMemcpy(D->sa_t, sa->grid_dims_theta_vals, sizeof(double) * sa->grid_dims_theta_n, cudaMemcpyHostToDevice));
+	P.sa_grid = D->sa_grid; P.sa_r_vals = D->sa_r; P.sa_t_vals = D->sa_t;
+	P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n;
+	// accumulators
+	const size_t slots = (size_t)P.n_int * ((size_t)P.nch + P.n_hist_slots);
+	if (D->acc_slots != slots) {
+		cudaFree(D->acc); cudaFree(D->limbs); cudaFree(D->counters);
+		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 2 * slots));
+		XMB_CUDA_OK(cudaMalloc(&D->limbs, sizeof(unsigned long long) * 2 * slots));
+		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * 8));
+		D->acc_slots = slots;
+	}
+	XMB_CUDA_OK(cudaMemsetAsync(D->acc, 0, sizeof(unsigned long long) * 2 * slots));
+	XMB_CUDA_OK(cudaMemsetAsync(D->counters, 0, sizeof(unsigned long long) * 8));
+	P.acc = D->acc; P.counters = D->counters;
+	// shard of global photon ids
+	const int nr = ex->n_ranks > 0 ? ex->n_ranks : 1, rk = ex->rank;
+	if (rk < 0 || rk >= nr) { xmb_set_error("rank %d outside 0..%d", rk, nr - 1); return 0; }
+	P.seed = ex->seed ? ex->seed : XMB_DEFAULT_SEED;
+	P.g_begin = D->n_total / nr * rk + std::min<uint64_t>(rk, D->n_total % nr);
+	P.g_end = P.g_begin + D->n_total / nr + ((uint64_t)rk < D->n_total % nr ? 1 : 0);
+	ex->n_histories = P.g_end - P.g_begin;
+	// launch
+	int sms = 148, occ = 1;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t smem = sizeof(double) * 2 * P.nL * HIST_THREADS;
+	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xmb_history_kernel, HIST_THREADS, smem));
+	if (occ < 1) occ = 1;
+	const uint64_t n_warps = (ex->n_histories + 31) / 32;
+	uint64_t blocks = (uint64_t)sms * occ;
+	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (n_warps + HIST_THREADS / 32 - 1) / (HIST_THREADS / 32)));
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0);
+	if (ex->n_histories > 0) xmb_history_kernel<<<(unsigned)blocks, HIST_THREADS, smem>>>(P);
+	cudaEventRecord(e1);
+	XMB_CUDA_OK(cudaGetLastError());
+	XMB_CUDA_OK(cudaEventSynchronize(e1));
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	ex->kernel_ms = ms;
+	ex->n_launches = ex->n_histories > 0 ? 1 : 0;
+	unsigned long long cnt[8];
+	XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+	ex->n_interactions = cnt[1];
+	if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
+	if (cnt[0] && options->verbose) fprintf(stderr, "detector_solid_angle_not_found: %llu\n", cnt[0]);
+	// read back as 48-bit limbs (safe to sum over ranks in uint64)
+	std::vector<unsigned long long> raw(2 * slots);
+	XMB_CUDA_OK(cudaMemcpy(raw.data(), D->acc, sizeof(unsigned long long) * 2 * slots, cudaMemcpyDeviceToHost));
+	uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
+	for (size_t i = 0; i < slots; i++) {
+		const unsigned long long lo = raw[2 * i], hi = raw[2 * i + 1];
+		out[2 * i] = lo & 0xFFFFFFFFFFFFULL;
+		out[2 * i + 1] = (lo >> 48) | (hi << 16);
+	}
+	*accum = out;
+	*n_slots = slots;
+	return 1;
+}
+
+extern "C" int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                                    const uint64_t *accum, size_t n_slots, double **channels, double **brute_history,
+                                    double **var_red_history) {
+	XmbInputF *in = xmb_as_input(inputF);
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!in || !h || !h->dev || !accum) { xmb_set_error("xmb_main_msim_finish: nothing to finish"); return 0; }
+	XmbDeviceTables *D = h->dev;
+	const int n_int = D->P.n_int, nch = D->P.nch;
+	const size_t row = (size_t)nch + D->n_hist_slots;
+	if (n_slots != (size_t)n_int * row) { xmb_set_error("xmb_main_msim_finish: slot count mismatch"); return 0; }
+	const double live_time = in->in.detector->live_time;
+	const double scale = D->W_max * live_time;
+	auto slot128 = [&](size_t i) { return (unsigned __int128)accum[2 * i] + ((unsigned __int128)accum[2 * i + 1] << 48); };
+	auto to_double = [&](unsigned __int128 v) {
+		const double hi = (double)(uint64_t)(v >> 64), lo = (double)(uint64_t)v;
+		return (hi * 18446744073709551616.0 + lo) * (1.0 / 72057594037927936.0) * scale;
+	};
+	double *ch = (double *)calloc((size_t)(n_int + 1) * nch, sizeof(double));
+	double *vr = (double *)calloc((size_t)100 * 385 * n_int, sizeof(double));
+	double *br = (double *)calloc((size_t)100 * 385 * n_int, sizeof(double));
+	std::vector<unsigned __int128> cum(nch, 0), cur(nch);
+	const xmb_tables_host &T = h->view;
+	for (int k = 0; k < n_int; k++) {
+		for (int c = 0; c < nch; c++) cur[c] = slot128((size_t)k * row + c);
+		// XRF deposits: channel content rebuilt from the per-line slots (exact integer sums)
+		for (int r = 0; r < D->n_rec; r++) {
+			const unsigned __int128 v = slot128((size_t)k * row + nch + D->rec_slot[r]);
+			if (D->rec_channel[r] >= 0) cur[D->rec_channel[r]] += v;
+			// var_red_history[Z-1][|line|-1][k]   (C order of the export, src/xmi_main.F90:934-940)
+			vr[((size_t)(T.Z[D->rec_zi[r]] - 1) * 385 + (D->rec_line[r] - 1)) * n_int + k] = to_double(v);
+		}
+		for (int z = 0; z < T.nZ; z++) {
+			vr[((size_t)(T.Z[z] - 1) * 385 + 383) * n_int + k] = to_double(slot128((size_t)k * row + nch + D->hist_base[z] + 0));
+			vr[((size_t)(T.Z[z] - 1) * 385 + 384) * n_int + k] = to_double(slot128((size_t)k * row + nch + D->hist_base[z] + 1));
+		}
+		// rows are cumulative over interaction order: channels(n_ia:, ch) += w
+		for (int c = 0; c < nch; c++) { cum[c] += cur[c]; ch[(size_t)(k + 1) * nch + c] = to_double(cum[c]); }
+	}
+	if (channels) *channels = ch; else free(ch);
+	if (var_red_history) *var_red_history = vr; else free(vr);
+	if (brute_history) *brute_history = br; else free(br);
+	(void)options;
+	return 1;
+}
+
+static int env_rank(int n) {
+	const char *names[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "RANK"};
+	for (const char *nm : names) { const char *v = getenv(nm); if (v) { int r = atoi(v); if (r >= 0 && r < n) return r; } }
+	return -1;
+}
+
+extern "C" int xmb_main_msim(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, int n_mpi_hosts, double **channels,
+                             const xmb_main_options *options, double **brute_history, double **var_red_history,
+                             const xmb_solid_angle *solid_angles) {
+	xmb_msim_ex ex{};
+	ex.n_ranks = n_mpi_hosts > 0 ? n_mpi_hosts : 1;
+	ex.rank = 0;
+	ex.device = -1;
+	if (ex.n_ranks > 1) {
+		ex.rank = env_rank(ex.n_ranks);
+		if (ex.rank < 0) { xmb_set_error("n_mpi_hosts > 1 but no rank in OMPI_COMM_WORLD_RANK / PMI_RANK / RANK"); return 0; }
+	}
+	if (options && options->verbose) { printf("Simulating interactions\n"); fflush(stdout); }
+	uint64_t *acc = nullptr;
+	size_t n = 0;
+	if (!xmb_main_msim_raw(inputF, hdf5F, options, solid_angles, &ex, &acc, &n)) return 0;
+	const int rv = xmb_main_msim_finish(inputF, hdf5F, options, acc, n, channels, brute_history, var_red_history);
+	free(acc);
+	if (rv && options && options->verbose) { printf("Simulating interactions at 100 %%\nInteractions simulation finished\n"); fflush(stdout); }
+	return rv;
+}

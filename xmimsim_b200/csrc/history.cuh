@@ -1,0 +1,80 @@
+// history.cuh -- device-side data layout of the photon-history engine (see DESIGN.md "HBM layout").
+#pragma once
+#include <cstdint>
+
+#define XMB_MAX_LAYERS 32
+#define XMB_ELEM_STRIDE 22         // per-element doubles in a node row
+#define XMB_EO_CS_TOTAL 0
+#define XMB_EO_P_RAYL 1
+#define XMB_EO_P_RAYL_COMPT 2
+#define XMB_EO_PHOTO_TOTAL 3
+#define XMB_EO_PHOTO_PARTIAL 4     // 9 values
+#define XMB_EO_VACANCY 13          // 9 values (selected cascade mode)
+#define XMB_FIXED_SHIFT 56         // deposits are accumulated as round(w_rel * 2^56) in 128-bit integers
+
+struct XmbSegDev {                 // one source segment: a valid continuous interval or a discrete line
+	int is_cont, distribution_type;
+	double energy, scale_parameter;          // discrete
+	double weight_rel;                       // discrete: (I_h+I_v) exc_corr / n_photons_line / W_max
+	double hor_ver_ratio;                    // discrete: I_h n_photons_line / (I_h+I_v)  (index rule)
+	double x1, x2, y1, y2, h1, h2;           // continuous: interval ends, total and horizontal intensities
+	double total_rel;                        // continuous: 0.5 (y1+y2)(x2-x1) / n_photons_interval / W_max
+	double sigma_x, sigma_y, sigma_xp, sigma_yp;
+};
+
+struct XmbLayerDev {
+	int n_elements, elem_begin;              // into elem_zi / elem_w
+	double density, Z_begin, Z_end;
+};
+
+struct XmbHistParams {
+	// run
+	uint64_t seed, g_begin, g_end;
+	uint64_t n_cont_seg, n_per_interval, n_per_line;
+	int n_seg, n_int, nch, nL, nZ;
+	int use_M_lines;
+	double zero, gain;
+	const XmbSegDev *segs;
+	// geometry
+	double n_sample[3], p_window[3], n_detector[3];
+	double ndo_new[9], ndo_inv[9];
+	double detector_radius, slit_x1_max, slit_y1_max, d_source_slit;
+	const XmbLayerDev *layers;
+	const int *elem_zi;                      // unique-element index per (layer, element)
+	const double *elem_w;                    // weight fraction
+	// node grid rows
+	int n_nodes, n_buckets, row_stride, off_exc, off_elem;
+	double bucket_E0, bucket_inv_dE;
+	const double *node_E;
+	const int *bucket_start;
+	const double *rows;                      // [n_nodes][row_stride]
+	// inverse CDFs
+	int n_icdf_E, n_icdf_R, n_phi_T, n_cp, n_q;
+	double cp_dR, q_max;
+	const double *icdf_E, *icdf_R, *phi_T, *cp_R;   // axis arrays
+	const double *rayl_icdf, *compt_icdf;    // [nZ][n_icdf_E][n_icdf_R]
+	const double *phi_icdf;                  // [n_phi_T][n_icdf_R]
+	const double *cp_icdf;                   // [nZ][n_cp]
+	const double *ff, *sf;                   // [nZ][n_q]
+	// per unique element
+	const double *atomic_weight;             // [nZ]
+	const double *edge_K;                    // [nZ]
+	const double *fluor_yield_corr;          // [nZ][9]
+	const double *cos_kron;                  // [nZ][13]
+	const double *rad_rate;                  // [nZ][384]
+	const double *line_energy;               // [nZ][384]
+	// forced-detection line records, grouped by (element, shell)
+	const int *rec_begin;                    // [nZ][10] record range of (zi, shell) = [rec_begin[zi*10+s], rec_begin[zi*10+s+1])
+	const double *rec_yr;                    // [n_rec] FluorYield(shell) * RadRate(line)
+	const double *rec_mu;                    // [n_rec][nL] mu of each layer at the line energy
+	const int *rec_slot;                     // [n_rec] history slot
+	const int *hist_base;                    // [nZ] first history slot of the element (+0 Rayleigh, +1 Compton)
+	int n_hist_slots;
+	// solid-angle grid
+	const double *sa_grid;                   // [n_theta][n_r]
+	int sa_nr, sa_nt;
+	const double *sa_r_vals, *sa_t_vals;
+	// accumulators: [n_int][nch + n_hist_slots] pairs (lo, hi)
+	unsigned long long *acc;
+	unsigned long long *counters;            // [0] off-grid solid angle lookups, [1] interactions, [2] fixed-point range errors
+};

@@ -94,6 +94,16 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 			nodes.push_back(e + 0.00001);
 			nodes.push_back(e - 0.00001);
 		}
+	// fluorescence-line energies and monochromatic source lines become nodes: lookups there are exact
+	for (int i = 0; i < nZ; i++)
+		for (int l = 1; l <= XMB_M5P5; l++) {
+			double e = xrl->LineEnergy(h->Z[i], -l);
+			if (e >= LOWE && e < top) nodes.push_back(e);
+		}
+	for (int i = 0; i < exc.n_discrete; i++)
+		if (exc.discrete[i].distribution_type == XMB_DISCRETE_MONOCHROMATIC && exc.discrete[i].energy >= LOWE &&
+		    exc.discrete[i].energy < top)
+			nodes.push_back(exc.discrete[i].energy);
 	std::sort(nodes.begin(), nodes.end());
 	nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
 	h->node_E = nodes;
@@ -131,7 +141,7 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 			h->p_rayl_compt[(size_t)i * nN + k] = com / tot + ray / tot;
 			for (int s = 0; s < 9; s++) h->cs_photo_partial[((size_t)i * 9 + s) * nN + k] = xrl->CS_Photo_Partial(Z, s, E);
 			for (int mode = 1; mode <= 4; mode++) {
-				double P[9];
+				double P[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 				for (int s = 0; s < 9; s++) {
 					P[s] = xrl->VacancyCS(Z, s, E, mode, P);
 					h->cs_vacancy[(((size_t)(mode - 1) * nZ + i) * 9 + s) * nN + k] = P[s];
@@ -268,50 +278,29 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 		}
 	}
 
-	// ---- quantities precalculated at fluorescence-line energies ----------------------------------------
-	const int NL = 220;   // |line| 0..219 (M5P5)
-	h->precalc_xrf_cs.assign((size_t)4 * nZ * 9 * nZ * NL, 0.0);
-	h->precalc_cs_total.assign((size_t)nZ * nZ * NL, 0.0);
-	h->precalc_p_rayl.assign((size_t)nZ * nZ * NL, 0.0);
-	h->precalc_p_rayl_compt.assign((size_t)nZ * nZ * NL, 0.0);
-	h->precalc_cs_photo_total.assign((size_t)nZ * nZ * NL, 0.0);
-	h->precalc_cs_photo_partial.assign((size_t)nZ * 9 * nZ * NL, 0.0);
-	h->precalc_mu_cs.assign((size_t)comp.n_layers * nZ * NL, 0.0);
-#pragma omp parallel for schedule(dynamic, 1) collapse(2)
-	for (int i = 0; i < nZ; i++)          // absorber
-		for (int j = 0; j < nZ; j++) {    // emitter
-			const int Z = h->Z[i];
-			for (int l = 1; l < NL; l++) {
-				const double E = h->line_energy[j * 384 + l];
-				if (E <= 0.0) continue;
-				const size_t o = ((size_t)i * nZ + j) * NL + l;
-				const double tot = xrl->CS_Total_Kissel(Z, E);
-				h->precalc_cs_total[o] = tot;
-				h->precalc_p_rayl[o] = xrl->CS_Rayl(Z, E) / tot;
-				h->precalc_p_rayl_compt[o] = (xrl->CS_Rayl(Z, E) + xrl->CS_Compt(Z, E)) / tot;
-				h->precalc_cs_photo_total[o] = xrl->CS_Photo_Total(Z, E);
-				for (int s = 0; s < 9; s++)
-					h->precalc_cs_photo_partial[(((size_t)i * 9 + s) * nZ + j) * NL + l] = xrl->CS_Photo_Partial(Z, s, E);
-				for (int mode = 1; mode <= 4; mode++) {
-					double P[9];
-					for (int s = 0; s < 9; s++) {
-						P[s] = xrl->VacancyCS(Z, s, E, mode, P);
-						h->precalc_xrf_cs[((((size_t)(mode - 1) * nZ + i) * 9 + s) * nZ + j) * NL + l] = P[s];
-					}
-				}
+	// ---- per-layer attenuation on the nodes (xmi_mu_calc, src/xmi_aux_f.F90:1109-1141) -----------------
+	h->mu_layer.assign((size_t)comp.n_layers * nN, 0.0);
+	for (int k = 0; k < comp.n_layers; k++)
+		for (int n = 0; n < nN; n++) {
+			double mu = 0.0;
+			for (int e = 0; e < comp.layers[k].n_elements; e++)
+				mu += h->cs_total[(size_t)h->uniqZ[comp.layers[k].Z[e]] * nN + n] * comp.layers[k].weight[e];
+			h->mu_layer[(size_t)k * nN + n] = mu;
+		}
+	// excitation-path absorbers (src/xmi_main.F90:366-372, :586-592): sum of mu*rho*t on the nodes
+	h->exc_murhod.assign(nN, 0.0);
+	{
+		const xmb_absorbers &ab = *in->in.absorbers;
+		if (ab.n_exc_layers > 0) {
+#pragma omp parallel for schedule(static)
+			for (int n = 0; n < nN; n++) {
+				double s = 0.0;
+				for (int k = 0; k < ab.n_exc_layers; k++)
+					s += ab.exc_layers[k].density * ab.exc_layers[k].thickness * xmb_host_mu_layer(xrl, &ab.exc_layers[k], nodes[n]);
+				h->exc_murhod[n] = s;
 			}
 		}
-	// precalc_mu_cs (src/xmi_main.F90:227-237): mu of every sample layer at every line energy
-	for (int k = 0; k < comp.n_layers; k++)
-		for (int j = 0; j < nZ; j++)
-			for (int l = 1; l < NL; l++) {
-				const double E = h->line_energy[j * 384 + l];
-				if (E <= 0.0) continue;
-				double mu = 0.0;
-				for (int e = 0; e < comp.layers[k].n_elements; e++)
-					mu += h->precalc_cs_total[((size_t)h->uniqZ[comp.layers[k].Z[e]] * nZ + j) * NL + l] * comp.layers[k].weight[e];
-				h->precalc_mu_cs[((size_t)k * nZ + j) * NL + l] = mu;
-			}
+	}
 
 	// ---- publish the view ------------------------------------------------------------------------------
 	xmb_tables_host &v = h->view;
@@ -329,11 +318,7 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	v.fluor_yield = h->fluor_yield.data(); v.fluor_yield_corr = h->fluor_yield_corr.data();
 	v.cos_kron = h->cos_kron.data(); v.rad_rate = h->rad_rate.data(); v.line_energy = h->line_energy.data();
 	v.edge_energy = h->edge_energy.data();
-	v.precalc_xrf_cs = h->precalc_xrf_cs.data(); v.n_layers = comp.n_layers; v.precalc_mu_cs = h->precalc_mu_cs.data();
-	v.precalc_cs_total = h->precalc_cs_total.data(); v.precalc_p_rayl = h->precalc_p_rayl.data();
-	v.precalc_p_rayl_compt = h->precalc_p_rayl_compt.data();
-	v.precalc_cs_photo_total = h->precalc_cs_photo_total.data();
-	v.precalc_cs_photo_partial = h->precalc_cs_photo_partial.data();
+	v.n_layers = comp.n_layers; v.mu_layer = h->mu_layer.data(); v.exc_murhod = h->exc_murhod.data();
 	*out = h;
 	return 1;
 }

@@ -104,6 +104,70 @@ class Simulation:
     def solid_angle_struct(self):
         return self._sa
 
+    def make_solid_angle(self, grid, r_vals, theta_vals):
+        """Wrap numpy arrays (grid[theta][r]) as an xmi_solid_angle struct (borrowed memory)."""
+        g = np.ascontiguousarray(grid, np.float64)
+        r = np.ascontiguousarray(r_vals, np.float64)
+        t = np.ascontiguousarray(theta_vals, np.float64)
+        sa = abi.SolidAngle(g.ctypes.data_as(abi.c_double_p), r.size, t.size, r.ctypes.data_as(abi.c_double_p),
+                            t.ctypes.data_as(abi.c_double_p), None)
+        sa._keep = (g, r, t)
+        return sa
+
+    # -- photon histories ----------------------------------------------------------------------------
+    def _sa_arg(self, sa):
+        if sa is None:
+            if self._sa is None:
+                raise RuntimeError("no solid-angle grid: call solid_angle_calculation first")
+            return self._sa
+        return C.pointer(sa) if isinstance(sa, abi.SolidAngle) else sa
+
+    def main_msim(self, options=None, sa=None, n_mpi_hosts=1):
+        """xmi_main_msim.  Returns (channels[(n_int+1)][nch], brute_history[100][385][n_int],
+        var_red_history[100][385][n_int]) -- the reference's three output arrays, x live_time."""
+        options = options or main_options()
+        ch, br, vr = abi.c_double_p(), abi.c_double_p(), abi.c_double_p()
+        if not self.L.xmb_main_msim(self.inputF, self.hdf5F, n_mpi_hosts, C.byref(ch), C.byref(options), C.byref(br),
+                                    C.byref(vr), self._sa_arg(sa)):
+            raise RuntimeError("xmb_main_msim: " + abi.last_error())
+        return self._take(ch, br, vr)
+
+    def _take(self, ch, br, vr):
+        n_int, nch = self.inp.n_interactions_trajectory, self.inp.nchannels
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        out = []
+        for ptr, shape in ((ch, (n_int + 1, nch)), (br, (100, 385, n_int)), (vr, (100, 385, n_int))):
+            out.append(_np_from_ptr(ptr, shape).copy())
+            libc.free(ptr)
+        return tuple(out)
+
+    def main_msim_raw(self, options=None, sa=None, rank=0, n_ranks=1, seed=0, device=-1):
+        """History kernels only: returns (limbs uint64[2*n_slots], MsimEx) -- exact fixed-point partial sums of
+        this rank's photon-id shard, safe to add across ranks in uint64."""
+        options = options or main_options()
+        ex = abi.MsimEx(rank, n_ranks, seed, device, 0, 0, 0.0, 0, 0)
+        acc = C.POINTER(C.c_uint64)()
+        n = C.c_size_t()
+        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa), C.byref(ex),
+                                        C.byref(acc), C.byref(n)):
+            raise RuntimeError("xmb_main_msim_raw: " + abi.last_error())
+        limbs = np.ctypeslib.as_array(acc, shape=(2 * n.value,)).copy()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(acc)
+        return limbs, ex
+
+    def main_msim_finish(self, limbs, options=None):
+        options = options or main_options()
+        limbs = np.ascontiguousarray(limbs, np.uint64)
+        ch, br, vr = abi.c_double_p(), abi.c_double_p(), abi.c_double_p()
+        if not self.L.xmb_main_msim_finish(self.inputF, self.hdf5F, C.byref(options),
+                                           limbs.ctypes.data_as(C.POINTER(C.c_uint64)), limbs.size // 2, C.byref(ch),
+                                           C.byref(br), C.byref(vr)):
+            raise RuntimeError("xmb_main_msim_finish: " + abi.last_error())
+        return self._take(ch, br, vr)
+
     def close(self):
         if self._sa is not None:
             self.L.xmb_free_solid_angle(self._sa)

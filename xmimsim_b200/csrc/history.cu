@@ -749,6 +749,9 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 				if (E < ENERGY_THRESHOLD) continue;                      // :579
 				const double yr = T.fluor_yield[z * 9 + s] * T.rad_rate[(size_t)z * 384 + l];
 				if (yr <= 0.0) continue;
+				// a line above the table window lies above the highest source energy: its shell can never be
+				// ionised (E_line < E_edge), the reference's P_shell == 0 skip (:589-645)
+				if (E >= T.node_E[nN - 1]) continue;
 				rec_yr.push_back(yr);
 				// mu of every layer at the line energy: exact node lookup (precalc_mu_cs, src/xmi_main.F90:227-237)
 				const double *ne = std::lower_bound(T.node_E, T.node_E + nN, E);

@@ -7,6 +7,9 @@ import orc
 import xmimsim_b200 as x
 
 
+DEFAULT_SEED = 0x584D494D53494D      # "XMIMSIM" 
+
+
 class Pair:
     def __init__(self, inp, quality=0):
         self.inp = inp
@@ -28,6 +31,7 @@ class Pair:
 
     def oracle(self, options, sa, seed, g0=0, g1=None, n_threads=16):
         g1 = self.n_total if g1 is None else g1
+        seed = seed or DEFAULT_SEED          # the engine maps seed 0 to its default Philox key
         ch, vr, cnt = orc.main_msim_range(C.pointer(self.ci.input), self.od, self.sim.L.xmb_get_tables(self.sim.hdf5F),
                                           options, sa, seed, g0, g1, self.inp.n_interactions_trajectory,
                                           self.inp.nchannels, n_threads)

@@ -372,6 +372,13 @@ typedef struct xmb_msim_ex {
 int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                       const xmb_solid_angle *solid_angles, xmb_msim_ex *ex,
                       uint64_t **accum, size_t *n_slots);
+/* Device pointer to the limbs of the last xmb_main_msim_raw run on this handle (uint64[n_words],
+ * valid until the next run): lets the multi-GPU harness all-reduce in HBM (NCCL, int64 sum). */
+int xmb_msim_device_limbs(xmb_hdf5FPtr hdf5F, uint64_t **dev_ptr, size_t *n_words);
+/* Workload description of the last run: out[0] = n_layers, then per layer (interactions simulated,
+ * n_elements, active forced-detection line records of its elements).  Feeds the algorithmic-bytes
+ * figure of SURVEY.md 8(d) / DESIGN.md. */
+int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity);
 /* Converts (summed) raw accumulators to the reference's three output arrays. */
 int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                          const uint64_t *accum, size_t n_slots, double **channels,

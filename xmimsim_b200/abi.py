@@ -186,6 +186,10 @@ def lib():
     L.xmb_main_msim_finish.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(C.c_uint64), C.c_size_t,
                                        C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p)]
     L.xmb_main_msim_finish.restype = C.c_int
+    L.xmb_msim_device_limbs.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.xmb_msim_device_limbs.restype = C.c_int
+    L.xmb_msim_workload_stats.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.c_int]
+    L.xmb_msim_workload_stats.restype = C.c_int
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

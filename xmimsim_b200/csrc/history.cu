@@ -315,6 +315,9 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 	const uint64_t warps_per_grid = (uint64_t)gridDim.x * (T >> 5);
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
 	unsigned long long n_inter_local = 0;
+	__shared__ unsigned int s_layer_cnt[XMB_MAX_LAYERS];
+	if (tid < XMB_MAX_LAYERS) s_layer_cnt[tid] = 0;
+	__syncthreads();
 
 	for (uint64_t w = (uint64_t)blockIdx.x * (T >> 5) + (tid >> 5); w < n_warps; w += warps_per_grid) {
 		const uint64_t g = P.g_begin + w * 32 + lane;
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					p.layer = my_index;
 					p.n_interactions++;
 					n_inter_local++;
+					atomicAdd(&s_layer_cnt[my_index], 1u);
 				}
 			}
 			if (!__any_sync(0xffffffffu, p.alive)) break;
@@ -601,6 +605,17 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 	}
 	n_inter_local = warp_sum_u64(n_inter_local);
 	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
+	__syncthreads();
+	if (tid < P.nL && s_layer_cnt[tid]) atomicAdd(&P.counters[8 + tid], (unsigned long long)s_layer_cnt[tid]);
+}
+
+// raw 128-bit accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
+__global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, unsigned long long *__restrict__ limbs, size_t n_slots) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long lo = acc[2 * i], hi = acc[2 * i + 1];
+		limbs[2 * i] = lo & 0xFFFFFFFFFFFFULL;
+		limbs[2 * i + 1] = (lo >> 48) | (hi << 16);
+	}
 }
 
 // =====================================================================================================
@@ -617,9 +632,11 @@ struct XmbDeviceTables {
 	uint64_t n_total = 0;
 	// solid-angle grid + accumulators (re-used across calls)
 	double *sa_grid = nullptr, *sa_r = nullptr, *sa_t = nullptr;
-	size_t sa_cap = 0;
+	size_t sa_cap = 0, sa_n = 0;
+	const double *sa_host = nullptr;
 	unsigned long long *acc = nullptr, *limbs = nullptr, *counters = nullptr;
 	size_t acc_slots = 0;
+	unsigned long long layer_interactions[XMB_MAX_LAYERS] = {0};
 	~XmbDeviceTables() {
 		for (void *p : allocs) cudaFree(p);
 		cudaFree(sa_grid); cudaFree(sa_r); cudaFree(sa_t); cudaFree(acc); cudaFree(limbs); cudaFree(counters);
@@ -864,9 +881,13 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		XMB_CUDA_OK(cudaMalloc(&D->sa_t, sizeof(double) * sa->grid_dims_theta_n));
 		D->sa_cap = nsa;
 	}
-	XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
-	XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * sa->grid_dims_r_n, cudaMemcpyHostToDevice));
-	XMB_CUDA_OK(cudaMemcpy(D->sa_t, sa->grid_dims_theta_vals, sizeof(double) * sa->grid_dims_theta_n, cudaMemcpyHostToDevice));
+	const bool resident = ex->keep_on_device && D->sa_host == sa->solid_angles && D->sa_n == nsa;
+	if (!resident) {
+		XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
+		XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * sa->grid_dims_r_n, cudaMemcpyHostToDevice));
+		XMB_CUDA_OK(cudaMemcpy(D->sa_t, sa->grid_dims_theta_vals, sizeof(double) * sa->grid_dims_theta_n, cudaMemcpyHostToDevice));
+		D->sa_host = sa->solid_angles; D->sa_n = nsa;
+	}
 	P.sa_grid = D->sa_grid; P.sa_r_vals = D->sa_r; P.sa_t_vals = D->sa_t;
 	P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n;
 	// accumulators
@@ -875,11 +896,11 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		cudaFree(D->acc); cudaFree(D->limbs); cudaFree(D->counters);
 		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 2 * slots));
 		XMB_CUDA_OK(cudaMalloc(&D->limbs, sizeof(unsigned long long) * 2 * slots));
-		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * 8));
+		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * (8 + XMB_MAX_LAYERS)));
 		D->acc_slots = slots;
 	}
 	XMB_CUDA_OK(cudaMemsetAsync(D->acc, 0, sizeof(unsigned long long) * 2 * slots));
-	XMB_CUDA_OK(cudaMemsetAsync(D->counters, 0, sizeof(unsigned long long) * 8));
+	XMB_CUDA_OK(cudaMemsetAsync(D->counters, 0, sizeof(unsigned long long) * (8 + XMB_MAX_LAYERS)));
 	P.acc = D->acc; P.counters = D->counters;
 	// shard of global photon ids
 	const int nr = ex->n_ranks > 0 ? ex->n_ranks : 1, rk = ex->rank;
@@ -902,29 +923,25 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	cudaEventRecord(e0);
 	if (ex->n_histories > 0) xmb_history_kernel<<<(unsigned)blocks, HIST_THREADS, smem>>>(P);
 	cudaEventRecord(e1);
+	xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 	XMB_CUDA_OK(cudaGetLastError());
 	XMB_CUDA_OK(cudaEventSynchronize(e1));
 	float ms = 0.f;
 	cudaEventElapsedTime(&ms, e0, e1);
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	ex->kernel_ms = ms;
-	ex->n_launches = ex->n_histories > 0 ? 1 : 0;
-	unsigned long long cnt[8];
+	ex->n_launches = (ex->n_histories > 0 ? 1 : 0) + 1;
+	unsigned long long cnt[8 + XMB_MAX_LAYERS];
 	XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < XMB_MAX_LAYERS; i++) D->layer_interactions[i] = cnt[8 + i];
 	ex->n_interactions = cnt[1];
 	if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
 	if (cnt[0] && options->verbose) fprintf(stderr, "detector_solid_angle_not_found: %llu\n", cnt[0]);
-	// read back as 48-bit limbs (safe to sum over ranks in uint64)
-	std::vector<unsigned long long> raw(2 * slots);
-	XMB_CUDA_OK(cudaMemcpy(raw.data(), D->acc, sizeof(unsigned long long) * 2 * slots, cudaMemcpyDeviceToHost));
-	uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
-	for (size_t i = 0; i < slots; i++) {
-		const unsigned long long lo = raw[2 * i], hi = raw[2 * i + 1];
-		out[2 * i] = lo & 0xFFFFFFFFFFFFULL;
-		out[2 * i + 1] = (lo >> 48) | (hi << 16);
-	}
-	*accum = out;
 	*n_slots = slots;
+	if (ex->keep_on_device) { *accum = nullptr; return 1; }   // limbs stay in HBM: xmb_msim_device_limbs()
+	uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
+	XMB_CUDA_OK(cudaMemcpy(out, D->limbs, sizeof(uint64_t) * 2 * slots, cudaMemcpyDeviceToHost));
+	*accum = out;
 	return 1;
 }
 
@@ -998,4 +1015,35 @@ extern "C" int xmb_main_msim(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, int n_mpi
 	free(acc);
 	if (rv && options && options->verbose) { printf("Simulating interactions at 100 %%\nInteractions simulation finished\n"); fflush(stdout); }
 	return rv;
+}
+
+// Device-resident view of the last run's limbs (for an NCCL all-reduce without host staging).
+extern "C" int xmb_msim_device_limbs(xmb_hdf5FPtr hdf5F, uint64_t **dev_ptr, size_t *n_words) {
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!h || !h->dev || !h->dev->limbs) { xmb_set_error("no device accumulators"); return 0; }
+	*dev_ptr = (uint64_t *)h->dev->limbs;
+	*n_words = 2 * h->dev->acc_slots;
+	return 1;
+}
+
+// Workload description of the last run, for the algorithmic-bytes figure of DESIGN.md / SURVEY.md 8d:
+// out[0] = n_layers, then per layer: interactions, n_elements, active line records of its elements.
+extern "C" int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity) {
+	XmbInputF *in = xmb_as_input(inputF);
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!in || !h || !h->dev) { xmb_set_error("no run to describe"); return 0; }
+	XmbDeviceTables *D = h->dev;
+	const xmb_composition &c = *in->in.composition;
+	if (capacity < 1 + 3 * c.n_layers) return 0;
+	std::vector<int> per_z(h->view.nZ, 0);
+	for (int r = 0; r < D->n_rec; r++) per_z[D->rec_zi[r]]++;
+	out[0] = c.n_layers;
+	for (int k = 0; k < c.n_layers; k++) {
+		uint64_t act = 0;
+		for (int e = 0; e < c.layers[k].n_elements; e++) act += per_z[h->view.uniqZ[c.layers[k].Z[e]]];
+		out[1 + 3 * k] = D->layer_interactions[k];
+		out[2 + 3 * k] = c.layers[k].n_elements;
+		out[3 + 3 * k] = act;
+	}
+	return 1;
 }

@@ -142,6 +142,33 @@ class Simulation:
             libc.free(ptr)
         return tuple(out)
 
+    def main_msim_device(self, options=None, sa=None, rank=0, n_ranks=1, seed=0, device=-1):
+        """History kernels with every input and output resident in HBM (the solid-angle grid is uploaded
+        only when its host buffer changes).  Returns MsimEx; read the limbs with device_limbs()."""
+        options = options or main_options()
+        ex = abi.MsimEx(rank, n_ranks, seed, device, 1, 0, 0.0, 0, 0)
+        acc = C.POINTER(C.c_uint64)()
+        n = C.c_size_t()
+        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa), C.byref(ex),
+                                        C.byref(acc), C.byref(n)):
+            raise RuntimeError("xmb_main_msim_raw: " + abi.last_error())
+        return ex
+
+    def device_limbs(self):
+        """(device pointer, n_words) of the last run's uint64 limbs."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        if not self.L.xmb_msim_device_limbs(self.hdf5F, C.byref(ptr), C.byref(n)):
+            raise RuntimeError(abi.last_error())
+        return ptr.value, n.value
+
+    def workload_stats(self):
+        """Per layer: (interactions of the last run, n_elements, active line records)."""
+        buf = (C.c_uint64 * 128)()
+        if not self.L.xmb_msim_workload_stats(self.inputF, self.hdf5F, buf, 128):
+            raise RuntimeError(abi.last_error())
+        nl = int(buf[0])
+        return [(int(buf[1 + 3 * k]), int(buf[2 + 3 * k]), int(buf[3 + 3 * k])) for k in range(nl)]
+
     def main_msim_raw(self, options=None, sa=None, rank=0, n_ranks=1, seed=0, device=-1):
         """History kernels only: returns (limbs uint64[2*n_slots], MsimEx) -- exact fixed-point partial sums of
         this rank's photon-id shard, safe to add across ranks in uint64."""

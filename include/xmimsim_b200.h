@@ -385,17 +385,29 @@ int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_mai
                          double **brute_history, double **var_red_history);
 
 /* Replaces xmi_detector_convolute_all / the plugin symbol xmi_detector_convolute_all_custom
- * (include/xmi_main.h:35-37; src/xmi_detector_f.F90:219-289).  channels_conv[i] are malloc'ed. */
+ * (include/xmi_main.h:35-37; src/xmi_detector_f.F90:219-289).  channels_noconv[i] point at the rows of the
+ * raw array (bin/xmimsim.c:496-498) and are MODIFIED IN PLACE by the efficiency correction, escape peaks
+ * and pile-up, exactly as the reference's pointer remap does (src/xmi_detector_f.F90:412-413);
+ * channels_conv[i] (i from zero_interaction?0:1 to n_interactions_all) are malloc'ed double[nchannels];
+ * the two histories are corrected in place (var_red_history may be NULL); escape_ratios may be NULL
+ * when escape peaks are off.  hdf5F supplies the cross-section provider (NULL: surrogate). */
 void xmb_detector_convolute_all(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double **channels_noconv,
                                 double **channels_conv, double *brute_history,
                                 double *var_red_history, const xmb_main_options *options,
                                 const xmb_escape_ratios *escape_ratios, int n_interactions_all,
                                 int zero_interaction);
-/* Replaces xmi_detector_convolute_spectrum (include/xmi_main.h:31; src/xmi_detector_f.F90:339-580). */
+/* Replaces xmi_detector_convolute_spectrum (include/xmi_main.h:31; src/xmi_detector_f.F90:339-580);
+ * channels_noconv is modified in place, *channels_conv is malloc'ed (NULL on failure). */
 void xmb_detector_convolute_spectrum(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
-                                     const double *channels_noconv, double **channels_conv,
+                                     double *channels_noconv, double **channels_conv,
                                      const xmb_main_options *options,
                                      const xmb_escape_ratios *escape_ratios, int n_interactions);
+/* Replaces xmi_detector_convolute_history (include/xmi_main.h:33; src/xmi_detector_f.F90:291-337). */
+void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double *history,
+                                    const xmb_main_options *options);
+/* Device time (ms) and kernel launches of the last detector-response call. */
+double xmb_detector_last_ms(void);
+uint64_t xmb_detector_last_launches(void);
 
 /* xmi_main_options_new defaults (src/xmi_data_structs.c:2531-2565). */
 void xmb_main_options_defaults(xmb_main_options *options);

@@ -72,6 +72,15 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
                              uint64_t g_begin, uint64_t g_end, int n_threads, double *channels,
                              double *var_red, uint64_t *counters);
 
+/* Detector response (src/xmi_detector_f.F90).  noconv[nch] is modified IN PLACE by the absorption
+ * correction, escape peaks and pile-up, as the reference does (:412-413); conv[nch] is the result. */
+double orc_detector_correction(const xmb_input *in, const xmb_xrl_provider *xrl, double E);
+void orc_detector_gaussian(const xmb_input *in, const double *temp, double *conv);
+void orc_detector_convolute_spectrum(const xmb_input *in, const xmb_xrl_provider *xrl, double *noconv, double *conv,
+                                     const xmb_main_options *opt, const xmb_escape_ratios *er, int n_interactions,
+                                     uint64_t seed);
+void orc_detector_convolute_history(const xmb_input *in, const xmb_xrl_provider *xrl, double *history);
+
 #ifdef __cplusplus
 }
 #endif

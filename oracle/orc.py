@@ -39,6 +39,12 @@ def lib():
         _lib.orc_solid_angle_axes.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         _lib.orc_solid_angle_axes.restype = C.c_int
         _lib.xmb_xrl_surrogate.restype = C.c_void_p
+        _lib.orc_detector_correction.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        _lib.orc_detector_correction.restype = C.c_double
+        _lib.orc_detector_gaussian.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_detector_convolute_spectrum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_int, C.c_uint64]
+        _lib.orc_detector_convolute_history.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_total_histories.argtypes = [C.c_void_p]
         _lib.orc_total_histories.restype = C.c_uint64
         _lib.orc_main_msim_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -92,3 +98,19 @@ def main_msim_range(cinput_ptr, d, tables_ptr, options, sa_struct, seed, g_begin
                               C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
                               g_begin, g_end, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
     return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt
+
+
+def detector_convolute_spectrum(cinput_ptr, spectrum, options, escape_ratios=None, n_interactions=1, seed=1):
+    """Oracle xmi_detector_convolute_spectrum: spectrum modified in place, returns conv."""
+    spectrum = np.ascontiguousarray(spectrum, np.float64)
+    conv = np.zeros_like(spectrum)
+    er = C.cast(C.pointer(escape_ratios), C.c_void_p) if escape_ratios is not None else None
+    lib().orc_detector_convolute_spectrum(C.cast(cinput_ptr, C.c_void_p), lib().xmb_xrl_surrogate(), spectrum.ctypes.data,
+                                          conv.ctypes.data, C.cast(C.pointer(options), C.c_void_p), er, n_interactions, seed)
+    return spectrum, conv
+
+
+def detector_convolute_history(cinput_ptr, history):
+    h = np.ascontiguousarray(history, np.float64).copy()
+    lib().orc_detector_convolute_history(C.cast(cinput_ptr, C.c_void_p), lib().xmb_xrl_surrogate(), h.ctypes.data)
+    return h

@@ -190,6 +190,17 @@ def lib():
     L.xmb_msim_device_limbs.restype = C.c_int
     L.xmb_msim_workload_stats.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.c_int]
     L.xmb_msim_workload_stats.restype = C.c_int
+    pp = C.POINTER(c_double_p)
+    L.xmb_detector_convolute_all.argtypes = [vp, vp, pp, pp, c_double_p, c_double_p, C.POINTER(MainOptions),
+                                             C.POINTER(EscapeRatios), C.c_int, C.c_int]
+    L.xmb_detector_convolute_all.restype = None
+    L.xmb_detector_convolute_spectrum.argtypes = [vp, vp, c_double_p, pp, C.POINTER(MainOptions),
+                                                  C.POINTER(EscapeRatios), C.c_int]
+    L.xmb_detector_convolute_spectrum.restype = None
+    L.xmb_detector_convolute_history.argtypes = [vp, vp, c_double_p, C.POINTER(MainOptions)]
+    L.xmb_detector_convolute_history.restype = None
+    L.xmb_detector_last_ms.restype = C.c_double
+    L.xmb_detector_last_launches.restype = C.c_uint64
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

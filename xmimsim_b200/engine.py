@@ -195,6 +195,61 @@ class Simulation:
             raise RuntimeError("xmb_main_msim_finish: " + abi.last_error())
         return self._take(ch, br, vr)
 
+    # -- detector response ----------------------------------------------------------------------------
+    def make_escape_ratios(self, Z, fluo_ratios, fluo_E, compt_ratios, compt_Ein, compt_Eout):
+        """xmi_escape_ratios struct from numpy arrays: fluo_ratios[n_E][109][n_Z] (element fastest, the
+        reference's Fortran (n_elements, 109, n_E) order), compt_ratios[n_out][n_in] (input fastest)."""
+        zz = np.ascontiguousarray(Z, np.int32)
+        a = [np.ascontiguousarray(v, np.float64) for v in (fluo_ratios, fluo_E, compt_ratios, compt_Ein, compt_Eout)]
+        er = abi.EscapeRatios(zz.size, a[1].size, a[3].size, a[4].size, zz.ctypes.data_as(abi.c_int_p),
+                              a[0].ctypes.data_as(abi.c_double_p), a[1].ctypes.data_as(abi.c_double_p),
+                              a[2].ctypes.data_as(abi.c_double_p), a[3].ctypes.data_as(abi.c_double_p),
+                              a[4].ctypes.data_as(abi.c_double_p), None)
+        er._keep = (zz, a)
+        return er
+
+    def detector_convolute_all(self, channels, brute_history=None, var_red_history=None, options=None, escape_ratios=None,
+                               zero_interaction=0):
+        """xmi_detector_convolute_all.  `channels` [(n_int+1)][nch] is modified in place (as the reference does);
+        returns channels_conv [(n_int+1)][nch] (row 0 zero unless zero_interaction)."""
+        options = options or main_options()
+        n_int, nch = self.inp.n_interactions_trajectory, self.inp.nchannels
+        assert channels.shape == (n_int + 1, nch) and channels.dtype == np.float64 and channels.flags.c_contiguous
+        rows = (abi.c_double_p * (n_int + 1))()
+        for i in range(n_int + 1):
+            rows[i] = C.cast(channels.ctypes.data + i * nch * 8, abi.c_double_p)
+        conv = (abi.c_double_p * (n_int + 1))()
+        bh = brute_history.ctypes.data_as(abi.c_double_p) if brute_history is not None else None
+        vh = var_red_history.ctypes.data_as(abi.c_double_p) if var_red_history is not None else None
+        er = C.byref(escape_ratios) if escape_ratios is not None else None
+        self.L.xmb_detector_convolute_all(self.inputF, self.hdf5F, rows, conv, bh, vh, C.byref(options), er, n_int,
+                                          zero_interaction)
+        out = np.zeros((n_int + 1, nch))
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        for i in range(0 if zero_interaction else 1, n_int + 1):
+            if not conv[i]:
+                raise RuntimeError("xmb_detector_convolute_all: " + abi.last_error())
+            out[i] = _np_from_ptr(conv[i], (nch,))
+            libc.free(conv[i])
+        return out
+
+    def detector_convolute_spectrum(self, spectrum, options=None, escape_ratios=None, n_interactions=1):
+        """xmi_detector_convolute_spectrum: spectrum[nch] modified in place, returns the convoluted spectrum."""
+        options = options or main_options()
+        assert spectrum.dtype == np.float64 and spectrum.flags.c_contiguous
+        conv = abi.c_double_p()
+        er = C.byref(escape_ratios) if escape_ratios is not None else None
+        self.L.xmb_detector_convolute_spectrum(self.inputF, self.hdf5F, spectrum.ctypes.data_as(abi.c_double_p), C.byref(conv),
+                                               C.byref(options), er, n_interactions)
+        if not conv:
+            raise RuntimeError("xmb_detector_convolute_spectrum: " + abi.last_error())
+        out = _np_from_ptr(conv, (spectrum.size,)).copy()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(conv)
+        return out
+
     def close(self):
         if self._sa is not None:
             self.L.xmb_free_solid_angle(self._sa)

@@ -3,7 +3,8 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 CC        := $(shell test -x /usr/bin/gcc && echo /usr/bin/gcc || echo gcc)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -ccbin $(CXX) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Ixmimsim_b200/csrc -Xcompiler -fPIC,-fopenmp,-O3 -Xptxas -v
+EXTRA_NVFLAGS ?=
+NVFLAGS   := $(EXTRA_NVFLAGS) -ccbin $(CXX) $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Ixmimsim_b200/csrc -Xcompiler -fPIC,-fopenmp,-O3 -Xptxas -v
 CXXFLAGS  := -O3 -fPIC -fopenmp -std=c++17 -Iinclude -Ixmimsim_b200/csrc -Wall -Wno-unknown-pragmas
 CFLAGS    := -O3 -fPIC -fopenmp -std=gnu99 -Iinclude -Ixmimsim_b200/csrc -Wall
 SRC       := xmimsim_b200/csrc

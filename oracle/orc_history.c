@@ -33,6 +33,34 @@
 #define AVOGNUM 0.602252
 #define RE2 0.07940775
 
+/* Random-number layout (shared with the GPU engine; the reference's MT19937 order is not reproducible across
+ * thread counts anyway): Philox4x32-10, key = seed,
+ * counter = (photon id lo, hi, (order << 20) | (stage << 16) | (element << 8) | block, 0x48).
+ *   order 0, stage 0        : source sampling, words consumed sequentially
+ *   order k, stage 1, blk 0 : {path length, detector point r, detector point phi, atom selection}
+ *   order k, stage 1, blk 1 : {interaction type, s0, s1, s2}  s* = first three draws of the interaction
+ *                             (Rayleigh: theta, phi; Compton: theta, phi, depolarisation; photo: shell, line, theta)
+ *   order k, stage 2, elem e: forced-detection Compton energy of element e, two trials per block
+ *   order k, stage 3        : further draws of the interaction (Doppler trials; photo: phi, Coster-Kronig hops)
+ * Every draw has a fixed address, so streams never depend on branch history. */
+static void draw_block(uint64_t seed, uint64_t g, int order, int stage, int elem, int block, double u[4]) {
+	uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+	uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32),
+	                   ((uint32_t)order << 20) | ((uint32_t)stage << 16) | ((uint32_t)elem << 8) | (uint32_t)block, ORC_TAG_HISTORY};
+	uint32_t out[4];
+	orc_philox4x32_10(ctr, key, out);
+	for (int i = 0; i < 4; i++) u[i] = out[i] * (1.0 / 4294967296.0);
+}
+/* sequential cursor over the blocks of one (order, stage, element) sub-stream */
+typedef struct { uint64_t seed, g; int order, stage, elem, block, have; double u[4]; } substream_t;
+static void sub_init(substream_t *s, uint64_t seed, uint64_t g, int order, int stage, int elem) {
+	s->seed = seed; s->g = g; s->order = order; s->stage = stage; s->elem = elem; s->block = 0; s->have = 0;
+}
+static double sub_uniform(substream_t *s) {
+	if (s->have == 0) { draw_block(s->seed, s->g, s->order, s->stage, s->elem, s->block & 0xFF, s->u); s->block++; s->have = 4; }
+	return s->u[4 - s->have--];
+}
+
 typedef struct {
 	double coords[3], dirv[3], elecv[3];
 	double energy, weight, theta, phi;
@@ -40,6 +68,7 @@ typedef struct {
 	int current_element;      /* Z */
 	int current_element_index;
 	int n_interactions, last_interaction;
+	uint64_t seed, g;         /* Philox key and stream (global photon id) */
 	int hist_line[32];        /* history(k,1): interaction code or negative line */
 	int hist_Z[32];           /* history(k,2) */
 	double mus[64];
@@ -181,7 +210,7 @@ static double elec_phi0(const photon_t *p) {
 
 /* ---- Doppler-broadened Compton energy (src/xmi_main.F90:4985-5067; VR variant
  *      src/xmi_variance_reduction.F90:1010-1101) ------------------------------------------------ */
-static double compton_energy(const ctx_t *c, int zi, double E0, double theta_i, orc_rng *rng, int varred) {
+static double compton_energy(const ctx_t *c, int zi, double E0, double theta_i, substream_t *rng, int varred) {
 	const double cc = 1.2399E-6, c0 = 4.85E-12, c1 = 1.456E-2;
 	const xmb_tables_host *T = c->T;
 	const double *icdf = T->cp_icdf + (size_t)zi * T->n_cp;
@@ -190,17 +219,17 @@ static double compton_energy(const ctx_t *c, int zi, double E0, double theta_i, 
 	double energy;
 	int tries = 0;
 	for (;;) {
-		double r = orc_rng_uniform(rng);
+		double r = sub_uniform(rng), r_sign = sub_uniform(rng);
 		int pos = (int)(r / (T->cp_R[1] - T->cp_R[0]));          /* 0-based INT(r/dr) */
 		if (varred && pos == T->n_cp - 2) continue;               /* :1058 skip the last interval */
 		if (pos > T->n_cp - 2) pos = T->n_cp - 2;
 		double pz = icdf[pos] + (icdf[pos + 1] - icdf[pos]) * (r - T->cp_R[pos]) / (T->cp_R[pos + 1] - T->cp_R[pos]);
-		if (orc_rng_uniform(rng) < 0.5) pz = -pz;
+		if (r_sign < 0.5) pz = -pz;
 		double dlamb = c0 * sth2 * sth2 - c1 * c_lamb0 * sth2 * pz;
 		double c_lamb = c_lamb0 + dlamb;
 		energy = cc / c_lamb / 1000.0;
 		if (energy <= E0) break;
-		if (varred && tries == 100) break;                         /* reference aborts the run here (:1084-1089) */
+		if (tries == (varred ? 100 : 500)) break;                  /* VR: reference aborts the run here (:1084-1089) */
 		tries++;
 	}
 	return energy;
@@ -245,13 +274,13 @@ static void deposit(ctx_t *c, int Z, int slot, int n_ia, double energy, double w
 }
 
 /* ---- xmi_variance_reduction (src/xmi_variance_reduction.F90:29-726) ------------------------ */
-static void variance_reduction(ctx_t *c, photon_t *p, orc_rng *rng) {
+static void variance_reduction(ctx_t *c, photon_t *p, double u_det_r, double u_det_phi) {
 	const xmb_tables_host *T = c->T;
 	const orc_derived *D = c->d;
 	const xmb_geometry *g = c->in->geometry;
 	if (p->energy <= ENERGY_THRESHOLD) return;                                   /* :79 */
-	double radius = sqrt(orc_rng_uniform(rng)) * D->detector_radius;              /* :91 */
-	double theta = 2.0 * M_PI * orc_rng_uniform(rng);
+	double radius = sqrt(u_det_r) * D->detector_radius;                           /* :91 */
+	double theta = 2.0 * M_PI * u_det_phi;
 	double detector_point[3] = {0.0, cos(theta) * radius, sin(theta) * radius};
 	double rel[3] = {p->coords[0] - g->p_detector_window[0], p->coords[1] - g->p_detector_window[1], p->coords[2] - g->p_detector_window[2]};
 	double lc_point[3], dirv[3], lc_dirv[3];
@@ -314,7 +343,9 @@ static void variance_reduction(ctx_t *c, photon_t *p, orc_rng *rng) {
 		deposit(c, Z, 383 + 1, n_ia, p->energy, Pconv * Pdir * Pesc_rayl * p->weight);
 		/* COMPTON  (xmi_compton_varred2, :949-1008) */
 		{
-			double e_c = compton_energy(c, zi, p->energy, theta, rng, 1);
+			substream_t cs;
+			sub_init(&cs, p->seed, p->g, n_ia, 2, i);
+			double e_c = compton_energy(c, zi, p->energy, theta, &cs, 1);
 			double mus_c[64];
 			mu_calc(c, e_c, mus_c);
 			double tm = 0.0;
@@ -364,15 +395,15 @@ static void variance_reduction(ctx_t *c, photon_t *p, orc_rng *rng) {
 }
 
 /* ---- interactions --------------------------------------------------------------------------- */
-static int do_rayleigh(ctx_t *c, photon_t *p, orc_rng *rng) {                     /* src/xmi_main.F90:1986-2101 */
+static int do_rayleigh(ctx_t *c, photon_t *p, const double *sd) {                  /* src/xmi_main.F90:1986-2101 */
 	const xmb_tables_host *T = c->T;
 	int zi = T->uniqZ[p->current_element];
-	double r = orc_rng_uniform(rng);
+	double r = sd[0];
 	double theta_i = bilinear(T->rayl_theta_icdf + (size_t)zi * T->n_icdf_E * T->n_icdf_R, T->n_icdf_R, T->icdf_E, T->n_icdf_E,
 	                          T->icdf_R, p->energy, r);
 	double tt = sin(theta_i) * sin(theta_i);
 	tt = tt / (4.0 - 2.0 * tt);
-	double phi_i = bilinear(T->phi_icdf, T->n_icdf_R, T->phi_T, T->n_phi_T, T->icdf_R, tt, orc_rng_uniform(rng));
+	double phi_i = bilinear(T->phi_icdf, T->n_icdf_R, T->phi_T, T->n_phi_T, T->icdf_R, tt, sd[1]);
 	double phi0 = elec_phi0(p);
 	update_dirv(p, theta_i, phi0 + phi_i);
 	update_elecv(p);
@@ -381,17 +412,19 @@ static int do_rayleigh(ctx_t *c, photon_t *p, orc_rng *rng) {                   
 	return 1;
 }
 
-static int do_compton(ctx_t *c, photon_t *p, orc_rng *rng) {                      /* :2103-2229 */
+static int do_compton(ctx_t *c, photon_t *p, const double *sd) {                   /* :2103-2229 */
 	const xmb_tables_host *T = c->T;
 	int zi = T->uniqZ[p->current_element];
 	double theta_i = bilinear(T->compt_theta_icdf + (size_t)zi * T->n_icdf_E * T->n_icdf_R, T->n_icdf_R, T->icdf_E, T->n_icdf_E,
-	                          T->icdf_R, p->energy, orc_rng_uniform(rng));
+	                          T->icdf_R, p->energy, sd[0]);
 	double K0K = 1.0 + p->energy * (1.0 - cos(theta_i)) / XMI_MEC2;
 	double tt = sin(theta_i) * sin(theta_i);
 	tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
-	double phi_i = bilinear(T->phi_icdf, T->n_icdf_R, T->phi_T, T->n_phi_T, T->icdf_R, tt, orc_rng_uniform(rng));
+	double phi_i = bilinear(T->phi_icdf, T->n_icdf_R, T->phi_T, T->n_phi_T, T->icdf_R, tt, sd[1]);
 	double phi0 = elec_phi0(p);
-	p->energy = compton_energy(c, zi, p->energy, theta_i, rng, 0);
+	substream_t ds;
+	sub_init(&ds, p->seed, p->g, p->n_interactions, 3, 0);
+	p->energy = compton_energy(c, zi, p->energy, theta_i, &ds, 0);
 	mu_calc(c, p->energy, p->mus);                                                /* :5059 */
 	if (p->energy == 0.0) return 1;
 	update_dirv(p, theta_i, phi_i + phi0);
@@ -400,7 +433,7 @@ static int do_compton(ctx_t *c, photon_t *p, orc_rng *rng) {                    
 	double rat = 1.0 / (1.0 + (1 - cos(theta_i)) * p->energy / 510.998910);
 	double rk = rat - 2.0 + 1.0 / rat;
 	pp = pp / (rk + pp);
-	double r = orc_rng_uniform(rng);
+	double r = sd[2];
 	double w_h = (1.0 + pp) / 2.0;
 	if (r > w_h) { double t[3]; cross3(p->dirv, p->elecv, t); memcpy(p->elecv, t, sizeof(t)); }
 	p->hist_line[p->n_interactions] = COMPTON;
@@ -409,12 +442,12 @@ static int do_compton(ctx_t *c, photon_t *p, orc_rng *rng) {                    
 }
 
 /* xmi_coster_kronig_check (:5184-5323) */
-static int coster_kronig(const ctx_t *c, int zi, int shell, orc_rng *rng) {
+static int coster_kronig(const ctx_t *c, int zi, int shell, substream_t *rng) {
 	const double *ck = c->T->cos_kron + (size_t)zi * XMB_N_CK;
 	static const int first[9] = {-1, XMB_FL12, XMB_FL23, -1, XMB_FM12, XMB_FM23, XMB_FM34, XMB_FM45, -1};
 	static const int ntr[9] = {0, 2, 1, 0, 4, 3, 2, 1, 0};
 	while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
-		double r = orc_rng_uniform(rng), sumz = 0.0;
+		double r = sub_uniform(rng), sumz = 0.0;
 		int found = -1;
 		for (int t = 0; t < ntr[shell]; t++) {
 			sumz += ck[first[shell] + t];
@@ -427,23 +460,26 @@ static int coster_kronig(const ctx_t *c, int zi, int shell, orc_rng *rng) {
 	return shell;
 }
 
-static int do_photo(ctx_t *c, photon_t *p, orc_rng *rng) {                        /* :2231-2411 */
+static int do_photo(ctx_t *c, photon_t *p, const double *sd) {                     /* :2231-2411 */
 	const xmb_tables_host *T = c->T;
 	int Z = p->current_element, zi = T->uniqZ[Z];
 	nodepos_t np = node_find(T, p->energy);
 	double photo_total = lerp_at(T->cs_photo_total + (size_t)zi * T->n_nodes, np);
-	double sumz = 0.0, r = orc_rng_uniform(rng);
+	double sumz = 0.0, r = sd[0];
 	int max_shell = c->opt->use_M_lines ? 8 : 3, shell, shell_found = 0;
 	for (shell = 0; shell <= max_shell; shell++) {
 		sumz += lerp_at(T->cs_photo_partial + ((size_t)zi * 9 + shell) * T->n_nodes, np) / photo_total;
 		if (r < sumz) { shell_found = 1; break; }
 	}
 	if (!shell_found) { p->energy = 0.0; return 1; }                              /* :2280-2291 */
-	(void)orc_rng_uniform(rng);                                                   /* drawn, unused: xmi_variance_reduction.F90:737 */
+	/* the reference draws one unused number here (xmi_variance_reduction.F90:737); not reproduced */
 	p->weight *= T->fluor_yield_corr[zi * 9 + shell];                             /* :745 */
-	shell = coster_kronig(c, zi, shell, rng);                                     /* :2329 */
+	substream_t xs;
+	sub_init(&xs, p->seed, p->g, p->n_interactions, 3, 0);
+	double u_phi = sub_uniform(&xs);
+	shell = coster_kronig(c, zi, shell, &xs);                                     /* :2329 */
 	/* xmi_fluorescence_line_check (:5352-5437) */
-	r = orc_rng_uniform(rng);
+	r = sd[1];
 	sumz = 0.0;
 	int line = 0;
 	for (int l = xmb_shell_line_first[shell]; l <= xmb_shell_line_last[shell]; l++) {
@@ -456,8 +492,8 @@ static int do_photo(ctx_t *c, photon_t *p, orc_rng *rng) {                      
 		nodepos_t lp = node_find(T, p->energy);                                   /* precalc_mu_cs, :2346-2349 */
 		for (int i = 0; i < c->nL; i++) p->mus[i] = lerp_at(T->mu_layer + (size_t)i * T->n_nodes, lp);
 	}
-	double theta_i = acos(-2.0 * orc_rng_uniform(rng) + 1.0);                     /* :2352-2353 */
-	double phi_i = 2.0 * M_PI * orc_rng_uniform(rng);
+	double theta_i = acos(-2.0 * sd[2] + 1.0);                                    /* :2352-2353 */
+	double phi_i = 2.0 * M_PI * u_phi;
 	update_dirv(p, theta_i, phi_i);
 	update_elecv(p);
 	p->hist_line[p->n_interactions] = -line;
@@ -466,7 +502,7 @@ static int do_photo(ctx_t *c, photon_t *p, orc_rng *rng) {                      
 }
 
 /* ---- xmi_simulate_photon, variance-reduction branch (src/xmi_main.F90:1188-1685) ------------ */
-static void simulate_photon(ctx_t *c, photon_t *p, orc_rng *rng) {
+static void simulate_photon(ctx_t *c, photon_t *p) {
 	const xmb_geometry *g = c->in->geometry;
 	const orc_derived *D = c->d;
 	const xmb_layer *layers = c->in->composition->layers;
@@ -475,8 +511,11 @@ static void simulate_photon(ctx_t *c, photon_t *p, orc_rng *rng) {
 		int step_max, step_dir;
 		if (dot3(p->dirv, g->n_sample_orientation) > 0.0) { step_max = c->nL - 1; step_dir = 1; }
 		else { step_max = 0; step_dir = -1; }
-		double interactionR = orc_rng_uniform(rng);                                /* :1264 */
 		if (p->n_interactions == c->n_int) break;                                  /* :1417-1420 */
+		double b0[4], b1[4];
+		draw_block(p->seed, p->g, p->n_interactions + 1, 1, 0, 0, b0);
+		draw_block(p->seed, p->g, p->n_interactions + 1, 1, 0, 1, b1);
+		double interactionR = b0[0];                                               /* :1264 */
 		double distances[64], lp[3] = {p->coords[0], p->coords[1], p->coords[2]};
 		for (int i = p->current_layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {   /* :1429-1449 */
 			double pp[3] = {0.0, 0.0, step_dir == 1 ? D->Z_coord_end[i] : D->Z_coord_begin[i]}, inter[3];
@@ -504,9 +543,9 @@ static void simulate_photon(ctx_t *c, photon_t *p, orc_rng *rng) {
 		p->current_layer = my_index;
 		p->n_interactions++;                                                       /* :1542 */
 		c->n_interactions_total++;
-		variance_reduction(c, p, rng);                                             /* :1548 */
+		variance_reduction(c, p, b0[1], b0[2]);                                    /* :1548 */
 		/* atom selection (:1558-1572) */
-		interactionR = orc_rng_uniform(rng);
+		interactionR = b0[3];
 		{
 			const xmb_layer *l = &layers[p->current_layer];
 			nodepos_t np = node_find(c->T, p->energy);
@@ -520,13 +559,13 @@ static void simulate_photon(ctx_t *c, photon_t *p, orc_rng *rng) {
 				}
 			}
 			/* interaction type (:1580-1652) */
-			interactionR = orc_rng_uniform(rng);
+			interactionR = b1[0];
 			int zi = c->T->uniqZ[p->current_element];
 			double pr = lerp_at(c->T->p_rayl + (size_t)zi * c->T->n_nodes, np);
 			double prc = lerp_at(c->T->p_rayl_compt + (size_t)zi * c->T->n_nodes, np);
-			if (interactionR < pr) { p->last_interaction = RAYLEIGH; do_rayleigh(c, p, rng); }
-			else if (interactionR < prc) { p->last_interaction = COMPTON; do_compton(c, p, rng); }
-			else { p->last_interaction = PHOTO; do_photo(c, p, rng); }
+			if (interactionR < pr) { p->last_interaction = RAYLEIGH; do_rayleigh(c, p, b1 + 1); }
+			else if (interactionR < prc) { p->last_interaction = COMPTON; do_compton(c, p, b1 + 1); }
+			else { p->last_interaction = PHOTO; do_photo(c, p, b1 + 1); }
 		}
 	}
 }
@@ -676,10 +715,11 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
 			while (s + 1 < nseg && gidx >= segs[s + 1].first) s++;
 			photon_t p;
 			orc_rng rng;
-			orc_rng_init(&rng, seed, gidx, ORC_TAG_HISTORY);
+			orc_rng_init(&rng, seed, gidx, ORC_TAG_HISTORY);   /* order 0, stage 0: ctr[2] = block */
 			int skip;
 			start_photon(&c, &p, &rng, &segs[s], gidx - segs[s].first, &skip);
-			if (!skip) simulate_photon(&c, &p, &rng);
+			p.seed = seed; p.g = gidx;
+			if (!skip) simulate_photon(&c, &p);
 		}
 #pragma omp critical
 		{

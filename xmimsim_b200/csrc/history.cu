@@ -15,7 +15,8 @@
 // independent of scheduling, launch shape and GPU count, bit for bit.
 // XRF deposits only touch the per-line history slot; the channel spectrum is rebuilt from those slots in
 // the epilogue (a line's channel is a constant), which halves the atomics of the inner loop.
-// Random numbers: Philox4x32-10, stream = global photon id, consumed sequentially.
+// Random numbers: Philox4x32-10 keyed by the run seed; every draw of photon g has a fixed counter address
+// (g, interaction order, stage, element, block), see draw_block().
 #include <cstdio>
 #include <vector>
 #include <algorithm>
@@ -31,6 +32,14 @@
 #define AVOGNUM 0.602252
 #define RE2 0.07940775
 #define HIST_THREADS 128
+#ifndef XMB_REC_UNROLL
+#define XMB_REC_UNROLL 1
+#endif
+#define XMB_PRAGMA(x) _Pragma(#x)
+#define XMB_UNROLL(n) XMB_PRAGMA(unroll n)
+#ifndef HIST_MIN_BLOCKS
+#define HIST_MIN_BLOCKS 4         // 128 registers/thread: 16 warps per SM (measured against 3 -> 168 regs, see profiles/)
+#endif
 
 __constant__ short d_shell_line_first[9] = {1, 30, 59, 86, 118, 140, 161, 182, 201};   // = xmb_shell_line_first
 __constant__ short d_shell_line_last[9] = {29, 58, 85, 113, 136, 158, 180, 200, 219};    // = xmb_shell_line_last
@@ -79,16 +88,34 @@ __device__ __forceinline__ double bilinear(const double *a, int n2, const double
 }
 
 // ---- exact accumulation ---------------------------------------------------------------------------
+// Every deposit is a non-negative 2^-56 fixed-point integer.  A slot is two 64-bit words: A accumulates the
+// low 32 bits of each addend, B the high 32 bits, so both updates are fire-and-forget REDs (no carry, no
+// returned value to wait for); total = A + (B << 32), exact for < 2^32 addends of < 2^63.
 __device__ __forceinline__ unsigned long long to_fixed(double w, unsigned long long *counters) {
-	// w >= 0 relative weight; 2^56 fixed point.  Out-of-range values are counted, never wrapped.
-	const double s = w * 72057594037927936.0;
-	if (!(s < 9.2e18)) { if (s == s) atomicAdd(&counters[2], 1ULL); return 0ULL; }
+	const double s = w * 72057594037927936.0;   // 2^56
+	if (!(s < 2.8e17)) { if (s == s) atomicAdd(&counters[2], 1ULL); return 0ULL; }   // w >= ~4: counted, never wrapped
 	return __double2ull_rn(s);
 }
-__device__ __forceinline__ void add128(unsigned long long *acc, size_t slot, unsigned long long v) {
+#ifndef XMB_SPLIT_RED
+#define XMB_SPLIT_RED 1
+#endif
+__device__ __forceinline__ void red128(unsigned long long *acc, size_t slot, unsigned long long v) {
 	if (v == 0ULL) return;
+#if XMB_SPLIT_RED
+	atomicAdd(&acc[2 * slot], v & 0xFFFFFFFFULL);
+	atomicAdd(&acc[2 * slot + 1], v >> 32);
+#else
+	// (lo, hi) with carry: one returning atomic, a second one only on overflow of the low word
 	const unsigned long long old = atomicAdd(&acc[2 * slot], v);
-	if (old + v < old) atomicAdd(&acc[2 * slot + 1], 1ULL);
+	if (old + v < old) atomicAdd(&acc[2 * slot + 1], 1ULL << 32);
+#endif
+}
+// exact warp sum of values < 2^58 with three REDUX.SUM on 21-bit pieces
+__device__ __forceinline__ unsigned long long warp_sum_fixed(unsigned long long v) {
+	const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0x1FFFFFULL));
+	const unsigned s1 = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 21) & 0x1FFFFFULL));
+	const unsigned s2 = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 42));
+	return (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42);
 }
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -96,17 +123,48 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	return v;
 }
 // all 32 lanes call; slot is warp-uniform
+#ifndef XMB_USE_REDUX
+#define XMB_USE_REDUX 0
+#endif
 __device__ __forceinline__ void deposit_uniform(unsigned long long *acc, size_t slot, unsigned long long v, int lane) {
+#if XMB_USE_REDUX
+	v = warp_sum_fixed(v);
+#else
 	v = warp_sum_u64(v);
-	if (lane == 0) add128(acc, slot, v);
+#endif
+	if (lane == 0) red128(acc, slot, v);
 }
 // all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
 __device__ __forceinline__ void deposit_varying(unsigned long long *acc, long slot, unsigned long long v, int lane) {
 	const long s0 = __shfl_sync(0xffffffffu, slot, 0);
 	if (__all_sync(0xffffffffu, slot == s0)) {
 		if (s0 >= 0) deposit_uniform(acc, (size_t)s0, v, lane);
-	} else if (slot >= 0) add128(acc, (size_t)slot, v);
+	} else if (slot >= 0) red128(acc, (size_t)slot, v);
 }
+
+// Random-number layout: counter = (photon id lo, hi, (order << 20) | (stage << 16) | (element << 8) | block, tag);
+// see DESIGN.md "Random numbers".  Every draw has a fixed address: all lanes of a warp generate their blocks at
+// the same program point (no divergent refills) and no generator state lives across the interaction loop.
+__device__ __forceinline__ uint4 draw_block(uint64_t seed, uint64_t g, int order, int stage, int elem, int block) {
+	return xmb_philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32),
+	                                    ((uint32_t)order << 20) | ((uint32_t)stage << 16) | ((uint32_t)elem << 8) | (uint32_t)block,
+	                                    XMB_TAG_HISTORY),
+	                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+struct SubStream {   // sequential cursor over the blocks of one (order, stage, element) sub-stream
+	uint64_t seed, g;
+	int order, stage, elem, block, have;
+	uint4 buf;
+	__device__ __forceinline__ void init(uint64_t seed_, uint64_t g_, int order_, int stage_, int elem_) {
+		seed = seed_; g = g_; order = order_; stage = stage_; elem = elem_; block = 0; have = 0;
+	}
+	__device__ __forceinline__ double uniform() {
+		if (have == 0) { buf = draw_block(seed, g, order, stage, elem, block & 0xFF); block++; have = 4; }
+		const uint32_t w = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
+		have--;
+		return xmb_u01(w);
+	}
+};
 
 struct Photon {
 	double cx, cy, cz, dx, dy, dz, ex, ey, ez;
@@ -166,27 +224,33 @@ __device__ __forceinline__ double elec_phi0(const Photon &p) {
 
 // Doppler-broadened Compton energy (src/xmi_main.F90:4985-5067; forced-detection variant
 // src/xmi_variance_reduction.F90:1010-1101)
-__device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi, double E0, double theta_i, XmbRng &rng, bool varred) {
+// sth2 = sin(theta/2) and c_lamb0 = 1.2399e-6 / (1000 E0) are hoisted by the callers (same for every element).
+// Two trials per Philox block: (pz, sign), (pz, sign).
+__device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi, double E0, double c_lamb0, double sth2, uint64_t g, int order,
+                                                 int stage, int elem, bool varred) {
 	const double cc = 1.2399E-6, c0 = 4.85E-12, c1 = 1.456E-2;
 	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp;
-	const double c_lamb0 = cc / (E0 * 1000.0);
-	const double sth2 = sin(theta_i / 2.0);
-	double energy;
+	const double shift = c0 * sth2 * sth2, slope = c1 * c_lamb0 * sth2;
+	double energy = 0.0;
 	int tries = 0;
-	for (;;) {
-		const double r = rng.uniform();
-		int pos = (int)(r / P.cp_dR);
-		if (varred && pos == P.n_cp - 2) continue;
-		pos = min(pos, P.n_cp - 2);
-		const double r0 = P.cp_R[pos], r1 = P.cp_R[pos + 1];
-		double pz = icdf[pos] + (icdf[pos + 1] - icdf[pos]) * (r - r0) / (r1 - r0);
-		if (rng.uniform() < 0.5) pz = -pz;
-		const double dlamb = c0 * sth2 * sth2 - c1 * c_lamb0 * sth2 * pz;
-		const double c_lamb = c_lamb0 + dlamb;
-		energy = cc / c_lamb / 1000.0;
-		if (energy <= E0) break;
-		if (varred && tries == 100) break;
-		tries++;
+	for (int blk = 0;; blk++) {
+		const uint4 w = draw_block(P.seed, g, order, stage, elem, blk & 0xFF);
+		bool done = false;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const double r = xmb_u01(h ? w.z : w.x), rs = xmb_u01(h ? w.w : w.y);
+			int pos = (int)(r / P.cp_dR);
+			if (varred && pos == P.n_cp - 2) continue;
+			pos = min(pos, P.n_cp - 2);
+			const double r0 = P.cp_R[pos], r1 = P.cp_R[pos + 1];
+			double pz = icdf[pos] + (icdf[pos + 1] - icdf[pos]) * (r - r0) / (r1 - r0);
+			if (rs < 0.5) pz = -pz;
+			const double c_lamb = c_lamb0 + (shift - slope * pz);
+			energy = cc / c_lamb / 1000.0;
+			if (energy <= E0 || tries == (varred ? 100 : 500)) { done = true; break; }
+			tries++;
+		}
+		if (done) break;
 	}
 	return energy;
 }
@@ -305,7 +369,7 @@ __device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x,
 	return true;
 }
 
-__global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
+__global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
 	extern __shared__ double smem[];
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
@@ -322,22 +386,24 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 	for (uint64_t w = (uint64_t)blockIdx.x * (T >> 5) + (tid >> 5); w < n_warps; w += warps_per_grid) {
 		const uint64_t g = P.g_begin + w * 32 + lane;
 		Photon p;
-		XmbRng rng;
 		p.alive = g < P.g_end;
 		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
 		if (p.alive) {
+			XmbRng rng;   // order 0, stage 0: sequential words, counter word 2 = block
 			rng.init(P.seed, g, XMB_TAG_HISTORY);
 			start_photon(P, p, rng, g, mus, T);
 		}
 		for (int it = 0; it < P.n_int; it++) {
 			// ---- forced interaction (src/xmi_main.F90:1229-1518) ------------------------------------
 			if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
+			const int order = it + 1;
+			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length, detector r, detector phi, atom}
 			double interactionR = 0.0;
 			int step_max = 0, step_dir = 1;
 			if (p.alive) {
 				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = P.nL - 1; step_dir = 1; }
 				else { step_max = 0; step_dir = -1; }
-				interactionR = rng.uniform();
+				interactionR = xmb_u01(b0.x);
 				double lx = p.cx, ly = p.cy, lz = p.cz;
 				double Pabs = 0.0;
 				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
@@ -366,7 +432,9 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					p.layer = my_index;
 					p.n_interactions++;
 					n_inter_local++;
+#ifndef XMB_NO_LAYER_CNT
 					atomicAdd(&s_layer_cnt[my_index], 1u);
+#endif
 				}
 			}
 			if (!__any_sync(0xffffffffu, p.alive)) break;
@@ -379,8 +447,8 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 			NodePos np;
 			np.pos = 0; np.f = 0.0;
 			if (vr) {
-				const double radius = sqrt(rng.uniform()) * P.detector_radius;
-				const double th = 2.0 * M_PI * rng.uniform();
+				const double radius = sqrt(xmb_u01(b0.y)) * P.detector_radius;
+				const double th = 2.0 * M_PI * xmb_u01(b0.z);
 				double sdp, cdp;
 				sincos(th, &sdp, &cdp);
 				const double dp0 = 0.0, dp1 = cdp * radius, dp2 = sdp * radius;
@@ -431,11 +499,13 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 				if (!__any_sync(0xffffffffu, mine)) continue;
 				const XmbLayerDev lay = P.layers[L];
 				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
-				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0;
+				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0, c_lamb0 = 0.0, sth2 = 0.0;
 				int qi = 0;
 				long ch_rayl = -1;
 				if (mine) {
-					const double q = p.energy / KEV2ANGST * sin(theta / 2.0);
+					sth2 = sin(theta / 2.0);
+					c_lamb0 = 1.2399E-6 / (p.energy * 1000.0);
+					const double q = p.energy / KEV2ANGST * sth2;
 					const double qx = q / P.q_max * (P.n_q - 1);
 					qi = min((int)qx, P.n_q - 2);
 					qf = qx - qi;
@@ -450,7 +520,6 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
 					const size_t hbase = (size_t)P.nch + P.hist_base[zi];
-					const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
 					// Rayleigh (:342-369)
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
@@ -466,7 +535,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					fx = 0ULL;
 					long ch_c = -1;
 					if (mine) {
-						const double e_c = compton_energy(P, zi, p.energy, theta, rng, true);
+						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true);
 						const NodePos cp = node_find(P, e_c);
 						double tm = 0.0;
 						for (int j = 0; j < P.nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
@@ -479,9 +548,11 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					}
 					deposit_uniform(acc_k, hbase + 1, fx, lane);
 					deposit_varying(acc_k, ch_c, fx, lane);
-					// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy
-					const double common = mine ? wfrac * inv_mu * (omega / 4.0 / M_PI) * p.weight : 0.0;   // Pconv/P_shell * Pdir_fluo * weight
+					// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy (after a
+					// fluorescence interaction that energy is a node of the grid: the reference's precalc_xrf_cs)
+					const double common = mine ? wfrac * inv_mu * (omega / 4.0 / M_PI) * p.weight : 0.0;
 					const bool aboveK = mine && p.energy >= P.edge_K[zi];
+					const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
 					const int n_sh = P.use_M_lines ? 9 : 4;
 					for (int s = 0; s < n_sh; s++) {
 						const int r0 = P.rec_begin[zi * 10 + s], r1 = P.rec_begin[zi * 10 + s + 1];
@@ -490,6 +561,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 						if (mine && (s > 0 || aboveK)) Ps = row_lerp(P, np, eoff + XMB_EO_VACANCY + s);
 						if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
 						const double pre = common * Ps;
+XMB_UNROLL(XMB_REC_UNROLL)
 						for (int r = r0; r < r1; r++) {
 							const double *mu = P.rec_mu + (size_t)r * P.nL;
 							double tm = 0.0;
@@ -505,7 +577,8 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 			if (p.alive) {
 				const XmbLayerDev lay = P.layers[p.layer];
 				const NodePos ep = node_find(P, p.energy);
-				double R2 = rng.uniform();
+				const uint4 b1 = draw_block(P.seed, g, order, 1, 0, 1);   // {interaction type, s0, s1, s2}
+				double R2 = xmb_u01(b0.w);
 				double thr = 0.0;
 				int zi = 0;
 				const double mu_cur = mus[p.layer * T];
@@ -515,27 +588,28 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					if (R2 < thr) break;
 				}
 				const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
-				R2 = rng.uniform();
+				R2 = xmb_u01(b1.x);
+				const double s0 = xmb_u01(b1.y), s1 = xmb_u01(b1.z), s2 = xmb_u01(b1.w);
 				const double pr = row_lerp(P, ep, eoff + XMB_EO_P_RAYL), prc = row_lerp(P, ep, eoff + XMB_EO_P_RAYL_COMPT);
 				if (R2 < pr) {
 					// Rayleigh (:1986-2101)
-					const double r = rng.uniform();
+					const double r = s0;
 					const double theta_i = bilinear(P.rayl_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, r);
 					double tt = sin(theta_i) * sin(theta_i);
 					tt = tt / (4.0 - 2.0 * tt);
-					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, rng.uniform());
+					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
 					const double phi0 = elec_phi0(p);
 					update_dirv(p, theta_i, phi0 + phi_i);
 					update_elecv(p);
 				} else if (R2 < prc) {
 					// Compton (:2103-2229)
-					const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, rng.uniform());
+					const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
 					const double K0K = 1.0 + p.energy * (1.0 - cos(theta_i)) / XMI_MEC2;
 					double tt = sin(theta_i) * sin(theta_i);
 					tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
-					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, rng.uniform());
+					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
 					const double phi0 = elec_phi0(p);
-					p.energy = compton_energy(P, zi, p.energy, theta_i, rng, false);
+					p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
 					{
 						const NodePos cp = node_find(P, p.energy);
 						for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, cp, i);
@@ -548,7 +622,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 						const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
 						const double rk = rat - 2.0 + 1.0 / rat;
 						pp = pp / (rk + pp);
-						const double r = rng.uniform();
+						const double r = s2;
 						const double w_h = (1.0 + pp) / 2.0;
 						if (r > w_h) {
 							const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
@@ -559,7 +633,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					// photo-electric effect with fluorescence (:2231-2411)
 					const double photo_total = row_lerp(P, ep, eoff + XMB_EO_PHOTO_TOTAL);
 					double sumz = 0.0;
-					const double r = rng.uniform();
+					const double r = s0;
 					const int max_shell = P.use_M_lines ? 8 : 3;
 					int shell = -1;
 					for (int s = 0; s <= max_shell; s++) {
@@ -568,14 +642,17 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 					}
 					if (shell < 0) { p.energy = 0.0; }
 					else {
-						(void)rng.uniform();   // drawn and unused by the reference (xmi_variance_reduction.F90:737)
+						// (the reference draws one unused number here, xmi_variance_reduction.F90:737; not reproduced)
 						p.weight *= P.fluor_yield_corr[zi * 9 + shell];
+						SubStream xs;
+						xs.init(P.seed, g, order, 3, 0);
+						const double u_phi = xs.uniform();
 						// Coster-Kronig (:5184-5323)
 						const double *ck = P.cos_kron + zi * XMB_N_CK;
 						while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
 							const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
 							const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
-							const double rr = rng.uniform();
+							const double rr = xs.uniform();
 							double sz = 0.0;
 							int found = -1;
 							for (int t = 0; t < ntr; t++) { sz += ck[first + t]; if (rr < sz) { found = t; break; } }
@@ -583,7 +660,7 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 							shell = shell + 1 + found;
 						}
 						// line (:5352-5437)
-						const double rl = rng.uniform();
+						const double rl = s1;
 						double sl = 0.0;
 						int line = 0;
 						const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
@@ -593,8 +670,8 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 							p.energy = P.line_energy[(size_t)zi * 384 + line];
 							const NodePos lp = node_find(P, p.energy);
 							for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, lp, i);
-							const double theta_i = acos(-2.0 * rng.uniform() + 1.0);
-							const double phi_i = 2.0 * M_PI * rng.uniform();
+							const double theta_i = acos(-2.0 * s2 + 1.0);
+							const double phi_i = 2.0 * M_PI * u_phi;
 							update_dirv(p, theta_i, phi_i);
 							update_elecv(p);
 						}
@@ -609,10 +686,13 @@ __global__ void __launch_bounds__(HIST_THREADS) xmb_history_kernel(const __grid_
 	if (tid < P.nL && s_layer_cnt[tid]) atomicAdd(&P.counters[8 + tid], (unsigned long long)s_layer_cnt[tid]);
 }
 
-// raw 128-bit accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
+// raw (A, B) accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
 __global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, unsigned long long *__restrict__ limbs, size_t n_slots) {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
-		const unsigned long long lo = acc[2 * i], hi = acc[2 * i + 1];
+		// total = A + (B << 32) as a 128-bit integer (lo, hi)
+		const unsigned long long A = acc[2 * i], B = acc[2 * i + 1];
+		const unsigned long long lo = A + (B << 32);
+		const unsigned long long hi = (B >> 32) + (lo < A ? 1ULL : 0ULL);
 		limbs[2 * i] = lo & 0xFFFFFFFFFFFFULL;
 		limbs[2 * i + 1] = (lo >> 48) | (hi << 16);
 	}

@@ -63,7 +63,7 @@ struct XmbHistParams {
 	const double *cos_kron;                  // [nZ][13]
 	const double *rad_rate;                  // [nZ][384]
 	const double *line_energy;               // [nZ][384]
-	// forced-detection line records, grouped by (element, shell)
+	// forced-detection line records (active lines only), grouped by (element, shell)
 	const int *rec_begin;                    // [nZ][10] record range of (zi, shell) = [rec_begin[zi*10+s], rec_begin[zi*10+s+1])
 	const double *rec_yr;                    // [n_rec] FluorYield(shell) * RadRate(line)
 	const double *rec_mu;                    // [n_rec][nL] mu of each layer at the line energy
@@ -74,7 +74,8 @@ struct XmbHistParams {
 	const double *sa_grid;                   // [n_theta][n_r]
 	int sa_nr, sa_nt;
 	const double *sa_r_vals, *sa_t_vals;
-	// accumulators: [n_int][nch + n_hist_slots] pairs (lo, hi)
+	// accumulators: [n_int][nch + n_hist_slots] pairs (A, B): A = sum of the low 32 bits of every deposit,
+	// B = sum of the high 32 bits; total = A + (B << 32).  Two carry-free REDs per deposit.
 	unsigned long long *acc;
 	unsigned long long *counters;            // [0] off-grid solid angle lookups, [1] interactions, [2] fixed-point range errors
 };

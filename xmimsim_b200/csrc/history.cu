@@ -31,14 +31,16 @@
 #define KEV2ANGST 12.39841930
 #define AVOGNUM 0.602252
 #define RE2 0.07940775
-#define HIST_THREADS 128
+#ifndef HIST_THREADS
+#define HIST_THREADS 1024        // one CTA per SM: every warp of the SM is in the same phase (I-cache locality)
+#endif
 #ifndef XMB_REC_UNROLL
 #define XMB_REC_UNROLL 1
 #endif
 #define XMB_PRAGMA(x) _Pragma(#x)
 #define XMB_UNROLL(n) XMB_PRAGMA(unroll n)
 #ifndef HIST_MIN_BLOCKS
-#define HIST_MIN_BLOCKS 4         // 128 registers/thread: 16 warps per SM (measured against 3 -> 168 regs, see profiles/)
+#define HIST_MIN_BLOCKS 1
 #endif
 
 __constant__ short d_shell_line_first[9] = {1, 30, 59, 86, 118, 140, 161, 182, 201};   // = xmb_shell_line_first
@@ -375,16 +377,18 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
 	double *rd = smem + (size_t)P.nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
 	const uint64_t n_total = P.g_end - P.g_begin;
-	const uint64_t n_warps = (n_total + 31) / 32;
-	const uint64_t warps_per_grid = (uint64_t)gridDim.x * (T >> 5);
+	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
 	unsigned long long n_inter_local = 0;
 	__shared__ unsigned int s_layer_cnt[XMB_MAX_LAYERS];
 	if (tid < XMB_MAX_LAYERS) s_layer_cnt[tid] = 0;
 	__syncthreads();
 
-	for (uint64_t w = (uint64_t)blockIdx.x * (T >> 5) + (tid >> 5); w < n_warps; w += warps_per_grid) {
-		const uint64_t g = P.g_begin + w * 32 + lane;
+	// The kernel is ~260 KB of SASS (fp64 transcendentals inlined at every site) against a 32 KB L1.5 I-cache: a
+	// CTA therefore walks the phases of an interaction in lock step (__syncthreads between phases), so all warps
+	// of the SM fetch the same few KB at any time (profiles/: stall_no_instruction 7.3 -> see r1 v3).
+	for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+		const uint64_t g = P.g_begin + chunk * T + tid;
 		Photon p;
 		p.alive = g < P.g_end;
 		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 #endif
 				}
 			}
-			if (!__any_sync(0xffffffffu, p.alive)) break;
+			if (!__syncthreads_or(p.alive)) break;   // block-uniform; also the phase barrier after transport
 			const int n_ia = it + 1;   // == p.n_interactions for every live lane
 			unsigned long long *acc_k = P.acc + 2 * (size_t)(n_ia - 1) * acc_row;
 
@@ -493,6 +497,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 					np = node_find(P, p.energy);
 				}
 			}
+			__syncthreads();   // phase: scatter deposits of every element
 			// warp-uniform loops over layers / elements / shells / line records
 			for (int L = 0; L < P.nL; L++) {
 				const bool mine = vr && p.layer == L;
@@ -548,6 +553,17 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 					}
 					deposit_uniform(acc_k, hbase + 1, fx, lane);
 					deposit_varying(acc_k, ch_c, fx, lane);
+				}
+			}
+			__syncthreads();   // phase: fluorescence-line deposits (small loop body: exp + exact warp sum + RED)
+			for (int L = 0; L < P.nL; L++) {
+				const bool mine = vr && p.layer == L;
+				if (!__any_sync(0xffffffffu, mine)) continue;
+				const XmbLayerDev lay = P.layers[L];
+				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
+				for (int e = 0; e < lay.n_elements; e++) {
+					const int zi = P.elem_zi[lay.elem_begin + e];
+					const double wfrac = P.elem_w[lay.elem_begin + e];
 					// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy (after a
 					// fluorescence interaction that energy is a node of the grid: the reference's precalc_xrf_cs)
 					const double common = mine ? wfrac * inv_mu * (omega / 4.0 / M_PI) * p.weight : 0.0;
@@ -574,6 +590,7 @@ XMB_UNROLL(XMB_REC_UNROLL)
 			}
 
 			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
+			__syncthreads();   // phase: selection + scattering
 			if (p.alive) {
 				const XmbLayerDev lay = P.layers[p.layer];
 				const NodePos ep = node_find(P, p.energy);
@@ -992,16 +1009,20 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	// launch
 	int sms = 148, occ = 1;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const size_t smem = sizeof(double) * 2 * P.nL * HIST_THREADS;
-	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xmb_history_kernel, HIST_THREADS, smem));
+	// threads per CTA: as many as the per-thread shared arrays (2 nL doubles) allow within 200 KB
+	int threads = HIST_THREADS;
+	while (threads > 64 && sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
+	const size_t smem = sizeof(double) * 2 * P.nL * threads;
+	XMB_CUDA_OK(cudaFuncSetAttribute(xmb_history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xmb_history_kernel, threads, smem));
 	if (occ < 1) occ = 1;
-	const uint64_t n_warps = (ex->n_histories + 31) / 32;
+	const uint64_t n_chunks = (ex->n_histories + threads - 1) / threads;
 	uint64_t blocks = (uint64_t)sms * occ;
-	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (n_warps + HIST_THREADS / 32 - 1) / (HIST_THREADS / 32)));
+	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, n_chunks));
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
 	cudaEventRecord(e0);
-	if (ex->n_histories > 0) xmb_history_kernel<<<(unsigned)blocks, HIST_THREADS, smem>>>(P);
+	if (ex->n_histories > 0) xmb_history_kernel<<<(unsigned)blocks, threads, smem>>>(P);
 	cudaEventRecord(e1);
 	xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 	XMB_CUDA_OK(cudaGetLastError());

@@ -19,7 +19,9 @@ HDRS      := $(wildcard include/*.h) $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.
 ORC_SRCS  := $(wildcard oracle/*.c)
 ORC_LIB   := oracle/_build/liborc.so
 
-all: $(LIB) $(ORC_LIB)
+PLUGIN    := xmimsim_b200/lib/xmimsim-cl.so
+
+all: $(LIB) $(PLUGIN) $(ORC_LIB)
 lib: $(LIB)
 oracle: $(ORC_LIB)
 
@@ -38,7 +40,12 @@ $(OBJ)/%.c.o: $(SRC)/%.c $(HDRS)
 
 $(LIB): $(OBJS)
 	@mkdir -p xmimsim_b200/lib
-	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(OBJS) -Xcompiler -fopenmp -lgomp -cudart static
+	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(OBJS) -Xcompiler -fopenmp -lgomp -ldl -cudart static
+
+# Drop-in plugin file name the reference's loader opens (src/xmi_solid_angle.c:121-136: "<dir>/xmimsim-cl.<so>");
+# the same symbols are inside $(LIB); this is that library under the expected name.
+$(PLUGIN): $(LIB)
+	cp $(LIB) $(PLUGIN)
 
 # The oracle links the surrogate provider object (third-party stand-in), never the engine.
 $(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h $(SRC)/xrl_surrogate.c

@@ -379,6 +379,14 @@ int xmb_msim_device_limbs(xmb_hdf5FPtr hdf5F, uint64_t **dev_ptr, size_t *n_word
  * n_elements, active forced-detection line records of its elements).  Feeds the algorithmic-bytes
  * figure of SURVEY.md 8(d) / DESIGN.md. */
 int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity);
+/* Host-side helpers of the sharded driver (no GPU needed): the contiguous photon-id shard of a rank, the total
+ * number of histories of an input, and the accumulator slot map: a row (one per interaction order) is
+ * nchannels channel slots followed by n_hist_slots history slots; history slot s holds (out_Z[s], out_line[s]),
+ * line 384 / 385 = Rayleigh / Compton.  xmb_msim_slot_map returns n_hist_slots (pass NULL arrays to query). */
+void xmb_msim_shard(uint64_t n_total, int rank, int n_ranks, uint64_t *begin, uint64_t *end);
+uint64_t xmb_msim_total_histories(xmb_inputFPtr inputF);
+int xmb_msim_slot_map(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                      int32_t *out_Z, int32_t *out_line, int capacity);
 /* Converts (summed) raw accumulators to the reference's three output arrays. */
 int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                          const uint64_t *accum, size_t n_slots, double **channels,
@@ -408,6 +416,21 @@ void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, do
 /* Device time (ms) and kernel launches of the last detector-response call. */
 double xmb_detector_last_ms(void);
 uint64_t xmb_detector_last_launches(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Plugin symbols under the reference's own names (plugin_shim.cpp).  They take the reference's
+ * opaque xmi_inputFPtr OR one of this library's handles.
+ * ------------------------------------------------------------------------------------------ */
+/* XmiSolidAngleCalculation (src/xmi_solid_angle.c:51), symbol name from src/xmi_solid_angle_cl.c:118-120. */
+int xmi_solid_angle_calculation_cl(void *inputFPtr, xmb_solid_angle **solid_angle, char *input_string,
+                                   xmb_main_options *options);
+/* XmiDetectorConvoluteAll (include/xmi_main.h:37), symbol looked up at bin/xmimsim.c:513. */
+void xmi_detector_convolute_all_custom(void *inputFPtr, double **channels_noconv, double **channels_conv,
+                                       double *brute_history, double *var_red_history,
+                                       xmb_main_options *options, xmb_escape_ratios *escape_ratios,
+                                       int n_interactions_all, int zero_interaction);
+/* Cross-section provider used by the two plugin symbols (NULL: analytic surrogate). */
+void xmb_plugin_set_provider(const xmb_xrl_provider *provider);
 
 /* xmi_main_options_new defaults (src/xmi_data_structs.c:2531-2565). */
 void xmb_main_options_defaults(xmb_main_options *options);

@@ -143,3 +143,13 @@ def test_tables_sanity():
     rr = np.ctypeslib.as_array(T.rad_rate, shape=(nZ, 384))
     assert abs(rr[i82, 1:30].sum() - 1.0) < 1e-12 and abs(rr[i82, 86:114].sum() - 1.0) < 1e-12
     sim.close()
+
+
+def test_plugin_file_exports_reference_symbol_names():
+    """The drop-in plugin file (name the reference's GModule loader opens, src/xmi_solid_angle.c:121-136) exports the
+    reference's symbol names (src/xmi_solid_angle_cl.c:118-120; bin/xmimsim.c:513)."""
+    import os
+    path = os.path.join(os.path.dirname(abi.LIB_PATH), "xmimsim-cl.so")
+    assert os.path.exists(path)
+    P = C.CDLL(path)
+    assert hasattr(P, "xmi_solid_angle_calculation_cl") and hasattr(P, "xmi_detector_convolute_all_custom")

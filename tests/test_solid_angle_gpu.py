@@ -97,3 +97,26 @@ def test_conical_shadow_is_zero_and_progress_strings(capfd):
     out = capfd.readouterr().out
     assert "Solid angle calculation at 100 %" in out and "Solid angle calculation finished" in out
     sim.close()
+
+
+def test_plugin_symbol_with_reference_signature():
+    """xmi_solid_angle_calculation_cl(inputFPtr, &solid_angle, input_string, options) -- the exact call the reference's
+    loader makes (src/xmi_solid_angle.c:149-153): returns 1, fills a 1024 x 1024 struct, keeps the caller's string."""
+    from xmimsim_b200 import abi
+    inp = example("srm1132")
+    sim = x.Simulation(inp, quality=0)
+    sa = C.POINTER(abi.SolidAngle)()
+    tag = C.create_string_buffer(b"<xml/>")
+    opt = x.main_options()
+    rv = sim.L.xmi_solid_angle_calculation_cl(sim.inputF, C.byref(sa), C.cast(tag, C.c_void_p), C.byref(opt))
+    assert rv == 1
+    s = sa.contents
+    assert s.grid_dims_r_n == 1024 and s.grid_dims_theta_n == 1024 and s.xmi_input_string == C.addressof(tag)
+    g = np.ctypeslib.as_array(s.solid_angles, shape=(1024, 1024))
+    ref, r, t = sim.solid_angle_calculation(hits_per_single=5000, seed=0)
+    assert np.array_equal(g, ref)
+    # a foreign pointer without xmi_input_F2C in the process must fail with 0 ("fall through to the next backend")
+    junk = (C.c_uint64 * 16)()
+    sa2 = C.POINTER(abi.SolidAngle)()
+    assert sim.L.xmi_solid_angle_calculation_cl(C.cast(junk, C.c_void_p), C.byref(sa2), None, C.byref(opt)) == 0
+    sim.close()

@@ -144,7 +144,7 @@ def declared_symbols():
     hdr = os.path.join(os.path.dirname(_HERE), "include", "xmimsim_b200.h")
     txt = open(hdr).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(xmb_[a-z0-9_A-Z]+)\s*\(", txt)) - {"xmb_discrete_distribution"})
+    return sorted(set(re.findall(r"\b(xm[bi]_[a-z0-9_A-Z]+)\s*\(", txt)) - {"xmb_discrete_distribution"})
 
 
 def lib():
@@ -201,6 +201,16 @@ def lib():
     L.xmb_detector_convolute_history.restype = None
     L.xmb_detector_last_ms.restype = C.c_double
     L.xmb_detector_last_launches.restype = C.c_uint64
+    L.xmi_solid_angle_calculation_cl.argtypes = [vp, C.POINTER(C.POINTER(SolidAngle)), C.c_void_p, C.POINTER(MainOptions)]
+    L.xmi_solid_angle_calculation_cl.restype = C.c_int
+    L.xmi_detector_convolute_all_custom.argtypes = [vp, pp, pp, c_double_p, c_double_p, C.POINTER(MainOptions),
+                                                    C.POINTER(EscapeRatios), C.c_int, C.c_int]
+    L.xmi_detector_convolute_all_custom.restype = None
+    L.xmb_msim_shard.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.xmb_msim_shard.restype = None
+    L.xmb_msim_total_histories.argtypes = [vp]; L.xmb_msim_total_histories.restype = C.c_uint64
+    L.xmb_msim_slot_map.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+    L.xmb_msim_slot_map.restype = C.c_int
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

@@ -742,9 +742,12 @@ struct XmbDeviceTables {
 
 void xmb_free_device_tables(XmbDeviceTables *dev) { delete dev; }
 
+static bool g_layout_only = false;   // build_device_tables: host-side layout without touching CUDA
+
 template <typename T>
 static T *upload(XmbDeviceTables *D, const T *src, size_t n, bool &ok) {
 	T *d = nullptr;
+	if (g_layout_only) return nullptr;
 	if (n == 0) n = 1;
 	if (cudaMalloc(&d, sizeof(T) * n) != cudaSuccess) { ok = false; return nullptr; }
 	D->allocs.push_back(d);
@@ -778,7 +781,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	XmbDeviceTables *D = new XmbDeviceTables();
 	D->cascade = cascade_mode(opt);
 	D->use_M_lines = opt->use_M_lines ? 1 : 0;
-	cudaGetDevice(&D->device);
+	if (g_layout_only) D->device = -2; else cudaGetDevice(&D->device);
 	XmbHistParams &P = D->P;
 	bool ok = true;
 	// ---- node rows -----------------------------------------------------------------------------------
@@ -1003,8 +1006,11 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const int nr = ex->n_ranks > 0 ? ex->n_ranks : 1, rk = ex->rank;
 	if (rk < 0 || rk >= nr) { xmb_set_error("rank %d outside 0..%d", rk, nr - 1); return 0; }
 	P.seed = ex->seed ? ex->seed : XMB_DEFAULT_SEED;
-	P.g_begin = D->n_total / nr * rk + std::min<uint64_t>(rk, D->n_total % nr);
-	P.g_end = P.g_begin + D->n_total / nr + ((uint64_t)rk < D->n_total % nr ? 1 : 0);
+	{
+		uint64_t gb, ge;
+		xmb_msim_shard(D->n_total, rk, nr, &gb, &ge);
+		P.g_begin = gb; P.g_end = ge;
+	}
 	ex->n_histories = P.g_end - P.g_begin;
 	// launch
 	int sms = 148, occ = 1;
@@ -1046,16 +1052,68 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	return 1;
 }
 
+// contiguous shard of the global photon ids [0, n_total) owned by `rank` (remainder spread over the first ranks)
+extern "C" void xmb_msim_shard(uint64_t n_total, int rank, int n_ranks, uint64_t *begin, uint64_t *end) {
+	if (n_ranks < 1) n_ranks = 1;
+	*begin = n_total / n_ranks * rank + std::min<uint64_t>(rank, n_total % n_ranks);
+	*end = *begin + n_total / n_ranks + ((uint64_t)rank < n_total % n_ranks ? 1 : 0);
+}
+
+// host-side layout (slot map, scale factors) without a GPU: enough for xmb_main_msim_finish and the slot map
+static XmbDeviceTables *ensure_layout(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt) {
+	if (h->dev && h->dev->cascade == cascade_mode(opt) && h->dev->use_M_lines == (opt->use_M_lines ? 1 : 0)) return h->dev;
+	if (h->dev) { delete h->dev; h->dev = nullptr; }
+	g_layout_only = true;
+	h->dev = build_device_tables(in, h, opt);
+	g_layout_only = false;
+	return h->dev;
+}
+
+extern "C" uint64_t xmb_msim_total_histories(xmb_inputFPtr inputF) {
+	XmbInputF *in = xmb_as_input(inputF);
+	if (!in) return 0;
+	const xmb_excitation &exc = *in->in.excitation;
+	uint64_t n = 0;
+	for (int i = 0; i + 1 < exc.n_continuous; i++) {
+		const double y1 = exc.continuous[i].vertical_intensity + exc.continuous[i].horizontal_intensity;
+		const double y2 = exc.continuous[i + 1].vertical_intensity + exc.continuous[i + 1].horizontal_intensity;
+		if ((y1 + y2) * (exc.continuous[i + 1].energy - exc.continuous[i].energy) / 2.0 != 0.0) n += (uint64_t)in->in.general->n_photons_interval;
+	}
+	return n + (uint64_t)exc.n_discrete * (uint64_t)in->in.general->n_photons_line;
+}
+
+// slot map of the accumulator rows: slots [0, nch) are channels; slot nch + s is history slot s with
+// (Z, line) = (out_Z[s], out_line[s]); line 384 / 385 = Rayleigh / Compton.  Returns n_hist_slots (0 on error).
+extern "C" int xmb_msim_slot_map(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options, int32_t *out_Z,
+                                 int32_t *out_line, int capacity) {
+	XmbInputF *in = xmb_as_input(inputF);
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!in || !h || !options) return 0;
+	XmbDeviceTables *D = ensure_layout(in, h, options);
+	if (!D) return 0;
+	if (out_Z && out_line) {
+		if (capacity < D->n_hist_slots) { xmb_set_error("slot map capacity"); return 0; }
+		for (int z = 0; z < h->view.nZ; z++) {
+			out_Z[D->hist_base[z]] = h->view.Z[z]; out_line[D->hist_base[z]] = 384;
+			out_Z[D->hist_base[z] + 1] = h->view.Z[z]; out_line[D->hist_base[z] + 1] = 385;
+		}
+		for (int r = 0; r < D->n_rec; r++) { out_Z[D->rec_slot[r]] = h->view.Z[D->rec_zi[r]]; out_line[D->rec_slot[r]] = D->rec_line[r]; }
+	}
+	return D->n_hist_slots;
+}
+
 extern "C" int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                                     const uint64_t *accum, size_t n_slots, double **channels, double **brute_history,
                                     double **var_red_history) {
 	XmbInputF *in = xmb_as_input(inputF);
 	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
-	if (!in || !h || !h->dev || !accum) { xmb_set_error("xmb_main_msim_finish: nothing to finish"); return 0; }
-	XmbDeviceTables *D = h->dev;
+	if (!in || !h || !accum || !options) { xmb_set_error("xmb_main_msim_finish: bad arguments"); return 0; }
+	XmbDeviceTables *D = ensure_layout(in, h, options);
+	if (!D) return 0;
 	const int n_int = D->P.n_int, nch = D->P.nch;
 	const size_t row = (size_t)nch + D->n_hist_slots;
 	if (n_slots != (size_t)n_int * row) { xmb_set_error("xmb_main_msim_finish: slot count mismatch"); return 0; }
+	(void)0;
 	const double live_time = in->in.detector->live_time;
 	const double scale = D->W_max * live_time;
 	auto slot128 = [&](size_t i) { return (unsigned __int128)accum[2 * i] + ((unsigned __int128)accum[2 * i + 1] << 48); };

@@ -1,0 +1,91 @@
+// plugin_shim.cpp -- the reference's plugin/ABI symbol names, forwarding to the xmb_* engine.
+//
+// Exported under the exact names and signatures the reference resolves with g_module_symbol / links:
+//   xmi_solid_angle_calculation_cl     typedef XmiSolidAngleCalculation, src/xmi_solid_angle.c:51; symbol looked up at :139
+//   xmi_detector_convolute_all_custom  typedef XmiDetectorConvoluteAll, include/xmi_main.h:37; looked up in bin/xmimsim.c:513
+//   xmi_main_msim                      include/xmi_main.h:29 (only with -DXMB_EXPORT_XMI_MAIN_MSIM: it would clash with libxmimsim's own)
+//
+// The reference passes an opaque xmi_inputFPtr (a Fortran derived type, not readable from C).  The shim accepts
+// either (a) one of this library's own handles (magic-tagged), or (b) a reference handle, which it converts
+// with the reference's own xmi_input_F2C (src/xmi_aux_f.F90:766-776; resolved lazily from the host process, as
+// custom-detector-response/detector-response2.c:39 does) and re-derives xmi_init_input's fields itself.
+// Tables come from the provider registered with xmb_plugin_set_provider (default: the analytic surrogate).
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstring>
+#include "engine.h"
+
+static const xmb_xrl_provider *g_provider = nullptr;
+static long g_hits_per_single_default = 5000;
+
+extern "C" void xmb_plugin_set_provider(const xmb_xrl_provider *p) { g_provider = p; }
+
+typedef void (*xmi_input_F2C_t)(void *, xmb_input **);
+
+// Resolve the caller's handle to one of ours.  *owned is set when a temporary handle was created.
+static int resolve_input(void *inputFPtr, xmb_inputFPtr *out, bool *owned) {
+	*owned = false;
+	XmbInputF *h = static_cast<XmbInputF *>(inputFPtr);
+	// our own handles start with the magic word; reading 8 bytes of a foreign object is safe (it is at least a struct)
+	if (h && h->magic == XMB_MAGIC_INPUT) { *out = h; return 1; }
+	xmi_input_F2C_t f2c = (xmi_input_F2C_t)dlsym(RTLD_DEFAULT, "xmi_input_F2C");
+	if (!f2c) { xmb_set_error("handle is not an xmb handle and xmi_input_F2C is not available in this process"); return 0; }
+	xmb_input *c_tree = nullptr;
+	f2c(inputFPtr, &c_tree);
+	if (!c_tree) { xmb_set_error("xmi_input_F2C returned NULL"); return 0; }
+	xmb_inputFPtr mine = nullptr;
+	if (!xmb_input_C2F(c_tree, &mine) || !xmb_init_input(&mine)) return 0;
+	*out = mine;
+	*owned = true;
+	return 1;
+}
+
+extern "C" int xmi_solid_angle_calculation_cl(void *inputFPtr, xmb_solid_angle **solid_angle, char *input_string, xmb_main_options *options) {
+	xmb_inputFPtr in = nullptr;
+	bool owned = false;
+	if (!resolve_input(inputFPtr, &in, &owned)) { fprintf(stderr, "xmimsim-b200: %s\n", xmb_last_error()); return 0; }
+	xmb_hdf5FPtr tables = nullptr;
+	int rv = 0;
+	if (xmb_init_from_provider(g_provider ? g_provider : xmb_xrl_surrogate(), in, 1, &tables)) {
+		// the reference reads its global `hits_per_single` (src/xmi_solid_angle_cl.c:54); honour it when the host exports it
+		long *hps = (long *)dlsym(RTLD_DEFAULT, "hits_per_single");
+		rv = xmb_solid_angle_calculation(in, tables, solid_angle, input_string, options, hps ? *hps : g_hits_per_single_default, 0);
+		xmb_free_hdf5_F(&tables);
+	}
+	if (!rv) fprintf(stderr, "xmimsim-b200: %s\n", xmb_last_error());   // 0 = caller falls through to its next backend
+	if (owned) xmb_free_input_F(&in);
+	return rv;
+}
+
+extern "C" void xmi_detector_convolute_all_custom(void *inputFPtr, double **channels_noconv, double **channels_conv, double *brute_history,
+                                                  double *var_red_history, xmb_main_options *options, xmb_escape_ratios *escape_ratios,
+                                                  int n_interactions_all, int zero_interaction) {
+	xmb_inputFPtr in = nullptr;
+	bool owned = false;
+	if (!resolve_input(inputFPtr, &in, &owned)) { fprintf(stderr, "xmimsim-b200: %s\n", xmb_last_error()); return; }
+	if (options && options->verbose) printf("xmimsim-b200 detector response (CUDA sm_100a)\n");
+	// provider for the absorber / crystal attenuation: registered provider or surrogate (hdf5F = NULL)
+	xmb_hdf5FPtr tables = nullptr;
+	XmbHdf5F shell;   // carries only the provider pointer
+	if (g_provider) { shell.xrl = g_provider; tables = &shell; }
+	xmb_detector_convolute_all(in, tables, channels_noconv, channels_conv, brute_history, var_red_history, options, escape_ratios,
+	                           n_interactions_all, zero_interaction);
+	if (owned) xmb_free_input_F(&in);
+}
+
+#ifdef XMB_EXPORT_XMI_MAIN_MSIM
+extern "C" int xmi_main_msim(void *inputFPtr, void *hdf5FPtr, int n_mpi_hosts, double **channels, xmb_main_options *options,
+                             double **brute_history, double **var_red_history, xmb_solid_angle *solid_angles) {
+	xmb_inputFPtr in = nullptr;
+	bool owned = false;
+	if (!resolve_input(inputFPtr, &in, &owned)) return 0;
+	XmbHdf5F *h = static_cast<XmbHdf5F *>(hdf5FPtr);
+	xmb_hdf5FPtr tables = (h && h->magic == XMB_MAGIC_HDF5) ? hdf5FPtr : nullptr;
+	bool own_tables = false;
+	if (!tables) { if (!xmb_init_from_provider(g_provider ? g_provider : xmb_xrl_surrogate(), in, 1, &tables)) return 0; own_tables = true; }
+	const int rv = xmb_main_msim(in, tables, n_mpi_hosts, channels, options, brute_history, var_red_history, solid_angles);
+	if (own_tables) xmb_free_hdf5_F(&tables);
+	if (owned) xmb_free_input_F(&in);
+	return rv;
+}
+#endif

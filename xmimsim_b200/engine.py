@@ -169,6 +169,23 @@ class Simulation:
         nl = int(buf[0])
         return [(int(buf[1 + 3 * k]), int(buf[2 + 3 * k]), int(buf[3 + 3 * k])) for k in range(nl)]
 
+    def shard(self, rank, n_ranks):
+        """[begin, end) of the global photon ids simulated by `rank`."""
+        b, e = C.c_uint64(), C.c_uint64()
+        self.L.xmb_msim_shard(self.L.xmb_msim_total_histories(self.inputF), rank, n_ranks, C.byref(b), C.byref(e))
+        return b.value, e.value
+
+    def slot_map(self, options=None):
+        """(Z[n_hist_slots], line[n_hist_slots]) of the history slots that follow the nch channel slots in a row."""
+        options = options or main_options()
+        n = self.L.xmb_msim_slot_map(self.inputF, self.hdf5F, C.byref(options), None, None, 0)
+        if n <= 0:
+            raise RuntimeError("xmb_msim_slot_map: " + abi.last_error())
+        z = np.zeros(n, np.int32); ln = np.zeros(n, np.int32)
+        self.L.xmb_msim_slot_map(self.inputF, self.hdf5F, C.byref(options), z.ctypes.data_as(C.POINTER(C.c_int32)),
+                                 ln.ctypes.data_as(C.POINTER(C.c_int32)), n)
+        return z, ln
+
     def main_msim_raw(self, options=None, sa=None, rank=0, n_ranks=1, seed=0, device=-1):
         """History kernels only: returns (limbs uint64[2*n_slots], MsimEx) -- exact fixed-point partial sums of
         this rank's photon-id shard, safe to add across ranks in uint64."""

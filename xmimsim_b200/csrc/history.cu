@@ -37,6 +37,8 @@
 #ifndef XMB_REC_UNROLL
 #define XMB_REC_UNROLL 1
 #endif
+#define XMB_MAX_ORDERS 64
+#define XMB_STATE_FIELDS 15      // 13 doubles of photon state + photon id + layer (mus[nL] follow)
 #define XMB_PRAGMA(x) _Pragma(#x)
 #define XMB_UNROLL(n) XMB_PRAGMA(unroll n)
 #ifndef HIST_MIN_BLOCKS
@@ -387,20 +389,67 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	// The kernel is ~260 KB of SASS (fp64 transcendentals inlined at every site) against a 32 KB L1.5 I-cache: a
 	// CTA therefore walks the phases of an interaction in lock step (__syncthreads between phases), so all warps
 	// of the SM fetch the same few KB at any time (profiles/: stall_no_instruction 7.3 -> see r1 v3).
-	for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-		const uint64_t g = P.g_begin + chunk * T + tid;
-		Photon p;
-		p.alive = g < P.g_end;
-		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
-		if (p.alive) {
-			XmbRng rng;   // order 0, stage 0: sequential words, counter word 2 = block
-			rng.init(P.seed, g, XMB_TAG_HISTORY);
-			start_photon(P, p, rng, g, mus, T);
+	//
+	// CTA-local wavefront with compaction: survivors of order k are appended, densely, to the CTA's queue for order
+	// k+1 (structure-of-arrays in global memory, coalesced); the CTA always runs the deepest order that has a full
+	// batch of T photons, otherwise samples a fresh chunk of source photons, and drains the queues at the end.
+	// Every batch therefore has all lanes alive and one interaction order; exact integer deposits and fixed-address
+	// random numbers make the result independent of this regrouping.
+	__shared__ int s_qcount[XMB_MAX_ORDERS];      // photons waiting to run order k+1
+	__shared__ int s_wsum[32];
+	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
+	__syncthreads();
+	const int NF = XMB_STATE_FIELDS + P.nL;
+	const size_t qcap = 2 * (size_t)T;
+	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * NF * qcap;
+	uint64_t next_chunk = blockIdx.x;
+	for (;;) {
+		// ---- scheduler (block-uniform) ---------------------------------------------------------------
+		int k = -1;
+		for (int kk = P.n_int - 1; kk >= 1; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
+		bool from_source = false;
+		if (k < 0) {
+			if (next_chunk < n_chunks) from_source = true;
+			else {
+				for (int kk = P.n_int - 1; kk >= 1; kk--) if (s_qcount[kk] > 0) { k = kk; break; }
+				if (k < 0) break;
+			}
 		}
-		for (int it = 0; it < P.n_int; it++) {
+		uint64_t g = 0;
+		Photon p;
+		p.alive = false;
+		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
+		int order = 1;
+		if (from_source) {
+			g = P.g_begin + next_chunk * T + tid;
+			next_chunk += gridDim.x;
+			p.alive = g < P.g_end;
+			if (p.alive) {
+				XmbRng rng;   // order 0, stage 0: sequential words, counter word 2 = block
+				rng.init(P.seed, g, XMB_TAG_HISTORY);
+				start_photon(P, p, rng, g, mus, T);
+			}
+		} else {
+			const int have = s_qcount[k], n = min(T, have), base = have - n;
+			order = k + 1;
+			if (tid < n) {
+				const double *q = qbase + (size_t)k * NF * qcap + base + tid;
+				p.cx = q[0 * qcap]; p.cy = q[1 * qcap]; p.cz = q[2 * qcap];
+				p.dx = q[3 * qcap]; p.dy = q[4 * qcap]; p.dz = q[5 * qcap];
+				p.ex = q[6 * qcap]; p.ey = q[7 * qcap]; p.ez = q[8 * qcap];
+				p.energy = q[9 * qcap]; p.weight = q[10 * qcap]; p.theta = q[11 * qcap]; p.phi = q[12 * qcap];
+				g = (uint64_t)__double_as_longlong(q[13 * qcap]);
+				p.layer = (int)__double_as_longlong(q[14 * qcap]);
+				for (int j = 0; j < P.nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
+				p.n_interactions = order - 1;
+				p.alive = true;
+			}
+			__syncthreads();
+			if (tid == 0) s_qcount[k] = base;
+		}
+		{
 			// ---- forced interaction (src/xmi_main.F90:1229-1518) ------------------------------------
 			if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
-			const int order = it + 1;
 			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length, detector r, detector phi, atom}
 			double interactionR = 0.0;
 			int step_max = 0, step_dir = 1;
@@ -441,8 +490,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 #endif
 				}
 			}
-			if (!__syncthreads_or(p.alive)) break;   // block-uniform; also the phase barrier after transport
-			const int n_ia = it + 1;   // == p.n_interactions for every live lane
+			__syncthreads();   // phase barrier after transport
+			const int n_ia = order;   // == p.n_interactions for every live lane
 			unsigned long long *acc_k = P.acc + 2 * (size_t)(n_ia - 1) * acc_row;
 
 			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
@@ -696,6 +745,29 @@ XMB_UNROLL(XMB_REC_UNROLL)
 				}
 			}
 		}
+		// ---- compaction: survivors go, densely packed, to the queue of the next order -------------------
+		if (order < P.n_int) {
+			const bool surv = p.alive && p.energy >= ENERGY_THRESHOLD;
+			const unsigned bal = __ballot_sync(0xffffffffu, surv);
+			if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
+			__syncthreads();
+			int off = 0, tot = 0;
+			for (int w = 0; w < (T >> 5); w++) { const int c = s_wsum[w]; if (w < (tid >> 5)) off += c; tot += c; }
+			const int have = s_qcount[order];
+			if (surv) {
+				double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
+				q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
+				q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
+				q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
+				q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
+				q[13 * qcap] = __longlong_as_double((long long)g);
+				q[14 * qcap] = __longlong_as_double((long long)p.layer);
+				for (int j = 0; j < P.nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+			}
+			__syncthreads();
+			if (tid == 0) s_qcount[order] = have + tot;
+		}
+		__syncthreads();
 	}
 	n_inter_local = warp_sum_u64(n_inter_local);
 	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
@@ -733,10 +805,12 @@ struct XmbDeviceTables {
 	const double *sa_host = nullptr;
 	unsigned long long *acc = nullptr, *limbs = nullptr, *counters = nullptr;
 	size_t acc_slots = 0;
+	double *queue = nullptr;
+	size_t queue_doubles = 0;
 	unsigned long long layer_interactions[XMB_MAX_LAYERS] = {0};
 	~XmbDeviceTables() {
 		for (void *p : allocs) cudaFree(p);
-		cudaFree(sa_grid); cudaFree(sa_r); cudaFree(sa_t); cudaFree(acc); cudaFree(limbs); cudaFree(counters);
+		cudaFree(sa_grid); cudaFree(sa_r); cudaFree(sa_t); cudaFree(acc); cudaFree(limbs); cudaFree(counters); cudaFree(queue);
 	}
 };
 
@@ -1025,6 +1099,16 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const uint64_t n_chunks = (ex->n_histories + threads - 1) / threads;
 	uint64_t blocks = (uint64_t)sms * occ;
 	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, n_chunks));
+	if (P.n_int > XMB_MAX_ORDERS) { xmb_set_error("more than %d interactions per trajectory", XMB_MAX_ORDERS); return 0; }
+	// per-CTA compaction queues: n_int orders x 2T photons x (15 + nL) doubles (structure of arrays)
+	const size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + P.nL) * 2 * threads;
+	if (D->queue_doubles < qd) {
+		cudaFree(D->queue);
+		D->queue = nullptr;
+		XMB_CUDA_OK(cudaMalloc(&D->queue, sizeof(double) * qd));
+		D->queue_doubles = qd;
+	}
+	P.queue = D->queue;
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
 	cudaEventRecord(e0);

@@ -40,6 +40,7 @@
 #define XMB_MAX_ORDERS 64
 #define XMB_STATE_FIELDS 15      // 13 doubles of photon state + photon id + layer (mus[nL] follow)
 #define XMB_PRAGMA(x) _Pragma(#x)
+#define XMB_UNROLL_NL _Pragma("unroll")
 #define XMB_UNROLL(n) XMB_PRAGMA(unroll n)
 #ifndef HIST_MIN_BLOCKS
 #define HIST_MIN_BLOCKS 1
@@ -53,10 +54,15 @@ struct NodePos { int pos; double f; };
 __device__ __forceinline__ NodePos node_find(const XmbHistParams &P, double E) {
 	int b = (int)floor((E - P.bucket_E0) * P.bucket_inv_dE);
 	b = max(0, min(b, P.n_buckets - 1));
-	int i = P.bucket_start[b];
-	while (i > 0 && P.node_E[i] > E) i--;
-	while (i + 1 < P.n_nodes - 1 && P.node_E[i + 1] <= E) i++;
-	i = min(i, P.n_nodes - 2);
+	// bit 31 of bucket_start marks a bucket whose only node is the uniform-grid node at its lower bound and whose
+	// upper bound is the next node: the bracket is known without scanning (one dependent load less on the chain)
+	const int bs = P.bucket_start[b];
+	int i = bs & 0x7FFFFFFF;
+	if (bs >= 0 || E < P.node_E[i] || E >= P.node_E[i + 1]) {
+		while (i > 0 && P.node_E[i] > E) i--;
+		while (i + 1 < P.n_nodes - 1 && P.node_E[i + 1] <= E) i++;
+		i = min(i, P.n_nodes - 2);
+	}
 	NodePos p;
 	p.pos = i;
 	const double e0 = P.node_E[i], e1 = P.node_E[i + 1];
@@ -92,34 +98,27 @@ __device__ __forceinline__ double bilinear(const double *a, int n2, const double
 }
 
 // ---- exact accumulation ---------------------------------------------------------------------------
-// Every deposit is a non-negative 2^-56 fixed-point integer.  A slot is two 64-bit words: A accumulates the
-// low 32 bits of each addend, B the high 32 bits, so both updates are fire-and-forget REDs (no carry, no
-// returned value to wait for); total = A + (B << 32), exact for < 2^32 addends of < 2^63.
+// Every deposit is a non-negative 2^-56 fixed-point integer.  Deposits of the batch a CTA is working on (one
+// interaction order) are staged in shared memory: a slot is two 64-bit words, A accumulates the low 32 bits of
+// each addend and B the high 32 bits, so a deposit is two carry-free shared-memory atomics (total = A + (B<<32),
+// exact for < 2^32 addends of < 2^63).  After the batch the CTA folds every non-zero slot into the global 128-bit
+// (lo, hi) accumulator.  Ablation on B200 (profiles/r1_history_ablation.txt): with per-lane global REDs the Compton
+// peak's ~50 hot channel words serialised in L2 and cost 47 % of the kernel.
 __device__ __forceinline__ unsigned long long to_fixed(double w, unsigned long long *counters) {
 	const double s = w * 72057594037927936.0;   // 2^56
 	if (!(s < 2.8e17)) { if (s == s) atomicAdd(&counters[2], 1ULL); return 0ULL; }   // w >= ~4: counted, never wrapped
 	return __double2ull_rn(s);
 }
-#ifndef XMB_SPLIT_RED
-#define XMB_SPLIT_RED 1
-#endif
+// hot-loop variant: no branch; out-of-range / NaN inputs are flagged in `bad` (reported once per thread at the end)
+__device__ __forceinline__ unsigned long long to_fixed_fast(double w, bool &bad) {
+	const double s = w * 72057594037927936.0;
+	bad |= !(s < 2.8e17);
+	return __double2ull_rn(fmin(s, 2.8e17));
+}
 __device__ __forceinline__ void red128(unsigned long long *acc, size_t slot, unsigned long long v) {
 	if (v == 0ULL) return;
-#if XMB_SPLIT_RED
 	atomicAdd(&acc[2 * slot], v & 0xFFFFFFFFULL);
 	atomicAdd(&acc[2 * slot + 1], v >> 32);
-#else
-	// (lo, hi) with carry: one returning atomic, a second one only on overflow of the low word
-	const unsigned long long old = atomicAdd(&acc[2 * slot], v);
-	if (old + v < old) atomicAdd(&acc[2 * slot + 1], 1ULL << 32);
-#endif
-}
-// exact warp sum of values < 2^58 with three REDUX.SUM on 21-bit pieces
-__device__ __forceinline__ unsigned long long warp_sum_fixed(unsigned long long v) {
-	const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0x1FFFFFULL));
-	const unsigned s1 = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 21) & 0x1FFFFFULL));
-	const unsigned s2 = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 42));
-	return (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42);
 }
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -127,15 +126,8 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	return v;
 }
 // all 32 lanes call; slot is warp-uniform
-#ifndef XMB_USE_REDUX
-#define XMB_USE_REDUX 0
-#endif
 __device__ __forceinline__ void deposit_uniform(unsigned long long *acc, size_t slot, unsigned long long v, int lane) {
-#if XMB_USE_REDUX
-	v = warp_sum_fixed(v);
-#else
 	v = warp_sum_u64(v);
-#endif
 	if (lane == 0) red128(acc, slot, v);
 }
 // all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
@@ -144,6 +136,19 @@ __device__ __forceinline__ void deposit_varying(unsigned long long *acc, long sl
 	if (__all_sync(0xffffffffu, slot == s0)) {
 		if (s0 >= 0) deposit_uniform(acc, (size_t)s0, v, lane);
 	} else if (slot >= 0) red128(acc, (size_t)slot, v);
+}
+// fold the CTA's staged slots into the global (lo, hi) accumulators of interaction order `order` and clear them
+__device__ __forceinline__ void flush_staged(unsigned long long *stage, unsigned long long *global_row, int n_slots, int tid, int T) {
+	for (int i = tid; i < n_slots; i += T) {
+		const unsigned long long A = stage[2 * i], B = stage[2 * i + 1];
+		if ((A | B) == 0ULL) continue;
+		stage[2 * i] = 0ULL; stage[2 * i + 1] = 0ULL;
+		const unsigned long long lo = A + (B << 32);
+		unsigned long long hi = (B >> 32) + (lo < A ? 1ULL : 0ULL);
+		const unsigned long long old = atomicAdd(&global_row[2 * i], lo);
+		if (old + lo < old) hi++;
+		if (hi) atomicAdd(&global_row[2 * i + 1], hi);
+	}
 }
 
 // Random-number layout: counter = (photon id lo, hi, (order << 20) | (stage << 16) | (element << 8) | block, tag);
@@ -230,15 +235,29 @@ __device__ __forceinline__ double elec_phi0(const Photon &p) {
 // src/xmi_variance_reduction.F90:1010-1101)
 // sth2 = sin(theta/2) and c_lamb0 = 1.2399e-6 / (1000 E0) are hoisted by the callers (same for every element).
 // Two trials per Philox block: (pz, sign), (pz, sign).
+// The first half-trial's random block and its two inverse-CDF entries may be handed in (software prefetch by the
+// element loop: the gather of element e+1 overlaps the dependent chain of element e).
+struct ComptonPrefetch { uint4 w; double i0, i1; int zi; double F0, F1, S0, S1; };
+
+__device__ __forceinline__ void compton_prefetch(const XmbHistParams &P, int zi, uint64_t g, int order, int elem, int qi, ComptonPrefetch &pf) {
+	pf.zi = zi;
+	pf.w = draw_block(P.seed, g, order, 2, elem, 0);
+	const int pos = min((int)(xmb_u01(pf.w.x) / P.cp_dR), P.n_cp - 2);
+	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp + pos;
+	pf.i0 = icdf[0]; pf.i1 = icdf[1];
+	const double *f = P.ff + (size_t)zi * P.n_q + qi, *sfp = P.sf + (size_t)zi * P.n_q + qi;
+	pf.F0 = f[0]; pf.F1 = f[1]; pf.S0 = sfp[0]; pf.S1 = sfp[1];
+}
+
 __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi, double E0, double c_lamb0, double sth2, uint64_t g, int order,
-                                                 int stage, int elem, bool varred) {
+                                                 int stage, int elem, bool varred, const ComptonPrefetch *pf = nullptr) {
 	const double cc = 1.2399E-6, c0 = 4.85E-12, c1 = 1.456E-2;
 	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp;
 	const double shift = c0 * sth2 * sth2, slope = c1 * c_lamb0 * sth2;
 	double energy = 0.0;
 	int tries = 0;
 	for (int blk = 0;; blk++) {
-		const uint4 w = draw_block(P.seed, g, order, stage, elem, blk & 0xFF);
+		const uint4 w = (pf && blk == 0) ? pf->w : draw_block(P.seed, g, order, stage, elem, blk & 0xFF);
 		bool done = false;
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
@@ -247,7 +266,9 @@ __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi,
 			if (varred && pos == P.n_cp - 2) continue;
 			pos = min(pos, P.n_cp - 2);
 			const double r0 = P.cp_R[pos], r1 = P.cp_R[pos + 1];
-			double pz = icdf[pos] + (icdf[pos + 1] - icdf[pos]) * (r - r0) / (r1 - r0);
+			const bool use_pf = pf && blk == 0 && h == 0;
+			const double ia = use_pf ? pf->i0 : icdf[pos], ib = use_pf ? pf->i1 : icdf[pos + 1];
+			double pz = ia + (ib - ia) * (r - r0) / (r1 - r0);
 			if (rs < 0.5) pz = -pz;
 			const double c_lamb = c_lamb0 + (shift - slope * pz);
 			energy = cc / c_lamb / 1000.0;
@@ -285,7 +306,9 @@ __device__ __forceinline__ double ran_gaussian(XmbRng &rng, double sigma) {
 }
 
 // ---- source sampling (src/xmi_main.F90:319-438, :579-724, :957-1186) -----------------------------------
+template <int NL>
 __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uint64_t g, double *mus /* [nL] stride T */, int T) {
+	const int nL = NL > 0 ? NL : P.nL;
 	int s;
 	uint64_t j;
 	const uint64_t n_cont = P.n_cont_seg * P.n_per_interval;
@@ -313,7 +336,8 @@ __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uin
 		hor_ver_ratio = hi / ti;
 		const NodePos np = node_find(P, p.energy);
 		p.weight = S.total_rel * exp(-row_lerp(P, np, P.off_exc));
-		for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, np, i);
+		XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, np, i);
 	} else {
 		hor_ver_ratio = S.hor_ver_ratio;
 		p.weight = S.weight_rel;
@@ -322,7 +346,8 @@ __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uin
 		else p.energy = S.energy;
 		if (p.energy <= ENERGY_THRESHOLD || p.energy > ENERGY_MAX) { p.alive = false; return; }
 		const NodePos np = node_find(P, p.energy);
-		for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, np, i);
+		XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, np, i);
 	}
 	double x1, y1;
 	if (fabs(S.sigma_x * S.sigma_y) < 1.0E-20) {
@@ -350,7 +375,7 @@ __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uin
 	// xmi_photon_shift_first_layer (:1140-1186)
 	p.layer = -1;
 	if (p.cz >= P.layers[0].Z_begin) {
-		for (int i = 0; i < P.nL; i++) if (p.cz < P.layers[i].Z_end) { p.layer = i; break; }
+		for (int i = 0; i < nL; i++) if (p.cz < P.layers[i].Z_end) { p.layer = i; break; }
 		if (p.layer < 0) { p.alive = false; return; }
 	} else {
 		const double ItimesN = p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2];
@@ -373,15 +398,20 @@ __device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x,
 	return true;
 }
 
+// NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
+template <int NL>
 __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
+	const int nL = NL > 0 ? NL : P.nL;
 	extern __shared__ double smem[];
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
-	double *rd = smem + (size_t)P.nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
+	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
+	unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][2]
 	const uint64_t n_total = P.g_end - P.g_begin;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
 	unsigned long long n_inter_local = 0;
+	bool bad_fixed = false;
 	__shared__ unsigned int s_layer_cnt[XMB_MAX_LAYERS];
 	if (tid < XMB_MAX_LAYERS) s_layer_cnt[tid] = 0;
 	__syncthreads();
@@ -398,8 +428,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	__shared__ int s_qcount[XMB_MAX_ORDERS];      // photons waiting to run order k+1
 	__shared__ int s_wsum[32];
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
+	for (int i = tid; i < 2 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0ULL;
 	__syncthreads();
-	const int NF = XMB_STATE_FIELDS + P.nL;
+	const int NF = XMB_STATE_FIELDS + nL;
 	const size_t qcap = 2 * (size_t)T;
 	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * NF * qcap;
 	uint64_t next_chunk = blockIdx.x;
@@ -427,7 +458,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			if (p.alive) {
 				XmbRng rng;   // order 0, stage 0: sequential words, counter word 2 = block
 				rng.init(P.seed, g, XMB_TAG_HISTORY);
-				start_photon(P, p, rng, g, mus, T);
+				start_photon<NL>(P, p, rng, g, mus, T);
 			}
 		} else {
 			const int have = s_qcount[k], n = min(T, have), base = have - n;
@@ -440,7 +471,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 				p.energy = q[9 * qcap]; p.weight = q[10 * qcap]; p.theta = q[11 * qcap]; p.phi = q[12 * qcap];
 				g = (uint64_t)__double_as_longlong(q[13 * qcap]);
 				p.layer = (int)__double_as_longlong(q[14 * qcap]);
-				for (int j = 0; j < P.nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
+				XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 				p.n_interactions = order - 1;
 				p.alive = true;
 			}
@@ -454,7 +486,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			double interactionR = 0.0;
 			int step_max = 0, step_dir = 1;
 			if (p.alive) {
-				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = P.nL - 1; step_dir = 1; }
+				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
 				else { step_max = 0; step_dir = -1; }
 				interactionR = xmb_u01(b0.x);
 				double lx = p.cx, ly = p.cy, lz = p.cz;
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			}
 			__syncthreads();   // phase barrier after transport
 			const int n_ia = order;   // == p.n_interactions for every live lane
-			unsigned long long *acc_k = P.acc + 2 * (size_t)(n_ia - 1) * acc_row;
+			unsigned long long *acc_k = stage;   // deposits of this batch are staged in shared memory, flushed below
 
 			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
 			bool vr = p.alive && p.energy > ENERGY_THRESHOLD;
@@ -527,8 +559,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 					dotprod = fmin(1.0, fmax(-1.0, dotprod));
 					phi = acos(dotprod);
 					int vmax, vdir;
-					if (n0 * P.n_sample[0] + n1 * P.n_sample[1] + n2 * P.n_sample[2] > 0.0) { vmax = P.nL - 1; vdir = 1; } else { vmax = 0; vdir = -1; }
-					for (int i = 0; i < P.nL; i++) rd[i * T] = 0.0;
+					if (n0 * P.n_sample[0] + n1 * P.n_sample[1] + n2 * P.n_sample[2] > 0.0) { vmax = nL - 1; vdir = 1; } else { vmax = 0; vdir = -1; }
+					XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					double tx = p.cx, ty = p.cy, tz = p.cz;
 					double temp_murhod = 0.0;
 					for (int i = p.layer; vdir > 0 ? i <= vmax : i >= vmax; i += vdir) {
@@ -548,7 +581,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			}
 			__syncthreads();   // phase: scatter deposits of every element
 			// warp-uniform loops over layers / elements / shells / line records
-			for (int L = 0; L < P.nL; L++) {
+			for (int L = 0; L < nL; L++) {
 				const bool mine = vr && p.layer == L;
 				if (!__any_sync(0xffffffffu, mine)) continue;
 				const XmbLayerDev lay = P.layers[L];
@@ -570,16 +603,26 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 					const int ch = (int)((p.energy - P.zero) / P.gain);
 					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
 				}
+				// software pipeline: the random block, inverse-CDF entries and form factors of element e+1 are requested
+				// before the dependent chain of element e (Compton energy -> energy bracket -> mu rows -> exp) runs
+#ifndef XMB_PREFETCH
+#define XMB_PREFETCH 1
+#endif
+				ComptonPrefetch pf_next;
+				if (XMB_PREFETCH && mine) compton_prefetch(P, P.elem_zi[lay.elem_begin], g, order, 0, qi, pf_next);
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
 					const size_t hbase = (size_t)P.nch + P.hist_base[zi];
+					ComptonPrefetch pf = pf_next;
+					if (XMB_PREFETCH) { if (mine && e + 1 < lay.n_elements) compton_prefetch(P, P.elem_zi[lay.elem_begin + e + 1], g, order, e + 1, qi, pf_next); }
+					else if (mine) compton_prefetch(P, zi, g, order, e, qi, pf);
 					// Rayleigh (:342-369)
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
 					if (mine) {
 						Pconv = wfrac / mus[L * T];
-						const double F = P.ff[(size_t)zi * P.n_q + qi] * (1.0 - qf) + P.ff[(size_t)zi * P.n_q + qi + 1] * qf;
+						const double F = pf.F0 * (1.0 - qf) + pf.F1 * qf;
 						const double dcsp = AVOGNUM / P.atomic_weight[zi] * F * F * RE2 * (1.0 - sin2cos2);
 						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
 					}
@@ -589,11 +632,12 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 					fx = 0ULL;
 					long ch_c = -1;
 					if (mine) {
-						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true);
+						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true, &pf);
 						const NodePos cp = node_find(P, e_c);
 						double tm = 0.0;
-						for (int j = 0; j < P.nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
-						const double S = P.sf[(size_t)zi * P.n_q + qi] * (1.0 - qf) + P.sf[(size_t)zi * P.n_q + qi + 1] * qf;
+						XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
 						const double dcsp_kn = RE2 / 2.0 * k0k * k0k * (k0k + 1.0 / k0k - 2.0 * sin2cos2);
 						const double Pdir = omega * AVOGNUM / P.atomic_weight[zi] * S * dcsp_kn;
 						fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight, P.counters);
@@ -605,7 +649,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 				}
 			}
 			__syncthreads();   // phase: fluorescence-line deposits (small loop body: exp + exact warp sum + RED)
-			for (int L = 0; L < P.nL; L++) {
+			for (int L = 0; L < nL; L++) {
 				const bool mine = vr && p.layer == L;
 				if (!__any_sync(0xffffffffu, mine)) continue;
 				const XmbLayerDev lay = P.layers[L];
@@ -628,18 +672,20 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 						const double pre = common * Ps;
 XMB_UNROLL(XMB_REC_UNROLL)
 						for (int r = r0; r < r1; r++) {
-							const double *mu = P.rec_mu + (size_t)r * P.nL;
+							const double *mu = P.rec_mu + (size_t)r * nL;
 							double tm = 0.0;
-							for (int j = 0; j < P.nL; j++) tm += mu[j] * rd[j * T];
+							XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
 							const double tw = pre * P.rec_yr[r] * exp(-tm);
-							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed(tw, P.counters) : 0ULL, lane);
+							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed_fast(tw, bad_fixed) : 0ULL, lane);
 						}
 					}
 				}
 			}
 
 			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
-			__syncthreads();   // phase: selection + scattering
+			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
+			flush_staged(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, tid, T);
 			if (p.alive) {
 				const XmbLayerDev lay = P.layers[p.layer];
 				const NodePos ep = node_find(P, p.energy);
@@ -678,7 +724,8 @@ XMB_UNROLL(XMB_REC_UNROLL)
 					p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
 					{
 						const NodePos cp = node_find(P, p.energy);
-						for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, cp, i);
+						XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
 					}
 					if (p.energy != 0.0) {
 						update_dirv(p, theta_i, phi_i + phi0);
@@ -735,7 +782,8 @@ XMB_UNROLL(XMB_REC_UNROLL)
 						else {
 							p.energy = P.line_energy[(size_t)zi * 384 + line];
 							const NodePos lp = node_find(P, p.energy);
-							for (int i = 0; i < P.nL; i++) mus[i * T] = row_lerp(P, lp, i);
+							XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, lp, i);
 							const double theta_i = acos(-2.0 * s2 + 1.0);
 							const double phi_i = 2.0 * M_PI * u_phi;
 							update_dirv(p, theta_i, phi_i);
@@ -762,7 +810,8 @@ XMB_UNROLL(XMB_REC_UNROLL)
 				q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
 				q[13 * qcap] = __longlong_as_double((long long)g);
 				q[14 * qcap] = __longlong_as_double((long long)p.layer);
-				for (int j = 0; j < P.nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+				XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			}
 			__syncthreads();
 			if (tid == 0) s_qcount[order] = have + tot;
@@ -771,17 +820,15 @@ XMB_UNROLL(XMB_REC_UNROLL)
 	}
 	n_inter_local = warp_sum_u64(n_inter_local);
 	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
+	if (bad_fixed) atomicAdd(&P.counters[2], 1ULL);
 	__syncthreads();
-	if (tid < P.nL && s_layer_cnt[tid]) atomicAdd(&P.counters[8 + tid], (unsigned long long)s_layer_cnt[tid]);
+	if (tid < nL && s_layer_cnt[tid]) atomicAdd(&P.counters[8 + tid], (unsigned long long)s_layer_cnt[tid]);
 }
 
-// raw (A, B) accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
+// raw (lo, hi) accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
 __global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, unsigned long long *__restrict__ limbs, size_t n_slots) {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
-		// total = A + (B << 32) as a 128-bit integer (lo, hi)
-		const unsigned long long A = acc[2 * i], B = acc[2 * i + 1];
-		const unsigned long long lo = A + (B << 32);
-		const unsigned long long hi = (B >> 32) + (lo < A ? 1ULL : 0ULL);
+		const unsigned long long lo = acc[2 * i], hi = acc[2 * i + 1];   // 128-bit total
 		limbs[2 * i] = lo & 0xFFFFFFFFFFFFULL;
 		limbs[2 * i + 1] = (lo >> 48) | (hi << 16);
 	}
@@ -883,7 +930,16 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	P.rows = upload(D, rows.data(), rows.size(), ok);
 	P.n_nodes = nN; P.n_buckets = T.n_buckets; P.bucket_E0 = T.bucket_E0; P.bucket_inv_dE = T.bucket_inv_dE;
 	P.node_E = upload(D, T.node_E, nN, ok);
-	P.bucket_start = upload(D, T.bucket_start, T.n_buckets + 1, ok);
+	{
+		std::vector<int> bs(T.bucket_start, T.bucket_start + T.n_buckets + 1);
+		for (int b = 0; b + 1 <= T.n_buckets; b++) {
+			const int i = T.bucket_start[b];
+			const double lo = T.bucket_E0 + b / T.bucket_inv_dE, hi = T.bucket_E0 + (b + 1) / T.bucket_inv_dE;
+			// simple: node i sits at the bucket's lower bound (within rounding) and node i+1 is at/after its upper bound
+			if (i + 1 < nN && std::fabs(T.node_E[i] - lo) < 1e-9 && T.node_E[i + 1] >= hi - 1e-9) bs[b] = i | (int)0x80000000;
+		}
+		P.bucket_start = upload(D, bs.data(), bs.size(), ok);
+	}
 	// ---- inverse CDFs, form factors ---------------------------------------------------------------------
 	P.n_icdf_E = T.n_icdf_E; P.n_icdf_R = T.n_icdf_R; P.n_phi_T = T.n_phi_T; P.n_cp = T.n_cp; P.n_q = T.n_q;
 	P.q_max = T.q_max; P.cp_dR = T.cp_R[1] - T.cp_R[0];
@@ -1091,10 +1147,14 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	// threads per CTA: as many as the per-thread shared arrays (2 nL doubles) allow within 200 KB
 	int threads = HIST_THREADS;
-	while (threads > 64 && sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
-	const size_t smem = sizeof(double) * 2 * P.nL * threads;
-	XMB_CUDA_OK(cudaFuncSetAttribute(xmb_history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xmb_history_kernel, threads, smem));
+	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
+	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
+	while (threads > 64 && stage_bytes + sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
+	const size_t smem = stage_bytes + sizeof(double) * 2 * P.nL * threads;
+	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
+	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
+	XMB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
 	if (occ < 1) occ = 1;
 	const uint64_t n_chunks = (ex->n_histories + threads - 1) / threads;
 	uint64_t blocks = (uint64_t)sms * occ;
@@ -1112,7 +1172,7 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
 	cudaEventRecord(e0);
-	if (ex->n_histories > 0) xmb_history_kernel<<<(unsigned)blocks, threads, smem>>>(P);
+	if (ex->n_histories > 0) kernel<<<(unsigned)blocks, threads, smem>>>(P);
 	cudaEventRecord(e1);
 	xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 	XMB_CUDA_OK(cudaGetLastError());

@@ -74,8 +74,7 @@ struct XmbHistParams {
 	const double *sa_grid;                   // [n_theta][n_r]
 	int sa_nr, sa_nt;
 	const double *sa_r_vals, *sa_t_vals;
-	// accumulators: [n_int][nch + n_hist_slots] pairs (A, B): A = sum of the low 32 bits of every deposit,
-	// B = sum of the high 32 bits; total = A + (B << 32).  Two carry-free REDs per deposit.
+	// global accumulators: [n_int][nch + n_hist_slots] 128-bit integers as (lo, hi) uint64 pairs
 	double *queue;                           // per-CTA compaction queues [CTA][order][field][2T]
 	unsigned long long *acc;
 	unsigned long long *counters;            // [0] off-grid solid angle lookups, [1] interactions, [2] fixed-point range errors

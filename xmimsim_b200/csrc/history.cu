@@ -115,10 +115,16 @@ __device__ __forceinline__ unsigned long long to_fixed_fast(double w, bool &bad)
 	bad |= !(s < 2.8e17);
 	return __double2ull_rn(fmin(s, 2.8e17));
 }
-__device__ __forceinline__ void red128(unsigned long long *acc, size_t slot, unsigned long long v) {
+// staged deposit: four native 32-bit shared-memory atomics on the 16-bit pieces of v (64-bit shared atomics are CAS
+// spin loops on sm_100a -- ATOMS.CAST.SPIN.64 -- and collapse when the lanes of a warp hit the same channel)
+__device__ __forceinline__ void red128(unsigned int *stage, size_t slot, unsigned long long v) {
 	if (v == 0ULL) return;
-	atomicAdd(&acc[2 * slot], v & 0xFFFFFFFFULL);
-	atomicAdd(&acc[2 * slot + 1], v >> 32);
+	unsigned int *w = stage + 4 * slot;
+	atomicAdd(&w[0], (unsigned int)(v & 0xFFFFULL));
+	atomicAdd(&w[1], (unsigned int)((v >> 16) & 0xFFFFULL));
+	atomicAdd(&w[2], (unsigned int)((v >> 32) & 0xFFFFULL));
+	const unsigned int top = (unsigned int)(v >> 48);
+	if (top) atomicAdd(&w[3], top);
 }
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -126,25 +132,31 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	return v;
 }
 // all 32 lanes call; slot is warp-uniform
-__device__ __forceinline__ void deposit_uniform(unsigned long long *acc, size_t slot, unsigned long long v, int lane) {
+__device__ __forceinline__ void deposit_uniform(unsigned int *acc, size_t slot, unsigned long long v, int lane) {
 	v = warp_sum_u64(v);
 	if (lane == 0) red128(acc, slot, v);
 }
 // all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
-__device__ __forceinline__ void deposit_varying(unsigned long long *acc, long slot, unsigned long long v, int lane) {
+__device__ __forceinline__ void deposit_varying(unsigned int *acc, long slot, unsigned long long v, int lane) {
 	const long s0 = __shfl_sync(0xffffffffu, slot, 0);
 	if (__all_sync(0xffffffffu, slot == s0)) {
 		if (s0 >= 0) deposit_uniform(acc, (size_t)s0, v, lane);
 	} else if (slot >= 0) red128(acc, (size_t)slot, v);
 }
 // fold the CTA's staged slots into the global (lo, hi) accumulators of interaction order `order` and clear them
-__device__ __forceinline__ void flush_staged(unsigned long long *stage, unsigned long long *global_row, int n_slots, int tid, int T) {
+__device__ __forceinline__ void flush_staged(unsigned int *stage, unsigned long long *global_row, int n_slots, int tid, int T) {
 	for (int i = tid; i < n_slots; i += T) {
-		const unsigned long long A = stage[2 * i], B = stage[2 * i + 1];
-		if ((A | B) == 0ULL) continue;
-		stage[2 * i] = 0ULL; stage[2 * i + 1] = 0ULL;
-		const unsigned long long lo = A + (B << 32);
-		unsigned long long hi = (B >> 32) + (lo < A ? 1ULL : 0ULL);
+		const uint4 w = *reinterpret_cast<uint4 *>(stage + 4 * i);
+		if ((w.x | w.y | w.z | w.w) == 0u) continue;
+		*reinterpret_cast<uint4 *>(stage + 4 * i) = make_uint4(0u, 0u, 0u, 0u);
+		// total = w0 + w1 2^16 + w2 2^32 + w3 2^48 as a 128-bit integer
+		const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 16);     // < 2^49
+		const unsigned long long t2 = (unsigned long long)w.z << 32, t3 = (unsigned long long)w.w << 48;
+		unsigned long long lo = t01 + t2;
+		unsigned long long hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.w >> 16);
+		const unsigned long long lo2 = lo + t3;
+		if (lo2 < lo) hi++;
+		lo = lo2;
 		const unsigned long long old = atomicAdd(&global_row[2 * i], lo);
 		if (old + lo < old) hi++;
 		if (hi) atomicAdd(&global_row[2 * i + 1], hi);
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
 	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
-	unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][2]
+	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] 16-bit pieces
 	const uint64_t n_total = P.g_end - P.g_begin;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	__shared__ int s_qcount[XMB_MAX_ORDERS];      // photons waiting to run order k+1
 	__shared__ int s_wsum[32];
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
-	for (int i = tid; i < 2 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0ULL;
+	for (int i = tid; i < 4 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0u;
 	__syncthreads();
 	const int NF = XMB_STATE_FIELDS + nL;
 	const size_t qcap = 2 * (size_t)T;
@@ -524,7 +536,7 @@ for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 			}
 			__syncthreads();   // phase barrier after transport
 			const int n_ia = order;   // == p.n_interactions for every live lane
-			unsigned long long *acc_k = stage;   // deposits of this batch are staged in shared memory, flushed below
+			unsigned int *acc_k = stage;   // deposits of this batch are staged in shared memory, flushed below
 
 			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
 			bool vr = p.alive && p.energy > ENERGY_THRESHOLD;
@@ -603,20 +615,15 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					const int ch = (int)((p.energy - P.zero) / P.gain);
 					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
 				}
-				// software pipeline: the random block, inverse-CDF entries and form factors of element e+1 are requested
-				// before the dependent chain of element e (Compton energy -> energy bracket -> mu rows -> exp) runs
-#ifndef XMB_PREFETCH
-#define XMB_PREFETCH 1
-#endif
-				ComptonPrefetch pf_next;
-				if (XMB_PREFETCH && mine) compton_prefetch(P, P.elem_zi[lay.elem_begin], g, order, 0, qi, pf_next);
+
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
 					const size_t hbase = (size_t)P.nch + P.hist_base[zi];
-					ComptonPrefetch pf = pf_next;
-					if (XMB_PREFETCH) { if (mine && e + 1 < lay.n_elements) compton_prefetch(P, P.elem_zi[lay.elem_begin + e + 1], g, order, e + 1, qi, pf_next); }
-					else if (mine) compton_prefetch(P, zi, g, order, e, qi, pf);
+					// the element's random block, first inverse-CDF bracket and form factors are requested together, ahead of
+					// the dependent chain Compton energy -> energy bracket -> mu rows -> exp
+					ComptonPrefetch pf;
+					if (mine) compton_prefetch(P, zi, g, order, e, qi, pf);
 					// Rayleigh (:342-369)
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
@@ -843,7 +850,7 @@ struct XmbDeviceTables {
 	XmbHistParams P{};
 	// host metadata for the epilogue
 	std::vector<int> rec_slot, rec_channel, rec_line, rec_zi, hist_base;
-	int n_rec = 0, n_hist_slots = 0;
+	int n_rec = 0, n_hist_slots = 0, max_nE = 1;
 	double W_max = 0.0;
 	uint64_t n_total = 0;
 	// solid-angle grid + accumulators (re-used across calls)
@@ -975,6 +982,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 		layers[k].Z_end = in->Z_coord_end[k];
 		for (int e = 0; e < l.n_elements; e++) { elem_zi.push_back(T.uniqZ[l.Z[e]]); elem_w.push_back(l.weight[e]); }
 	}
+	for (int k = 0; k < nL; k++) D->max_nE = std::max(D->max_nE, layers[k].n_elements);
 	P.layers = upload(D, layers.data(), nL, ok);
 	P.elem_zi = upload(D, elem_zi.data(), elem_zi.size(), ok);
 	P.elem_w = upload(D, elem_w.data(), elem_w.size(), ok);
@@ -1150,6 +1158,8 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
 	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
 	while (threads > 64 && stage_bytes + sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
+	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch
+	while (threads > 64 && (size_t)threads * std::max(1, D->max_nE) > 60000) threads -= 32;
 	const size_t smem = stage_bytes + sizeof(double) * 2 * P.nL * threads;
 	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;

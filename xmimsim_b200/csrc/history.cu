@@ -131,10 +131,27 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
 }
-// all 32 lanes call; slot is warp-uniform
+// all 32 lanes call; slot is warp-uniform.  The four 16-bit pieces are summed across the warp with REDUX (sums < 2^21)
+// and lane 0 adds them to the slot's four staging words.
+#ifndef XMB_REDUX_PIECES
+#define XMB_REDUX_PIECES 1
+#endif
 __device__ __forceinline__ void deposit_uniform(unsigned int *acc, size_t slot, unsigned long long v, int lane) {
+#if XMB_REDUX_PIECES
+	const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+	const unsigned int s0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), s1 = __reduce_add_sync(0xffffffffu, lo >> 16);
+	const unsigned int s2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), s3 = __reduce_add_sync(0xffffffffu, hi >> 16);
+	if (lane == 0) {
+		unsigned int *w = acc + 4 * slot;
+		if (s0) atomicAdd(&w[0], s0);
+		if (s1) atomicAdd(&w[1], s1);
+		if (s2) atomicAdd(&w[2], s2);
+		if (s3) atomicAdd(&w[3], s3);
+	}
+#else
 	v = warp_sum_u64(v);
 	if (lane == 0) red128(acc, slot, v);
+#endif
 }
 // all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
 __device__ __forceinline__ void deposit_varying(unsigned int *acc, long slot, unsigned long long v, int lane) {
@@ -254,7 +271,7 @@ struct ComptonPrefetch { uint4 w; double i0, i1; int zi; double F0, F1, S0, S1; 
 __device__ __forceinline__ void compton_prefetch(const XmbHistParams &P, int zi, uint64_t g, int order, int elem, int qi, ComptonPrefetch &pf) {
 	pf.zi = zi;
 	pf.w = draw_block(P.seed, g, order, 2, elem, 0);
-	const int pos = min((int)(xmb_u01(pf.w.x) / P.cp_dR), P.n_cp - 2);
+	const int pos = min((int)(xmb_u01(pf.w.x) * P.cp_inv_dR), P.n_cp - 2);
 	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp + pos;
 	pf.i0 = icdf[0]; pf.i1 = icdf[1];
 	const double *f = P.ff + (size_t)zi * P.n_q + qi, *sfp = P.sf + (size_t)zi * P.n_q + qi;
@@ -274,16 +291,16 @@ __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi,
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
 			const double r = xmb_u01(h ? w.z : w.x), rs = xmb_u01(h ? w.w : w.y);
-			int pos = (int)(r / P.cp_dR);
+			const double rs_ = r * P.cp_inv_dR;      // uniform axis: position in units of the step
+			int pos = (int)rs_;
 			if (varred && pos == P.n_cp - 2) continue;
 			pos = min(pos, P.n_cp - 2);
-			const double r0 = P.cp_R[pos], r1 = P.cp_R[pos + 1];
 			const bool use_pf = pf && blk == 0 && h == 0;
 			const double ia = use_pf ? pf->i0 : icdf[pos], ib = use_pf ? pf->i1 : icdf[pos + 1];
-			double pz = ia + (ib - ia) * (r - r0) / (r1 - r0);
+			double pz = ia + (ib - ia) * (rs_ - pos);
 			if (rs < 0.5) pz = -pz;
 			const double c_lamb = c_lamb0 + (shift - slope * pz);
-			energy = cc / c_lamb / 1000.0;
+			energy = (cc / 1000.0) / c_lamb;
 			if (energy <= E0 || tries == (varred ? 100 : 500)) { done = true; break; }
 			tries++;
 		}
@@ -598,7 +615,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 				if (!__any_sync(0xffffffffu, mine)) continue;
 				const XmbLayerDev lay = P.layers[L];
 				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
-				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0, c_lamb0 = 0.0, sth2 = 0.0;
+				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0, c_lamb0 = 0.0, sth2 = 0.0, dcsp_kn = 0.0;
 				int qi = 0;
 				long ch_rayl = -1;
 				if (mine) {
@@ -612,6 +629,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					sincos(theta, &st, &ct);
 					sin2cos2 = st * st * cp * cp;
 					k0k = 1.0 / (1.0 + (1.0 - ct) * p.energy / 510.998928);
+					dcsp_kn = RE2 / 2.0 * k0k * k0k * (k0k + 1.0 / k0k - 2.0 * sin2cos2);
 					const int ch = (int)((p.energy - P.zero) / P.gain);
 					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
 				}
@@ -628,9 +646,9 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
 					if (mine) {
-						Pconv = wfrac / mus[L * T];
+						Pconv = wfrac * inv_mu;
 						const double F = pf.F0 * (1.0 - qf) + pf.F1 * qf;
-						const double dcsp = AVOGNUM / P.atomic_weight[zi] * F * F * RE2 * (1.0 - sin2cos2);
+						const double dcsp = P.avog_over_A[zi] * F * F * RE2 * (1.0 - sin2cos2);
 						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
 					}
 					deposit_uniform(acc_k, hbase + 0, fx, lane);
@@ -645,8 +663,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
-						const double dcsp_kn = RE2 / 2.0 * k0k * k0k * (k0k + 1.0 / k0k - 2.0 * sin2cos2);
-						const double Pdir = omega * AVOGNUM / P.atomic_weight[zi] * S * dcsp_kn;
+						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
 						fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight, P.counters);
 						const int ch = (int)((e_c - P.zero) / P.gain);
 						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
@@ -949,7 +966,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	}
 	// ---- inverse CDFs, form factors ---------------------------------------------------------------------
 	P.n_icdf_E = T.n_icdf_E; P.n_icdf_R = T.n_icdf_R; P.n_phi_T = T.n_phi_T; P.n_cp = T.n_cp; P.n_q = T.n_q;
-	P.q_max = T.q_max; P.cp_dR = T.cp_R[1] - T.cp_R[0];
+	P.q_max = T.q_max; P.cp_dR = T.cp_R[1] - T.cp_R[0]; P.cp_inv_dR = (double)(T.n_cp - 1);
 	P.icdf_E = upload(D, T.icdf_E, T.n_icdf_E, ok);
 	P.icdf_R = upload(D, T.icdf_R, T.n_icdf_R, ok);
 	P.phi_T = upload(D, T.phi_T, T.n_phi_T, ok);
@@ -962,6 +979,11 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	P.sf = upload(D, T.sf, (size_t)nZ * T.n_q, ok);
 	// ---- per-element constants ----------------------------------------------------------------------------
 	P.atomic_weight = upload(D, T.atomic_weight, nZ, ok);
+	{
+		std::vector<double> aoa(nZ);
+		for (int z = 0; z < nZ; z++) aoa[z] = AVOGNUM / T.atomic_weight[z];
+		P.avog_over_A = upload(D, aoa.data(), nZ, ok);
+	}
 	std::vector<double> edgeK(nZ);
 	for (int z = 0; z < nZ; z++) edgeK[z] = T.edge_energy[z * 9 + 0];
 	P.edge_K = upload(D, edgeK.data(), nZ, ok);

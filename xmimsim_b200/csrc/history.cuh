@@ -50,7 +50,7 @@ struct XmbHistParams {
 	const double *rows;                      // [n_nodes][row_stride]
 	// inverse CDFs
 	int n_icdf_E, n_icdf_R, n_phi_T, n_cp, n_q;
-	double cp_dR, q_max;
+	double cp_dR, cp_inv_dR, q_max;
 	const double *icdf_E, *icdf_R, *phi_T, *cp_R;   // axis arrays
 	const double *rayl_icdf, *compt_icdf;    // [nZ][n_icdf_E][n_icdf_R]
 	const double *phi_icdf;                  // [n_phi_T][n_icdf_R]
@@ -58,6 +58,7 @@ struct XmbHistParams {
 	const double *ff, *sf;                   // [nZ][n_q]
 	// per unique element
 	const double *atomic_weight;             // [nZ]
+	const double *avog_over_A;               // [nZ] N_A / A (xraylib AVOGNUM units)
 	const double *edge_K;                    // [nZ]
 	const double *fluor_yield_corr;          // [nZ][9]
 	const double *cos_kron;                  // [nZ][13]

@@ -413,6 +413,40 @@ void xmb_detector_convolute_spectrum(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
 /* Replaces xmi_detector_convolute_history (include/xmi_main.h:33; src/xmi_detector_f.F90:291-337). */
 void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double *history,
                                     const xmb_main_options *options);
+/* ------------------------------------------------------------------------------------------
+ * Escape-peak ratios of the detector crystal (Monte Carlo, one interaction per photon).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct xmb_escape_ratios_options {   /* struct _xmi_escape_ratios_options, include/xmi_detector.h:42-51 */
+	long n_input_energies;            /* default 1990 */
+	long n_compton_output_energies;   /* default 1999 */
+	long n_photons;                   /* default 500000 */
+	double input_energy_min;          /* default 1.0 keV */
+	double input_energy_delta;        /* default 0.1 keV */
+	double compton_output_energy_min; /* default 0.1 keV */
+	double compton_output_energy_delta;/* default 0.1 keV */
+} xmb_escape_ratios_options;
+/* xmi_get_default_escape_ratios_options (src/xmi_detector.c:643-655). */
+xmb_escape_ratios_options xmb_get_default_escape_ratios_options(void);
+/* The input the reference simulates for the ratios (src/xmi_detector.c:91-141 +
+ * xmi_init_input_escape_ratios, src/xmi_main.F90:1687-1738): composition = the crystal layers,
+ * pencil beam at normal incidence one cm upstream, one interaction per trajectory; the input
+ * energies of `ero` become its discrete lines (so that they are nodes of the table bundle).
+ * Host only.  Returns an initialised handle (xmb_init_input already applied) or 0. */
+int xmb_escape_ratios_input(const xmb_input *input, const xmb_escape_ratios_options *ero, xmb_inputFPtr *out);
+/* Replaces xmi_escape_ratios_calculation (include/xmi_detector.h:57; src/xmi_detector.c:91-141 and
+ * xmi_escape_ratios_calculation_fortran, src/xmi_main.F90:5473-5801).  The HDF5 file argument of the
+ * reference becomes the cross-section provider (NULL: surrogate).  *escape_ratios and its arrays are
+ * malloc'ed (xmb_free_escape_ratios); input_string is stored, not copied, as in the reference.
+ * `seed` 0 = library default.  Returns 1 / 0 (the reference is void and exits on failure). */
+int xmb_escape_ratios_calculation(const xmb_input *input, xmb_escape_ratios **escape_ratios, char *input_string,
+                                  const xmb_xrl_provider *xrl, const xmb_main_options *options,
+                                  xmb_escape_ratios_options ero, uint64_t seed);
+/* The Monte Carlo proper on an escape-mode handle pair (the two calls above + xmb_init_from_provider). */
+int xmb_escape_ratios_run(xmb_inputFPtr esc_inputF, xmb_hdf5FPtr esc_hdf5F, const xmb_escape_ratios_options *ero,
+                          uint64_t seed, xmb_escape_ratios **escape_ratios, char *input_string);
+void xmb_free_escape_ratios(xmb_escape_ratios **escape_ratios);
+double xmb_escape_ratios_last_ms(void);
+
 /* Device time (ms) and kernel launches of the last detector-response call. */
 double xmb_detector_last_ms(void);
 uint64_t xmb_detector_last_launches(void);

@@ -72,6 +72,13 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
                              uint64_t g_begin, uint64_t g_end, int n_threads, double *channels,
                              double *var_red, uint64_t *counters);
 
+/* Escape-peak ratios of the crystal (src/xmi_main.F90:5473-5801) on the escape-mode input (its discrete lines
+ * are the input energies).  fluo[(i*109 + line-1)*nZ + zi] and compt[c*nE + i] are the Fortran layouts
+ * fluo_escape_ratios(element, line, i) / compton_escape_ratios(i, c), already divided by photons_interacted. */
+int orc_escape_ratios(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, uint64_t seed,
+                      long n_photons, int n_out, double out_min, double out_delta, int n_threads,
+                      double *fluo, double *compt);
+
 /* Detector response (src/xmi_detector_f.F90).  noconv[nch] is modified IN PLACE by the absorption
  * correction, escape peaks and pile-up, as the reference does (:412-413); conv[nch] is the result. */
 double orc_detector_correction(const xmb_input *in, const xmb_xrl_provider *xrl, double E);

@@ -51,6 +51,9 @@ def lib():
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p]
         _lib.orc_main_msim_range.restype = C.c_uint64
+        _lib.orc_escape_ratios.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_uint64, C.c_long, C.c_int,
+                                           C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.orc_escape_ratios.restype = C.c_int
     return _lib
 
 
@@ -98,6 +101,15 @@ def main_msim_range(cinput_ptr, d, tables_ptr, options, sa_struct, seed, g_begin
                               C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
                               g_begin, g_end, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
     return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt
+
+
+def escape_ratios(cinput_ptr, d, tables_ptr, seed, n_energies, nZ, n_photons, n_out, out_min, out_delta, n_threads=8):
+    """Oracle escape-ratio Monte Carlo on an escape-mode input.  Returns (fluo[nE][109][nZ], compton[n_out][nE])."""
+    fluo = np.zeros((n_energies, 109, nZ))
+    compt = np.zeros((n_out, n_energies))
+    lib().orc_escape_ratios(C.cast(cinput_ptr, C.c_void_p), C.byref(d), C.cast(tables_ptr, C.c_void_p), seed, n_photons,
+                            n_out, out_min, out_delta, n_threads, fluo.ctypes.data, compt.ctypes.data)
+    return fluo, compt
 
 
 def detector_convolute_spectrum(cinput_ptr, spectrum, options, escape_ratios=None, n_interactions=1, seed=1):

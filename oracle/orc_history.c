@@ -64,6 +64,7 @@ static double sub_uniform(substream_t *s) {
 typedef struct {
 	double coords[3], dirv[3], elecv[3];
 	double energy, weight, theta, phi;
+	double weight_escape;     /* escape-ratio mode only (src/xmi_main.F90:1462-1464) */
 	int current_layer;        /* 0-based */
 	int current_element;      /* Z */
 	int current_element_index;
@@ -81,6 +82,7 @@ typedef struct {
 	const xmb_main_options *opt;
 	const xmb_solid_angle *sa;
 	int cascade;              /* 1..4 */
+	int escape_mode;          /* options%escape_ratios_mode */
 	int n_int, nch, nL;
 	double *channels;         /* [(n_int+1)][nch] */
 	double *var_red;          /* Fortran (100,385,n_int) stored as [k][line][Z] -> index ((k*385+line)*100+Z) */
@@ -473,7 +475,8 @@ static int do_photo(ctx_t *c, photon_t *p, const double *sd) {                  
 	}
 	if (!shell_found) { p->energy = 0.0; return 1; }                              /* :2280-2291 */
 	/* the reference draws one unused number here (xmi_variance_reduction.F90:737); not reproduced */
-	p->weight *= T->fluor_yield_corr[zi * 9 + shell];                             /* :745 */
+	if (c->escape_mode) p->weight_escape *= T->fluor_yield_corr[zi * 9 + shell];  /* xmi_variance_reduction.F90:740-744 */
+	else p->weight *= T->fluor_yield_corr[zi * 9 + shell];                        /* :745 */
 	substream_t xs;
 	sub_init(&xs, p->seed, p->g, p->n_interactions, 3, 0);
 	double u_phi = sub_uniform(&xs);
@@ -732,4 +735,147 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
 	if (counters) { counters[0] = c0; counters[1] = c1; }
 	free(segs);
 	return g_end - g_begin;
+}
+
+/* ---- escape-peak ratios (src/xmi_main.F90:5473-5801; driver src/xmi_detector.c:91-141) ---------------------
+ * `in` is the escape-mode input (composition = crystal, pencil beam, one interaction; its discrete lines are
+ * the input energies).  Streams: g = energy index * n_photons + j; order 0 = source draws (slit x, slit y,
+ * polarisation angle), order 1 = the forced interaction, order 2 stage 1 block 0 word 0 = analogue free path.
+ * fluo[(i*109 + line-1)*nZ + zi], compt[c*nE + i] (the Fortran layouts), both divided by photons_interacted. */
+int orc_escape_ratios(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, uint64_t seed, long n_photons,
+                      int n_out, double out_min, double out_delta, int n_threads, double *fluo, double *compt) {
+	const xmb_geometry *g = in->geometry;
+	const xmb_layer *layers = in->composition->layers;
+	const int nE = in->excitation->n_discrete, nL = in->composition->n_layers, nZ = T->nZ;
+	xmb_main_options opt;
+	memset(&opt, 0, sizeof(opt));
+	opt.escape_ratios_mode = 1;                                                    /* :5561-5569 */
+	memset(fluo, 0, sizeof(double) * (size_t)nE * 109 * nZ);
+	memset(compt, 0, sizeof(double) * (size_t)nE * n_out);
+	if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads)
+	for (int i = 0; i < nE; i++) {
+		ctx_t c;
+		memset(&c, 0, sizeof(c));
+		c.in = in; c.d = d; c.T = T; c.opt = &opt; c.cascade = 1; c.n_int = 1; c.nL = nL; c.escape_mode = 1;
+		const double E0 = in->excitation->discrete[i].energy;
+		double initial_mus[64];
+		mu_calc(&c, E0, initial_mus);                                              /* :5608-5610 */
+		double photons_interacted = 0.0;
+		double *fl = fluo + (size_t)i * 109 * nZ;
+		for (long j = 0; j < n_photons; j++) {
+			photon_t p;
+			memset(&p, 0, sizeof(p));
+			p.seed = seed; p.g = (uint64_t)i * (uint64_t)n_photons + (uint64_t)j;
+			orc_rng rng;
+			orc_rng_init(&rng, seed, p.g, ORC_TAG_HISTORY);
+			p.energy = E0;
+			memcpy(p.mus, initial_mus, sizeof(double) * nL);
+			/* xmi_coords_dir, point source (:957-1136) */
+			double x1_max = atan(g->slit_size_x / g->d_source_slit / 2.0), y1_max = atan(g->slit_size_y / g->d_source_slit / 2.0);
+			double x1 = x1_max * (-1.0 + 2.0 * orc_rng_uniform(&rng));
+			double y1 = y1_max * (-1.0 + 2.0 * orc_rng_uniform(&rng));
+			p.dirv[0] = tan(x1); p.dirv[1] = tan(y1); p.dirv[2] = 1.0;
+			normalize3(p.dirv);
+			p.theta = acos(p.dirv[2]);
+			p.phi = atan2(p.dirv[1], p.dirv[0]);
+			p.weight = 1.0;                                                        /* :5644-5645 */
+			p.weight_escape = p.weight;
+			double theta_elecv = orc_rng_uniform(&rng) * M_PI * 2.0;               /* :5646-5649 */
+			p.elecv[0] = cos(theta_elecv); p.elecv[1] = sin(theta_elecv); p.elecv[2] = 0.0;
+			double cosalfa = dot3(p.elecv, p.dirv);
+			double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+			for (int k = 0; k < 3; k++) p.elecv[k] = c_ae * p.elecv[k] + c_be * p.dirv[k];
+			{   /* xmi_photon_shift_first_layer (:1140-1186) */
+				double pp[3] = {0.0, 0.0, d->Z_coord_begin[0]}, inter[3];
+				if (!plane_line(pp, g->n_sample_orientation, p.coords, p.dirv, inter)) continue;
+				memcpy(p.coords, inter, sizeof(inter));
+				p.current_layer = 0;
+			}
+			/* first pass of xmi_simulate_photon: forced interaction (:1417-1518), no forced detection */
+			double b0[4], b1[4];
+			draw_block(seed, p.g, 1, 1, 0, 0, b0);
+			draw_block(seed, p.g, 1, 1, 0, 1, b1);
+			{
+				double distances[64], lp[3] = {p.coords[0], p.coords[1], p.coords[2]}, Pabs = 0.0;
+				int ok = 1;
+				for (int k = 0; k < nL; k++) {
+					double pp[3] = {0.0, 0.0, d->Z_coord_end[k]}, inter[3];
+					if (!plane_line(pp, g->n_sample_orientation, lp, p.dirv, inter)) { ok = 0; break; }
+					distances[k] = dist3(lp, inter);
+					memcpy(lp, inter, sizeof(inter));
+					Pabs += p.mus[k] * layers[k].density * distances[k];
+				}
+				if (!ok) continue;
+				double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
+				p.weight *= Pabs2;
+				p.weight_escape = p.weight;                                        /* :1462-1464 */
+				double l1p = log1p(-1.0 * b0[0] * Pabs2), negln = -1.0 * l1p;
+				int my_index = 0;
+				double my_sum = 0.0;
+				for (int k = 0; k < nL; k++) {
+					my_sum += p.mus[k] * layers[k].density * distances[k];
+					if (my_sum > negln) { my_index = k; break; }
+				}
+				double temp_sum = 0.0;
+				for (int k = 0; k <= my_index; k++)
+					temp_sum += (1.0 - (p.mus[k] * layers[k].density / (p.mus[my_index] * layers[my_index].density))) * distances[k];
+				temp_sum = temp_sum - 1.0 * l1p / (p.mus[my_index] * layers[my_index].density);
+				for (int k = 0; k < 3; k++) p.coords[k] += temp_sum * p.dirv[k];
+				p.current_layer = my_index;
+				p.n_interactions = 1;
+			}
+			photons_interacted += p.weight;                                        /* :5685-5688 */
+			{   /* atom and interaction type (:1558-1652) */
+				const xmb_layer *l = &layers[p.current_layer];
+				nodepos_t np = node_find(T, p.energy);
+				double thr = 0.0;
+				for (int k = 0; k < l->n_elements; k++) {
+					thr += l->weight[k] * cs_total(&c, l->Z[k], np) / p.mus[p.current_layer];
+					if (b0[3] < thr || k == l->n_elements - 1) { p.current_element = l->Z[k]; p.current_element_index = k; break; }
+				}
+				int zi = T->uniqZ[p.current_element];
+				double pr = lerp_at(T->p_rayl + (size_t)zi * T->n_nodes, np), prc = lerp_at(T->p_rayl_compt + (size_t)zi * T->n_nodes, np);
+				if (b1[0] < pr) { p.last_interaction = RAYLEIGH; do_rayleigh(&c, &p, b1 + 1); }
+				else if (b1[0] < prc) { p.last_interaction = COMPTON; do_compton(&c, &p, b1 + 1); }
+				else { p.last_interaction = PHOTO; p.hist_line[1] = 0; do_photo(&c, &p, b1 + 1); }
+			}
+			/* second pass: energy cut (:1229-1231), then the analogue step of escape mode (:1274-1413) */
+			if (p.energy < ENERGY_THRESHOLD) continue;
+			int inside = 0;
+			{
+				int step_max, step_dir;
+				if (dot3(p.dirv, g->n_sample_orientation) > 0.0) { step_max = nL - 1; step_dir = 1; } else { step_max = 0; step_dir = -1; }
+				double u[4];
+				draw_block(seed, p.g, 2, 1, 0, 0, u);
+				double interactionR = u[0], blbs = 1.0, max_random_layer = 0.0;
+				double cur[3] = {p.coords[0], p.coords[1], p.coords[2]};
+				for (int k = p.current_layer; step_dir > 0 ? k <= step_max : k >= step_max; k += step_dir) {
+					double pp[3] = {0.0, 0.0, step_dir == 1 ? d->Z_coord_end[k] : d->Z_coord_begin[k]}, inter[3];
+					if (!plane_line(pp, g->n_sample_orientation, cur, p.dirv, inter)) { inside = 1; break; }
+					double dist = dist3(cur, inter);
+					double temp_prod = -1.0 * dist * layers[k].density * p.mus[k];
+					double tempexp = exp(temp_prod);
+					max_random_layer = max_random_layer - blbs * expm1(temp_prod);
+					if (interactionR <= max_random_layer) { inside = 1; break; }
+					memcpy(cur, inter, sizeof(inter));
+					blbs = blbs * tempexp;
+				}
+			}
+			if (inside) continue;                                                  /* :5692-5693 */
+			if (p.last_interaction == COMPTON) {                                   /* :5701-5713 */
+				int ci = (int)((p.energy - out_min) / out_delta) + 1;
+				if (ci >= 1 && ci <= n_out) {
+#pragma omp atomic
+					compt[(size_t)(ci - 1) * nE + i] += p.weight;
+				}
+			} else if (p.last_interaction == PHOTO) {                              /* :5714-5732 */
+				int line = -p.hist_line[1];
+				if (line >= 1 && line <= 109) fl[(size_t)(line - 1) * nZ + T->uniqZ[p.current_element]] += p.weight_escape;
+			}
+		}
+		for (size_t k = 0; k < (size_t)109 * nZ; k++) fl[k] /= photons_interacted;  /* :5757-5760 */
+		for (int k = 0; k < n_out; k++) compt[(size_t)k * nE + i] /= photons_interacted;
+	}
+	return 1;
 }

@@ -90,6 +90,12 @@ class EscapeRatios(C.Structure):
                 ("xmi_input_string", C.c_void_p)]
 
 
+class EscapeRatiosOptions(C.Structure):
+    _fields_ = [("n_input_energies", C.c_long), ("n_compton_output_energies", C.c_long), ("n_photons", C.c_long),
+                ("input_energy_min", C.c_double), ("input_energy_delta", C.c_double),
+                ("compton_output_energy_min", C.c_double), ("compton_output_energy_delta", C.c_double)]
+
+
 class Derived(C.Structure):
     _fields_ = [("n_sample_orientation", C.c_double * 3), ("n_detector_orientation", C.c_double * 3),
                 ("detector_radius", C.c_double), ("collimator_present", C.c_int), ("collimator_radius", C.c_double),
@@ -200,6 +206,18 @@ def lib():
     L.xmb_detector_convolute_history.argtypes = [vp, vp, c_double_p, C.POINTER(MainOptions)]
     L.xmb_detector_convolute_history.restype = None
     L.xmb_detector_last_ms.restype = C.c_double
+    L.xmb_get_default_escape_ratios_options.restype = EscapeRatiosOptions
+    L.xmb_escape_ratios_input.argtypes = [C.POINTER(Input), C.POINTER(EscapeRatiosOptions), vpp]
+    L.xmb_escape_ratios_input.restype = C.c_int
+    L.xmb_escape_ratios_run.argtypes = [vp, vp, C.POINTER(EscapeRatiosOptions), C.c_uint64,
+                                        C.POINTER(C.POINTER(EscapeRatios)), C.c_void_p]
+    L.xmb_escape_ratios_run.restype = C.c_int
+    L.xmb_escape_ratios_calculation.argtypes = [C.POINTER(Input), C.POINTER(C.POINTER(EscapeRatios)), C.c_void_p,
+                                                C.POINTER(XrlProvider), C.POINTER(MainOptions), EscapeRatiosOptions,
+                                                C.c_uint64]
+    L.xmb_escape_ratios_calculation.restype = C.c_int
+    L.xmb_free_escape_ratios.argtypes = [C.POINTER(C.POINTER(EscapeRatios))]; L.xmb_free_escape_ratios.restype = None
+    L.xmb_escape_ratios_last_ms.restype = C.c_double
     L.xmb_detector_last_launches.restype = C.c_uint64
     L.xmi_solid_angle_calculation_cl.argtypes = [vp, C.POINTER(C.POINTER(SolidAngle)), C.c_void_p, C.POINTER(MainOptions)]
     L.xmi_solid_angle_calculation_cl.restype = C.c_int

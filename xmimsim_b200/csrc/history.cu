@@ -427,6 +427,126 @@ __device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x,
 	return true;
 }
 
+// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------
+// ESC: escape-ratio mode (the fluorescence yield goes to weight_escape, src/xmi_variance_reduction.F90:697-750).
+// out_type: 1 Rayleigh, 2 Compton, 3 photo-electric; out_zi: element slot; out_line: |line macro| or 0.
+template <int NL, bool ESC>
+__device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photon &p, uint64_t g, int order, double *mus, int T,
+                                                   uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line) {
+	const int nL = NL > 0 ? NL : P.nL;
+	out_line = 0;
+	const XmbLayerDev lay = P.layers[p.layer];
+	const NodePos ep = node_find(P, p.energy);
+	const uint4 b1 = draw_block(P.seed, g, order, 1, 0, 1);   // {interaction type, s0, s1, s2}
+	double R2 = xmb_u01(atom_word);
+	double thr = 0.0;
+	int zi = 0;
+	const double mu_cur = mus[p.layer * T];
+	for (int i = 0; i < lay.n_elements; i++) {
+		zi = P.elem_zi[lay.elem_begin + i];
+		thr += P.elem_w[lay.elem_begin + i] * row_lerp(P, ep, P.off_elem + zi * XMB_ELEM_STRIDE + XMB_EO_CS_TOTAL) / mu_cur;
+		if (R2 < thr) break;
+	}
+	const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
+	R2 = xmb_u01(b1.x);
+	const double s0 = xmb_u01(b1.y), s1 = xmb_u01(b1.z), s2 = xmb_u01(b1.w);
+	const double pr = row_lerp(P, ep, eoff + XMB_EO_P_RAYL), prc = row_lerp(P, ep, eoff + XMB_EO_P_RAYL_COMPT);
+	out_zi = zi;
+	if (R2 < pr) {
+		out_type = 1;
+		// Rayleigh (:1986-2101)
+		const double r = s0;
+		const double theta_i = bilinear(P.rayl_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, r);
+		double tt = sin(theta_i) * sin(theta_i);
+		tt = tt / (4.0 - 2.0 * tt);
+		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
+		const double phi0 = elec_phi0(p);
+		update_dirv(p, theta_i, phi0 + phi_i);
+		update_elecv(p);
+	} else if (R2 < prc) {
+		out_type = 2;
+		// Compton (:2103-2229)
+		const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
+		const double K0K = 1.0 + p.energy * (1.0 - cos(theta_i)) / XMI_MEC2;
+		double tt = sin(theta_i) * sin(theta_i);
+		tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
+		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
+		const double phi0 = elec_phi0(p);
+		p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
+		{
+			const NodePos cp = node_find(P, p.energy);
+			XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
+		}
+		if (p.energy != 0.0) {
+			update_dirv(p, theta_i, phi_i + phi0);
+			update_elecv(p);
+			const double cti = cos(theta_i), cpi = cos(phi_i), spi = sin(phi_i);
+			double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
+			const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
+			const double rk = rat - 2.0 + 1.0 / rat;
+			pp = pp / (rk + pp);
+			const double r = s2;
+			const double w_h = (1.0 + pp) / 2.0;
+			if (r > w_h) {
+				const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
+				p.ex = tx; p.ey = ty; p.ez = tz;
+			}
+		}
+	} else {
+		out_type = 3;
+		// photo-electric effect with fluorescence (:2231-2411)
+		const double photo_total = row_lerp(P, ep, eoff + XMB_EO_PHOTO_TOTAL);
+		double sumz = 0.0;
+		const double r = s0;
+		const int max_shell = P.use_M_lines ? 8 : 3;
+		int shell = -1;
+		for (int s = 0; s <= max_shell; s++) {
+			sumz += row_lerp(P, ep, eoff + XMB_EO_PHOTO_PARTIAL + s) / photo_total;
+			if (r < sumz) { shell = s; break; }
+		}
+		if (shell < 0) { p.energy = 0.0; }
+		else {
+			// (the reference draws one unused number here, xmi_variance_reduction.F90:737; not reproduced)
+			if (ESC) weight_escape *= P.fluor_yield_corr[zi * 9 + shell];   // escape-ratio mode, src/xmi_variance_reduction.F90:697-750
+			else p.weight *= P.fluor_yield_corr[zi * 9 + shell];
+			SubStream xs;
+			xs.init(P.seed, g, order, 3, 0);
+			const double u_phi = xs.uniform();
+			// Coster-Kronig (:5184-5323)
+			const double *ck = P.cos_kron + zi * XMB_N_CK;
+			while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
+				const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
+				const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
+				const double rr = xs.uniform();
+				double sz = 0.0;
+				int found = -1;
+				for (int t = 0; t < ntr; t++) { sz += ck[first + t]; if (rr < sz) { found = t; break; } }
+				if (found < 0) break;
+				shell = shell + 1 + found;
+			}
+			// line (:5352-5437)
+			const double rl = s1;
+			double sl = 0.0;
+			int line = 0;
+			const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
+			for (int l = lf; l <= ll; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
+			if (!line) p.energy = 0.0;
+			else {
+				out_line = line;
+				p.energy = P.line_energy[(size_t)zi * 384 + line];
+				const NodePos lp = node_find(P, p.energy);
+				XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, lp, i);
+				const double theta_i = acos(-2.0 * s2 + 1.0);
+				const double phi_i = 2.0 * M_PI * u_phi;
+				update_dirv(p, theta_i, phi_i);
+				update_elecv(p);
+			}
+		}
+	}
+}
+
 // NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
 template <int NL>
 __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
@@ -711,110 +831,9 @@ for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
 			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
 			flush_staged(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, tid, T);
 			if (p.alive) {
-				const XmbLayerDev lay = P.layers[p.layer];
-				const NodePos ep = node_find(P, p.energy);
-				const uint4 b1 = draw_block(P.seed, g, order, 1, 0, 1);   // {interaction type, s0, s1, s2}
-				double R2 = xmb_u01(b0.w);
-				double thr = 0.0;
-				int zi = 0;
-				const double mu_cur = mus[p.layer * T];
-				for (int i = 0; i < lay.n_elements; i++) {
-					zi = P.elem_zi[lay.elem_begin + i];
-					thr += P.elem_w[lay.elem_begin + i] * row_lerp(P, ep, P.off_elem + zi * XMB_ELEM_STRIDE + XMB_EO_CS_TOTAL) / mu_cur;
-					if (R2 < thr) break;
-				}
-				const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
-				R2 = xmb_u01(b1.x);
-				const double s0 = xmb_u01(b1.y), s1 = xmb_u01(b1.z), s2 = xmb_u01(b1.w);
-				const double pr = row_lerp(P, ep, eoff + XMB_EO_P_RAYL), prc = row_lerp(P, ep, eoff + XMB_EO_P_RAYL_COMPT);
-				if (R2 < pr) {
-					// Rayleigh (:1986-2101)
-					const double r = s0;
-					const double theta_i = bilinear(P.rayl_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, r);
-					double tt = sin(theta_i) * sin(theta_i);
-					tt = tt / (4.0 - 2.0 * tt);
-					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
-					const double phi0 = elec_phi0(p);
-					update_dirv(p, theta_i, phi0 + phi_i);
-					update_elecv(p);
-				} else if (R2 < prc) {
-					// Compton (:2103-2229)
-					const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
-					const double K0K = 1.0 + p.energy * (1.0 - cos(theta_i)) / XMI_MEC2;
-					double tt = sin(theta_i) * sin(theta_i);
-					tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
-					const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
-					const double phi0 = elec_phi0(p);
-					p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
-					{
-						const NodePos cp = node_find(P, p.energy);
-						XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
-					}
-					if (p.energy != 0.0) {
-						update_dirv(p, theta_i, phi_i + phi0);
-						update_elecv(p);
-						const double cti = cos(theta_i), cpi = cos(phi_i), spi = sin(phi_i);
-						double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
-						const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
-						const double rk = rat - 2.0 + 1.0 / rat;
-						pp = pp / (rk + pp);
-						const double r = s2;
-						const double w_h = (1.0 + pp) / 2.0;
-						if (r > w_h) {
-							const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
-							p.ex = tx; p.ey = ty; p.ez = tz;
-						}
-					}
-				} else {
-					// photo-electric effect with fluorescence (:2231-2411)
-					const double photo_total = row_lerp(P, ep, eoff + XMB_EO_PHOTO_TOTAL);
-					double sumz = 0.0;
-					const double r = s0;
-					const int max_shell = P.use_M_lines ? 8 : 3;
-					int shell = -1;
-					for (int s = 0; s <= max_shell; s++) {
-						sumz += row_lerp(P, ep, eoff + XMB_EO_PHOTO_PARTIAL + s) / photo_total;
-						if (r < sumz) { shell = s; break; }
-					}
-					if (shell < 0) { p.energy = 0.0; }
-					else {
-						// (the reference draws one unused number here, xmi_variance_reduction.F90:737; not reproduced)
-						p.weight *= P.fluor_yield_corr[zi * 9 + shell];
-						SubStream xs;
-						xs.init(P.seed, g, order, 3, 0);
-						const double u_phi = xs.uniform();
-						// Coster-Kronig (:5184-5323)
-						const double *ck = P.cos_kron + zi * XMB_N_CK;
-						while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
-							const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
-							const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
-							const double rr = xs.uniform();
-							double sz = 0.0;
-							int found = -1;
-							for (int t = 0; t < ntr; t++) { sz += ck[first + t]; if (rr < sz) { found = t; break; } }
-							if (found < 0) break;
-							shell = shell + 1 + found;
-						}
-						// line (:5352-5437)
-						const double rl = s1;
-						double sl = 0.0;
-						int line = 0;
-						const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
-						for (int l = lf; l <= ll; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
-						if (!line) p.energy = 0.0;
-						else {
-							p.energy = P.line_energy[(size_t)zi * 384 + line];
-							const NodePos lp = node_find(P, p.energy);
-							XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, lp, i);
-							const double theta_i = acos(-2.0 * s2 + 1.0);
-							const double phi_i = 2.0 * M_PI * u_phi;
-							update_dirv(p, theta_i, phi_i);
-							update_elecv(p);
-						}
-					}
-				}
+				double we_unused = 0.0;
+				int t_unused, z_unused, l_unused;
+				select_and_scatter<NL, false>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused);
 			}
 		}
 		// ---- compaction: survivors go, densely packed, to the queue of the next order -------------------
@@ -1381,4 +1400,242 @@ extern "C" int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
 		out[3 + 3 * k] = act;
 	}
 	return 1;
+}
+
+// =====================================================================================================
+// Escape-peak ratios of the detector crystal (src/xmi_main.F90:5473-5801): per input energy, n_photons
+// pencil-beam photons are forced to interact once in the crystal (weight = interaction probability);
+// a photon whose secondary (Compton-scattered or K/L fluorescence) leaves the crystal without a second
+// interaction is tallied.  Streams: photon id g = energy index * n_photons + j; order 0 = source
+// (slit x, slit y, polarisation angle), order 1 = the interaction (same addresses as the history kernel),
+// order 2 stage 1 block 0 word 0 = free path of the secondary.
+// Tallies are exact: weights <= 1 in 2^-40 fixed point, 64-bit integer sums.
+// =====================================================================================================
+#define XMB_ESC_SHIFT 40
+struct XmbEscParams {
+	uint64_t n_photons;
+	int n_out;
+	double out_min, out_delta;
+	unsigned long long *fluo;        // [nE][109][nZ]
+	unsigned long long *compt;       // [n_out][nE]
+	unsigned long long *interacted;  // [nE]
+};
+
+__device__ __forceinline__ unsigned long long esc_fixed(double w) { return (unsigned long long)(w * (double)(1ULL << XMB_ESC_SHIFT) + 0.5); }
+
+template <int NL>
+__global__ void __launch_bounds__(256) xmb_escape_kernel(const __grid_constant__ XmbHistParams P, const XmbEscParams R) {
+	const int nL = NL > 0 ? NL : P.nL;
+	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
+	const int iE = blockIdx.y;
+	const int nE = gridDim.y;
+	const double E0 = P.segs[iE].energy;
+	double mus0[NLA];
+	{
+		const NodePos np = node_find(P, E0);
+		for (int i = 0; i < nL; i++) mus0[i] = row_lerp(P, np, i);
+	}
+	unsigned long long interacted = 0;
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < R.n_photons; j += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t g = (uint64_t)iE * R.n_photons + j;
+		Photon p;
+		double mus[NLA], rd[NLA];
+		for (int i = 0; i < nL; i++) mus[i] = mus0[i];
+		// ---- source (:5641-5668): point source through the slit, random polarisation ---------------------
+		XmbRng rng;
+		rng.init(P.seed, g, XMB_TAG_HISTORY);
+		p.energy = E0; p.weight = 1.0; p.alive = true; p.n_interactions = 0;
+		const double x1 = P.slit_x1_max * (-1.0 + 2.0 * rng.uniform());
+		const double y1 = P.slit_y1_max * (-1.0 + 2.0 * rng.uniform());
+		p.cx = p.cy = p.cz = 0.0;
+		p.dx = tan(x1); p.dy = tan(y1); p.dz = 1.0;
+		normalize3(p.dx, p.dy, p.dz);
+		p.theta = acos(p.dz);
+		p.phi = atan2(p.dy, p.dx);
+		{
+			double se, ce;
+			sincos(rng.uniform() * M_PI * 2.0, &se, &ce);
+			p.ex = ce; p.ey = se; p.ez = 0.0;
+			const double cosalfa = p.ex * p.dx + p.ey * p.dy + p.ez * p.dz;
+			const double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+			p.ex = c_ae * p.ex + c_be * p.dx; p.ey = c_ae * p.ey + c_be * p.dy; p.ez = c_ae * p.ez + c_be * p.dz;
+		}
+		// xmi_photon_shift_first_layer (:1140-1186); the source sits upstream of the crystal
+		{
+			double d;
+			if (!step_to_plane(P, p.cx, p.cy, p.cz, p.dx, p.dy, p.dz, P.layers[0].Z_begin, d)) continue;
+			p.layer = 0;
+		}
+		// ---- first iteration: forced interaction (:1417-1518), weight_escape = weight (:1462-1464) --------
+		const uint4 b0 = draw_block(P.seed, g, 1, 1, 0, 0);
+		{
+			const double interactionR = xmb_u01(b0.x);
+			double lx = p.cx, ly = p.cy, lz = p.cz, Pabs = 0.0;
+			bool ok = true;
+			for (int i = 0; i < nL; i++) {     // moving towards higher layers (dirv . n > 0)
+				double dist;
+				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, P.layers[i].Z_end, dist)) { ok = false; break; }
+				rd[i] = dist;
+				Pabs += mus[i] * P.layers[i].density * dist;
+			}
+			if (!ok) continue;
+			const double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
+			p.weight *= Pabs2;
+			const double l1p = log1p(-1.0 * interactionR * Pabs2);
+			const double negln = -1.0 * l1p;
+			int my_index = 0;
+			double my_sum = 0.0;
+			for (int i = 0; i < nL; i++) {
+				my_sum += mus[i] * P.layers[i].density * rd[i];
+				if (my_sum > negln) { my_index = i; break; }
+			}
+			const double murho_idx = mus[my_index] * P.layers[my_index].density;
+			double temp_sum = 0.0;
+			for (int i = 0; i <= my_index; i++) temp_sum += (1.0 - (mus[i] * P.layers[i].density / murho_idx)) * rd[i];
+			temp_sum = temp_sum - 1.0 * l1p / murho_idx;
+			p.cx += temp_sum * p.dx; p.cy += temp_sum * p.dy; p.cz += temp_sum * p.dz;
+			p.layer = my_index;
+			p.n_interactions = 1;
+		}
+		double weight_escape = p.weight;
+		interacted += esc_fixed(p.weight);   // photons_interacted (:5685-5688): every photon interacts, forced
+		int type = 0, zi = 0, line = 0;
+		select_and_scatter<NL, true>(P, p, g, 1, mus, 1, b0.w, weight_escape, type, zi, line);
+		// ---- second iteration: analogue free path (:1229-1413); escaped = no interaction before the surface ----
+		if (p.energy < ENERGY_THRESHOLD) continue;   // EXIT main with inside still true (:1229-1231)
+		bool escaped = true;
+		{
+			int step_max, step_dir;
+			if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
+			else { step_max = 0; step_dir = -1; }
+			const double interactionR = xmb_u01(draw_block(P.seed, g, 2, 1, 0, 0).x);
+			double blbs = 1.0, max_random_layer = 0.0;
+			double lx = p.cx, ly = p.cy, lz = p.cz;
+			for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+				double dist;
+				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { escaped = false; break; }
+				const double temp_prod = -1.0 * dist * P.layers[i].density * mus[i];
+				const double tempexp = exp(temp_prod);
+				max_random_layer = max_random_layer - blbs * expm1(temp_prod);
+				if (interactionR <= max_random_layer) { escaped = false; break; }
+				blbs = blbs * tempexp;
+			}
+		}
+		if (!escaped) continue;
+		if (type == 2) {
+			const int ci = (int)((p.energy - R.out_min) / R.out_delta);   // 0-based (:5705-5713)
+			if (ci >= 0 && ci < R.n_out) atomicAdd(&R.compt[(size_t)ci * nE + iE], esc_fixed(p.weight));
+		} else if (type == 3 && line >= 1 && line <= 109) {
+			atomicAdd(&R.fluo[((size_t)iE * 109 + (line - 1)) * P.nZ + zi], esc_fixed(weight_escape));
+		}
+	}
+	interacted = warp_sum_u64(interacted);
+	if ((threadIdx.x & 31) == 0 && interacted) atomicAdd(&R.interacted[iE], interacted);
+}
+
+static double g_escape_ms = 0.0;
+extern "C" double xmb_escape_ratios_last_ms(void) { return g_escape_ms; }
+
+extern "C" void xmb_free_escape_ratios(xmb_escape_ratios **p) {
+	if (!p || !*p) return;
+	xmb_escape_ratios *e = *p;
+	free(e->Z); free(e->fluo_escape_ratios); free(e->fluo_escape_input_energies); free(e->compton_escape_ratios);
+	free(e->compton_escape_output_energies);   // compton_escape_input_energies aliases fluo_escape_input_energies (:5525)
+	free(e);
+	*p = nullptr;
+}
+
+extern "C" int xmb_escape_ratios_run(xmb_inputFPtr esc_inputF, xmb_hdf5FPtr esc_hdf5F, const xmb_escape_ratios_options *ero,
+                                     uint64_t seed, xmb_escape_ratios **out, char *input_string) {
+	XmbInputF *in = xmb_as_input(esc_inputF);
+	XmbHdf5F *h = xmb_as_hdf5(esc_hdf5F);
+	if (!in || !h || !in->inited || !ero || !out) { xmb_set_error("xmb_escape_ratios_run: bad arguments"); return 0; }
+	if (in->in.excitation->n_discrete != ero->n_input_energies || in->in.excitation->n_continuous != 0 ||
+	    in->in.general->n_photons_line != ero->n_photons) {
+		xmb_set_error("xmb_escape_ratios_run: handle was not made by xmb_escape_ratios_input with these options");
+		return 0;
+	}
+	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: xmb_escape_ratios_calculation has no CPU fallback"); return 0; }
+	// options of the reference's escape run (:5561-5569): no M lines, no cascade
+	xmb_main_options opt;
+	xmb_main_options_defaults(&opt);
+	opt.use_M_lines = 0; opt.use_cascade_auger = 0; opt.use_cascade_radiative = 0; opt.use_variance_reduction = 0;
+	opt.escape_ratios_mode = 1;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	XmbDeviceTables *D = h->dev;
+	if (!D || D->cascade != cascade_mode(&opt) || D->use_M_lines != 0 || D->device != dev) {
+		if (D) delete D;
+		h->dev = D = build_device_tables(in, h, &opt);
+		if (!D) return 0;
+	}
+	XmbHistParams P = D->P;
+	P.seed = seed ? seed : XMB_DEFAULT_SEED;
+	const int nE = (int)ero->n_input_energies, nO = (int)ero->n_compton_output_energies, nZ = P.nZ;
+	const size_t n_fluo = (size_t)nE * 109 * nZ, n_compt = (size_t)nE * nO;
+	unsigned long long *d_all = nullptr;
+	XMB_CUDA_OK(cudaMalloc(&d_all, sizeof(unsigned long long) * (n_fluo + n_compt + nE)));
+	XMB_CUDA_OK(cudaMemsetAsync(d_all, 0, sizeof(unsigned long long) * (n_fluo + n_compt + nE)));
+	XmbEscParams R;
+	R.n_photons = (uint64_t)ero->n_photons; R.n_out = nO; R.out_min = ero->compton_output_energy_min; R.out_delta = ero->compton_output_energy_delta;
+	R.fluo = d_all; R.compt = d_all + n_fluo; R.interacted = d_all + n_fluo + n_compt;
+	const int threads = 256;
+	// each thread walks >= 64 photons when there are that many; the grid is nE rows of gx CTAs
+	unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(64, (R.n_photons + (uint64_t)threads * 64 - 1) / ((uint64_t)threads * 64)));
+	dim3 grid(gx, (unsigned)nE);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0);
+	switch (P.nL) {
+	case 1: xmb_escape_kernel<1><<<grid, threads>>>(P, R); break;
+	case 2: xmb_escape_kernel<2><<<grid, threads>>>(P, R); break;
+	default: xmb_escape_kernel<0><<<grid, threads>>>(P, R); break;
+	}
+	cudaEventRecord(e1);
+	XMB_CUDA_OK(cudaGetLastError());
+	XMB_CUDA_OK(cudaEventSynchronize(e1));
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	g_escape_ms = ms;
+	std::vector<unsigned long long> hst(n_fluo + n_compt + nE);
+	XMB_CUDA_OK(cudaMemcpy(hst.data(), d_all, sizeof(unsigned long long) * hst.size(), cudaMemcpyDeviceToHost));
+	cudaFree(d_all);
+	// ---- reference-shaped result (:5521-5557, :5762-5783) ---------------------------------------------------------
+	xmb_escape_ratios *er = (xmb_escape_ratios *)calloc(1, sizeof(xmb_escape_ratios));
+	er->n_elements = nZ;
+	er->n_fluo_input_energies = nE; er->n_compton_input_energies = nE; er->n_compton_output_energies = nO;
+	er->Z = (int *)malloc(sizeof(int) * nZ);
+	for (int z = 0; z < nZ; z++) er->Z[z] = h->view.Z[z];
+	er->fluo_escape_input_energies = (double *)malloc(sizeof(double) * nE);
+	er->compton_escape_input_energies = er->fluo_escape_input_energies;
+	for (int i = 0; i < nE; i++) er->fluo_escape_input_energies[i] = ero->input_energy_min + i * ero->input_energy_delta;
+	er->compton_escape_output_energies = (double *)malloc(sizeof(double) * nO);
+	for (int i = 0; i < nO; i++) er->compton_escape_output_energies[i] = ero->compton_output_energy_min + i * ero->compton_output_energy_delta;
+	er->fluo_escape_ratios = (double *)malloc(sizeof(double) * n_fluo);
+	er->compton_escape_ratios = (double *)malloc(sizeof(double) * n_compt);
+	const unsigned long long *h_fluo = hst.data(), *h_compt = hst.data() + n_fluo, *h_int = hst.data() + n_fluo + n_compt;
+	// ratio of two exact integer sums; the common 2^-40 scale cancels
+	for (int i = 0; i < nE; i++) {
+		const double den = (double)h_int[i];
+		for (size_t k = 0; k < (size_t)109 * nZ; k++) er->fluo_escape_ratios[(size_t)i * 109 * nZ + k] = (double)h_fluo[(size_t)i * 109 * nZ + k] / den;
+		for (int c = 0; c < nO; c++) er->compton_escape_ratios[(size_t)c * nE + i] = (double)h_compt[(size_t)c * nE + i] / den;
+	}
+	er->xmi_input_string = input_string;
+	*out = er;
+	return 1;
+}
+
+extern "C" int xmb_escape_ratios_calculation(const xmb_input *input, xmb_escape_ratios **escape_ratios, char *input_string,
+                                             const xmb_xrl_provider *xrl, const xmb_main_options *options,
+                                             xmb_escape_ratios_options ero, uint64_t seed) {
+	xmb_inputFPtr ein = nullptr;
+	xmb_hdf5FPtr eh = nullptr;
+	if (!xmb_escape_ratios_input(input, &ero, &ein)) return 0;
+	if (!xmb_init_from_provider(xrl, ein, 1, &eh)) { xmb_free_input_F(&ein); return 0; }
+	const int rv = xmb_escape_ratios_run(ein, eh, &ero, seed, escape_ratios, input_string);
+	if (rv && options && options->verbose) { printf("Escape peak ratios calculation finished\n"); fflush(stdout); }
+	xmb_free_hdf5_F(&eh);
+	xmb_free_input_F(&ein);
+	return rv;
 }

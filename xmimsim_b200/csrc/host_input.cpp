@@ -253,3 +253,55 @@ double xmb_host_mu_layer(const xmb_xrl_provider *xrl, const xmb_layer *layer, do
 	for (int i = 0; i < layer->n_elements; i++) rv += xrl->CS_Total_Kissel(layer->Z[i], E) * layer->weight[i];
 	return rv;
 }
+
+// ---- escape-ratio mode input (src/xmi_detector.c:91-141, src/xmi_main.F90:1687-1738) -------------------------
+extern "C" xmb_escape_ratios_options xmb_get_default_escape_ratios_options(void) {
+	xmb_escape_ratios_options rv = {1990, 1999, 500000, 1.0, 0.1, 0.1, 0.1};
+	return rv;
+}
+
+extern "C" int xmb_escape_ratios_input(const xmb_input *input, const xmb_escape_ratios_options *ero, xmb_inputFPtr *out) {
+	if (!input || !ero || !out || !input->detector || !input->general || !input->geometry || !input->absorbers) {
+		xmb_set_error("xmb_escape_ratios_input: bad arguments");
+		return 0;
+	}
+	if (input->detector->n_crystal_layers < 1) { xmb_set_error("xmb_escape_ratios_input: detector has no crystal"); return 0; }
+	if (ero->n_input_energies < 1 || ero->n_compton_output_energies < 1 || ero->n_photons < 1 ||
+	    ero->n_photons >= (1L << 23) || ero->n_input_energies > 65535) {
+		xmb_set_error("xmb_escape_ratios_input: options out of range");
+		return 0;
+	}
+	// shallow tree with the reference's overrides; xmb_input_C2F takes the deep copy
+	xmb_general gen = *input->general;
+	gen.n_interactions_trajectory = 1;
+	gen.n_photons_line = ero->n_photons;
+	xmb_composition comp;
+	comp.n_layers = input->detector->n_crystal_layers;
+	comp.layers = input->detector->crystal_layers;
+	comp.reference_layer = 1;
+	xmb_geometry geo = *input->geometry;
+	geo.d_sample_source = 1.0;
+	geo.d_source_slit = 1.0;
+	geo.slit_size_x = 0.0001;
+	geo.slit_size_y = 0.0001;
+	geo.n_sample_orientation[0] = 0.0; geo.n_sample_orientation[1] = 0.0; geo.n_sample_orientation[2] = 1.0;
+	std::vector<xmb_energy_discrete> lines((size_t)ero->n_input_energies);
+	for (long i = 0; i < ero->n_input_energies; i++) {
+		xmb_energy_discrete &e = lines[i];
+		memset(&e, 0, sizeof(e));
+		e.energy = ero->input_energy_min + i * ero->input_energy_delta;   // src/xmi_main.F90:5534-5537
+		e.horizontal_intensity = 0.5; e.vertical_intensity = 0.5;
+		e.distribution_type = XMB_DISCRETE_MONOCHROMATIC;
+	}
+	xmb_excitation exc;
+	exc.n_discrete = (int)lines.size(); exc.discrete = lines.data();
+	exc.n_continuous = 0; exc.continuous = nullptr;
+	xmb_absorbers abs = *input->absorbers;
+	abs.n_exc_layers = 0; abs.exc_layers = nullptr;
+	xmb_input esc;
+	esc.general = &gen; esc.composition = &comp; esc.geometry = &geo; esc.excitation = &exc; esc.absorbers = &abs;
+	esc.detector = input->detector;
+	if (!xmb_input_C2F(&esc, out)) return 0;
+	if (!xmb_init_input(out)) { xmb_free_input_F(out); return 0; }
+	return 1;
+}

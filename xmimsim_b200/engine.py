@@ -225,6 +225,54 @@ class Simulation:
         er._keep = (zz, a)
         return er
 
+    def escape_ratios_options(self, **kw):
+        """xmi_get_default_escape_ratios_options with overrides."""
+        ero = self.L.xmb_get_default_escape_ratios_options()
+        for k, v in kw.items():
+            if not hasattr(ero, k):
+                raise AttributeError(k)
+            setattr(ero, k, v)
+        return ero
+
+    def escape_ratios_handles(self, ero, quality=0):
+        """(inputF, hdf5F) of the escape-mode run (composition = crystal): for the parity tests, which hand the same
+        host tables to the oracle.  Caller frees with xmb_free_hdf5_F / xmb_free_input_F."""
+        ein, eh = C.c_void_p(), C.c_void_p()
+        if not self.L.xmb_escape_ratios_input(C.byref(self.cinput.input), C.byref(ero), C.byref(ein)):
+            raise RuntimeError("xmb_escape_ratios_input: " + abi.last_error())
+        if not self.L.xmb_init_from_provider(self.provider, ein, quality, C.byref(eh)):
+            raise RuntimeError("xmb_init_from_provider: " + abi.last_error())
+        return ein, eh
+
+    def escape_ratios_run(self, ein, eh, ero, seed=0):
+        er = C.POINTER(abi.EscapeRatios)()
+        if not self.L.xmb_escape_ratios_run(ein, eh, C.byref(ero), seed, C.byref(er), None):
+            raise RuntimeError("xmb_escape_ratios_run: " + abi.last_error())
+        return er
+
+    def escape_ratios_calculation(self, ero=None, options=None, seed=0):
+        """xmi_escape_ratios_calculation: returns a pointer to a malloc'ed xmi_escape_ratios
+        (free with escape_ratios_free); `.contents` is what detector_convolute_all takes."""
+        ero = ero or self.escape_ratios_options()
+        options = options or main_options()
+        er = C.POINTER(abi.EscapeRatios)()
+        if not self.L.xmb_escape_ratios_calculation(C.byref(self.cinput.input), C.byref(er), None, self.provider,
+                                                    C.byref(options), ero, seed):
+            raise RuntimeError("xmb_escape_ratios_calculation: " + abi.last_error())
+        return er
+
+    @staticmethod
+    def escape_ratios_arrays(er):
+        """numpy copies of an xmi_escape_ratios: (Z, fluo[nE][109][nZ], E_in, compton[n_out][n_in], E_out)."""
+        e = er.contents
+        nZ, nE, nO = e.n_elements, e.n_fluo_input_energies, e.n_compton_output_energies
+        Z = np.array([e.Z[i] for i in range(nZ)], np.int32)
+        return (Z, _np_from_ptr(e.fluo_escape_ratios, (nE, 109, nZ)).copy(), _np_from_ptr(e.fluo_escape_input_energies, (nE,)).copy(),
+                _np_from_ptr(e.compton_escape_ratios, (nO, nE)).copy(), _np_from_ptr(e.compton_escape_output_energies, (nO,)).copy())
+
+    def escape_ratios_free(self, er):
+        self.L.xmb_free_escape_ratios(C.byref(er))
+
     def detector_convolute_all(self, channels, brute_history=None, var_red_history=None, options=None, escape_ratios=None,
                                zero_interaction=0):
         """xmi_detector_convolute_all.  `channels` [(n_int+1)][nch] is modified in place (as the reference does);

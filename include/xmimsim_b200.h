@@ -199,6 +199,12 @@ typedef struct xmb_xrl_provider {
 	 * 3 radiative, 4 full: src/xmi_aux_f.F90:662-665), given the already-evaluated P[] of the
 	 * deeper shells (P[0]=PK ...).  Restates xraylib's P{L1..M5}_{pure,auger,rad,full}_kissel. */
 	double (*VacancyCS)(int Z, int shell, double E, int cascade, const double *P);
+	/* xraylib AugerRate(Z, <shell>_<new1><new2>_AUGER): fraction of the non-radiative decays of a
+	 * vacancy in `shell` (K, L1..L3) that leave vacancies in new1 and new2 (ordered pair, as
+	 * xraylib's macros are).  Shell numbers are xraylib's (K 0, L1 1 ... M5 8, N1 9 ... Q3 30).
+	 * Only used by the brute-force mode (src/xmi_main.F90:2413-2481).  May be NULL: no Auger
+	 * cascade offspring are then simulated. */
+	double (*AugerRate)(int Z, int shell, int shell_new1, int shell_new2);
 } xmb_xrl_provider;
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void);
@@ -285,7 +291,12 @@ typedef struct xmb_tables_host {
 	int n_layers;
 	const double *mu_layer;        /* [n_layers][n_nodes]  sum_i w_i CS_Total_Kissel(Z_i, E) */
 	const double *exc_murhod;      /* [n_nodes] sum over excitation-path absorbers of mu*rho*t */
+	/* Auger transition rates in the reference's enumeration (src/xmi_main.F90:2482-4418):
+	 * index 0..239 = K_<X><Y>, X in L1..M5 (8), Y in L1..Q3 (30): x*30 + y;
+	 * 240 + 135*(s-1) + x*27 + y = L<s>_<X><Y>, X in M1..M5 (5), Y in M1..Q3 (27). */
+	const double *auger_rate;      /* [nZ][XMB_N_AUGER] */
 } xmb_tables_host;
+#define XMB_N_AUGER 645
 
 /* ------------------------------------------------------------------------------------------
  * Entry points
@@ -343,7 +354,10 @@ void xmb_free_solid_angle(xmb_solid_angle *sa);   /* xmi_free_solid_angle, src/x
 /* Replaces xmi_main_msim (include/xmi_main.h:29; src/xmi_main.F90:66-954).
  * channels:        malloc'ed double[(n_int+1)][nchannels], rows cumulative over interaction order, x live_time
  * brute_history:   malloc'ed double[100][385][n_int]  (all zero with variance reduction on)
- * var_red_history: malloc'ed double[100][385][n_int]  (NULL if variance reduction off)
+ * var_red_history: malloc'ed double[100][385][n_int]  (all zero with variance reduction off)
+ * options->use_variance_reduction = 0 selects the brute-force mode (analogue walk, detector/collimator hit
+ * tests src/xmi_aux_f.F90:1622-1833, Auger/radiative cascade offspring src/xmi_main.F90:2413-4783);
+ * solid_angles may then be NULL and channels row 0 holds the photons detected without interaction.
  * n_mpi_hosts/rank semantic: this rank simulates photon ids [rank*N/n, (rank+1)*N/n) of every
  * source line; outputs are *partial sums* to be summed over ranks (see xmb_main_msim_ex).
  * Returns 1 / 0. */
@@ -379,6 +393,10 @@ int xmb_msim_device_limbs(xmb_hdf5FPtr hdf5F, uint64_t **dev_ptr, size_t *n_word
  * n_elements, active forced-detection line records of its elements).  Feeds the algorithmic-bytes
  * figure of SURVEY.md 8(d) / DESIGN.md. */
 int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity);
+/* Counters of the last brute-force run (options->use_variance_reduction = 0): out[1] interactions,
+ * out[3] photons that reached the detector, out[4] cascade offspring photons walked, out[5] detected
+ * photons whose line has no history slot. */
+int xmb_msim_brute_counters(xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity);
 /* Host-side helpers of the sharded driver (no GPU needed): the contiguous photon-id shard of a rank, the total
  * number of histories of an input, and the accumulator slot map: a row (one per interaction order) is
  * nchannels channel slots followed by n_hist_slots history slots; history slot s holds (out_Z[s], out_line[s]),

@@ -72,6 +72,14 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
                              uint64_t g_begin, uint64_t g_end, int n_threads, double *channels,
                              double *var_red, uint64_t *counters);
 
+/* Brute-force mode (use_variance_reduction = 0; src/xmi_main.F90:1229-1416, :1920-1984, :2231-4783;
+ * src/xmi_aux_f.F90:1622-1833): analogue walk, detector/collimator hit tests, Auger and radiative cascade offspring.
+ * channels[(n_int+1)][nch] cumulative from the photon's interaction count; brute[n_int][385][100] =
+ * Fortran brute_history(Z, slot, k).  RAW sums.  counters[0] detector hits, [1] interactions, [2] offspring. */
+uint64_t orc_main_msim_brute_range(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T,
+                                   const xmb_main_options *opt, uint64_t seed, uint64_t g_begin, uint64_t g_end,
+                                   int n_threads, double *channels, double *brute, uint64_t *counters);
+
 /* Escape-peak ratios of the crystal (src/xmi_main.F90:5473-5801) on the escape-mode input (its discrete lines
  * are the input energies).  fluo[(i*109 + line-1)*nZ + zi] and compt[c*nE + i] are the Fortran layouts
  * fluo_escape_ratios(element, line, i) / compton_escape_ratios(i, c), already divided by photons_interacted. */

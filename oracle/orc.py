@@ -51,6 +51,9 @@ def lib():
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p]
         _lib.orc_main_msim_range.restype = C.c_uint64
+        _lib.orc_main_msim_brute_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_uint64,
+                                                   C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_main_msim_brute_range.restype = C.c_uint64
         _lib.orc_escape_ratios.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_uint64, C.c_long, C.c_int,
                                            C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.orc_escape_ratios.restype = C.c_int
@@ -101,6 +104,18 @@ def main_msim_range(cinput_ptr, d, tables_ptr, options, sa_struct, seed, g_begin
                               C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
                               g_begin, g_end, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
     return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt
+
+
+def main_msim_brute_range(cinput_ptr, d, tables_ptr, options, seed, g_begin, g_end, n_int, nch, n_threads=8):
+    """Oracle brute-force histories for photon ids [g_begin, g_end).  Returns (channels[(n_int+1)][nch],
+    brute_history[100][385][n_int] in the reference's exported C order, counters[hits, interactions, offspring])."""
+    ch = np.zeros((n_int + 1, nch))
+    br = np.zeros((n_int, 385, 100))
+    cnt = np.zeros(3, np.uint64)
+    lib().orc_main_msim_brute_range(C.cast(cinput_ptr, C.c_void_p), C.byref(d), C.cast(tables_ptr, C.c_void_p),
+                                    C.cast(C.pointer(options), C.c_void_p), seed, g_begin, g_end, n_threads,
+                                    ch.ctypes.data, br.ctypes.data, cnt.ctypes.data)
+    return ch, np.ascontiguousarray(br.transpose(2, 1, 0)), cnt
 
 
 def escape_ratios(cinput_ptr, d, tables_ptr, seed, n_energies, nZ, n_photons, n_out, out_min, out_delta, n_threads=8):

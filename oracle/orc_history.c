@@ -69,6 +69,7 @@ typedef struct {
 	int current_element;      /* Z */
 	int current_element_index;
 	int n_interactions, last_interaction;
+	int gen;                  /* 0, or GEN_BIT for a cascade offspring (brute-force mode): OR-ed into the RNG order field */
 	uint64_t seed, g;         /* Philox key and stream (global photon id) */
 	int hist_line[32];        /* history(k,1): interaction code or negative line */
 	int hist_Z[32];           /* history(k,2) */
@@ -425,7 +426,7 @@ static int do_compton(ctx_t *c, photon_t *p, const double *sd) {                
 	double phi_i = bilinear(T->phi_icdf, T->n_icdf_R, T->phi_T, T->n_phi_T, T->icdf_R, tt, sd[1]);
 	double phi0 = elec_phi0(p);
 	substream_t ds;
-	sub_init(&ds, p->seed, p->g, p->n_interactions, 3, 0);
+	sub_init(&ds, p->seed, p->g, p->n_interactions | p->gen, 3, 0);
 	p->energy = compton_energy(c, zi, p->energy, theta_i, &ds, 0);
 	mu_calc(c, p->energy, p->mus);                                                /* :5059 */
 	if (p->energy == 0.0) return 1;
@@ -878,4 +879,358 @@ int orc_escape_ratios(const xmb_input *in, const orc_derived *d, const xmb_table
 		for (int k = 0; k < n_out; k++) compt[(size_t)k * nE + i] /= photons_interacted;
 	}
 	return 1;
+}
+
+/* =====================================================================================================
+ * Brute-force mode (options%use_variance_reduction = 0): analogue random walk, photons are scored only
+ * when they actually reach the detector; Auger / radiative cascades spawn one offspring photon.
+ * src/xmi_main.F90:1229-1416 (analogue step), :1920-1984, :2231-2411, :2413-4783; src/xmi_aux_f.F90:1622-1833.
+ *
+ * Random-number addresses (counter word 2 = (gen<<31)|(order<<20)|(stage<<16)|(elem<<8)|block, gen = 1 for an
+ * offspring photon's own walk):
+ *   order k, stage 1, blk 0 : {free path, -, -, atom}          blk 1 : {interaction type, s0, s1, s2}
+ *   order k, stage 3        : Compton: Doppler trials; photo: phi, yield check, Coster-Kronig hops
+ *   order k, stage 4, elem 0: Auger cascade: transition, then the parent's re-emission (yield, CK hops, line,
+ *                             theta, phi, polarisation angle);  elem 1: the same for the offspring
+ *   order k, stage 5        : radiative cascade: yield, CK hops, line, theta, phi, polarisation angle
+ * ===================================================================================================== */
+#define GEN_BIT 0x800   /* OR-ed into the order field: bit 31 of the counter word */
+
+enum { DET_NONE = 0, DET_HIT = 1, DET_COLLIMATOR = 2, DET_BAD = 3 };
+
+/* xmi_check_detector_intersection (src/xmi_aux_f.F90:1622-1833) for the segment begin -> end */
+static int check_detector_intersection(const ctx_t *c, const double *begin, const double *end) {
+	const orc_derived *D = c->d;
+	const xmb_geometry *g = c->in->geometry;
+	double b[3], e[3], t[3];
+	for (int i = 0; i < 3; i++) t[i] = begin[i] - g->p_detector_window[i];
+	matvec(D->ndo_inv, t, b);
+	for (int i = 0; i < 3; i++) t[i] = end[i] - g->p_detector_window[i];
+	matvec(D->ndo_inv, t, e);
+	const double pp[3] = {0.0, 0.0, 0.0}, pn[3] = {1.0, 0.0, 0.0};
+	double dirv[3] = {e[0] - b[0], e[1] - b[1], e[2] - b[2]}, inter[3];
+	if (!D->collimator_present) {
+		if (b[0] * e[0] > 0) return DET_NONE;
+		/* (the reference assigns the scalar norm to the direction here, :1662 -- SURVEY App. A quirk; the segment
+		 * direction is used instead) */
+		if (!plane_line(pp, pn, e, dirv, inter)) return DET_NONE;
+		inter[0] = 0.0;
+		if (norm3(inter) <= D->detector_radius) return dot3(dirv, pn) >= 0.0 ? DET_BAD : DET_HIT;
+		return DET_NONE;
+	}
+	/* conical collimator: quadric intersection of the line with the cone (:1690-1830) */
+	if (dirv[0] == 0.0) return DET_NONE;
+	const double t_begin = (b[0] - e[0]) / dirv[0], t_end = 0.0;
+	double delta[3] = {e[0] - D->vertex[0], e[1] - D->vertex[1], e[2] - D->vertex[2]};
+	const double cos2theta = cos(D->half_apex) * cos(D->half_apex);
+	const double M[3] = {1.0 - cos2theta, -cos2theta, -cos2theta};
+	double dM[3] = {dirv[0] * M[0], dirv[1] * M[1], dirv[2] * M[2]}, deltaM[3] = {delta[0] * M[0], delta[1] * M[1], delta[2] * M[2]};
+	const double c2 = dot3(dM, dirv), c1 = dot3(dM, delta), c0 = dot3(deltaM, delta);
+	const double disc = c1 * c1 - c0 * c2;
+	if (disc < 0.0) return DET_NONE;
+	const double t1 = (-c1 + sqrt(disc)) / c2, t2 = (-c1 - sqrt(disc)) / c2;
+	const double X1x = e[0] + t1 * dirv[0], X2x = e[0] + t2 * dirv[0];
+	const int v1 = -(X1x - D->vertex[0]) >= 0.0, v2 = -(X2x - D->vertex[0]) >= 0.0;
+	const double tmax = fmax(t_begin, t_end), tmin = fmin(t_begin, t_end);
+	const int in1 = t1 <= tmax && t1 >= tmin && X1x <= g->collimator_height;
+	const int in2 = t2 <= tmax && t2 >= tmin && X2x <= g->collimator_height;
+	if (!v1 && !v2) return DET_NONE;
+	if (v1 && v2) return (in1 || in2) ? DET_COLLIMATOR : DET_NONE;
+	if (v1 ? in1 : in2) return DET_COLLIMATOR;
+	if (!plane_line(pp, pn, e, dirv, inter)) return DET_NONE;
+	inter[0] = 0.0;
+	if (norm3(inter) <= D->detector_radius && dist3(b, inter) <= dist3(b, e)) return dot3(dirv, pn) >= 0.0 ? DET_BAD : DET_HIT;
+	return DET_NONE;
+}
+
+/* xmi_check_photon_detector_hit (src/xmi_main.F90:1920-1984): a photon that left the sample */
+static int check_photon_detector_hit(const ctx_t *c, const photon_t *p) {
+	const orc_derived *D = c->d;
+	const xmb_geometry *g = c->in->geometry;
+	if (dot3(p->dirv, g->n_detector_orientation) >= 0.0) return 0;
+	double dd[3], cd[3], t[3], inter[3];
+	matvec(D->ndo_inv, p->dirv, dd);
+	for (int i = 0; i < 3; i++) t[i] = p->coords[i] - g->p_detector_window[i];
+	matvec(D->ndo_inv, t, cd);
+	double pp[3] = {0.0, 0.0, 0.0};
+	const double pn[3] = {1.0, 0.0, 0.0};
+	if (!plane_line(pp, pn, cd, dd, inter)) return 0;
+	if (norm3(inter) > D->detector_radius) return 0;
+	if (!D->collimator_present) return 1;
+	pp[0] = g->collimator_height;
+	if (!plane_line(pp, pn, cd, dd, inter)) return 0;
+	inter[0] = 0.0;
+	if (norm3(inter) > D->collimator_radius) return 0;
+	return 1;
+}
+
+static int line_from_shell(const xmb_tables_host *T, int zi, int shell, double r) {     /* xmi_fluorescence_line_check (:5352-5437) */
+	if (shell < 0 || shell > 8) return 0;
+	double sumz = 0.0;
+	for (int l = xmb_shell_line_first[shell]; l <= xmb_shell_line_last[shell]; l++) {
+		sumz += T->rad_rate[(size_t)zi * 384 + l];
+		if (r < sumz) return l;
+	}
+	return 0;
+}
+
+/* isotropic re-emission of a cascade photon (:4455-4481, :4733-4767): direction set directly from (theta, phi) */
+static void cascade_emit(ctx_t *c, photon_t *q, int line, substream_t *xs) {
+	q->energy = c->T->line_energy[(size_t)c->T->uniqZ[q->current_element] * 384 + line];
+	mu_calc(c, q->energy, q->mus);
+	q->theta = acos(2.0 * sub_uniform(xs) - 1.0);
+	q->phi = 2.0 * M_PI * sub_uniform(xs);
+	q->dirv[0] = sin(q->theta) * cos(q->phi); q->dirv[1] = sin(q->theta) * sin(q->phi); q->dirv[2] = cos(q->theta);
+	q->hist_line[q->n_interactions] = -line;
+	q->hist_Z[q->n_interactions] = q->current_element;
+	double r = 2.0 * M_PI * sub_uniform(xs);
+	q->elecv[0] = cos(r); q->elecv[1] = sin(r); q->elecv[2] = 0.0;
+	q->last_interaction = PHOTO;
+	double cosalfa = dot3(q->elecv, q->dirv);
+	double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+	for (int i = 0; i < 3; i++) q->elecv[i] = c_ae * q->elecv[i] + c_be * q->dirv[i];
+}
+
+/* one vacancy of a cascade: yield check (:5325-5350), Coster-Kronig, line; returns the line or 0 */
+static int cascade_vacancy(ctx_t *c, int zi, int shell, substream_t *xs, double *energy) {
+	const xmb_tables_host *T = c->T;
+	if (shell > 8) return 0;                                                       /* N..Q vacancies: no tabulated yield */
+	if (shell >= 4 && !c->opt->use_M_lines) return 0;
+	if (sub_uniform(xs) > T->fluor_yield_corr[zi * 9 + shell]) return 0;
+	shell = coster_kronig(c, zi, shell, xs);
+	int line = line_from_shell(T, zi, shell, sub_uniform(xs));
+	if (!line) return 0;
+	*energy = T->line_energy[(size_t)zi * 384 + line];
+	if (*energy <= ENERGY_THRESHOLD) return 0;
+	return line;
+}
+
+typedef struct { int use_auger, use_rad; } cascade_opt_t;
+
+/* xmi_simulate_photon_cascade_auger (:2413-4594): p has energy 0 on entry (the yield check failed) */
+static void cascade_auger(ctx_t *c, photon_t *p, int shell, cascade_opt_t *co, photon_t *off, int *have_off) {
+	const xmb_tables_host *T = c->T;
+	if (shell < 0 || shell > 3) return;
+	const int zi = T->uniqZ[p->current_element];
+	const double *a = T->auger_rate + (size_t)zi * XMB_N_AUGER;
+	const int first = shell == 0 ? 0 : 240 + 135 * (shell - 1), n = shell == 0 ? 240 : 135;
+	substream_t xs;
+	sub_init(&xs, p->seed, p->g, p->n_interactions | p->gen, 4, 0);
+	const double r = sub_uniform(&xs);
+	double sumz = 0.0;
+	int found = -1;
+	for (int k = 0; k < n; k++) { sumz += a[first + k]; if (r < sumz) { found = k; break; } }
+	if (found < 0) return;
+	const int new1 = shell == 0 ? 1 + found / 30 : 4 + found / 27, new2 = shell == 0 ? 1 + found % 30 : 4 + found % 27;
+	/* the offspring starts as a copy of the parent (:4421-4440) */
+	photon_t o = *p;
+	double e1 = 0.0, e2 = 0.0;
+	int l1 = cascade_vacancy(c, zi, new1, &xs, &e1);
+	if (l1) {
+		co->use_auger = co->use_rad = 0;                                           /* :4452-4453 */
+		cascade_emit(c, p, l1, &xs);
+	}
+	substream_t ys;
+	sub_init(&ys, p->seed, p->g, p->n_interactions | p->gen, 4, 1);
+	int l2 = cascade_vacancy(c, zi, new2, &ys, &e2);
+	if (l2) {
+		cascade_emit(c, &o, l2, &ys);
+		*off = o;
+		*have_off = 1;
+	}
+}
+
+/* xmi_simulate_photon_cascade_radiative (:4596-4783): vacancy left behind by the emitted line */
+static void cascade_radiative(ctx_t *c, photon_t *p, int shell, int line, cascade_opt_t *co, photon_t *off, int *have_off) {
+	const xmb_tables_host *T = c->T;
+	int shell_new = -1;
+	if (shell == 0) { if (line >= 1 && line <= 8) shell_new = line; }             /* KL1..KM5 -> L1..M5 (lines 1..8) */
+	else if (shell >= 1 && shell <= 3 && c->opt->use_M_lines) {
+		const int base = shell == 1 ? XMB_L1M1 : shell == 2 ? XMB_L2M1 : XMB_L3M1;
+		if (line >= base && line <= base + 4) shell_new = 4 + (line - base);
+	} else return;
+	if (shell_new < 0) return;
+	if (shell_new >= 4 && !c->opt->use_M_lines) return;
+	const int zi = T->uniqZ[p->current_element];
+	substream_t xs;
+	sub_init(&xs, p->seed, p->g, p->n_interactions | p->gen, 5, 0);
+	double e = 0.0;
+	int l = cascade_vacancy(c, zi, shell_new, &xs, &e);
+	if (!l) return;
+	photon_t o = *p;
+	co->use_auger = co->use_rad = 0;                                               /* :4727-4728 */
+	cascade_emit(c, &o, l, &xs);
+	*off = o;
+	*have_off = 1;
+}
+
+static void do_photo_brute(ctx_t *c, photon_t *p, const double *sd, cascade_opt_t *co, photon_t *off, int *have_off) {
+	const xmb_tables_host *T = c->T;
+	int Z = p->current_element, zi = T->uniqZ[Z];
+	nodepos_t np = node_find(T, p->energy);
+	double photo_total = lerp_at(T->cs_photo_total + (size_t)zi * T->n_nodes, np);
+	double sumz = 0.0;
+	int max_shell = c->opt->use_M_lines ? 8 : 3, shell, shell_found = 0;
+	for (shell = 0; shell <= max_shell; shell++) {
+		sumz += lerp_at(T->cs_photo_partial + ((size_t)zi * 9 + shell) * T->n_nodes, np) / photo_total;
+		if (sd[0] < sumz) { shell_found = 1; break; }
+	}
+	if (!shell_found) { p->energy = 0.0; return; }
+	substream_t xs;
+	sub_init(&xs, p->seed, p->g, p->n_interactions | p->gen, 3, 0);
+	double u_phi = sub_uniform(&xs);
+	if (sub_uniform(&xs) > T->fluor_yield_corr[zi * 9 + shell]) {                  /* :2297-2319, :5335-5339 */
+		p->energy = 0.0;
+		if (co->use_auger) cascade_auger(c, p, shell, co, off, have_off);
+		return;
+	}
+	shell = coster_kronig(c, zi, shell, &xs);
+	int line = line_from_shell(T, zi, shell, sd[1]);
+	if (!line) { p->energy = 0.0; return; }
+	p->energy = T->line_energy[(size_t)zi * 384 + line];
+	{
+		nodepos_t lp = node_find(T, p->energy);
+		for (int i = 0; i < c->nL; i++) p->mus[i] = lerp_at(T->mu_layer + (size_t)i * T->n_nodes, lp);
+	}
+	update_dirv(p, acos(-2.0 * sd[2] + 1.0), 2.0 * M_PI * u_phi);
+	update_elecv(p);
+	p->hist_line[p->n_interactions] = -line;
+	p->hist_Z[p->n_interactions] = Z;
+	if (co->use_rad) cascade_radiative(c, p, shell, line, co, off, have_off);
+}
+
+/* xmi_simulate_photon, analogue branch.  Returns 1 if the photon reached the detector. */
+static int simulate_photon_brute(ctx_t *c, photon_t *p, cascade_opt_t *co, photon_t *off, int *have_off) {
+	const xmb_geometry *g = c->in->geometry;
+	const orc_derived *D = c->d;
+	const xmb_layer *layers = c->in->composition->layers;
+	for (;;) {
+		if (p->energy < ENERGY_THRESHOLD) return 0;                                /* :1229 */
+		int step_max, step_dir;
+		if (dot3(p->dirv, g->n_sample_orientation) > 0.0) { step_max = c->nL - 1; step_dir = 1; } else { step_max = 0; step_dir = -1; }
+		double b0[4], b1[4];
+		const int order = (p->n_interactions + 1) | p->gen;
+		draw_block(p->seed, p->g, order, 1, 0, 0, b0);
+		draw_block(p->seed, p->g, order, 1, 0, 1, b1);
+		const double interactionR = b0[0];
+		double blbs = 1.0, max_random_layer = 0.0, min_random_layer;
+		int inside = 0;
+		for (int i = p->current_layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {   /* :1278-1413 */
+			double pp[3] = {0.0, 0.0, step_dir == 1 ? D->Z_coord_end[i] : D->Z_coord_begin[i]}, inter[3];
+			if (!plane_line(pp, g->n_sample_orientation, p->coords, p->dirv, inter)) return 0;
+			double dist = dist3(p->coords, inter);
+			double temp_prod = -1.0 * dist * layers[i].density * p->mus[i];
+			double tempexp = exp(temp_prod);
+			min_random_layer = max_random_layer;
+			max_random_layer = max_random_layer - blbs * expm1(temp_prod);
+			if (interactionR <= max_random_layer) {
+				dist = -1.0 * log1p(-1.0 * (interactionR - min_random_layer) / blbs) / p->mus[i] / layers[i].density;
+				double old[3] = {p->coords[0], p->coords[1], p->coords[2]};
+				for (int k = 0; k < 3; k++) p->coords[k] += dist * p->dirv[k];       /* xmi_move_photon_with_dist */
+				int rv = check_detector_intersection(c, old, p->coords);
+				if (rv == DET_COLLIMATOR || rv == DET_BAD) return 0;
+				if (rv == DET_HIT) return 1;
+				p->current_layer = i;
+				inside = 1;
+				break;
+			}
+			int rv = check_detector_intersection(c, p->coords, inter);
+			if (rv == DET_COLLIMATOR || rv == DET_BAD) return 0;
+			if (rv == DET_HIT) return 1;
+			memcpy(p->coords, inter, sizeof(inter));
+			blbs = blbs * tempexp;
+		}
+		if (!inside) return check_photon_detector_hit(c, p);                       /* :1525-1533 */
+		if (p->n_interactions == c->n_int) return 0;                               /* :1536-1539 */
+		p->n_interactions++;
+		c->n_interactions_total++;
+		{
+			const xmb_layer *l = &layers[p->current_layer];
+			nodepos_t np = node_find(c->T, p->energy);
+			double thr = 0.0;
+			for (int i = 0; i < l->n_elements; i++) {
+				thr += l->weight[i] * cs_total(c, l->Z[i], np) / p->mus[p->current_layer];
+				if (b0[3] < thr || i == l->n_elements - 1) { p->current_element = l->Z[i]; p->current_element_index = i; break; }
+			}
+			int zi = c->T->uniqZ[p->current_element];
+			double pr = lerp_at(c->T->p_rayl + (size_t)zi * c->T->n_nodes, np);
+			double prc = lerp_at(c->T->p_rayl_compt + (size_t)zi * c->T->n_nodes, np);
+			if (b1[0] < pr) { p->last_interaction = RAYLEIGH; do_rayleigh(c, p, b1 + 1); }
+			else if (b1[0] < prc) { p->last_interaction = COMPTON; do_compton(c, p, b1 + 1); }
+			else { p->last_interaction = PHOTO; do_photo_brute(c, p, b1 + 1, co, off, have_off); }
+		}
+	}
+}
+
+/* Brute-force counterpart of orc_main_msim_range.  channels[(n_int+1)][nch] cumulative from the row of the
+ * photon's interaction count upwards (:470-485); brute[n_int][385][100] = Fortran brute_history(Z, slot, k) (:497-523).
+ * RAW sums (no live_time).  counters: [0] detector hits, [1] interactions, [2] offspring photons simulated. */
+uint64_t orc_main_msim_brute_range(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, const xmb_main_options *opt,
+                                   uint64_t seed, uint64_t g_begin, uint64_t g_end, int n_threads, double *channels, double *brute,
+                                   uint64_t *counters) {
+	segment_t *segs;
+	int nseg = build_segments(in, &segs);
+	int n_int = in->general->n_interactions_trajectory, nch = in->detector->nchannels, nL = in->composition->n_layers;
+	size_t nchn = (size_t)(n_int + 1) * nch, nbr = (size_t)n_int * 385 * 100;
+	memset(channels, 0, sizeof(double) * nchn);
+	memset(brute, 0, sizeof(double) * nbr);
+	if (n_threads < 1) n_threads = 1;
+	uint64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel num_threads(n_threads)
+	{
+		ctx_t c;
+		memset(&c, 0, sizeof(c));
+		c.in = in; c.d = d; c.T = T; c.opt = opt; c.cascade = 1; c.n_int = n_int; c.nch = nch; c.nL = nL;
+		double *ch = (double *)calloc(nchn, sizeof(double)), *br = (double *)calloc(nbr, sizeof(double));
+		uint64_t hits = 0, n_off = 0;
+#pragma omp for schedule(dynamic, 256)
+		for (uint64_t gidx = g_begin; gidx < g_end; gidx++) {
+			int s = 0;
+			while (s + 1 < nseg && gidx >= segs[s + 1].first) s++;
+			photon_t p, off;
+			orc_rng rng;
+			orc_rng_init(&rng, seed, gidx, ORC_TAG_HISTORY);
+			int skip, have_off = 0;
+			start_photon(&c, &p, &rng, &segs[s], gidx - segs[s].first, &skip);
+			p.seed = seed; p.g = gidx;
+			if (skip) continue;
+			cascade_opt_t co = {opt->use_cascade_auger, opt->use_cascade_radiative};
+			photon_t *cur = &p;
+			for (int gen = 0; gen < 2; gen++) {
+				int hit;
+				if (gen == 0) hit = simulate_photon_brute(&c, cur, &co, &off, &have_off);
+				else {
+					cascade_opt_t none = {0, 0};
+					int dummy = 0;
+					photon_t unused;
+					off.gen = GEN_BIT;
+					n_off++;
+					cur = &off;
+					hit = simulate_photon_brute(&c, cur, &none, &unused, &dummy);
+				}
+				if (hit) {                                                         /* :443-523 */
+					hits++;
+					int channel = cur->energy >= ENERGY_THRESHOLD ? (int)((cur->energy - in->detector->zero) / in->detector->gain) : -1;
+					if (channel >= 0 && channel < nch)
+						for (int k = cur->n_interactions; k <= n_int; k++) ch[(size_t)k * nch + channel] += cur->weight;
+					if (cur->n_interactions > 0) {
+						int k = cur->n_interactions, hl = cur->hist_line[k], Zel = cur->hist_Z[k];
+						int slot = hl < 0 ? -hl : hl == RAYLEIGH ? 384 : hl == COMPTON ? 385 : 0;
+						if (slot) br[((size_t)(k - 1) * 385 + (slot - 1)) * 100 + (Zel - 1)] += cur->weight;
+					}
+				}
+				if (!have_off) break;
+			}
+		}
+#pragma omp critical
+		{
+			for (size_t i = 0; i < nchn; i++) channels[i] += ch[i];
+			for (size_t i = 0; i < nbr; i++) brute[i] += br[i];
+			c0 += hits; c1 += c.n_interactions_total; c2 += n_off;
+		}
+		free(ch); free(br);
+	}
+	if (counters) { counters[0] = c0; counters[1] = c1; counters[2] = c2; }
+	free(segs);
+	return g_end - g_begin;
 }

@@ -94,3 +94,18 @@ def ebel_like(n_intervals=1000, n_photons_interval=10000, n_photons_line=10000, 
     d.gain = 0.025
     d.zero = 0.0
     return d
+
+
+def close_detector(n_photons=200000, n_int=2):
+    """A geometry in which analogue (brute-force) photons actually reach the detector: 3 cm2 window 2 cm from a
+    45-degree steel-like slab, no collimator, one 20 keV line -- solid angle ~ 5 % of 4 pi."""
+    return x.InputD(
+        n_photons_line=n_photons, n_interactions_trajectory=n_int,
+        layers=[x.LayerD([24, 26, 28], [0.18, 0.72, 0.10], 7.9, 0.05)],
+        reference_layer=1, d_sample_source=100.0, n_sample_orientation=[0, 1, 1],
+        p_detector_window=[0, -2, 100], n_detector_orientation=[0, 1, 0], area_detector=3.0,
+        collimator_height=0.0, collimator_diameter=0.0, d_source_slit=100.0, slit_size_x=0.001, slit_size_y=0.001,
+        discrete=[x.DiscreteD(20.0, 1e9, 1e9)],
+        det_layers=[x.LayerD([4], [1.0], 1.85, 0.002)], detector_type=0, live_time=1.0, pulse_width=1e-5,
+        gain=0.02, zero=0.0, fano=0.12, noise=0.1, nchannels=2048,
+        crystal_layers=[x.LayerD([14], [1.0], 2.33, 0.5)])

@@ -118,7 +118,8 @@ class TablesHost(C.Structure):
                 ("n_q", C.c_int), ("q_max", C.c_double), ("ff", c_double_p), ("sf", c_double_p),
                 ("fluor_yield", c_double_p), ("fluor_yield_corr", c_double_p), ("cos_kron", c_double_p),
                 ("rad_rate", c_double_p), ("line_energy", c_double_p), ("edge_energy", c_double_p),
-                ("n_layers", C.c_int), ("mu_layer", c_double_p), ("exc_murhod", c_double_p)]
+                ("n_layers", C.c_int), ("mu_layer", c_double_p), ("exc_murhod", c_double_p),
+                ("auger_rate", c_double_p)]
 
 
 class XrlProvider(C.Structure):
@@ -132,7 +133,8 @@ class XrlProvider(C.Structure):
                 ("CS_Rayl", C.CFUNCTYPE(_D, _I, _D)), ("CS_Compt", C.CFUNCTYPE(_D, _I, _D)),
                 ("FF_Rayl", C.CFUNCTYPE(_D, _I, _D)), ("SF_Compt", C.CFUNCTYPE(_D, _I, _D)),
                 ("ComptonProfile", C.CFUNCTYPE(_D, _I, _D)),
-                ("VacancyCS", C.CFUNCTYPE(_D, _I, _I, _D, _I, c_double_p))]
+                ("VacancyCS", C.CFUNCTYPE(_D, _I, _I, _D, _I, c_double_p)),
+                ("AugerRate", C.CFUNCTYPE(_D, _I, _I, _I, _I))]
 
 
 class MsimEx(C.Structure):
@@ -196,6 +198,8 @@ def lib():
     L.xmb_msim_device_limbs.restype = C.c_int
     L.xmb_msim_workload_stats.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.c_int]
     L.xmb_msim_workload_stats.restype = C.c_int
+    L.xmb_msim_brute_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
+    L.xmb_msim_brute_counters.restype = C.c_int
     pp = C.POINTER(c_double_p)
     L.xmb_detector_convolute_all.argtypes = [vp, vp, pp, pp, c_double_p, c_double_p, C.POINTER(MainOptions),
                                              C.POINTER(EscapeRatios), C.c_int, C.c_int]

@@ -30,7 +30,7 @@ struct XmbHdf5F {
 	std::vector<double> atomic_weight, node_E, cs_total, cs_photo_total, p_rayl, p_rayl_compt,
 	    cs_photo_partial, cs_vacancy, icdf_E, icdf_R, rayl_theta_icdf, compt_theta_icdf, phi_T,
 	    phi_icdf, cp_R, cp_icdf, ff, sf, fluor_yield, fluor_yield_corr, cos_kron, rad_rate,
-	    line_energy, edge_energy, mu_layer, exc_murhod;
+	    line_energy, edge_energy, mu_layer, exc_murhod, auger_rate;
 	double e_max = 0.0;
 	XmbDeviceTables *dev = nullptr;   // lazily built device-side layouts (device.cu)
 };

@@ -428,13 +428,18 @@ __device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x,
 }
 
 // ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------
-// ESC: escape-ratio mode (the fluorescence yield goes to weight_escape, src/xmi_variance_reduction.F90:697-750).
-// out_type: 1 Rayleigh, 2 Compton, 3 photo-electric; out_zi: element slot; out_line: |line macro| or 0.
-template <int NL, bool ESC>
+// MODE 0: forced detection (the fluorescence yield multiplies the weight); 1: escape-ratio mode (it goes to
+// weight_escape, src/xmi_variance_reduction.F90:697-750); 2: brute force (analogue yield check, :2297-2319 / :5325-5350:
+// on failure the energy is zeroed and out_type = 4 tells the caller to run the Auger cascade on out_shell).
+// out_type: 1 Rayleigh, 2 Compton, 3 photo-electric (4: Auger); out_zi: element slot; out_line: |line macro| or 0;
+// out_shell: the ionised shell, after Coster-Kronig when a line was emitted.
+template <int NL, int MODE>
 __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photon &p, uint64_t g, int order, double *mus, int T,
-                                                   uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line) {
+                                                   uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line,
+                                                   int &out_shell) {
 	const int nL = NL > 0 ? NL : P.nL;
 	out_line = 0;
+	out_shell = -1;
 	const XmbLayerDev lay = P.layers[p.layer];
 	const NodePos ep = node_find(P, p.energy);
 	const uint4 b1 = draw_block(P.seed, g, order, 1, 0, 1);   // {interaction type, s0, s1, s2}
@@ -508,11 +513,13 @@ for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
 		if (shell < 0) { p.energy = 0.0; }
 		else {
 			// (the reference draws one unused number here, xmi_variance_reduction.F90:737; not reproduced)
-			if (ESC) weight_escape *= P.fluor_yield_corr[zi * 9 + shell];   // escape-ratio mode, src/xmi_variance_reduction.F90:697-750
-			else p.weight *= P.fluor_yield_corr[zi * 9 + shell];
+			if (MODE == 1) weight_escape *= P.fluor_yield_corr[zi * 9 + shell];
+			else if (MODE == 0) p.weight *= P.fluor_yield_corr[zi * 9 + shell];
 			SubStream xs;
 			xs.init(P.seed, g, order, 3, 0);
 			const double u_phi = xs.uniform();
+			out_shell = shell;
+			if (MODE == 2 && xs.uniform() > P.fluor_yield_corr[zi * 9 + shell]) { p.energy = 0.0; out_type = 4; return; }
 			// Coster-Kronig (:5184-5323)
 			const double *ck = P.cos_kron + zi * XMB_N_CK;
 			while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
@@ -534,6 +541,7 @@ for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
 			if (!line) p.energy = 0.0;
 			else {
 				out_line = line;
+				out_shell = shell;
 				p.energy = P.line_energy[(size_t)zi * 384 + line];
 				const NodePos lp = node_find(P, p.energy);
 				XMB_UNROLL_NL
@@ -832,8 +840,8 @@ for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
 			flush_staged(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, tid, T);
 			if (p.alive) {
 				double we_unused = 0.0;
-				int t_unused, z_unused, l_unused;
-				select_and_scatter<NL, false>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused);
+				int t_unused, z_unused, l_unused, s_unused;
+				select_and_scatter<NL, 0>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused);
 			}
 		}
 		// ---- compaction: survivors go, densely packed, to the queue of the next order -------------------
@@ -878,6 +886,295 @@ __global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, uns
 }
 
 // =====================================================================================================
+// Brute-force mode (options->use_variance_reduction = 0): analogue random walk; a photon is scored only
+// when it reaches the detector (src/xmi_main.F90:1229-1416, :1525-1533, :1920-1984; detector / collimator
+// segment tests src/xmi_aux_f.F90:1622-1833); Auger and radiative cascades spawn one offspring photon
+// (src/xmi_main.F90:2413-4783), walked by the same thread after its parent.
+// Random-number addresses: counter word 2 = (gen<<31)|(order<<20)|(stage<<16)|(elem<<8)|block, gen = 1 for
+// the offspring's own walk; stage 1 block 0 {free path, -, -, atom}, block 1 {type, s0, s1, s2}; stage 3
+// Doppler trials / photo (phi, yield check, Coster-Kronig hops); stage 4 elem 0 Auger transition + the
+// parent's re-emission, elem 1 the offspring's; stage 5 radiative cascade.
+// Deposits are rare (detector hits): exact 128-bit integer adds straight into the global accumulators,
+// rows 0..n_int (row = interactions before detection), [nch channels | history slots].
+// =====================================================================================================
+#define XMB_GEN_BIT 0x800
+enum { XMB_DET_NONE = 0, XMB_DET_HIT = 1, XMB_DET_COLLIMATOR = 2, XMB_DET_BAD = 3 };
+
+struct XmbBruteParams {
+	int use_auger, use_rad;
+	double collimator_height, collimator_radius, half_apex, vertex_x, vertex_y, vertex_z;
+	int collimator_present;
+	const int *line_slot;        // [nZ][384]: compact history slot of a line, -1 = not an active line
+	const double *auger_rate;    // [nZ][XMB_N_AUGER]
+};
+
+__device__ __forceinline__ void add128(unsigned long long *acc, size_t slot, unsigned long long v) {
+	const unsigned long long old = atomicAdd(&acc[2 * slot], v);
+	if (old + v < old) atomicAdd(&acc[2 * slot + 1], 1ULL);   // carry out of the low word: exact, order independent
+}
+
+// detector frame: x along the detector normal (n_detector_orientation_inverse * (r - p_detector_window))
+__device__ __forceinline__ void to_detector_frame(const XmbHistParams &P, double x, double y, double z, bool point, double *o) {
+	const double *B = P.ndo_inv;
+	if (point) { x -= P.p_window[0]; y -= P.p_window[1]; z -= P.p_window[2]; }
+	o[0] = B[0] * x + B[1] * y + B[2] * z;
+	o[1] = B[3] * x + B[4] * y + B[5] * z;
+	o[2] = B[6] * x + B[7] * y + B[8] * z;
+}
+
+// xmi_check_detector_intersection (src/xmi_aux_f.F90:1622-1833) for the segment b -> e (lab coordinates)
+__device__ int check_detector_intersection(const XmbHistParams &P, const XmbBruteParams &B, double bx, double by, double bz,
+                                           double ex, double ey, double ez) {
+	double b[3], e[3];
+	to_detector_frame(P, bx, by, bz, true, b);
+	to_detector_frame(P, ex, ey, ez, true, e);
+	const double d0 = e[0] - b[0], d1 = e[1] - b[1], d2 = e[2] - b[2];
+	if (!B.collimator_present) {
+		if (b[0] * e[0] > 0) return XMB_DET_NONE;
+		// (the reference assigns the scalar norm to the direction here, :1662; the segment direction is used instead)
+		if (d0 == 0.0) return XMB_DET_NONE;
+		const double t = (0.0 - e[0]) / d0;
+		const double iy = t * d1 + e[1], iz = t * d2 + e[2];
+		if (sqrt(iy * iy + iz * iz) <= P.detector_radius) return d0 >= 0.0 ? XMB_DET_BAD : XMB_DET_HIT;
+		return XMB_DET_NONE;
+	}
+	if (d0 == 0.0) return XMB_DET_NONE;
+	const double t_begin = (b[0] - e[0]) / d0, t_end = 0.0;
+	const double l0 = e[0] - B.vertex_x, l1 = e[1] - B.vertex_y, l2 = e[2] - B.vertex_z;
+	const double ch = cos(B.half_apex);
+	const double cos2theta = ch * ch;
+	const double M0 = 1.0 - cos2theta, M1 = -cos2theta;
+	const double c2 = (d0 * M0) * d0 + (d1 * M1) * d1 + (d2 * M1) * d2;
+	const double c1 = (d0 * M0) * l0 + (d1 * M1) * l1 + (d2 * M1) * l2;
+	const double c0 = (l0 * M0) * l0 + (l1 * M1) * l1 + (l2 * M1) * l2;
+	const double disc = c1 * c1 - c0 * c2;
+	if (disc < 0.0) return XMB_DET_NONE;
+	const double sq = sqrt(disc);
+	const double t1 = (-c1 + sq) / c2, t2 = (-c1 - sq) / c2;
+	const double X1x = e[0] + t1 * d0, X2x = e[0] + t2 * d0;
+	const bool v1 = -(X1x - B.vertex_x) >= 0.0, v2 = -(X2x - B.vertex_x) >= 0.0;
+	const double tmax = fmax(t_begin, t_end), tmin = fmin(t_begin, t_end);
+	const bool in1 = t1 <= tmax && t1 >= tmin && X1x <= B.collimator_height;
+	const bool in2 = t2 <= tmax && t2 >= tmin && X2x <= B.collimator_height;
+	if (!v1 && !v2) return XMB_DET_NONE;
+	if (v1 && v2) return (in1 || in2) ? XMB_DET_COLLIMATOR : XMB_DET_NONE;
+	if (v1 ? in1 : in2) return XMB_DET_COLLIMATOR;
+	const double t = (0.0 - e[0]) / d0;
+	const double iy = t * d1 + e[1], iz = t * d2 + e[2];
+	const double db = sqrt(b[0] * b[0] + (b[1] - iy) * (b[1] - iy) + (b[2] - iz) * (b[2] - iz));
+	const double de = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+	if (sqrt(iy * iy + iz * iz) <= P.detector_radius && db <= de) return d0 >= 0.0 ? XMB_DET_BAD : XMB_DET_HIT;
+	return XMB_DET_NONE;
+}
+
+// xmi_check_photon_detector_hit (src/xmi_main.F90:1920-1984): a photon that left the sample
+__device__ bool check_photon_detector_hit(const XmbHistParams &P, const XmbBruteParams &B, const Photon &p) {
+	if (p.dx * P.n_detector[0] + p.dy * P.n_detector[1] + p.dz * P.n_detector[2] >= 0.0) return false;
+	double dd[3], cd[3];
+	to_detector_frame(P, p.dx, p.dy, p.dz, false, dd);
+	to_detector_frame(P, p.cx, p.cy, p.cz, true, cd);
+	if (dd[0] == 0.0) return false;
+	double t = (0.0 - cd[0]) / dd[0];
+	double ix = t * dd[0] + cd[0], iy = t * dd[1] + cd[1], iz = t * dd[2] + cd[2];
+	if (sqrt(ix * ix + iy * iy + iz * iz) > P.detector_radius) return false;
+	if (!B.collimator_present) return true;
+	t = (B.collimator_height - cd[0]) / dd[0];
+	iy = t * dd[1] + cd[1]; iz = t * dd[2] + cd[2];
+	return !(sqrt(iy * iy + iz * iz) > B.collimator_radius);
+}
+
+__device__ __forceinline__ int ck_walk(const XmbHistParams &P, int zi, int shell, SubStream &xs) {   // xmi_coster_kronig_check (:5184-5323)
+	const double *ck = P.cos_kron + zi * XMB_N_CK;
+	while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
+		const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
+		const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
+		const double rr = xs.uniform();
+		double sz = 0.0;
+		int found = -1;
+		for (int t = 0; t < ntr; t++) { sz += ck[first + t]; if (rr < sz) { found = t; break; } }
+		if (found < 0) break;
+		shell = shell + 1 + found;
+	}
+	return shell;
+}
+
+// one vacancy of a cascade: yield check (:5325-5350), Coster-Kronig, line (:5352-5437); returns the line or 0
+__device__ int cascade_vacancy(const XmbHistParams &P, int zi, int shell, SubStream &xs) {
+	if (shell > 8) return 0;
+	if (shell >= 4 && !P.use_M_lines) return 0;
+	if (xs.uniform() > P.fluor_yield_corr[zi * 9 + shell]) return 0;
+	shell = ck_walk(P, zi, shell, xs);
+	const double rl = xs.uniform();
+	double sl = 0.0;
+	int line = 0;
+	const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
+	for (int l = lf; l <= ll; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
+	if (!line) return 0;
+	if (P.line_energy[(size_t)zi * 384 + line] <= ENERGY_THRESHOLD) return 0;
+	return line;
+}
+
+// isotropic re-emission of a cascade photon (:4455-4481, :4733-4767)
+template <int NL>
+__device__ void cascade_emit(const XmbHistParams &P, Photon &q, double *mus, int zi, int line, SubStream &xs) {
+	const int nL = NL > 0 ? NL : P.nL;
+	q.energy = P.line_energy[(size_t)zi * 384 + line];
+	const NodePos lp = node_find(P, q.energy);
+	for (int i = 0; i < nL; i++) mus[i] = row_lerp(P, lp, i);
+	q.theta = acos(2.0 * xs.uniform() - 1.0);
+	q.phi = 2.0 * M_PI * xs.uniform();
+	q.dx = sin(q.theta) * cos(q.phi); q.dy = sin(q.theta) * sin(q.phi); q.dz = cos(q.theta);
+	const double r = 2.0 * M_PI * xs.uniform();
+	q.ex = cos(r); q.ey = sin(r); q.ez = 0.0;
+	const double cosalfa = q.ex * q.dx + q.ey * q.dy + q.ez * q.dz;
+	const double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+	q.ex = c_ae * q.ex + c_be * q.dx; q.ey = c_ae * q.ey + c_be * q.dy; q.ez = c_ae * q.ez + c_be * q.dz;
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ XmbHistParams P, const XmbBruteParams B) {
+	const int nL = NL > 0 ? NL : P.nL;
+	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
+	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
+	unsigned long long n_inter = 0, n_hits = 0, n_off = 0, n_noslot = 0;
+	for (uint64_t g = P.g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.g_end; g += (uint64_t)gridDim.x * blockDim.x) {
+		Photon p, off;
+		double mus[NLA], off_mus[NLA];
+		{
+			XmbRng rng;
+			rng.init(P.seed, g, XMB_TAG_HISTORY);
+			start_photon<NL>(P, p, rng, g, mus, 1);
+		}
+		if (!p.alive) continue;
+		bool co_auger = B.use_auger != 0, co_rad = B.use_rad != 0, have_off = false;
+		int last_type = 0, last_zi = 0, last_line = 0, off_zi = 0, off_line = 0;
+		for (int gen = 0; gen < 2; gen++) {
+			const int gen_bit = gen ? XMB_GEN_BIT : 0;
+			bool hit = false;
+			// ---- xmi_simulate_photon, analogue branch -------------------------------------------------------
+			for (;;) {
+				if (p.energy < ENERGY_THRESHOLD) break;
+				int step_max, step_dir;
+				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
+				else { step_max = 0; step_dir = -1; }
+				const int order = (p.n_interactions + 1) | gen_bit;
+				const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);
+				const double interactionR = xmb_u01(b0.x);
+				double blbs = 1.0, max_random_layer = 0.0;
+				bool inside = false, stop = false;
+				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+					double nx = p.cx, ny = p.cy, nz = p.cz, dist;
+					if (!step_to_plane(P, nx, ny, nz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { stop = true; break; }
+					const double temp_prod = -1.0 * dist * P.layers[i].density * mus[i];
+					const double tempexp = exp(temp_prod);
+					const double min_random_layer = max_random_layer;
+					max_random_layer = max_random_layer - blbs * expm1(temp_prod);
+					if (interactionR <= max_random_layer) {
+						dist = -1.0 * log1p(-1.0 * (interactionR - min_random_layer) / blbs) / mus[i] / P.layers[i].density;
+						const double ox = p.cx, oy = p.cy, oz = p.cz;
+						p.cx += dist * p.dx; p.cy += dist * p.dy; p.cz += dist * p.dz;
+						const int rv = check_detector_intersection(P, B, ox, oy, oz, p.cx, p.cy, p.cz);
+						if (rv == XMB_DET_COLLIMATOR || rv == XMB_DET_BAD) { stop = true; break; }
+						if (rv == XMB_DET_HIT) { hit = true; stop = true; break; }
+						p.layer = i;
+						inside = true;
+						break;
+					}
+					const int rv = check_detector_intersection(P, B, p.cx, p.cy, p.cz, nx, ny, nz);
+					if (rv == XMB_DET_COLLIMATOR || rv == XMB_DET_BAD) { stop = true; break; }
+					if (rv == XMB_DET_HIT) { hit = true; stop = true; break; }
+					p.cx = nx; p.cy = ny; p.cz = nz;
+					blbs = blbs * tempexp;
+				}
+				if (stop) break;
+				if (!inside) { hit = check_photon_detector_hit(P, B, p); break; }   // :1525-1533
+				if (p.n_interactions == P.n_int) break;                                // :1536-1539
+				p.n_interactions++;
+				n_inter++;
+				double we_unused = 0.0;
+				int shell = -1;
+				select_and_scatter<NL, 2>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
+				if (last_type == 4) {
+					// ---- xmi_simulate_photon_cascade_auger (:2413-4594): the primary vacancy decays without radiation
+					last_type = 3;
+					if (co_auger && shell >= 0 && shell <= 3) {
+						const double *a = B.auger_rate + (size_t)last_zi * XMB_N_AUGER;
+						const int first = shell == 0 ? 0 : 240 + 135 * (shell - 1), n = shell == 0 ? 240 : 135;
+						SubStream xs;
+						xs.init(P.seed, g, order, 4, 0);
+						const double r = xs.uniform();
+						double sumz = 0.0;
+						int found = -1;
+						for (int k = 0; k < n; k++) { sumz += a[first + k]; if (r < sumz) { found = k; break; } }
+						if (found >= 0) {
+							const int new1 = shell == 0 ? 1 + found / 30 : 4 + found / 27, new2 = shell == 0 ? 1 + found % 30 : 4 + found % 27;
+							off = p;   // the offspring starts as a copy of the parent (:4421-4440)
+							const int l1 = cascade_vacancy(P, last_zi, new1, xs);
+							if (l1) { co_auger = co_rad = false; last_line = l1; cascade_emit<NL>(P, p, mus, last_zi, l1, xs); }
+							SubStream ys;
+							ys.init(P.seed, g, order, 4, 1);
+							const int l2 = cascade_vacancy(P, last_zi, new2, ys);
+							if (l2) { cascade_emit<NL>(P, off, off_mus, last_zi, l2, ys); have_off = true; off_zi = last_zi; off_line = l2; }
+						}
+					}
+				} else if (last_type == 3 && last_line && co_rad) {
+					// ---- xmi_simulate_photon_cascade_radiative (:4596-4783): the vacancy the emitted line left behind
+					int shell_new = -1;
+					if (shell == 0) { if (last_line >= 1 && last_line <= XMB_KM5) shell_new = last_line; }
+					else if (shell >= 1 && shell <= 3 && P.use_M_lines) {
+						const int base = shell == 1 ? XMB_L1M1 : shell == 2 ? XMB_L2M1 : XMB_L3M1;
+						if (last_line >= base && last_line <= base + 4) shell_new = 4 + (last_line - base);
+					}
+					if (shell_new >= 0 && !(shell_new >= 4 && !P.use_M_lines)) {
+						SubStream xs;
+						xs.init(P.seed, g, order, 5, 0);
+						const int l = cascade_vacancy(P, last_zi, shell_new, xs);
+						if (l) {
+							off = p;
+							co_auger = co_rad = false;
+							cascade_emit<NL>(P, off, off_mus, last_zi, l, xs);
+							have_off = true; off_zi = last_zi; off_line = l;
+						}
+					}
+				}
+			}
+			// ---- scoring (src/xmi_main.F90:443-523) -------------------------------------------------------------
+			if (hit) {
+				n_hits++;
+				const unsigned long long fx = to_fixed(p.weight, P.counters);
+				const int k = p.n_interactions;
+				if (p.energy >= ENERGY_THRESHOLD) {
+					const int ch = (int)((p.energy - P.zero) / P.gain);
+					if (ch >= 0 && ch < P.nch) add128(P.acc, (size_t)k * acc_row + ch, fx);
+				}
+				if (k > 0) {
+					int slot = -1;
+					if (last_type == 1) slot = P.hist_base[last_zi];
+					else if (last_type == 2) slot = P.hist_base[last_zi] + 1;
+					else if (last_type == 3 && last_line) slot = B.line_slot[(size_t)last_zi * 384 + last_line];
+					if (slot >= 0) add128(P.acc, (size_t)k * acc_row + P.nch + slot, fx);
+					else n_noslot++;
+				}
+			}
+			if (!have_off || gen == 1) break;
+			// walk the offspring next (its cascades are switched off, :4509-4511, :4729-4731)
+			p = off;
+			for (int i = 0; i < nL; i++) mus[i] = off_mus[i];
+			last_type = 3; last_zi = off_zi; last_line = off_line;
+			co_auger = co_rad = false;
+			n_off++;
+		}
+	}
+	n_inter = warp_sum_u64(n_inter); n_hits = warp_sum_u64(n_hits); n_off = warp_sum_u64(n_off); n_noslot = warp_sum_u64(n_noslot);
+	if ((threadIdx.x & 31) == 0) {
+		if (n_inter) atomicAdd(&P.counters[1], n_inter);
+		if (n_hits) atomicAdd(&P.counters[3], n_hits);
+		if (n_off) atomicAdd(&P.counters[4], n_off);
+		if (n_noslot) atomicAdd(&P.counters[5], n_noslot);
+	}
+}
+
+// =====================================================================================================
 // Host side: device layouts, launch, exact reduction epilogue.
 // =====================================================================================================
 struct XmbDeviceTables {
@@ -897,6 +1194,9 @@ struct XmbDeviceTables {
 	size_t acc_slots = 0;
 	double *queue = nullptr;
 	size_t queue_doubles = 0;
+	int *line_slot = nullptr;          // [nZ][384] compact history slot of a line (brute-force scoring)
+	double *auger_rate = nullptr;      // [nZ][XMB_N_AUGER]
+	unsigned long long brute_counters[8] = {0};
 	unsigned long long layer_interactions[XMB_MAX_LAYERS] = {0};
 	~XmbDeviceTables() {
 		for (void *p : allocs) cudaFree(p);
@@ -1072,6 +1372,12 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	P.rec_mu = upload(D, rec_mu.data(), rec_mu.size(), ok);
 	P.rec_slot = upload(D, D->rec_slot.data(), D->rec_slot.size(), ok);
 	P.hist_base = upload(D, D->hist_base.data(), nZ, ok);
+	{
+		std::vector<int> ls((size_t)nZ * 384, -1);
+		for (int r = 0; r < D->n_rec; r++) ls[(size_t)D->rec_zi[r] * 384 + D->rec_line[r]] = D->rec_slot[r];
+		D->line_slot = upload(D, ls.data(), ls.size(), ok);
+		D->auger_rate = upload(D, T.auger_rate, (size_t)nZ * XMB_N_AUGER, ok);
+	}
 	// ---- source segments (src/xmi_main.F90:319-338, :579-601) --------------------------------------------------
 	const xmb_excitation &exc = *I.excitation;
 	const xmb_general &gen = *I.general;
@@ -1136,10 +1442,10 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	XmbInputF *in = xmb_as_input(inputF);
 	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
 	if (!in || !h || !in->inited || !options || !ex || !accum || !n_slots) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
-	if (!options->use_variance_reduction) { xmb_set_error("brute-force mode (use_variance_reduction=0) is not implemented on the GPU path"); return 0; }
+	const bool brute = !options->use_variance_reduction;
 	if (options->use_advanced_compton) { xmb_set_error("use_advanced_compton is not implemented on the GPU path"); return 0; }
 	if (options->escape_ratios_mode) { xmb_set_error("escape_ratios_mode is not implemented on the GPU path"); return 0; }
-	if (!sa || !sa->solid_angles) { xmb_set_error("variance reduction needs a solid-angle grid"); return 0; }
+	if (!brute && (!sa || !sa->solid_angles)) { xmb_set_error("variance reduction needs a solid-angle grid"); return 0; }
 	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: xmb_main_msim has no CPU fallback"); return 0; }
 	if (ex->device >= 0) XMB_CUDA_OK(cudaSetDevice(ex->device));
 	int dev = 0;
@@ -1152,15 +1458,15 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	}
 	XmbHistParams P = D->P;
 	// solid-angle grid: an argument of the call -> copied host->device every call
-	const size_t nsa = (size_t)sa->grid_dims_r_n * sa->grid_dims_theta_n;
-	if (D->sa_cap < nsa || !D->sa_grid) {
+	const size_t nsa = brute ? 0 : (size_t)sa->grid_dims_r_n * sa->grid_dims_theta_n;
+	if (!brute && (D->sa_cap < nsa || !D->sa_grid)) {
 		cudaFree(D->sa_grid); cudaFree(D->sa_r); cudaFree(D->sa_t);
 		XMB_CUDA_OK(cudaMalloc(&D->sa_grid, sizeof(double) * nsa));
 		XMB_CUDA_OK(cudaMalloc(&D->sa_r, sizeof(double) * sa->grid_dims_r_n));
 		XMB_CUDA_OK(cudaMalloc(&D->sa_t, sizeof(double) * sa->grid_dims_theta_n));
 		D->sa_cap = nsa;
 	}
-	const bool resident = ex->keep_on_device && D->sa_host == sa->solid_angles && D->sa_n == nsa;
+	const bool resident = brute || (ex->keep_on_device && D->sa_host == sa->solid_angles && D->sa_n == nsa);
 	if (!resident) {
 		XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
 		XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * sa->grid_dims_r_n, cudaMemcpyHostToDevice));
@@ -1168,9 +1474,9 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		D->sa_host = sa->solid_angles; D->sa_n = nsa;
 	}
 	P.sa_grid = D->sa_grid; P.sa_r_vals = D->sa_r; P.sa_t_vals = D->sa_t;
-	P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n;
-	// accumulators
-	const size_t slots = (size_t)P.n_int * ((size_t)P.nch + P.n_hist_slots);
+	if (!brute) { P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n; }
+	// accumulators: one row per interaction order (brute force: rows 0..n_int, row = interactions before detection)
+	const size_t slots = (size_t)(P.n_int + (brute ? 1 : 0)) * ((size_t)P.nch + P.n_hist_slots);
 	if (D->acc_slots != slots) {
 		cudaFree(D->acc); cudaFree(D->limbs); cudaFree(D->counters);
 		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 2 * slots));
@@ -1194,6 +1500,49 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	// launch
 	int sms = 148, occ = 1;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (brute) {
+		XmbBruteParams B{};
+		B.use_auger = options->use_cascade_auger ? 1 : 0; B.use_rad = options->use_cascade_radiative ? 1 : 0;
+		B.collimator_present = in->der.collimator_present; B.collimator_height = in->der.collimator_height;
+		B.collimator_radius = in->der.collimator_radius; B.half_apex = in->der.half_apex;
+		B.vertex_x = in->der.vertex[0]; B.vertex_y = in->der.vertex[1]; B.vertex_z = in->der.vertex[2];
+		B.line_slot = D->line_slot; B.auger_rate = D->auger_rate;
+		const int bt = 256;
+		const uint64_t want = (ex->n_histories + bt - 1) / bt;
+		const unsigned bg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sms * 16));
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0);
+		if (ex->n_histories > 0) {
+			switch (P.nL) {
+			case 1: xmb_brute_kernel<1><<<bg, bt>>>(P, B); break;
+			case 2: xmb_brute_kernel<2><<<bg, bt>>>(P, B); break;
+			case 3: xmb_brute_kernel<3><<<bg, bt>>>(P, B); break;
+			default: xmb_brute_kernel<0><<<bg, bt>>>(P, B); break;
+			}
+		}
+		cudaEventRecord(e1);
+		xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
+		XMB_CUDA_OK(cudaGetLastError());
+		XMB_CUDA_OK(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
+		ex->kernel_ms = ms;
+		ex->n_launches = (ex->n_histories > 0 ? 1 : 0) + 1;
+		unsigned long long cnt[8];
+		XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+		for (int i = 0; i < 8; i++) D->brute_counters[i] = cnt[i];
+		ex->n_interactions = cnt[1];
+		if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
+		if (cnt[5] && options->verbose) fprintf(stderr, "detected photons of lines without a history slot: %llu\n", cnt[5]);
+		*n_slots = slots;
+		if (ex->keep_on_device) { *accum = nullptr; return 1; }
+		uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
+		XMB_CUDA_OK(cudaMemcpy(out, D->limbs, sizeof(uint64_t) * 2 * slots, cudaMemcpyDeviceToHost));
+		*accum = out;
+		return 1;
+	}
 	// threads per CTA: as many as the per-thread shared arrays (2 nL doubles) allow within 200 KB
 	int threads = HIST_THREADS;
 	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
@@ -1307,8 +1656,8 @@ extern "C" int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, co
 	if (!D) return 0;
 	const int n_int = D->P.n_int, nch = D->P.nch;
 	const size_t row = (size_t)nch + D->n_hist_slots;
-	if (n_slots != (size_t)n_int * row) { xmb_set_error("xmb_main_msim_finish: slot count mismatch"); return 0; }
-	(void)0;
+	const bool brute = !options->use_variance_reduction;
+	if (n_slots != (size_t)(n_int + (brute ? 1 : 0)) * row) { xmb_set_error("xmb_main_msim_finish: slot count mismatch"); return 0; }
 	const double live_time = in->in.detector->live_time;
 	const double scale = D->W_max * live_time;
 	auto slot128 = [&](size_t i) { return (unsigned __int128)accum[2 * i] + ((unsigned __int128)accum[2 * i + 1] << 48); };
@@ -1321,6 +1670,25 @@ extern "C" int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, co
 	double *br = (double *)calloc((size_t)100 * 385 * n_int, sizeof(double));
 	std::vector<unsigned __int128> cum(nch, 0), cur(nch);
 	const xmb_tables_host &T = h->view;
+	if (brute) {
+		// rows 0..n_int hold what photons with that many interactions left in the detector: channels(k:, ch) += w
+		// (src/xmi_main.F90:470-485); history slots go to brute_history(Z, slot, k) (:497-523)
+		for (int k = 0; k <= n_int; k++) {
+			for (int c = 0; c < nch; c++) { cum[c] += slot128((size_t)k * row + c); ch[(size_t)k * nch + c] = to_double(cum[c]); }
+			if (k == 0) continue;
+			for (int r = 0; r < D->n_rec; r++)
+				br[((size_t)(T.Z[D->rec_zi[r]] - 1) * 385 + (D->rec_line[r] - 1)) * n_int + (k - 1)] =
+				    to_double(slot128((size_t)k * row + nch + D->rec_slot[r]));
+			for (int z = 0; z < T.nZ; z++) {
+				br[((size_t)(T.Z[z] - 1) * 385 + 383) * n_int + (k - 1)] = to_double(slot128((size_t)k * row + nch + D->hist_base[z] + 0));
+				br[((size_t)(T.Z[z] - 1) * 385 + 384) * n_int + (k - 1)] = to_double(slot128((size_t)k * row + nch + D->hist_base[z] + 1));
+			}
+		}
+		if (channels) *channels = ch; else free(ch);
+		if (var_red_history) *var_red_history = vr; else free(vr);
+		if (brute_history) *brute_history = br; else free(br);
+		return 1;
+	}
 	for (int k = 0; k < n_int; k++) {
 		for (int c = 0; c < nch; c++) cur[c] = slot128((size_t)k * row + c);
 		// XRF deposits: channel content rebuilt from the per-line slots (exact integer sums)
@@ -1377,6 +1745,15 @@ extern "C" int xmb_msim_device_limbs(xmb_hdf5FPtr hdf5F, uint64_t **dev_ptr, siz
 	if (!h || !h->dev || !h->dev->limbs) { xmb_set_error("no device accumulators"); return 0; }
 	*dev_ptr = (uint64_t *)h->dev->limbs;
 	*n_words = 2 * h->dev->acc_slots;
+	return 1;
+}
+
+// Counters of the last brute-force run: [1] interactions, [3] detector hits, [4] offspring photons walked,
+// [5] detected photons whose line has no history slot.
+extern "C" int xmb_msim_brute_counters(xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity) {
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!h || !h->dev || !out) { xmb_set_error("no run to describe"); return 0; }
+	for (int i = 0; i < capacity && i < 8; i++) out[i] = h->dev->brute_counters[i];
 	return 1;
 }
 
@@ -1499,8 +1876,8 @@ __global__ void __launch_bounds__(256) xmb_escape_kernel(const __grid_constant__
 		}
 		double weight_escape = p.weight;
 		interacted += esc_fixed(p.weight);   // photons_interacted (:5685-5688): every photon interacts, forced
-		int type = 0, zi = 0, line = 0;
-		select_and_scatter<NL, true>(P, p, g, 1, mus, 1, b0.w, weight_escape, type, zi, line);
+		int type = 0, zi = 0, line = 0, shell_unused;
+		select_and_scatter<NL, 1>(P, p, g, 1, mus, 1, b0.w, weight_escape, type, zi, line, shell_unused);
 		// ---- second iteration: analogue free path (:1229-1413); escaped = no interaction before the surface ----
 		if (p.energy < ENERGY_THRESHOLD) continue;   // EXIT main with inside still true (:1229-1231)
 		bool escaped = true;
@@ -1639,3 +2016,4 @@ extern "C" int xmb_escape_ratios_calculation(const xmb_input *input, xmb_escape_
 	xmb_free_input_F(&ein);
 	return rv;
 }
+

@@ -278,6 +278,18 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 		}
 	}
 
+	// Auger transition rates in the reference's enumeration order (src/xmi_main.F90:2441-2470, :2482-4418)
+	h->auger_rate.assign((size_t)nZ * XMB_N_AUGER, 0.0);
+	if (xrl->AugerRate)
+		for (int i = 0; i < nZ; i++) {
+			double *a = &h->auger_rate[(size_t)i * XMB_N_AUGER];
+			for (int x = 0; x < 8; x++)
+				for (int y = 0; y < 30; y++) a[x * 30 + y] = xrl->AugerRate(h->Z[i], 0, 1 + x, 1 + y);
+			for (int s = 1; s <= 3; s++)
+				for (int x = 0; x < 5; x++)
+					for (int y = 0; y < 27; y++) a[240 + 135 * (s - 1) + x * 27 + y] = xrl->AugerRate(h->Z[i], s, 4 + x, 4 + y);
+		}
+
 	// ---- per-layer attenuation on the nodes (xmi_mu_calc, src/xmi_aux_f.F90:1109-1141) -----------------
 	h->mu_layer.assign((size_t)comp.n_layers * nN, 0.0);
 	for (int k = 0; k < comp.n_layers; k++)
@@ -317,6 +329,7 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	v.n_q = n_q; v.q_max = q_max; v.ff = h->ff.data(); v.sf = h->sf.data();
 	v.fluor_yield = h->fluor_yield.data(); v.fluor_yield_corr = h->fluor_yield_corr.data();
 	v.cos_kron = h->cos_kron.data(); v.rad_rate = h->rad_rate.data(); v.line_energy = h->line_energy.data();
+	v.auger_rate = h->auger_rate.data();
 	v.edge_energy = h->edge_energy.data();
 	v.n_layers = comp.n_layers; v.mu_layer = h->mu_layer.data(); v.exc_murhod = h->exc_murhod.data();
 	*out = h;

@@ -360,6 +360,19 @@ static double auger_yield(int Z, int shell) {
 	return a < 0.0 ? 0.0 : a;
 }
 
+/* AugerRate: ordered pair distribution whose expected vacancy counts reproduce auger_transfer(), so that the explicit
+ * cascade of the brute-force mode and the analytic cascade of the forced-detection mode (VacancyCS) agree:
+ * p(X,Y) = t(X) t(Y) / (2 S), S = sum t  =>  sum_Y p(lo,Y) + sum_X p(X,lo) = t(lo), total S/2 <= 1. */
+static double s_AugerRate(int Z, int shell, int n1, int n2) {
+	int lo0, lo1, s;
+	double S = 0.0;
+	if (shell == 0) { lo0 = 1; lo1 = 8; } else if (shell >= 1 && shell <= 3) { lo0 = 4; lo1 = 8; } else return 0.0;
+	if (n1 < lo0 || n1 > lo1 || n2 < lo0 || n2 > lo1) return 0.0;   /* outer partners (N..Q) carry no weight here */
+	for (s = lo0; s <= lo1; s++) S += auger_transfer(Z, shell, s);
+	if (S <= 0.0) return 0.0;
+	return auger_transfer(Z, shell, n1) * auger_transfer(Z, shell, n2) / (2.0 * S);
+}
+
 static int line_index(int up, int lo) {
 	int l;
 	for (l = 1; l <= XMB_M5P5; l++) if (xmb_line_upper[l] == up && xmb_line_lower[l] == lo) return l;
@@ -390,7 +403,7 @@ static const xmb_xrl_provider surrogate = {
 	"xrl-surrogate-1 (analytic stand-in, NOT xraylib data)",
 	s_AtomicWeight, s_EdgeEnergy, s_LineEnergy, s_FluorYield, s_RadRate, s_CosKron, s_JumpFactor,
 	s_CS_Total, s_CS_Photo_Total, s_CS_Photo_Partial, s_CS_Rayl, s_CS_Compt, s_FF, s_SF,
-	s_ComptonProfile, s_VacancyCS};
+	s_ComptonProfile, s_VacancyCS, s_AugerRate};
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void) {
 	if (!edge_ready) build_edges();

@@ -115,8 +115,10 @@ class Simulation:
         return sa
 
     # -- photon histories ----------------------------------------------------------------------------
-    def _sa_arg(self, sa):
+    def _sa_arg(self, sa, options=None):
         if sa is None:
+            if options is not None and not options.use_variance_reduction:
+                return None                      # brute-force mode needs no solid-angle grid
             if self._sa is None:
                 raise RuntimeError("no solid-angle grid: call solid_angle_calculation first")
             return self._sa
@@ -128,7 +130,7 @@ class Simulation:
         options = options or main_options()
         ch, br, vr = abi.c_double_p(), abi.c_double_p(), abi.c_double_p()
         if not self.L.xmb_main_msim(self.inputF, self.hdf5F, n_mpi_hosts, C.byref(ch), C.byref(options), C.byref(br),
-                                    C.byref(vr), self._sa_arg(sa)):
+                                    C.byref(vr), self._sa_arg(sa, options)):
             raise RuntimeError("xmb_main_msim: " + abi.last_error())
         return self._take(ch, br, vr)
 
@@ -149,7 +151,7 @@ class Simulation:
         ex = abi.MsimEx(rank, n_ranks, seed, device, 1, 0, 0.0, 0, 0)
         acc = C.POINTER(C.c_uint64)()
         n = C.c_size_t()
-        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa), C.byref(ex),
+        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa, options), C.byref(ex),
                                         C.byref(acc), C.byref(n)):
             raise RuntimeError("xmb_main_msim_raw: " + abi.last_error())
         return ex
@@ -168,6 +170,13 @@ class Simulation:
             raise RuntimeError(abi.last_error())
         nl = int(buf[0])
         return [(int(buf[1 + 3 * k]), int(buf[2 + 3 * k]), int(buf[3 + 3 * k])) for k in range(nl)]
+
+    def brute_counters(self):
+        """dict of the last brute-force run's counters."""
+        buf = (C.c_uint64 * 8)()
+        if not self.L.xmb_msim_brute_counters(self.hdf5F, buf, 8):
+            raise RuntimeError(abi.last_error())
+        return {"interactions": int(buf[1]), "hits": int(buf[3]), "offspring": int(buf[4]), "no_slot": int(buf[5])}
 
     def shard(self, rank, n_ranks):
         """[begin, end) of the global photon ids simulated by `rank`."""
@@ -193,7 +202,7 @@ class Simulation:
         ex = abi.MsimEx(rank, n_ranks, seed, device, 0, 0, 0.0, 0, 0)
         acc = C.POINTER(C.c_uint64)()
         n = C.c_size_t()
-        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa), C.byref(ex),
+        if not self.L.xmb_main_msim_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa, options), C.byref(ex),
                                         C.byref(acc), C.byref(n)):
             raise RuntimeError("xmb_main_msim_raw: " + abi.last_error())
         limbs = np.ctypeslib.as_array(acc, shape=(2 * n.value,)).copy()

@@ -231,6 +231,11 @@ def run_ours(args):
         tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed = float(tt.item())
+    per_rank_kernel_ms = [sum(kernel_ms) / len(kernel_ms)]
+    if dist is not None:
+        gathered = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor(per_rank_kernel_ms, device="cuda", dtype=torch.float64))
+        per_rank_kernel_ms = [float(t.item()) for t in gathered]
     stats = sim.workload_stats()
     n_hist_rank = int(ex.n_histories)
     interactions = int(ex.n_interactions)
@@ -281,7 +286,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": traffic, "peak_source": pk_src, "kernel": "xmb_history_kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": bytes_launch,
+                         "algorithmic_bytes_per_launch": bytes_launch, "per_rank_kernel_ms": per_rank_kernel_ms,
                          "bytes_per_history": bytes_launch / max(1, n_hist_rank),
                          "mean_interactions_per_history": interactions / max(1, n_hist_rank),
                          "note": "gather+atomic workload: issue/latency-bound, see DESIGN.md; frac is vs the HBM copy peak"},

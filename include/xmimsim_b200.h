@@ -397,11 +397,14 @@ int xmb_msim_workload_stats(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, uint64_t *
  * out[3] photons that reached the detector, out[4] cascade offspring photons walked, out[5] detected
  * photons whose line has no history slot. */
 int xmb_msim_brute_counters(xmb_hdf5FPtr hdf5F, uint64_t *out, int capacity);
-/* Host-side helpers of the sharded driver (no GPU needed): the contiguous photon-id shard of a rank, the total
+/* Host-side helpers of the sharded driver (no GPU needed): the block-cyclic photon-id shard of a rank (ids are
+ * dealt in blocks of 1024, block b to rank b % n_ranks, so every rank simulates the same share of every source
+ * line, as the reference's MPI split does: src/xmi_main.F90:314,574), the total
  * number of histories of an input, and the accumulator slot map: a row (one per interaction order) is
  * nchannels channel slots followed by n_hist_slots history slots; history slot s holds (out_Z[s], out_line[s]),
  * line 384 / 385 = Rayleigh / Compton.  xmb_msim_slot_map returns n_hist_slots (pass NULL arrays to query). */
-void xmb_msim_shard(uint64_t n_total, int rank, int n_ranks, uint64_t *begin, uint64_t *end);
+int xmb_msim_shard_owner(uint64_t photon_id, int n_ranks);
+uint64_t xmb_msim_shard_count(uint64_t n_total, int rank, int n_ranks);
 uint64_t xmb_msim_total_histories(xmb_inputFPtr inputF);
 int xmb_msim_slot_map(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                       int32_t *out_Z, int32_t *out_line, int capacity);

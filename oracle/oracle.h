@@ -72,6 +72,11 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
                              uint64_t g_begin, uint64_t g_end, int n_threads, double *channels,
                              double *var_red, uint64_t *counters);
 
+/* Same for the block-cyclic shard of `rank` (blocks of 1024 ids, block b to rank b % n_ranks). */
+uint64_t orc_main_msim_shard(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T,
+                             const xmb_main_options *opt, const xmb_solid_angle *sa, uint64_t seed, int rank,
+                             int n_ranks, int n_threads, double *channels, double *var_red, uint64_t *counters);
+
 /* Brute-force mode (use_variance_reduction = 0; src/xmi_main.F90:1229-1416, :1920-1984, :2231-4783;
  * src/xmi_aux_f.F90:1622-1833): analogue walk, detector/collimator hit tests, Auger and radiative cascade offspring.
  * channels[(n_int+1)][nch] cumulative from the photon's interaction count; brute[n_int][385][100] =

@@ -51,6 +51,9 @@ def lib():
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p]
         _lib.orc_main_msim_range.restype = C.c_uint64
+        _lib.orc_main_msim_shard.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_main_msim_shard.restype = C.c_uint64
         _lib.orc_main_msim_brute_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_uint64,
                                                    C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_main_msim_brute_range.restype = C.c_uint64
@@ -104,6 +107,17 @@ def main_msim_range(cinput_ptr, d, tables_ptr, options, sa_struct, seed, g_begin
                               C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
                               g_begin, g_end, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
     return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt
+
+
+def main_msim_shard(cinput_ptr, d, tables_ptr, options, sa_struct, seed, rank, n_ranks, n_int, nch, n_threads=8):
+    """Oracle histories of the block-cyclic shard of `rank`.  Returns (channels, var_red, counters, n_histories)."""
+    ch = np.zeros((n_int + 1, nch))
+    vr = np.zeros((n_int, 385, 100))
+    cnt = np.zeros(2, np.uint64)
+    n = lib().orc_main_msim_shard(C.cast(cinput_ptr, C.c_void_p), C.byref(d), C.cast(tables_ptr, C.c_void_p),
+                                  C.cast(C.pointer(options), C.c_void_p), C.cast(C.pointer(sa_struct), C.c_void_p), seed,
+                                  rank, n_ranks, n_threads, ch.ctypes.data, vr.ctypes.data, cnt.ctypes.data)
+    return ch, np.ascontiguousarray(vr.transpose(2, 1, 0)), cnt, int(n)
 
 
 def main_msim_brute_range(cinput_ptr, d, tables_ptr, options, seed, g_begin, g_end, n_int, nch, n_threads=8):

@@ -694,9 +694,27 @@ uint64_t orc_total_histories(const xmb_input *in) {
  *   channels[(n_int+1)][nch] cumulative over interaction order (as the reference's channels(0:n_int, :))
  *   var_red[n_int][385][100]  (k, slot, Z-1)  -- Fortran var_red_history(Z, slot, k)
  * Returns the number of histories run. */
+static uint64_t main_msim_sharded(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, const xmb_main_options *opt,
+                                  const xmb_solid_angle *sa, uint64_t seed, uint64_t g_begin, uint64_t g_end, int shard_rank, int shard_n,
+                                  int n_threads, double *channels, double *var_red, uint64_t *counters);
+
 uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, const xmb_main_options *opt,
                              const xmb_solid_angle *sa, uint64_t seed, uint64_t g_begin, uint64_t g_end, int n_threads,
                              double *channels, double *var_red, uint64_t *counters /* [2]: sa_not_found, interactions */) {
+	return main_msim_sharded(in, d, T, opt, sa, seed, g_begin, g_end, 0, 1, n_threads, channels, var_red, counters);
+}
+
+/* The block-cyclic shard of a rank (blocks of 1024 photon ids, block b to rank b % n_ranks: every rank simulates the
+ * same share of every source line, as the reference's MPI split does, src/xmi_main.F90:314,574). */
+uint64_t orc_main_msim_shard(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, const xmb_main_options *opt,
+                             const xmb_solid_angle *sa, uint64_t seed, int rank, int n_ranks, int n_threads,
+                             double *channels, double *var_red, uint64_t *counters) {
+	return main_msim_sharded(in, d, T, opt, sa, seed, 0, orc_total_histories(in), rank, n_ranks, n_threads, channels, var_red, counters);
+}
+
+static uint64_t main_msim_sharded(const xmb_input *in, const orc_derived *d, const xmb_tables_host *T, const xmb_main_options *opt,
+                                  const xmb_solid_angle *sa, uint64_t seed, uint64_t g_begin, uint64_t g_end, int shard_rank, int shard_n,
+                                  int n_threads, double *channels, double *var_red, uint64_t *counters) {
 	segment_t *segs;
 	int nseg = build_segments(in, &segs);
 	int n_int = in->general->n_interactions_trajectory, nch = in->detector->nchannels, nL = in->composition->n_layers;
@@ -705,8 +723,8 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
 	memset(channels, 0, sizeof(double) * nchn);
 	memset(var_red, 0, sizeof(double) * nvr);
 	if (n_threads < 1) n_threads = 1;
-	uint64_t c0 = 0, c1 = 0;
-#pragma omp parallel num_threads(n_threads)
+	uint64_t c0 = 0, c1 = 0, n_run = 0;
+#pragma omp parallel num_threads(n_threads) reduction(+ : n_run)
 	{
 		ctx_t c;
 		memset(&c, 0, sizeof(c));
@@ -715,6 +733,8 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
 		c.var_red = (double *)calloc(nvr, sizeof(double));
 #pragma omp for schedule(dynamic, 256)
 		for (uint64_t gidx = g_begin; gidx < g_end; gidx++) {
+			if ((int)((gidx >> 10) % (uint64_t)shard_n) != shard_rank) continue;
+			n_run++;
 			int s = 0;
 			while (s + 1 < nseg && gidx >= segs[s + 1].first) s++;
 			photon_t p;
@@ -735,7 +755,7 @@ uint64_t orc_main_msim_range(const xmb_input *in, const orc_derived *d, const xm
 	}
 	if (counters) { counters[0] = c0; counters[1] = c1; }
 	free(segs);
-	return g_end - g_begin;
+	return n_run;
 }
 
 /* ---- escape-peak ratios (src/xmi_main.F90:5473-5801; driver src/xmi_detector.c:91-141) ---------------------

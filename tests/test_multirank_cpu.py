@@ -25,19 +25,25 @@ def _worker(rank, world, port, q):
         inp.n_photons_line = 301                      # 26 lines x 301: not divisible by the world size
         P = Pair(inp)
         opt = x.main_options()
-        # --- 1. shards partition the id range exactly --------------------------------------------------------
-        b, e = P.sim.shard(rank, world)
-        spans = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(spans, torch.tensor([b, e], dtype=torch.int64))
-        spans = sorted((int(s[0]), int(s[1])) for s in spans)
-        assert spans[0][0] == 0 and spans[-1][1] == P.n_total
-        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        # --- 1. block-cyclic shards partition the id range exactly -----------------------------------------------
+        mine_n = P.sim.shard_count(rank, world)
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([mine_n], dtype=torch.int64))
+        assert sum(int(c[0]) for c in counts) == P.n_total
+        owners = np.array([P.sim.shard_owner(g, world) for g in range(P.n_total)])
+        assert int((owners == rank).sum()) == mine_n
+        assert max(int(c[0]) for c in counts) - min(int(c[0]) for c in counts) <= 1024
         # --- 2. histories are independent of the sharding: oracle on my shard, summed over ranks == full run ----
         r_full, t_full = P.sim.solid_angle_inputs()
         r = np.linspace(r_full[0], r_full[-1], 48); t = np.linspace(t_full[0], t_full[-1], 48)
         sa_g, _ = orc.solid_angle_grid(P.od, r, np.arange(48), t, np.arange(48), 48, 300, 1, n_threads=2)
         sa = P.sim.make_solid_angle(sa_g, r, t)
-        ch, vr, _ = P.oracle(opt, sa, 0, b, e, n_threads=2)
+        import ctypes as C
+        from helpers import DEFAULT_SEED
+        ch, vr, _, n_run = orc.main_msim_shard(C.pointer(P.ci.input), P.od, P.sim.L.xmb_get_tables(P.sim.hdf5F), opt, sa,
+                                               DEFAULT_SEED, rank, world, inp.n_interactions_trajectory, inp.nchannels, 2)
+        assert n_run == mine_n
+        ch *= inp.live_time; vr *= inp.live_time
         tch, tvr = torch.from_numpy(ch.copy()), torch.from_numpy(vr.copy())
         dist.all_reduce(tch); dist.all_reduce(tvr)
         if rank == 0:
@@ -100,11 +106,11 @@ def test_two_rank_gloo_sharding_and_exact_reduction():
 def test_shard_helper_edge_cases():
     from xmimsim_b200 import abi
     L = abi.lib()
-    for n, w in ((0, 3), (5, 8), (1000, 7), (2 ** 40 + 5, 8)):
-        prev = 0
-        for r in range(w):
-            b, e = C.c_uint64(), C.c_uint64()
-            L.xmb_msim_shard(n, r, w, C.byref(b), C.byref(e))
-            assert b.value == prev and e.value >= b.value
-            prev = e.value
-        assert prev == n
+    for n, w in ((0, 3), (5, 8), (1000, 7), (1024 * 9 + 17, 4), (2 ** 40 + 5, 8)):
+        counts = [L.xmb_msim_shard_count(n, r, w) for r in range(w)]
+        assert sum(counts) == n
+        assert max(counts) - min(counts) <= 1024
+        for g in (0, 1023, 1024, n - 1):
+            if 0 <= g < n:
+                assert L.xmb_msim_shard_owner(g, w) == (g // 1024) % w
+    assert L.xmb_msim_shard_count(100, 5, 3) == 0          # rank outside 0..n-1

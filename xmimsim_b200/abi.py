@@ -228,8 +228,8 @@ def lib():
     L.xmi_detector_convolute_all_custom.argtypes = [vp, pp, pp, c_double_p, c_double_p, C.POINTER(MainOptions),
                                                     C.POINTER(EscapeRatios), C.c_int, C.c_int]
     L.xmi_detector_convolute_all_custom.restype = None
-    L.xmb_msim_shard.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    L.xmb_msim_shard.restype = None
+    L.xmb_msim_shard_owner.argtypes = [C.c_uint64, C.c_int]; L.xmb_msim_shard_owner.restype = C.c_int
+    L.xmb_msim_shard_count.argtypes = [C.c_uint64, C.c_int, C.c_int]; L.xmb_msim_shard_count.restype = C.c_uint64
     L.xmb_msim_total_histories.argtypes = [vp]; L.xmb_msim_total_histories.restype = C.c_uint64
     L.xmb_msim_slot_map.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
     L.xmb_msim_slot_map.restype = C.c_int

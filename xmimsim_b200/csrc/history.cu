@@ -334,6 +334,11 @@ __device__ __forceinline__ double ran_gaussian(XmbRng &rng, double sigma) {
 	return sigma * sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * M_PI * u2);
 }
 
+// local index of this rank -> global photon id (block-cyclic: block b of XMB_SHARD_BLOCK ids belongs to rank b % n)
+__device__ __forceinline__ uint64_t shard_global_id(const XmbHistParams &P, uint64_t lid) {
+	return (((lid >> XMB_SHARD_SHIFT) * (uint64_t)P.shard_n + (uint64_t)P.shard_rank) << XMB_SHARD_SHIFT) | (lid & (XMB_SHARD_BLOCK - 1));
+}
+
 // ---- source sampling (src/xmi_main.F90:319-438, :579-724, :957-1186) -----------------------------------
 template <int NL>
 __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uint64_t g, double *mus /* [nL] stride T */, int T) {
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
 	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
 	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] 16-bit pieces
-	const uint64_t n_total = P.g_end - P.g_begin;
+	const uint64_t n_total = P.n_local_span;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
 	unsigned long long n_inter_local = 0;
@@ -609,9 +614,10 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
 		int order = 1;
 		if (from_source) {
-			g = P.g_begin + next_chunk * T + tid;
+			const uint64_t lid = next_chunk * T + tid;
+			g = shard_global_id(P, lid);
 			next_chunk += gridDim.x;
-			p.alive = g < P.g_end;
+			p.alive = lid < P.n_local_span && g < P.n_total;
 			if (p.alive) {
 				XmbRng rng;   // order 0, stage 0: sequential words, counter word 2 = block
 				rng.init(P.seed, g, XMB_TAG_HISTORY);
@@ -1037,7 +1043,9 @@ __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ 
 	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
 	unsigned long long n_inter = 0, n_hits = 0, n_off = 0, n_noslot = 0;
-	for (uint64_t g = P.g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < P.g_end; g += (uint64_t)gridDim.x * blockDim.x) {
+	for (uint64_t lid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_local_span; lid += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t g = shard_global_id(P, lid);
+		if (g >= P.n_total) continue;
 		Photon p, off;
 		double mus[NLA], off_mus[NLA];
 		{
@@ -1491,12 +1499,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const int nr = ex->n_ranks > 0 ? ex->n_ranks : 1, rk = ex->rank;
 	if (rk < 0 || rk >= nr) { xmb_set_error("rank %d outside 0..%d", rk, nr - 1); return 0; }
 	P.seed = ex->seed ? ex->seed : XMB_DEFAULT_SEED;
+	P.n_total = D->n_total; P.shard_rank = rk; P.shard_n = nr;
 	{
-		uint64_t gb, ge;
-		xmb_msim_shard(D->n_total, rk, nr, &gb, &ge);
-		P.g_begin = gb; P.g_end = ge;
+		const uint64_t blocks = (D->n_total + XMB_SHARD_BLOCK - 1) / XMB_SHARD_BLOCK;
+		P.n_local_span = (blocks / nr + ((uint64_t)rk < blocks % nr ? 1 : 0)) * XMB_SHARD_BLOCK;
 	}
-	ex->n_histories = P.g_end - P.g_begin;
+	ex->n_histories = xmb_msim_shard_count(D->n_total, rk, nr);
 	// launch
 	int sms = 148, occ = 1;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1596,14 +1604,25 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	return 1;
 }
 
-// contiguous shard of the global photon ids [0, n_total) owned by `rank` (remainder spread over the first ranks)
-extern "C" void xmb_msim_shard(uint64_t n_total, int rank, int n_ranks, uint64_t *begin, uint64_t *end) {
+// Block-cyclic shard of the global photon ids [0, n_total): ids are dealt in blocks of XMB_SHARD_BLOCK, block b to
+// rank b % n_ranks -- every rank gets the same mix of source lines (the reference gives each MPI host
+// n_photons/n_hosts photons of EVERY line, src/xmi_main.F90:314,574), so the ranks finish together.
+extern "C" int xmb_msim_shard_owner(uint64_t g, int n_ranks) {
 	if (n_ranks < 1) n_ranks = 1;
-	*begin = n_total / n_ranks * rank + std::min<uint64_t>(rank, n_total % n_ranks);
-	*end = *begin + n_total / n_ranks + ((uint64_t)rank < n_total % n_ranks ? 1 : 0);
+	return (int)((g >> XMB_SHARD_SHIFT) % (uint64_t)n_ranks);
+}
+extern "C" uint64_t xmb_msim_shard_count(uint64_t n_total, int rank, int n_ranks) {
+	if (n_ranks < 1) n_ranks = 1;
+	if (rank < 0 || rank >= n_ranks) return 0;
+	const uint64_t blocks = (n_total + XMB_SHARD_BLOCK - 1) / XMB_SHARD_BLOCK;
+	if (blocks == 0) return 0;
+	uint64_t owned = blocks / n_ranks + ((uint64_t)rank < blocks % n_ranks ? 1 : 0);
+	uint64_t n = owned * XMB_SHARD_BLOCK;
+	// the last global block may be partial
+	if ((blocks - 1) % n_ranks == (uint64_t)rank) n -= blocks * XMB_SHARD_BLOCK - n_total;
+	return n;
 }
 
-// host-side layout (slot map, scale factors) without a GPU: enough for xmb_main_msim_finish and the slot map
 static XmbDeviceTables *ensure_layout(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt) {
 	if (h->dev && h->dev->cascade == cascade_mode(opt) && h->dev->use_M_lines == (opt->use_M_lines ? 1 : 0)) return h->dev;
 	if (h->dev) { delete h->dev; h->dev = nullptr; }

@@ -3,6 +3,8 @@
 #include <cstdint>
 
 #define XMB_MAX_LAYERS 32
+#define XMB_SHARD_BLOCK 1024
+#define XMB_SHARD_SHIFT 10
 #define XMB_ELEM_STRIDE 22         // per-element doubles in a node row
 #define XMB_EO_CS_TOTAL 0
 #define XMB_EO_P_RAYL 1
@@ -29,7 +31,11 @@ struct XmbLayerDev {
 
 struct XmbHistParams {
 	// run
-	uint64_t seed, g_begin, g_end;
+	uint64_t seed;
+	// block-cyclic shard of the global photon ids [0, n_total): blocks of XMB_SHARD_BLOCK ids, block b belongs to
+	// rank b % shard_n; n_local_span = owned blocks * XMB_SHARD_BLOCK (local index range, the last block may be partial)
+	uint64_t n_total, n_local_span;
+	int shard_rank, shard_n;
 	uint64_t n_cont_seg, n_per_interval, n_per_line;
 	int n_seg, n_int, nch, nL, nZ;
 	int use_M_lines;

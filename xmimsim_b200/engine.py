@@ -178,11 +178,12 @@ class Simulation:
             raise RuntimeError(abi.last_error())
         return {"interactions": int(buf[1]), "hits": int(buf[3]), "offspring": int(buf[4]), "no_slot": int(buf[5])}
 
-    def shard(self, rank, n_ranks):
-        """[begin, end) of the global photon ids simulated by `rank`."""
-        b, e = C.c_uint64(), C.c_uint64()
-        self.L.xmb_msim_shard(self.L.xmb_msim_total_histories(self.inputF), rank, n_ranks, C.byref(b), C.byref(e))
-        return b.value, e.value
+    def shard_count(self, rank, n_ranks):
+        """Number of histories `rank` simulates (block-cyclic shard of the global photon ids)."""
+        return int(self.L.xmb_msim_shard_count(self.L.xmb_msim_total_histories(self.inputF), rank, n_ranks))
+
+    def shard_owner(self, photon_id, n_ranks):
+        return int(self.L.xmb_msim_shard_owner(photon_id, n_ranks))
 
     def slot_map(self, options=None):
         """(Z[n_hist_slots], line[n_hist_slots]) of the history slots that follow the nch channel slots in a row."""

@@ -205,6 +205,11 @@ typedef struct xmb_xrl_provider {
 	 * Only used by the brute-force mode (src/xmi_main.F90:2413-2481).  May be NULL: no Auger
 	 * cascade offspring are then simulated. */
 	double (*AugerRate)(int Z, int shell, int shell_new1, int shell_new2);
+	/* xraylib ElectronConfig_Biggs(Z, shell) and ComptonProfile_Partial(Z, shell, pz), shell 0..30
+	 * (K .. Q3).  Only used with options->use_advanced_compton (src/xmi_main.F90:4785-4983,
+	 * src/xmi_variance_reduction.F90:752-947; tables src/xmi_data_f.F90:1120-1235).  May be NULL. */
+	double (*ElectronConfig_Biggs)(int Z, int shell);
+	double (*ComptonProfile_Partial)(int Z, int shell, double pz);
 } xmb_xrl_provider;
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void);
@@ -295,6 +300,16 @@ typedef struct xmb_tables_host {
 	 * index 0..239 = K_<X><Y>, X in L1..M5 (8), Y in L1..Q3 (30): x*30 + y;
 	 * 240 + 135*(s-1) + x*27 + y = L<s>_<X><Y>, X in M1..M5 (5), Y in M1..Q3 (27). */
 	const double *auger_rate;      /* [nZ][XMB_N_AUGER] */
+	/* Shell-resolved Compton profiles (use_advanced_compton), built on demand by
+	 * xmb_tables_enable_advanced_compton; n_adv_rows = 0 until then.  Element zi owns rows
+	 * adv_off[zi] .. adv_off[zi+1]-1, one per occupied subshell (src/xmi_data_f.F90:1126-1145). */
+	int n_adv_rows;
+	const int *adv_off;            /* [nZ+1] */
+	const int *adv_shell;          /* [n_adv_rows] xraylib shell number */
+	const double *adv_config;      /* [n_adv_rows] ElectronConfig_Biggs */
+	const double *adv_edge;        /* [n_adv_rows] EdgeEnergy of the subshell (0 when unknown) */
+	const double *adv_cdf;         /* [n_adv_rows][n_cp] profile_partial_cdf on Q = 100 j/(n_cp-1), normalised to 0.5 at Q = 100 */
+	const double *adv_qinv;        /* [n_adv_rows][n_cp] Qs_inv on cdf = 0.5 j/(n_cp-1) */
 } xmb_tables_host;
 #define XMB_N_AUGER 645
 
@@ -324,6 +339,9 @@ const xmb_derived *xmb_get_derived(xmb_inputFPtr inputF);
 int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality,
                            xmb_hdf5FPtr *out);
 const xmb_tables_host *xmb_get_tables(xmb_hdf5FPtr hdf5F);
+/* Builds the shell-resolved Compton tables (idempotent; host, OpenMP).  xmb_main_msim calls it itself when
+ * options->use_advanced_compton is set.  Returns 1 / 0 (provider lacks the two partial-profile calls). */
+int xmb_tables_enable_advanced_compton(xmb_hdf5FPtr hdf5F);
 void xmb_free_hdf5_F(xmb_hdf5FPtr *hdf5F);
 
 /* Replaces xmi_solid_angle_inputs_f (src/xmi_solid_angle_f.F90:62-301): allocates the grid

@@ -238,6 +238,70 @@ static double compton_energy(const ctx_t *c, int zi, double E0, double theta_i, 
 	return energy;
 }
 
+
+/* ---- shell-resolved ("advanced") Compton: src/xmi_aux_f.F90:1951-2073, src/xmi_main.F90:4785-4983,
+ *      src/xmi_variance_reduction.F90:752-947 --------------------------------------------------------- */
+static double adv_qimax(double energy, double Ii, double theta) {                  /* xmi_get_qimax */
+	if (Ii != 0.0 && energy < Ii) return 0.0;
+	double EminIi = energy - Ii, costheta = cos(theta);
+	double Q = 137.0 * (EminIi * energy * (1.0 - costheta) / XMI_MEC2 - Ii);
+	return Q / sqrt(EminIi * EminIi + energy * energy - 2.0 * EminIi * energy * costheta);
+}
+static double adv_q_from_energy(double e0, double e1, double theta) {              /* xmi_get_q_from_energy */
+	double ct = cos(theta);
+	double Q = 137.0 * (e1 - e0 + (1.0 - ct) * e0 * e1 / XMI_MEC2);
+	return Q / sqrt(e1 * e1 + e0 * e0 - 2.0 * e0 * e1 * ct);
+}
+static double adv_energy_from_q(double e0, double Q, double theta) {               /* xmi_get_energy_from_q */
+	double a = e0, b = XMI_MEC2, c = cos(theta);
+	if (fabs(c - 1.0) < 1E-8) return 0.0;
+	if (fabs(Q) < 1E-4) return e0 / (1.0 + e0 * (1.0 - c) / XMI_MEC2);
+	double d = 1.0 + a / b - a * c / b;
+	double aq = 137.0 * 137.0 * d * d - Q * Q;
+	double bq = -2.0 * 137.0 * 137.0 * a * d + 2.0 * a * c * Q * Q;
+	double cq = 137.0 * 137.0 * a * a - a * a * Q * Q;
+	double E1 = 0.0, E2 = 0.0;
+	if (orc_poly_solve_quadratic(aq, bq, cq, &E1, &E2) == 0) return 0.0;
+	double Q1 = adv_q_from_energy(e0, E1, theta), Q2 = adv_q_from_energy(e0, E2, theta);
+	if (Q * Q1 > 0.0) return E1;
+	if (Q * Q2 > 0.0) return E2;
+	if (fabs(E1 - E2) < 1E-10 || fabs(Q1 - Q2) < 1E-10) return E1;
+	return 0.0;                                                                    /* the reference exits here */
+}
+/* cumulative probability of the subshell row r up to Qimax (:4808-4848) */
+static double adv_shell_cdf(const xmb_tables_host *T, int r, double energy, double theta) {
+	const double Qimax = adv_qimax(energy, T->adv_edge[r], theta);
+	if (Qimax < -100.0) return 0.0;
+	if (Qimax > 100.0) return 1.0;
+	const double *cdf = T->adv_cdf + (size_t)r * T->n_cp;
+	const double dq = 100.0 / (T->n_cp - 1.0), qa = fabs(Qimax);
+	int pos = (int)(qa / dq);
+	if (pos > T->n_cp - 2) pos = T->n_cp - 2;
+	const double v = cdf[pos] + (cdf[pos + 1] - cdf[pos]) * (qa - dq * pos) / dq;
+	return Qimax < 0.0 ? 1.0 - (0.5 + v) : 0.5 + v;
+}
+/* Q for the cumulative value cdf in [0, cdfs(r)] (:4880-4940) */
+static double adv_sample_q(const xmb_tables_host *T, int r, double cdf) {
+	const double *qinv = T->adv_qinv + (size_t)r * T->n_cp;
+	const double dc = 0.5 / (T->n_cp - 1.0), cp = cdf < 0.5 ? 0.5 - cdf : cdf - 0.5;
+	int pos = (int)(cp / dc);
+	if (pos > T->n_cp - 2) pos = T->n_cp - 2;
+	const double q = qinv[pos] + (qinv[pos + 1] - qinv[pos]) * (cp - dc * pos) / dc;
+	return cdf < 0.5 ? -q : q;
+}
+/* xmi_update_photon_energy_compton (:4785-4983): two draws {subshell, Q} */
+static double compton_energy_adv(const ctx_t *c, int zi, double E0, double theta_i, double u_shell, double u_q) {
+	const xmb_tables_host *T = c->T;
+	const int r0 = T->adv_off[zi], r1 = T->adv_off[zi + 1];
+	double cdfs[32], cdf_sum = 0.0;
+	for (int r = r0; r < r1; r++) { cdfs[r - r0] = adv_shell_cdf(T, r, E0, theta_i); cdf_sum += T->adv_config[r] * cdfs[r - r0]; }
+	if (cdf_sum == 0.0) return 0.0;
+	double temp_sum = 0.0;
+	int i = r1 - 1;
+	for (int r = r0; r < r1; r++) { temp_sum += T->adv_config[r] * cdfs[r - r0] / cdf_sum; if (u_shell <= temp_sum) { i = r; break; } }
+	return adv_energy_from_q(E0, adv_sample_q(T, i, u_q * cdfs[i - r0]), theta_i);
+}
+
 /* ---- xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801) ------------------------------- */
 static double get_solid_angle(ctx_t *c, const double *coords) {
 	const xmb_solid_angle *sa = c->sa;
@@ -344,22 +408,41 @@ static void variance_reduction(ctx_t *c, photon_t *p, double u_det_r, double u_d
 		double dcsp_rayl = AVOGNUM / T->atomic_weight[zi] * F * F * RE2 * (1.0 - sin(theta) * sin(theta) * cos(phi) * cos(phi));
 		double Pdir = detector_solid_angle * dcsp_rayl;
 		deposit(c, Z, 383 + 1, n_ia, p->energy, Pconv * Pdir * Pesc_rayl * p->weight);
-		/* COMPTON  (xmi_compton_varred2, :949-1008) */
+		/* COMPTON  (xmi_compton_varred2, :949-1008; shell-resolved xmi_compton_varred, :752-947) */
 		{
-			substream_t cs;
-			sub_init(&cs, p->seed, p->g, n_ia, 2, i);
-			double e_c = compton_energy(c, zi, p->energy, theta, &cs, 1);
-			double mus_c[64];
-			mu_calc(c, e_c, mus_c);
-			double tm = 0.0;
-			for (int j = p->current_layer; step_dir > 0 ? j <= step_max : j >= step_max; j += step_dir)
-				tm += mus_c[j] * layers[j].density * distances[j];
-			double Pesc_comp = exp(-tm);
 			double S = T->sf[(size_t)zi * T->n_q + qi] * (1.0 - qf) + T->sf[(size_t)zi * T->n_q + qi + 1] * qf;
 			double k0k = 1.0 / (1.0 + (1.0 - cos(theta)) * p->energy / 510.998928);
 			double dcsp_kn = RE2 / 2.0 * k0k * k0k * (k0k + 1.0 / k0k - 2.0 * sin(theta) * sin(theta) * cos(phi) * cos(phi));
 			double Pdir_c = detector_solid_angle * AVOGNUM / T->atomic_weight[zi] * S * dcsp_kn;
-			deposit(c, Z, 383 + 2, n_ia, e_c, Pconv * Pdir_c * Pesc_comp * p->weight);
+			if (c->opt->use_advanced_compton) {
+				const int r0 = T->adv_off[zi], r1 = T->adv_off[zi + 1];
+				double cdfs[32], cdf_sum = 0.0;
+				for (int r = r0; r < r1; r++) { cdfs[r - r0] = adv_shell_cdf(T, r, p->energy, theta); cdf_sum += T->adv_config[r] * cdfs[r - r0]; }
+				for (int r = r0; r < r1 && cdf_sum != 0.0; r++) {
+					double shell_weight = T->adv_config[r] * cdfs[r - r0] / cdf_sum;
+					if (shell_weight == 0.0) continue;
+					double u[4];
+					draw_block(p->seed, p->g, n_ia, 2, i, (r - r0) >> 2, u);          /* one word per subshell */
+					double e_c = adv_energy_from_q(p->energy, adv_sample_q(T, r, u[(r - r0) & 3] * cdfs[r - r0]), theta);
+					if (e_c == 0.0) continue;
+					double mus_c[64], tm = 0.0;
+					mu_calc(c, e_c, mus_c);
+					for (int j = p->current_layer; step_dir > 0 ? j <= step_max : j >= step_max; j += step_dir)
+						tm += mus_c[j] * layers[j].density * distances[j];
+					deposit(c, Z, 383 + 2, n_ia, e_c, Pconv * Pdir_c * exp(-tm) * p->weight * shell_weight);
+				}
+			} else {
+				substream_t cs;
+				sub_init(&cs, p->seed, p->g, n_ia, 2, i);
+				double e_c = compton_energy(c, zi, p->energy, theta, &cs, 1);
+				double mus_c[64];
+				mu_calc(c, e_c, mus_c);
+				double tm = 0.0;
+				for (int j = p->current_layer; step_dir > 0 ? j <= step_max : j >= step_max; j += step_dir)
+					tm += mus_c[j] * layers[j].density * distances[j];
+				double Pesc_comp = exp(-tm);
+				deposit(c, Z, 383 + 2, n_ia, e_c, Pconv * Pdir_c * Pesc_comp * p->weight);
+			}
 		}
 		/* FLUORESCENCE  (:391-709).  Shell vacancy cross sections under the selected cascade mode at the
 		 * photon energy; after a fluorescence interaction that energy is a line energy, which is a node of
@@ -427,7 +510,11 @@ static int do_compton(ctx_t *c, photon_t *p, const double *sd) {                
 	double phi0 = elec_phi0(p);
 	substream_t ds;
 	sub_init(&ds, p->seed, p->g, p->n_interactions | p->gen, 3, 0);
-	p->energy = compton_energy(c, zi, p->energy, theta_i, &ds, 0);
+	if (c->opt->use_advanced_compton) {
+		double u_shell = sub_uniform(&ds), u_q = sub_uniform(&ds);
+		p->energy = compton_energy_adv(c, zi, p->energy, theta_i, u_shell, u_q);
+	} else
+		p->energy = compton_energy(c, zi, p->energy, theta_i, &ds, 0);
 	mu_calc(c, p->energy, p->mus);                                                /* :5059 */
 	if (p->energy == 0.0) return 1;
 	update_dirv(p, theta_i, phi_i + phi0);

@@ -152,7 +152,7 @@ def test_unsupported_modes_fail_loudly():
     inp.n_photons_line = 100
     P = Pair(inp)
     sa = P.grid(n=64)
-    for kw in (dict(use_advanced_compton=1), dict(escape_ratios_mode=1)):
+    for kw in (dict(escape_ratios_mode=1),):
         with pytest.raises(RuntimeError, match="not implemented"):
             P.sim.main_msim(x.main_options(**kw), sa)
     P.close()

@@ -119,7 +119,9 @@ class TablesHost(C.Structure):
                 ("fluor_yield", c_double_p), ("fluor_yield_corr", c_double_p), ("cos_kron", c_double_p),
                 ("rad_rate", c_double_p), ("line_energy", c_double_p), ("edge_energy", c_double_p),
                 ("n_layers", C.c_int), ("mu_layer", c_double_p), ("exc_murhod", c_double_p),
-                ("auger_rate", c_double_p)]
+                ("auger_rate", c_double_p),
+                ("n_adv_rows", C.c_int), ("adv_off", c_int_p), ("adv_shell", c_int_p), ("adv_config", c_double_p),
+                ("adv_edge", c_double_p), ("adv_cdf", c_double_p), ("adv_qinv", c_double_p)]
 
 
 class XrlProvider(C.Structure):
@@ -134,7 +136,8 @@ class XrlProvider(C.Structure):
                 ("FF_Rayl", C.CFUNCTYPE(_D, _I, _D)), ("SF_Compt", C.CFUNCTYPE(_D, _I, _D)),
                 ("ComptonProfile", C.CFUNCTYPE(_D, _I, _D)),
                 ("VacancyCS", C.CFUNCTYPE(_D, _I, _I, _D, _I, c_double_p)),
-                ("AugerRate", C.CFUNCTYPE(_D, _I, _I, _I, _I))]
+                ("AugerRate", C.CFUNCTYPE(_D, _I, _I, _I, _I)),
+                ("ElectronConfig_Biggs", C.CFUNCTYPE(_D, _I, _I)), ("ComptonProfile_Partial", C.CFUNCTYPE(_D, _I, _I, _D))]
 
 
 class MsimEx(C.Structure):
@@ -174,6 +177,7 @@ def lib():
     L.xmb_init_from_provider.argtypes = [C.POINTER(XrlProvider), vp, C.c_int, vpp]; L.xmb_init_from_provider.restype = C.c_int
     L.xmb_get_tables.argtypes = [vp]; L.xmb_get_tables.restype = C.POINTER(TablesHost)
     L.xmb_free_hdf5_F.argtypes = [vpp]; L.xmb_free_hdf5_F.restype = None
+    L.xmb_tables_enable_advanced_compton.argtypes = [vp]; L.xmb_tables_enable_advanced_compton.restype = C.c_int
     L.xmb_solid_angle_inputs.argtypes = [vp, vp, C.POINTER(C.POINTER(SolidAngle))]; L.xmb_solid_angle_inputs.restype = C.c_int
     L.xmb_solid_angle_calculation.argtypes = [vp, vp, C.POINTER(C.POINTER(SolidAngle)), C.c_void_p,
                                               C.POINTER(MainOptions), C.c_long, C.c_uint64]

@@ -31,6 +31,9 @@ struct XmbHdf5F {
 	    cs_photo_partial, cs_vacancy, icdf_E, icdf_R, rayl_theta_icdf, compt_theta_icdf, phi_T,
 	    phi_icdf, cp_R, cp_icdf, ff, sf, fluor_yield, fluor_yield_corr, cos_kron, rad_rate,
 	    line_energy, edge_energy, mu_layer, exc_murhod, auger_rate;
+	std::vector<int> adv_off, adv_shell;
+	std::vector<double> adv_config, adv_edge, adv_cdf, adv_qinv;
+	int quality = 0;
 	double e_max = 0.0;
 	XmbDeviceTables *dev = nullptr;   // lazily built device-side layouts (device.cu)
 };

@@ -432,13 +432,82 @@ __device__ __forceinline__ bool step_to_plane(const XmbHistParams &P, double &x,
 	return true;
 }
 
+// ---- shell-resolved ("advanced") Compton: src/xmi_aux_f.F90:1951-2073, src/xmi_main.F90:4785-4983,
+//      src/xmi_variance_reduction.F90:752-947 ----------------------------------------------------------------
+__device__ __forceinline__ double adv_q_from_energy(double e0, double e1, double ct) {
+	const double Q = 137.0 * (e1 - e0 + (1.0 - ct) * e0 * e1 / XMI_MEC2);
+	return Q / sqrt(e1 * e1 + e0 * e0 - 2.0 * e0 * e1 * ct);
+}
+__device__ double adv_energy_from_q(double e0, double Q, double theta) {
+	const double a = e0, b = XMI_MEC2, c = cos(theta);
+	if (fabs(c - 1.0) < 1E-8) return 0.0;
+	if (fabs(Q) < 1E-4) return e0 / (1.0 + e0 * (1.0 - c) / XMI_MEC2);
+	const double d = 1.0 + a / b - a * c / b;
+	const double aq = 137.0 * 137.0 * d * d - Q * Q;
+	const double bq = -2.0 * 137.0 * 137.0 * a * d + 2.0 * a * c * Q * Q;
+	const double cq = 137.0 * 137.0 * a * a - a * a * Q * Q;
+	double E1, E2;
+	if (aq == 0.0) {                                   // xmi_poly_solve_quadratic (src/xmi_aux_f.F90:1872-1905)
+		if (bq == 0.0) return 0.0;
+		E1 = E2 = -1.0 * cq / bq;
+	} else {
+		const double delta = bq * bq - 4.0 * aq * cq;
+		if (delta < 0.0) return 0.0;
+		if (delta == 0.0) E1 = E2 = -bq / 2.0 / aq;
+		else { const double sq = sqrt(delta), t1 = (-bq + sq) / 2.0 / aq, t2 = (-bq - sq) / 2.0 / aq; E1 = fmin(t1, t2); E2 = fmax(t1, t2); }
+	}
+	const double Q1 = adv_q_from_energy(e0, E1, c), Q2 = adv_q_from_energy(e0, E2, c);
+	if (Q * Q1 > 0.0) return E1;
+	if (Q * Q2 > 0.0) return E2;
+	if (fabs(E1 - E2) < 1E-10 || fabs(Q1 - Q2) < 1E-10) return E1;
+	return 0.0;
+}
+__device__ double adv_shell_cdf(const XmbHistParams &P, int r, double energy, double theta) {
+	const double Ii = P.adv_edge[r];
+	double Qimax = 0.0;
+	if (!(Ii != 0.0 && energy < Ii)) {
+		const double EminIi = energy - Ii, costheta = cos(theta);
+		Qimax = 137.0 * (EminIi * energy * (1.0 - costheta) / XMI_MEC2 - Ii);
+		Qimax = Qimax / sqrt(EminIi * EminIi + energy * energy - 2.0 * EminIi * energy * costheta);
+	}
+	if (Qimax < -100.0) return 0.0;
+	if (Qimax > 100.0) return 1.0;
+	const double *cdf = P.adv_cdf + (size_t)r * P.n_cp;
+	const double dq = 100.0 / (P.n_cp - 1.0), qa = fabs(Qimax);
+	const int pos = min((int)(qa / dq), P.n_cp - 2);
+	const double v = cdf[pos] + (cdf[pos + 1] - cdf[pos]) * (qa - dq * pos) / dq;
+	return Qimax < 0.0 ? 1.0 - (0.5 + v) : 0.5 + v;
+}
+__device__ double adv_sample_q(const XmbHistParams &P, int r, double cdf) {
+	const double *qinv = P.adv_qinv + (size_t)r * P.n_cp;
+	const double dc = 0.5 / (P.n_cp - 1.0), cp = cdf < 0.5 ? 0.5 - cdf : cdf - 0.5;
+	const int pos = min((int)(cp / dc), P.n_cp - 2);
+	const double q = qinv[pos] + (qinv[pos + 1] - qinv[pos]) * (cp - dc * pos) / dc;
+	return cdf < 0.5 ? -q : q;
+}
+// xmi_update_photon_energy_compton (:4785-4983): two draws {subshell, Q}
+__device__ double compton_energy_adv(const XmbHistParams &P, int zi, double E0, double theta_i, double u_shell, double u_q) {
+	const int r0 = P.adv_off[zi], r1 = P.adv_off[zi + 1];
+	double cdf_sum = 0.0;
+	for (int r = r0; r < r1; r++) cdf_sum += P.adv_config[r] * adv_shell_cdf(P, r, E0, theta_i);
+	if (cdf_sum == 0.0) return 0.0;
+	double temp_sum = 0.0, cdf_i = 0.0;
+	int i = r1 - 1;
+	for (int r = r0; r < r1; r++) {
+		cdf_i = adv_shell_cdf(P, r, E0, theta_i);
+		temp_sum += P.adv_config[r] * cdf_i / cdf_sum;
+		if (u_shell <= temp_sum) { i = r; break; }
+	}
+	return adv_energy_from_q(E0, adv_sample_q(P, i, u_q * cdf_i), theta_i);
+}
+
 // ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------
 // MODE 0: forced detection (the fluorescence yield multiplies the weight); 1: escape-ratio mode (it goes to
 // weight_escape, src/xmi_variance_reduction.F90:697-750); 2: brute force (analogue yield check, :2297-2319 / :5325-5350:
 // on failure the energy is zeroed and out_type = 4 tells the caller to run the Auger cascade on out_shell).
 // out_type: 1 Rayleigh, 2 Compton, 3 photo-electric (4: Auger); out_zi: element slot; out_line: |line macro| or 0;
 // out_shell: the ionised shell, after Coster-Kronig when a line was emitted.
-template <int NL, int MODE>
+template <int NL, int MODE, bool ADV = false>
 __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photon &p, uint64_t g, int order, double *mus, int T,
                                                    uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line,
                                                    int &out_shell) {
@@ -482,7 +551,11 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 		tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
 		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
 		const double phi0 = elec_phi0(p);
-		p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
+		if (ADV) {
+			const uint4 w = draw_block(P.seed, g, order, 3, 0, 0);
+			p.energy = compton_energy_adv(P, zi, p.energy, theta_i, xmb_u01(w.x), xmb_u01(w.y));
+		} else
+			p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
 		{
 			const NodePos cp = node_find(P, p.energy);
 			XMB_UNROLL_NL
@@ -561,7 +634,7 @@ for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, lp, i);
 }
 
 // NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
-template <int NL>
+template <int NL, bool ADV = false>
 __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
 	const int nL = NL > 0 ? NL : P.nL;
 	extern __shared__ double smem[];
@@ -775,7 +848,8 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					// the element's random block, first inverse-CDF bracket and form factors are requested together, ahead of
 					// the dependent chain Compton energy -> energy bracket -> mu rows -> exp
 					ComptonPrefetch pf;
-					if (mine) compton_prefetch(P, zi, g, order, e, qi, pf);
+					if (mine && !ADV) compton_prefetch(P, zi, g, order, e, qi, pf);
+					if (mine && ADV) { const double *f = P.ff + (size_t)zi * P.n_q + qi, *sfp = P.sf + (size_t)zi * P.n_q + qi; pf.F0 = f[0]; pf.F1 = f[1]; pf.S0 = sfp[0]; pf.S1 = sfp[1]; }
 					// Rayleigh (:342-369)
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
@@ -787,6 +861,41 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					}
 					deposit_uniform(acc_k, hbase + 0, fx, lane);
 					deposit_varying(acc_k, ch_rayl, fx, lane);
+					if (ADV) {
+						// shell-resolved Compton (xmi_compton_varred, :752-947): one deposit per occupied subshell
+						const int r0 = P.adv_off[zi], r1 = P.adv_off[zi + 1];
+						double cdf_sum = 0.0, Pdir = 0.0;
+						if (mine) {
+							for (int r = r0; r < r1; r++) cdf_sum += P.adv_config[r] * adv_shell_cdf(P, r, p.energy, theta);
+							const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
+							Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
+						}
+						for (int r = r0; r < r1; r++) {
+							fx = 0ULL;
+							long ch_c = -1;
+							if (mine && cdf_sum != 0.0) {
+								const double cdf_r = adv_shell_cdf(P, r, p.energy, theta);
+								const double shell_weight = P.adv_config[r] * cdf_r / cdf_sum;
+								if (shell_weight != 0.0) {
+									const uint4 w = draw_block(P.seed, g, order, 2, e, (r - r0) >> 2);
+									const int k = (r - r0) & 3;
+									const double u = xmb_u01(k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w);
+									const double e_c = adv_energy_from_q(p.energy, adv_sample_q(P, r, u * cdf_r), theta);
+									if (e_c != 0.0) {
+										const NodePos cp = node_find(P, e_c);
+										double tm = 0.0;
+										for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+										fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight * shell_weight, P.counters);
+										const int ch = (int)((e_c - P.zero) / P.gain);
+										if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
+									}
+								}
+							}
+							deposit_uniform(acc_k, hbase + 1, fx, lane);
+							deposit_varying(acc_k, ch_c, fx, lane);
+						}
+						continue;
+					}
 					// Compton (xmi_compton_varred2, :949-1008)
 					fx = 0ULL;
 					long ch_c = -1;
@@ -847,7 +956,7 @@ for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
 			if (p.alive) {
 				double we_unused = 0.0;
 				int t_unused, z_unused, l_unused, s_unused;
-				select_and_scatter<NL, 0>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused);
+				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused);
 			}
 		}
 		// ---- compaction: survivors go, densely packed, to the queue of the next order -------------------
@@ -1037,7 +1146,7 @@ __device__ void cascade_emit(const XmbHistParams &P, Photon &q, double *mus, int
 	q.ex = c_ae * q.ex + c_be * q.dx; q.ey = c_ae * q.ey + c_be * q.dy; q.ez = c_ae * q.ez + c_be * q.dz;
 }
 
-template <int NL>
+template <int NL, bool ADV = false>
 __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ XmbHistParams P, const XmbBruteParams B) {
 	const int nL = NL > 0 ? NL : P.nL;
 	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
@@ -1101,7 +1210,7 @@ __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ 
 				n_inter++;
 				double we_unused = 0.0;
 				int shell = -1;
-				select_and_scatter<NL, 2>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
+				select_and_scatter<NL, 2, ADV>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
 				if (last_type == 4) {
 					// ---- xmi_simulate_photon_cascade_auger (:2413-4594): the primary vacancy decays without radiation
 					last_type = 3;
@@ -1302,6 +1411,13 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	P.compt_icdf = upload(D, T.compt_theta_icdf, (size_t)nZ * T.n_icdf_E * T.n_icdf_R, ok);
 	P.phi_icdf = upload(D, T.phi_icdf, (size_t)T.n_phi_T * T.n_icdf_R, ok);
 	P.cp_icdf = upload(D, T.cp_icdf, (size_t)nZ * T.n_cp, ok);
+	if (T.n_adv_rows > 0) {
+		P.adv_off = upload(D, T.adv_off, nZ + 1, ok);
+		P.adv_config = upload(D, T.adv_config, T.n_adv_rows, ok);
+		P.adv_edge = upload(D, T.adv_edge, T.n_adv_rows, ok);
+		P.adv_cdf = upload(D, T.adv_cdf, (size_t)T.n_adv_rows * T.n_cp, ok);
+		P.adv_qinv = upload(D, T.adv_qinv, (size_t)T.n_adv_rows * T.n_cp, ok);
+	}
 	P.ff = upload(D, T.ff, (size_t)nZ * T.n_q, ok);
 	P.sf = upload(D, T.sf, (size_t)nZ * T.n_q, ok);
 	// ---- per-element constants ----------------------------------------------------------------------------
@@ -1451,7 +1567,7 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
 	if (!in || !h || !in->inited || !options || !ex || !accum || !n_slots) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
 	const bool brute = !options->use_variance_reduction;
-	if (options->use_advanced_compton) { xmb_set_error("use_advanced_compton is not implemented on the GPU path"); return 0; }
+	if (options->use_advanced_compton && !xmb_tables_enable_advanced_compton(hdf5F)) return 0;   // builds the subshell tables once
 	if (options->escape_ratios_mode) { xmb_set_error("escape_ratios_mode is not implemented on the GPU path"); return 0; }
 	if (!brute && (!sa || !sa->solid_angles)) { xmb_set_error("variance reduction needs a solid-angle grid"); return 0; }
 	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: xmb_main_msim has no CPU fallback"); return 0; }
@@ -1522,7 +1638,8 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		cudaEventCreate(&e0); cudaEventCreate(&e1);
 		cudaEventRecord(e0);
 		if (ex->n_histories > 0) {
-			switch (P.nL) {
+			if (options->use_advanced_compton) xmb_brute_kernel<0, true><<<bg, bt>>>(P, B);
+			else switch (P.nL) {
 			case 1: xmb_brute_kernel<1><<<bg, bt>>>(P, B); break;
 			case 2: xmb_brute_kernel<2><<<bg, bt>>>(P, B); break;
 			case 3: xmb_brute_kernel<3><<<bg, bt>>>(P, B); break;
@@ -1557,10 +1674,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
 	while (threads > 64 && stage_bytes + sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
 	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch
-	while (threads > 64 && (size_t)threads * std::max(1, D->max_nE) > 60000) threads -= 32;
+	const size_t per_photon = (size_t)std::max(1, D->max_nE) * (options->use_advanced_compton ? 32 : 1);   // + one addend per subshell
+	while (threads > 64 && (size_t)threads * per_photon > 60000) threads -= 32;
 	const size_t smem = stage_bytes + sizeof(double) * 2 * P.nL * threads;
 	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
+	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation
 	XMB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
 	if (occ < 1) occ = 1;

@@ -61,6 +61,9 @@ struct XmbHistParams {
 	const double *rayl_icdf, *compt_icdf;    // [nZ][n_icdf_E][n_icdf_R]
 	const double *phi_icdf;                  // [n_phi_T][n_icdf_R]
 	const double *cp_icdf;                   // [nZ][n_cp]
+	// shell-resolved Compton profiles (use_advanced_compton); rows adv_off[zi] .. adv_off[zi+1]-1
+	const int *adv_off;
+	const double *adv_config, *adv_edge, *adv_cdf, *adv_qinv;
 	const double *ff, *sf;                   // [nZ][n_q]
 	// per unique element
 	const double *atomic_weight;             // [nZ]

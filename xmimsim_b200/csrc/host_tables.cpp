@@ -55,6 +55,7 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	const xmb_excitation &exc = *in->in.excitation;
 	XmbHdf5F *h = new XmbHdf5F();
 	h->xrl = xrl;
+	h->quality = quality;
 
 	// ---- unique elements (ascending) ----------------------------------------------------------
 	std::set<int> zs;
@@ -330,6 +331,7 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	v.fluor_yield = h->fluor_yield.data(); v.fluor_yield_corr = h->fluor_yield_corr.data();
 	v.cos_kron = h->cos_kron.data(); v.rad_rate = h->rad_rate.data(); v.line_energy = h->line_energy.data();
 	v.auger_rate = h->auger_rate.data();
+	v.n_adv_rows = 0;
 	v.edge_energy = h->edge_energy.data();
 	v.n_layers = comp.n_layers; v.mu_layer = h->mu_layer.data(); v.exc_murhod = h->exc_murhod.data();
 	*out = h;
@@ -423,3 +425,82 @@ extern "C" void xmb_free_solid_angle(xmb_solid_angle *sa) {
 
 // overridden by the strong definition in history.cu once device layouts exist
 __attribute__((weak)) void xmb_free_device_tables(XmbDeviceTables *) {}
+
+
+// ---- shell-resolved Compton profiles (src/xmi_data_f.F90:1120-1235), built on demand ------------------------------
+extern "C" int xmb_tables_enable_advanced_compton(xmb_hdf5FPtr p) {
+	XmbHdf5F *h = xmb_as_hdf5(p);
+	if (!h) { xmb_set_error("xmb_tables_enable_advanced_compton: bad handle"); return 0; }
+	if (h->view.n_adv_rows > 0) return 1;
+	const xmb_xrl_provider *xrl = h->xrl;
+	if (!xrl->ElectronConfig_Biggs || !xrl->ComptonProfile_Partial) {
+		xmb_set_error("use_advanced_compton: the cross-section provider has no ElectronConfig_Biggs / ComptonProfile_Partial");
+		return 0;
+	}
+	const int nZ = (int)h->Z.size();
+	const long n_pz = h->quality >= 1 ? 10000000 : 400000;
+	h->adv_off.assign(nZ + 1, 0);
+	h->adv_shell.clear(); h->adv_config.clear(); h->adv_edge.clear();
+	for (int i = 0; i < nZ; i++) {
+		h->adv_off[i] = (int)h->adv_shell.size();
+		for (int s = 0; s <= 30; s++) {                    // K always, then the occupied subshells (:1126-1145)
+			const double n = xrl->ElectronConfig_Biggs(h->Z[i], s);
+			if (s > 0 && !(n > 0)) continue;
+			h->adv_shell.push_back(s);
+			h->adv_config.push_back(n);
+			h->adv_edge.push_back(xrl->EdgeEnergy(h->Z[i], s));
+		}
+	}
+	h->adv_off[nZ] = (int)h->adv_shell.size();
+	const int rows = (int)h->adv_shell.size();
+	h->adv_cdf.assign((size_t)rows * N_CP, 0.0);
+	h->adv_qinv.assign((size_t)rows * N_CP, 0.0);
+	std::vector<int> row_Z(rows);
+	for (int i = 0; i < nZ; i++) for (int r = h->adv_off[i]; r < h->adv_off[i + 1]; r++) row_Z[r] = h->Z[i];
+#pragma omp parallel
+	{
+		std::vector<double> big(n_pz);
+#pragma omp for schedule(dynamic, 1)
+		for (int r = 0; r < rows; r++) {
+			const int Z = row_Z[r], s = h->adv_shell[r];
+			double *cdf = &h->adv_cdf[(size_t)r * N_CP], *qinv = &h->adv_qinv[(size_t)r * N_CP];
+			// cumulative trapezoid on the coarse grid Qs, normalised to 0.5 at Q = 100 (:1189-1197)
+			const double dq = MAXPZ / (N_CP - 1.0);
+			double prev = xrl->ComptonProfile_Partial(Z, s, 0.0);
+			cdf[0] = 0.0;
+			for (int j = 1; j < N_CP; j++) {
+				const double next = xrl->ComptonProfile_Partial(Z, s, MAXPZ * j / (N_CP - 1.0));
+				cdf[j] = cdf[j - 1] + dq * (next + prev) * 0.5;
+				prev = next;
+			}
+			const double last = cdf[N_CP - 1];
+			if (last > 0.0) for (int j = 0; j < N_CP; j++) cdf[j] = cdf[j] * 0.5 / last;
+			// inverse on the fine grid (:1199-1232)
+			const double dqb = MAXPZ / (n_pz - 1.0);
+			prev = xrl->ComptonProfile_Partial(Z, s, 0.0);
+			big[0] = 0.0;
+			for (long j = 1; j < n_pz; j++) {
+				const double next = xrl->ComptonProfile_Partial(Z, s, MAXPZ * j / (n_pz - 1.0));
+				big[j] = big[j - 1] + dqb * (next + prev) * 0.5;
+				prev = next;
+			}
+			const double lastb = big[n_pz - 1];
+			if (lastb > 0.0) for (long j = 0; j < n_pz; j++) big[j] = big[j] * 0.5 / lastb;
+			long pos = 0;
+			for (int j = 0; j < N_CP; j++) {
+				const double c = 0.5 * j / (N_CP - 1.0);
+				while (pos < n_pz - 2 && big[pos + 1] <= c) pos++;      // findpos: big[pos] <= c < big[pos+1]
+				const double d = big[pos + 1] - big[pos];
+				const double q0 = MAXPZ * pos / (n_pz - 1.0), q1 = MAXPZ * (pos + 1) / (n_pz - 1.0);
+				qinv[j] = d > 0.0 ? q0 + (q1 - q0) * (c - big[pos]) / d : q0;
+			}
+			qinv[0] = 0.0;
+		}
+	}
+	xmb_tables_host &v = h->view;
+	v.adv_off = h->adv_off.data(); v.adv_shell = h->adv_shell.data(); v.adv_config = h->adv_config.data();
+	v.adv_edge = h->adv_edge.data(); v.adv_cdf = h->adv_cdf.data(); v.adv_qinv = h->adv_qinv.data();
+	v.n_adv_rows = rows;
+	if (h->dev) { xmb_free_device_tables(h->dev); h->dev = nullptr; }   // device layouts are rebuilt with the new tables
+	return 1;
+}

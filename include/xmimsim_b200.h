@@ -453,6 +453,22 @@ void xmb_detector_convolute_spectrum(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
 void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double *history,
                                     const xmb_main_options *options);
 /* ------------------------------------------------------------------------------------------
+ * X-ray tube source generator.
+ * ------------------------------------------------------------------------------------------ */
+/* Replaces xmi_tube_ebel (include/xmi_ebel.h; src/xmi_ebel.F90:114-521): Ebel's bremsstrahlung continuum on
+ * 1 keV .. voltage in steps of delta_energy plus the anode's K and L lines, attenuated by the window and filter
+ * (first element of each layer, as the reference), scaled by solid angle and current, optionally by a
+ * transmission-efficiency curve (natural cubic spline, src/xmi_spline.c).  xrl NULL = surrogate.  *spectrum and
+ * its arrays are malloc'ed (xmb_free_excitation).  The reference's CS_Total is taken from CS_Total_Kissel.
+ * Returns 1 / 0. */
+int xmb_tube_ebel(const xmb_xrl_provider *xrl, const xmb_layer *tube_anode, const xmb_layer *tube_window,
+                  const xmb_layer *tube_filter, double tube_voltage, double tube_current,
+                  double tube_angle_electron, double tube_angle_xray, double tube_delta_energy,
+                  double tube_solid_angle, int tube_transmission, size_t tube_nefficiencies,
+                  const double *tube_energies, const double *tube_efficiencies, xmb_excitation **spectrum);
+void xmb_free_excitation(xmb_excitation **spectrum);
+
+/* ------------------------------------------------------------------------------------------
  * Escape-peak ratios of the detector crystal (Monte Carlo, one interaction per photon).
  * ------------------------------------------------------------------------------------------ */
 typedef struct xmb_escape_ratios_options {   /* struct _xmi_escape_ratios_options, include/xmi_detector.h:42-51 */

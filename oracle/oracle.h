@@ -92,6 +92,13 @@ int orc_escape_ratios(const xmb_input *in, const orc_derived *d, const xmb_table
                       long n_photons, int n_out, double out_min, double out_delta, int n_threads,
                       double *fluo, double *compt);
 
+/* X-ray tube spectrum (xmi_tube_ebel, src/xmi_ebel.F90:114-521) and its spline (src/xmi_spline.c). */
+double orc_cubic_spline(const double *x, const double *y, size_t n, double v);
+int orc_tube_ebel(const xmb_xrl_provider *xrl, const xmb_layer *anode, const xmb_layer *window, const xmb_layer *filter,
+                  double V, double current, double angle_e, double angle_x, double dE, double solid_angle,
+                  int transmission, size_t n_eff, const double *eff_E, const double *eff, double *cont_E,
+                  double *cont_I, int *ndisc_out, double *disc_E, double *disc_I);
+
 /* Detector response (src/xmi_detector_f.F90).  noconv[nch] is modified IN PLACE by the absorption
  * correction, escape peaks and pile-up, as the reference does (:412-413); conv[nch] is the result. */
 double orc_detector_correction(const xmb_input *in, const xmb_xrl_provider *xrl, double E);

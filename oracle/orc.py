@@ -57,6 +57,10 @@ def lib():
         _lib.orc_main_msim_brute_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_uint64,
                                                    C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_main_msim_brute_range.restype = C.c_uint64
+        _lib.orc_cubic_spline.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]
+        _lib.orc_cubic_spline.restype = C.c_double
+        _lib.orc_tube_ebel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_double] * 6 + [C.c_int, C.c_size_t] + [C.c_void_p] * 7
+        _lib.orc_tube_ebel.restype = C.c_int
         _lib.orc_escape_ratios.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_uint64, C.c_long, C.c_int,
                                            C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.orc_escape_ratios.restype = C.c_int

@@ -6,4 +6,4 @@ library or a GPU is missing.
 """
 from . import abi            # noqa: F401
 from .xmsi import InputD, LayerD, DiscreteD, ContinuousD, read_xmsi, read_xmso, CInput   # noqa: F401
-from .engine import Simulation, main_options   # noqa: F401
+from .engine import Simulation, main_options, tube_ebel   # noqa: F401

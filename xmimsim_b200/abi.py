@@ -214,6 +214,11 @@ def lib():
     L.xmb_detector_convolute_history.argtypes = [vp, vp, c_double_p, C.POINTER(MainOptions)]
     L.xmb_detector_convolute_history.restype = None
     L.xmb_detector_last_ms.restype = C.c_double
+    L.xmb_tube_ebel.argtypes = [C.POINTER(XrlProvider), C.POINTER(Layer), C.POINTER(Layer), C.POINTER(Layer), C.c_double,
+                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_size_t,
+                                c_double_p, c_double_p, C.POINTER(C.POINTER(Excitation))]
+    L.xmb_tube_ebel.restype = C.c_int
+    L.xmb_free_excitation.argtypes = [C.POINTER(C.POINTER(Excitation))]; L.xmb_free_excitation.restype = None
     L.xmb_get_default_escape_ratios_options.restype = EscapeRatiosOptions
     L.xmb_escape_ratios_input.argtypes = [C.POINTER(Input), C.POINTER(EscapeRatiosOptions), vpp]
     L.xmb_escape_ratios_input.restype = C.c_int

@@ -32,6 +32,42 @@ def _np_from_ptr(ptr, shape, dtype=np.float64):
     return buf.reshape(shape)
 
 
+def _c_layer(l, keep):
+    z = (C.c_int * len(l.Z))(*l.Z)
+    w = (C.c_double * len(l.weight))(*l.weight)
+    keep += [z, w]
+    return abi.Layer(len(l.Z), C.cast(z, abi.c_int_p), C.cast(w, abi.c_double_p), l.density, l.thickness)
+
+
+def tube_ebel(anode, voltage, current=1.0, angle_electron=60.0, angle_xray=60.0, delta_energy=0.1, solid_angle=1e-4,
+              window=None, filt=None, transmission=False, eff_energies=None, efficiencies=None, provider=None):
+    """xmi_tube_ebel: returns (continuous[(E, I_h, I_v)], discrete[(E, I_h, I_v)]) as two numpy arrays; anode / window /
+    filt are LayerD.  Feed the result into InputD.continuous / .discrete (ContinuousD / DiscreteD)."""
+    L = abi.lib()
+    keep = []
+    la = _c_layer(anode, keep)
+    lw = _c_layer(window, keep) if window is not None else None
+    lf = _c_layer(filt, keep) if filt is not None else None
+    n_eff, pe, pv = 0, None, None
+    if eff_energies is not None:
+        ee = np.ascontiguousarray(eff_energies, np.float64); ev = np.ascontiguousarray(efficiencies, np.float64)
+        keep += [ee, ev]
+        n_eff, pe, pv = ee.size, ee.ctypes.data_as(abi.c_double_p), ev.ctypes.data_as(abi.c_double_p)
+    out = C.POINTER(abi.Excitation)()
+    ok = L.xmb_tube_ebel(provider, C.byref(la), C.byref(lw) if lw is not None else None, C.byref(lf) if lf is not None else None,
+                         voltage, current, angle_electron, angle_xray, delta_energy, solid_angle, int(bool(transmission)),
+                         n_eff, pe, pv, C.byref(out))
+    if not ok:
+        raise RuntimeError("xmb_tube_ebel: " + abi.last_error())
+    e = out.contents
+    cont = np.array([(e.continuous[i].energy, e.continuous[i].horizontal_intensity, e.continuous[i].vertical_intensity)
+                     for i in range(e.n_continuous)]).reshape(-1, 3)
+    disc = np.array([(e.discrete[i].energy, e.discrete[i].horizontal_intensity, e.discrete[i].vertical_intensity)
+                     for i in range(e.n_discrete)]).reshape(-1, 3)
+    L.xmb_free_excitation(C.byref(out))
+    return cont, disc
+
+
 class Simulation:
     """Owns the two opaque handles (input + tables) of one simulation."""
 

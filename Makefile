@@ -22,7 +22,7 @@ ORC_LIB   := oracle/_build/liborc.so
 PLUGIN    := xmimsim_b200/lib/xmimsim-cl.so
 
 all: $(LIB) $(PLUGIN) $(ORC_LIB)
-lib: $(LIB)
+lib: $(LIB) $(PLUGIN)
 oracle: $(ORC_LIB)
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(HDRS)
@@ -43,9 +43,9 @@ $(LIB): $(OBJS)
 	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(OBJS) -Xcompiler -fopenmp -lgomp -ldl -cudart static
 
 # Drop-in plugin file name the reference's loader opens (src/xmi_solid_angle.c:121-136: "<dir>/xmimsim-cl.<so>");
-# the same symbols are inside $(LIB); this is that library under the expected name.
+# the same symbols are inside $(LIB); this is that library under the expected name (a relative symlink).
 $(PLUGIN): $(LIB)
-	cp $(LIB) $(PLUGIN)
+	ln -sf $(notdir $(LIB)) $(PLUGIN)
 
 # The oracle links the surrogate provider object (third-party stand-in), never the engine.
 $(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h $(SRC)/xrl_surrogate.c

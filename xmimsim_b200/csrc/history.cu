@@ -501,6 +501,25 @@ __device__ double compton_energy_adv(const XmbHistParams &P, int zi, double E0, 
 	return adv_energy_from_q(E0, adv_sample_q(P, i, u_q * cdf_i), theta_i);
 }
 
+// exp(-t) for t >= 0 in ~15 instructions (the library exp is ~30 and the line loop evaluates one per active line and
+// interaction): 2^(-y) with y = t log2(e) = (j + r) / 64, |r| <= 1/2; 2^(-j/64) = 2^(-(j >> 6)) tab[j & 63] with a 64-entry
+// table in shared memory, and exp(-r ln2 / 64) by its Taylor polynomial of degree 5 (|x| < 0.0055: remainder 4e-17).
+// Relative error <= 2^-53 t + 3e-16, i.e. 1e-13 at the largest exponents that still matter.
+__device__ __forceinline__ double exp_neg(double t, const double *tab) {
+	const double y = t * (64.0 * 1.4426950408889634074);
+	if (!(y < 64.0 * 1000.0)) return 0.0;                       // exp(-693) = 1e-301: below anything a deposit can represent
+	const double jf = rint(y);
+	const int j = (int)jf;
+	const double x = (jf - y) * (0.69314718055994530942 / 64.0);
+	double pl = fma(x, 1.0 / 120.0, 1.0 / 24.0);
+	pl = fma(pl, x, 1.0 / 6.0);
+	pl = fma(pl, x, 0.5);
+	pl = fma(pl, x, 1.0);
+	pl = fma(pl, x, 1.0);
+	const double scale = __hiloint2double((1023 - (j >> 6)) << 20, 0);   // 2^(-(j >> 6)), j >> 6 <= 1000
+	return pl * tab[j & 63] * scale;
+}
+
 // ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------
 // MODE 0: forced detection (the fluorescence yield multiplies the weight); 1: escape-ratio mode (it goes to
 // weight_escape, src/xmi_variance_reduction.F90:697-750); 2: brute force (analogue yield check, :2297-2319 / :5325-5350:
@@ -531,50 +550,36 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 	const double s0 = xmb_u01(b1.y), s1 = xmb_u01(b1.z), s2 = xmb_u01(b1.w);
 	const double pr = row_lerp(P, ep, eoff + XMB_EO_P_RAYL), prc = row_lerp(P, ep, eoff + XMB_EO_P_RAYL_COMPT);
 	out_zi = zi;
-	if (R2 < pr) {
-		out_type = 1;
-		// Rayleigh (:1986-2101)
-		const double r = s0;
-		const double theta_i = bilinear(P.rayl_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, r);
-		double tt = sin(theta_i) * sin(theta_i);
-		tt = tt / (4.0 - 2.0 * tt);
-		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
-		const double phi0 = elec_phi0(p);
-		update_dirv(p, theta_i, phi0 + phi_i);
-		update_elecv(p);
-	} else if (R2 < prc) {
-		out_type = 2;
-		// Compton (:2103-2229)
-		const double theta_i = bilinear(P.compt_icdf + (size_t)zi * P.n_icdf_E * P.n_icdf_R, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
-		const double K0K = 1.0 + p.energy * (1.0 - cos(theta_i)) / XMI_MEC2;
-		double tt = sin(theta_i) * sin(theta_i);
-		tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
-		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
-		const double phi0 = elec_phi0(p);
-		if (ADV) {
-			const uint4 w = draw_block(P.seed, g, order, 3, 0, 0);
-			p.energy = compton_energy_adv(P, zi, p.energy, theta_i, xmb_u01(w.x), xmb_u01(w.y));
-		} else
-			p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
-		{
-			const NodePos cp = node_find(P, p.energy);
-			XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
+	// The three interaction branches only decide (theta_i, phi_rot, new energy); the lookups they share and the
+	// rotation of the direction / polarisation vectors run once, after the branches, with the warp converged
+	// (profiles/r1_history_kernel_v8_*: the rotation code ran at 10 of 32 lanes when it was inlined per branch).
+	const bool is_rayl = R2 < pr, is_compt = !is_rayl && R2 < prc;
+	double theta_i = 0.0, phi_i = 0.0, phi_rot = 0.0;
+	bool rotate = false, new_energy = false;
+	if (is_rayl || is_compt) {
+		out_type = is_rayl ? 1 : 2;
+		// Rayleigh (:1986-2101) / Compton (:2103-2229): theta from the element's inverse CDF, phi from the polarisation table
+		const double *icdf = (is_rayl ? P.rayl_icdf : P.compt_icdf) + (size_t)zi * P.n_icdf_E * P.n_icdf_R;
+		theta_i = bilinear(icdf, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
+		double sti, cti;
+		sincos(theta_i, &sti, &cti);
+		double tt = sti * sti;
+		if (is_rayl) tt = tt / (4.0 - 2.0 * tt);
+		else {
+			const double K0K = 1.0 + p.energy * (1.0 - cti) / XMI_MEC2;
+			tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
 		}
-		if (p.energy != 0.0) {
-			update_dirv(p, theta_i, phi_i + phi0);
-			update_elecv(p);
-			const double cti = cos(theta_i), cpi = cos(phi_i), spi = sin(phi_i);
-			double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
-			const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
-			const double rk = rat - 2.0 + 1.0 / rat;
-			pp = pp / (rk + pp);
-			const double r = s2;
-			const double w_h = (1.0 + pp) / 2.0;
-			if (r > w_h) {
-				const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
-				p.ex = tx; p.ey = ty; p.ez = tz;
-			}
+		phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
+		phi_rot = phi_i + elec_phi0(p);
+		rotate = true;
+		if (is_compt) {
+			if (ADV) {
+				const uint4 w = draw_block(P.seed, g, order, 3, 0, 0);
+				p.energy = compton_energy_adv(P, zi, p.energy, theta_i, xmb_u01(w.x), xmb_u01(w.y));
+			} else
+				p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
+			new_energy = true;
+			rotate = p.energy != 0.0;
 		}
 	} else {
 		out_type = 3;
@@ -621,13 +626,35 @@ for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
 				out_line = line;
 				out_shell = shell;
 				p.energy = P.line_energy[(size_t)zi * 384 + line];
-				const NodePos lp = node_find(P, p.energy);
-				XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, lp, i);
-				const double theta_i = acos(-2.0 * s2 + 1.0);
-				const double phi_i = 2.0 * M_PI * u_phi;
-				update_dirv(p, theta_i, phi_i);
-				update_elecv(p);
+				new_energy = true;
+				theta_i = acos(-2.0 * s2 + 1.0);
+				phi_rot = 2.0 * M_PI * u_phi;
+				rotate = true;
+			}
+		}
+	}
+	// ---- common tail: attenuation coefficients at the new energy, rotation of direction and polarisation ----------
+	if (new_energy) {
+		const NodePos cp = node_find(P, p.energy);
+		XMB_UNROLL_NL
+for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
+	}
+	if (rotate) {
+		update_dirv(p, theta_i, phi_rot);
+		update_elecv(p);
+		if (is_compt) {
+			// depolarisation of the Compton-scattered photon (:2201-2211)
+			double spi, cpi;
+			sincos(phi_i, &spi, &cpi);
+			const double cti = cos(theta_i);
+			double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
+			const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
+			const double rk = rat - 2.0 + 1.0 / rat;
+			pp = pp / (rk + pp);
+			const double w_h = (1.0 + pp) / 2.0;
+			if (s2 > w_h) {
+				const double tx = p.dy * p.ez - p.dz * p.ey, ty = p.dz * p.ex - p.dx * p.ez, tz = p.dx * p.ey - p.dy * p.ex;
+				p.ex = tx; p.ey = ty; p.ez = tz;
 			}
 		}
 	}
@@ -648,7 +675,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	unsigned long long n_inter_local = 0;
 	bool bad_fixed = false;
 	__shared__ unsigned int s_layer_cnt[XMB_MAX_LAYERS];
+	__shared__ double s_exp_tab[64];              // 2^(-k/64), see exp_neg()
 	if (tid < XMB_MAX_LAYERS) s_layer_cnt[tid] = 0;
+	if (tid < 64) s_exp_tab[tid] = exp2(-(double)tid / 64.0);
 	__syncthreads();
 
 	// The kernel is ~260 KB of SASS (fp64 transcendentals inlined at every site) against a 32 KB L1.5 I-cache: a
@@ -907,7 +936,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
 						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
-						fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight, P.counters);
+						fx = to_fixed(Pconv * Pdir * exp_neg(tm, s_exp_tab) * p.weight, P.counters);
 						const int ch = (int)((e_c - P.zero) / P.gain);
 						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
 					}
@@ -943,7 +972,7 @@ XMB_UNROLL(XMB_REC_UNROLL)
 							double tm = 0.0;
 							XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
-							const double tw = pre * P.rec_yr[r] * exp(-tm);
+							const double tw = pre * P.rec_yr[r] * exp_neg(tm, s_exp_tab);
 							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed_fast(tw, bad_fixed) : 0ULL, lane);
 						}
 					}

@@ -21,8 +21,10 @@ ORC_LIB   := oracle/_build/liborc.so
 
 PLUGIN    := xmimsim_b200/lib/xmimsim-cl.so
 
-all: $(LIB) $(PLUGIN) $(ORC_LIB)
-lib: $(LIB) $(PLUGIN)
+CLI       := bin/xmimsim-b200
+
+all: $(LIB) $(PLUGIN) $(ORC_LIB) $(CLI)
+lib: $(LIB) $(PLUGIN) $(CLI)
 oracle: $(ORC_LIB)
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(HDRS)
@@ -47,11 +49,15 @@ $(LIB): $(OBJS)
 $(PLUGIN): $(LIB)
 	ln -sf $(notdir $(LIB)) $(PLUGIN)
 
+# Command-line driver with the reference's options (bin/xmimsim.c); finds the library next to the package.
+$(CLI): bin/xmimsim_main.cpp $(LIB) include/xmimsim_b200.h
+	$(CXX) -O2 -std=c++17 -Iinclude -o $@ bin/xmimsim_main.cpp -Lxmimsim_b200/lib -lxmimsim_b200 -Wl,-rpath,'$$ORIGIN/../xmimsim_b200/lib'
+
 # The oracle links the surrogate provider object (third-party stand-in), never the engine.
 $(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h $(SRC)/xrl_surrogate.c
 	@mkdir -p oracle/_build
 	$(CC) $(CFLAGS) -Ioracle -shared -o $@ $(ORC_SRCS) $(SRC)/xrl_surrogate.c -lm
 
 clean:
-	rm -rf build xmimsim_b200/lib oracle/_build
+	rm -rf build xmimsim_b200/lib oracle/_build $(CLI)
 .PHONY: all lib oracle clean

@@ -1,0 +1,145 @@
+// xmimsim-b200 -- command-line driver with the reference's options and progress lines (bin/xmimsim.c:78-700):
+//   xmimsim-b200 [options] inputfile.xmsi
+// reads the XMSI file, computes the solid-angle grid, runs the histories on the GPU, computes the escape ratios of
+// the detector crystal when escape peaks are on, applies the detector response and writes the XMSO file named in
+// the input (plus optional SPE / CSV spectra).  The HDF5 caches of the reference (~/.local/share/XMI-MSIM/*.h5) are
+// not used: both the grid and the escape ratios are recomputed on the GPU (54 ms and 0.6 s on a B200).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "xmimsim_b200.h"
+
+static void usage(FILE *f) {
+	fputs("Usage:\n  xmimsim-b200 [OPTION...] inputfile\n\n"
+	      "xmimsim-b200: Monte-Carlo simulation of X-ray fluorescence spectra on an NVIDIA B200\n\n"
+	      "  --enable-M-lines / --disable-M-lines                      M lines (default: enabled)\n"
+	      "  --enable-auger-cascade / --disable-auger-cascade          non-radiative cascade (default: enabled)\n"
+	      "  --enable-radiative-cascade / --disable-radiative-cascade  radiative cascade (default: enabled)\n"
+	      "  --enable-variance-reduction / --disable-variance-reduction forced detection (default: enabled)\n"
+	      "  --enable-pile-up / --disable-pile-up                      pulse pile-up (default: disabled)\n"
+	      "  --enable-escape-peaks / --disable-escape-peaks            escape peaks (default: enabled)\n"
+	      "  --enable-poisson / --disable-poisson                      Poisson noise (default: disabled)\n"
+	      "  --enable-advanced-compton / --disable-advanced-compton    shell-resolved Compton (default: disabled)\n"
+	      "  --spe-file=F --spe-file-unconvoluted=F                    write F_<order>.spe\n"
+	      "  --csv-file=F --csv-file-unconvoluted=F                    write CSV spectra\n"
+	      "  --set-seed=N                                              Philox key (default: library seed)\n"
+	      "  --table-quality=0|1                                       inverse-CDF integration resolution (default 1 = reference)\n"
+	      "  -v, --verbose    -V, --very-verbose    --version\n", f);
+}
+
+int main(int argc, char **argv) {
+	xmb_main_options opt;
+	xmb_main_options_defaults(&opt);
+	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile;
+	unsigned long long seed = 0;
+	int quality = 1;
+	struct Flag { const char *name; int *target; };
+	const Flag flags[] = {{"M-lines", &opt.use_M_lines}, {"auger-cascade", &opt.use_cascade_auger}, {"radiative-cascade", &opt.use_cascade_radiative},
+	                      {"variance-reduction", &opt.use_variance_reduction}, {"pile-up", &opt.use_sum_peaks}, {"escape-peaks", &opt.use_escape_peaks},
+	                      {"poisson", &opt.use_poisson}, {"advanced-compton", &opt.use_advanced_compton}, {"gpu", &opt.use_gpu},
+	                      {"default-seeds", &opt.use_default_seeds}};
+	for (int i = 1; i < argc; i++) {
+		const std::string a = argv[i];
+		bool done = false;
+		for (const Flag &f : flags) {
+			if (a == std::string("--enable-") + f.name) { *f.target = 1; done = true; }
+			else if (a == std::string("--disable-") + f.name) { *f.target = 0; done = true; }
+		}
+		if (done) continue;
+		auto val = [&](const char *key, std::string &out) {
+			const std::string k = std::string(key) + "=";
+			if (a.compare(0, k.size(), k) == 0) { out = a.substr(k.size()); return true; }
+			if (a == key && i + 1 < argc) { out = argv[++i]; return true; }
+			return false;
+		};
+		std::string tmp;
+		if (val("--spe-file-unconvoluted", spe_noconv) || val("--spe-file", spe_conv) || val("--csv-file-unconvoluted", csv_noconv) || val("--csv-file", csv_conv)) continue;
+		if (val("--set-seed", tmp)) { seed = strtoull(tmp.c_str(), nullptr, 0); continue; }
+		if (val("--table-quality", tmp)) { quality = atoi(tmp.c_str()); continue; }
+		if (val("--set-threads", tmp)) { opt.omp_num_threads = atoi(tmp.c_str()); continue; }
+		if (a == "-v" || a == "--verbose") { opt.verbose = 1; continue; }
+		if (a == "-V" || a == "--very-verbose") { opt.verbose = 1; opt.extra_verbose = 1; continue; }
+		if (a == "--version") { printf("%s\n", xmb_version()); return 0; }
+		if (a == "-h" || a == "--help") { usage(stdout); return 0; }
+		if (!a.empty() && a[0] == '-') { fprintf(stderr, "Unknown option %s\n", a.c_str()); usage(stderr); return 1; }
+		infile = a;
+	}
+	if (infile.empty()) { usage(stderr); return 1; }
+	if (xmb_cuda_device_count() < 1) { fprintf(stderr, "No CUDA device found: xmimsim-b200 has no CPU fallback\n"); return 1; }
+
+	xmb_input *input = nullptr;
+	if (!xmb_input_read_from_xml_file(infile.c_str(), &input)) { fprintf(stderr, "Could not read %s: %s\n", infile.c_str(), xmb_last_error()); return 1; }
+	if (opt.verbose) printf("Inputfile %s successfully parsed\n", infile.c_str());
+	xmb_inputFPtr inputF = nullptr;
+	xmb_hdf5FPtr tables = nullptr;
+	if (!xmb_input_C2F(input, &inputF) || !xmb_init_input(&inputF)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+	if (opt.verbose) printf("Building cross-section tables (%s)\n", xmb_xrl_surrogate()->name);
+	if (!xmb_init_from_provider(xmb_xrl_surrogate(), inputF, quality, &tables)) { fprintf(stderr, "Could not build the tables: %s\n", xmb_last_error()); return 1; }
+
+	const int n_int = input->general->n_interactions_trajectory, nch = input->detector->nchannels;
+	xmb_solid_angle *sa = nullptr;
+	if (opt.use_variance_reduction) {
+		if (opt.verbose) printf("Precalculating solid angle grid\n");
+		if (!xmb_solid_angle_calculation(inputF, tables, &sa, nullptr, &opt, 5000, seed)) { fprintf(stderr, "Solid angle calculation failed: %s\n", xmb_last_error()); return 1; }
+		if (opt.verbose) printf("Solid angle calculation finished\n");
+	}
+	double *channels = nullptr, *brute = nullptr, *var_red = nullptr;
+	if (!xmb_main_msim(inputF, tables, 1, &channels, &opt, &brute, &var_red, sa)) { fprintf(stderr, "Error in xmi_main_msim: %s\n", xmb_last_error()); return 1; }
+	double zero_sum = 0.0;
+	for (int j = 0; j < nch; j++) zero_sum += channels[j];
+	const int first = zero_sum > 0.0 ? 0 : 1;                                     // bin/xmimsim.c:436, 499
+
+	xmb_escape_ratios *er = nullptr;
+	if (opt.use_escape_peaks) {
+		if (opt.verbose) printf("Calculating escape peak ratios\n");
+		if (!xmb_escape_ratios_calculation(input, &er, nullptr, xmb_xrl_surrogate(), &opt, xmb_get_default_escape_ratios_options(), seed)) {
+			fprintf(stderr, "Escape ratios calculation failed: %s\n", xmb_last_error());
+			return 1;
+		}
+	}
+	// keep the raw spectra: the response corrects its input rows in place (src/xmi_detector_f.F90:412-413)
+	std::vector<double> raw(channels, channels + (size_t)(n_int + 1) * nch);
+	std::vector<double *> rows(n_int + 1), conv(n_int + 1, nullptr), raw_rows(n_int + 1);
+	for (int i = 0; i <= n_int; i++) { rows[i] = channels + (size_t)i * nch; raw_rows[i] = raw.data() + (size_t)i * nch; }
+	xmb_detector_convolute_all(inputF, tables, rows.data(), conv.data(), brute, var_red, &opt, er, n_int, first == 0 ? 1 : 0);
+	for (int i = first; i <= n_int; i++) if (!conv[i]) { fprintf(stderr, "Detector response failed: %s\n", xmb_last_error()); return 1; }
+	if (!conv[0]) conv[0] = (double *)calloc(nch, sizeof(double));
+
+	for (int i = first; i <= n_int; i++) {
+		char name[4096];
+		if (!spe_noconv.empty()) {
+			snprintf(name, sizeof(name), "%s_%d.spe", spe_noconv.c_str(), i);
+			if (!xmb_write_spe_file(name, input, raw_rows[i])) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+			if (opt.verbose) printf("Writing to SPE file %s\n", name);
+		}
+		if (!spe_conv.empty()) {
+			snprintf(name, sizeof(name), "%s_%d.spe", spe_conv.c_str(), i);
+			if (!xmb_write_spe_file(name, input, conv[i])) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+			if (opt.verbose) printf("Writing to SPE file %s\n", name);
+		}
+	}
+	if (!csv_noconv.empty()) {
+		if (!xmb_write_csv_file(csv_noconv.c_str(), input, raw_rows.data(), first)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+		if (opt.verbose) printf("Writing to CSV file %s\n", csv_noconv.c_str());
+	}
+	if (!csv_conv.empty()) {
+		if (!xmb_write_csv_file(csv_conv.c_str(), input, conv.data(), first)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+		if (opt.verbose) printf("Writing to CSV file %s\n", csv_conv.c_str());
+	}
+	if (!xmb_output_write_to_xml_file(input, infile.c_str(), input->general->outputfile, raw.data(), conv.data(), brute,
+	                                  opt.use_variance_reduction ? var_red : nullptr, first == 0 ? 1 : 0, xmb_xrl_surrogate())) {
+		fprintf(stderr, "Could not write to %s: %s\n", input->general->outputfile, xmb_last_error());
+		return 1;
+	}
+	if (opt.verbose) printf("Output written to XMSO file %s\n", input->general->outputfile);
+	for (int i = 0; i <= n_int; i++) free(conv[i]);
+	free(channels); free(brute); free(var_red);
+	if (er) xmb_free_escape_ratios(&er);
+	if (sa) xmb_free_solid_angle(sa);
+	xmb_free_hdf5_F(&tables);
+	xmb_free_input_F(&inputF);
+	xmb_input_free(&input);
+	return 0;
+}

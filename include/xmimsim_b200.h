@@ -453,6 +453,29 @@ void xmb_detector_convolute_spectrum(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F,
 void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, double *history,
                                     const xmb_main_options *options);
 /* ------------------------------------------------------------------------------------------
+ * On-disk formats (host_io.cpp; no libxml2: a small built-in XML reader).
+ * ------------------------------------------------------------------------------------------ */
+/* Replaces xmi_input_read_from_xml_file (include/xmi_xml.h; src/xmi_xml.c:966-1340) with the reference reader's
+ * conventions: weight fractions in any positive scale, |w| < 1e-20 dropped, elements sorted by Z and normalised,
+ * lines and continuous points sorted by energy, nchannels optional (2048).  Also accepts an .xmso (reads its
+ * <xmimsim-input>).  *input is malloc'ed: xmb_input_free.  Returns 1 / 0. */
+int xmb_input_read_from_xml_file(const char *xmsifile, xmb_input **input);
+void xmb_input_free(xmb_input **input);
+/* Replaces xmi_input_write_to_xml_file (src/xmi_xml.c:1405-1450). */
+int xmb_input_write_to_xml_file(const xmb_input *input, const char *xmsifile);
+/* Replaces xmi_output_new + xmi_output_write_to_xml_file (src/xmi_data_structs.c:1369-1519;
+ * src/xmi_xml.c:1453-1700): channels_unconv is the raw [(n_int+1)][nchannels] array of xmb_main_msim,
+ * channels_conv the rows returned by the detector response, the histories [100][385][n_int] (NULL = empty).
+ * The optional <svg_graphs> block is not written.  xrl NULL = surrogate (line energies in the history). */
+int xmb_output_write_to_xml_file(const xmb_input *input, const char *inputfile, const char *xmsofile,
+                                 const double *channels_unconv, double *const *channels_conv,
+                                 const double *brute_history, const double *var_red_history,
+                                 int use_zero_interactions, const xmb_xrl_provider *xrl);
+/* The SPE / CSV spectrum files of bin/xmimsim.c:546-640 (--spe-file*, --csv-file*). */
+int xmb_write_spe_file(const char *filename, const xmb_input *input, const double *spectrum);
+int xmb_write_csv_file(const char *filename, const xmb_input *input, double *const *rows, int first_row);
+
+/* ------------------------------------------------------------------------------------------
  * X-ray tube source generator.
  * ------------------------------------------------------------------------------------------ */
 /* Replaces xmi_tube_ebel (include/xmi_ebel.h; src/xmi_ebel.F90:114-521): Ebel's bremsstrahlung continuum on

@@ -214,6 +214,14 @@ def lib():
     L.xmb_detector_convolute_history.argtypes = [vp, vp, c_double_p, C.POINTER(MainOptions)]
     L.xmb_detector_convolute_history.restype = None
     L.xmb_detector_last_ms.restype = C.c_double
+    L.xmb_input_read_from_xml_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(Input))]; L.xmb_input_read_from_xml_file.restype = C.c_int
+    L.xmb_input_free.argtypes = [C.POINTER(C.POINTER(Input))]; L.xmb_input_free.restype = None
+    L.xmb_input_write_to_xml_file.argtypes = [C.POINTER(Input), C.c_char_p]; L.xmb_input_write_to_xml_file.restype = C.c_int
+    L.xmb_output_write_to_xml_file.argtypes = [C.POINTER(Input), C.c_char_p, C.c_char_p, c_double_p, pp, c_double_p, c_double_p,
+                                               C.c_int, C.POINTER(XrlProvider)]
+    L.xmb_output_write_to_xml_file.restype = C.c_int
+    L.xmb_write_spe_file.argtypes = [C.c_char_p, C.POINTER(Input), c_double_p]; L.xmb_write_spe_file.restype = C.c_int
+    L.xmb_write_csv_file.argtypes = [C.c_char_p, C.POINTER(Input), pp, C.c_int]; L.xmb_write_csv_file.restype = C.c_int
     L.xmb_tube_ebel.argtypes = [C.POINTER(XrlProvider), C.POINTER(Layer), C.POINTER(Layer), C.POINTER(Layer), C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_size_t,
                                 c_double_p, c_double_p, C.POINTER(C.POINTER(Excitation))]

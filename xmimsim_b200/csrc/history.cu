@@ -1049,7 +1049,7 @@ struct XmbBruteParams {
 	double collimator_height, collimator_radius, half_apex, vertex_x, vertex_y, vertex_z;
 	int collimator_present;
 	const int *line_slot;        // [nZ][384]: compact history slot of a line, -1 = not an active line
-	const double *auger_rate;    // [nZ][XMB_N_AUGER]
+	const double *auger_rate;    // [nZ][XMB_N_AUGER] running sums within each block (K: 240, L1..L3: 135 each)
 };
 
 __device__ __forceinline__ void add128(unsigned long long *acc, size_t slot, unsigned long long v) {
@@ -1175,39 +1175,82 @@ __device__ void cascade_emit(const XmbHistParams &P, Photon &q, double *mus, int
 	q.ex = c_ae * q.ex + c_be * q.dx; q.ey = c_ae * q.ey + c_be * q.dy; q.ez = c_ae * q.ez + c_be * q.dz;
 }
 
+// Persistent lanes, phase-synchronous CTA.  The first version (one thread = one history, start to end) ran at 7.7 of
+// 32 threads per instruction and 14 % issue utilisation with 8.8 warps stalled on instruction fetch
+// (profiles/r1_brute_kernel_v1_*): histories differ in length and every warp sat somewhere else in ~200 KB of code.
+// Here every iteration of the CTA is: refill (a lane without a photon takes its pending cascade offspring, else the
+// next unsimulated photon id) | __syncthreads | analogue step + detector tests + scoring | __syncthreads | interaction
+// + cascades | __syncthreads -- all lanes busy in every phase, all warps in the same code.  Photon ids are handed out
+// by a warp-aggregated atomic counter; results do not depend on the assignment (fixed-address random numbers,
+// integer deposits).
+#ifndef XMB_BRUTE_THREADS
+#define XMB_BRUTE_THREADS 1024
+#endif
 template <int NL, bool ADV = false>
-__global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ XmbHistParams P, const XmbBruteParams B) {
+__global__ void __launch_bounds__(XMB_BRUTE_THREADS, 1) xmb_brute_kernel(const __grid_constant__ XmbHistParams P, const XmbBruteParams B) {
 	const int nL = NL > 0 ? NL : P.nL;
 	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
+	const int lane = threadIdx.x & 31;
 	unsigned long long n_inter = 0, n_hits = 0, n_off = 0, n_noslot = 0;
-	for (uint64_t lid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_local_span; lid += (uint64_t)gridDim.x * blockDim.x) {
-		const uint64_t g = shard_global_id(P, lid);
-		if (g >= P.n_total) continue;
-		Photon p, off;
-		double mus[NLA], off_mus[NLA];
-		{
-			XmbRng rng;
-			rng.init(P.seed, g, XMB_TAG_HISTORY);
-			start_photon<NL>(P, p, rng, g, mus, 1);
+	Photon p, off;
+	double mus[NLA], off_mus[NLA];
+	uint64_t g = 0;
+	bool have = false, exhausted = false, pending_off = false, co_auger = false, co_rad = false;
+	int gen_bit = 0, last_type = 0, last_zi = 0, last_line = 0, off_zi = 0, off_line = 0;
+	p.alive = false; p.energy = 0.0; p.n_interactions = 0; p.layer = 0;
+	for (;;) {
+		// ---- phase 0: refill ---------------------------------------------------------------------------------
+		if (!have && pending_off) {
+			// walk the offspring next (its cascades are switched off, src/xmi_main.F90:4509-4511, :4729-4731)
+			p = off;
+			for (int i = 0; i < nL; i++) mus[i] = off_mus[i];
+			last_type = 3; last_zi = off_zi; last_line = off_line;
+			co_auger = co_rad = false;
+			gen_bit = XMB_GEN_BIT;
+			pending_off = false;
+			have = true;
+			n_off++;
 		}
-		if (!p.alive) continue;
-		bool co_auger = B.use_auger != 0, co_rad = B.use_rad != 0, have_off = false;
-		int last_type = 0, last_zi = 0, last_line = 0, off_zi = 0, off_line = 0;
-		for (int gen = 0; gen < 2; gen++) {
-			const int gen_bit = gen ? XMB_GEN_BIT : 0;
-			bool hit = false;
-			// ---- xmi_simulate_photon, analogue branch -------------------------------------------------------
-			for (;;) {
-				if (p.energy < ENERGY_THRESHOLD) break;
+		{
+			const bool want = !have && !exhausted;
+			const unsigned m = __ballot_sync(0xffffffffu, want);
+			if (m) {
+				unsigned long long base = 0;
+				if (lane == __ffs(m) - 1) base = atomicAdd(&P.counters[6], (unsigned long long)__popc(m));
+				base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+				if (want) {
+					const uint64_t lid = base + __popc(m & ((1u << lane) - 1u));
+					g = shard_global_id(P, lid);
+					if (lid >= P.n_local_span) exhausted = true;
+					else if (g < P.n_total) {
+						XmbRng rng;
+						rng.init(P.seed, g, XMB_TAG_HISTORY);
+						start_photon<NL>(P, p, rng, g, mus, 1);
+						have = p.alive;
+						gen_bit = 0;
+						co_auger = B.use_auger != 0; co_rad = B.use_rad != 0;
+						last_type = 0; last_zi = 0; last_line = 0;
+					}
+				}
+			}
+		}
+		if (!__syncthreads_or(have ? 1 : 0)) break;
+		// ---- phase 1: analogue step through the layer stack, detector / collimator tests (:1229-1416, :1525-1533) ----------
+		bool interact = false, hit = false;
+		uint4 b0 = make_uint4(0u, 0u, 0u, 0u);
+		int order = 0;
+		if (have) {
+			if (p.energy < ENERGY_THRESHOLD) have = false;
+			else {
 				int step_max, step_dir;
 				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
 				else { step_max = 0; step_dir = -1; }
-				const int order = (p.n_interactions + 1) | gen_bit;
-				const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);
+				order = (p.n_interactions + 1) | gen_bit;
+				b0 = draw_block(P.seed, g, order, 1, 0, 0);
 				const double interactionR = xmb_u01(b0.x);
 				double blbs = 1.0, max_random_layer = 0.0;
-				bool inside = false, stop = false;
+				bool stop = false;
 				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
 					double nx = p.cx, ny = p.cy, nz = p.cz, dist;
 					if (!step_to_plane(P, nx, ny, nz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { stop = true; break; }
@@ -1223,7 +1266,7 @@ __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ 
 						if (rv == XMB_DET_COLLIMATOR || rv == XMB_DET_BAD) { stop = true; break; }
 						if (rv == XMB_DET_HIT) { hit = true; stop = true; break; }
 						p.layer = i;
-						inside = true;
+						interact = true;
 						break;
 					}
 					const int rv = check_detector_intersection(P, B, p.cx, p.cy, p.cz, nx, ny, nz);
@@ -1232,59 +1275,11 @@ __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ 
 					p.cx = nx; p.cy = ny; p.cz = nz;
 					blbs = blbs * tempexp;
 				}
-				if (stop) break;
-				if (!inside) { hit = check_photon_detector_hit(P, B, p); break; }   // :1525-1533
-				if (p.n_interactions == P.n_int) break;                                // :1536-1539
-				p.n_interactions++;
-				n_inter++;
-				double we_unused = 0.0;
-				int shell = -1;
-				select_and_scatter<NL, 2, ADV>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
-				if (last_type == 4) {
-					// ---- xmi_simulate_photon_cascade_auger (:2413-4594): the primary vacancy decays without radiation
-					last_type = 3;
-					if (co_auger && shell >= 0 && shell <= 3) {
-						const double *a = B.auger_rate + (size_t)last_zi * XMB_N_AUGER;
-						const int first = shell == 0 ? 0 : 240 + 135 * (shell - 1), n = shell == 0 ? 240 : 135;
-						SubStream xs;
-						xs.init(P.seed, g, order, 4, 0);
-						const double r = xs.uniform();
-						double sumz = 0.0;
-						int found = -1;
-						for (int k = 0; k < n; k++) { sumz += a[first + k]; if (r < sumz) { found = k; break; } }
-						if (found >= 0) {
-							const int new1 = shell == 0 ? 1 + found / 30 : 4 + found / 27, new2 = shell == 0 ? 1 + found % 30 : 4 + found % 27;
-							off = p;   // the offspring starts as a copy of the parent (:4421-4440)
-							const int l1 = cascade_vacancy(P, last_zi, new1, xs);
-							if (l1) { co_auger = co_rad = false; last_line = l1; cascade_emit<NL>(P, p, mus, last_zi, l1, xs); }
-							SubStream ys;
-							ys.init(P.seed, g, order, 4, 1);
-							const int l2 = cascade_vacancy(P, last_zi, new2, ys);
-							if (l2) { cascade_emit<NL>(P, off, off_mus, last_zi, l2, ys); have_off = true; off_zi = last_zi; off_line = l2; }
-						}
-					}
-				} else if (last_type == 3 && last_line && co_rad) {
-					// ---- xmi_simulate_photon_cascade_radiative (:4596-4783): the vacancy the emitted line left behind
-					int shell_new = -1;
-					if (shell == 0) { if (last_line >= 1 && last_line <= XMB_KM5) shell_new = last_line; }
-					else if (shell >= 1 && shell <= 3 && P.use_M_lines) {
-						const int base = shell == 1 ? XMB_L1M1 : shell == 2 ? XMB_L2M1 : XMB_L3M1;
-						if (last_line >= base && last_line <= base + 4) shell_new = 4 + (last_line - base);
-					}
-					if (shell_new >= 0 && !(shell_new >= 4 && !P.use_M_lines)) {
-						SubStream xs;
-						xs.init(P.seed, g, order, 5, 0);
-						const int l = cascade_vacancy(P, last_zi, shell_new, xs);
-						if (l) {
-							off = p;
-							co_auger = co_rad = false;
-							cascade_emit<NL>(P, off, off_mus, last_zi, l, xs);
-							have_off = true; off_zi = last_zi; off_line = l;
-						}
-					}
-				}
+				if (!stop && !interact) hit = check_photon_detector_hit(P, B, p);   // left the sample (:1525-1533)
+				if (interact && p.n_interactions == P.n_int) interact = false;       // :1536-1539
+				if (!interact) have = false;
 			}
-			// ---- scoring (src/xmi_main.F90:443-523) -------------------------------------------------------------
+			// ---- scoring (src/xmi_main.F90:443-523) ---------------------------------------------------------------
 			if (hit) {
 				n_hits++;
 				const unsigned long long fx = to_fixed(p.weight, P.counters);
@@ -1302,17 +1297,66 @@ __global__ void __launch_bounds__(256) xmb_brute_kernel(const __grid_constant__ 
 					else n_noslot++;
 				}
 			}
-			if (!have_off || gen == 1) break;
-			// walk the offspring next (its cascades are switched off, :4509-4511, :4729-4731)
-			p = off;
-			for (int i = 0; i < nL; i++) mus[i] = off_mus[i];
-			last_type = 3; last_zi = off_zi; last_line = off_line;
-			co_auger = co_rad = false;
-			n_off++;
 		}
+		__syncthreads();
+		// ---- phase 2: interaction, cascades ----------------------------------------------------------------------------
+		if (have) {
+			p.n_interactions++;
+			n_inter++;
+			double we_unused = 0.0;
+			int shell = -1;
+			select_and_scatter<NL, 2, ADV>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
+			if (last_type == 4) {
+				// xmi_simulate_photon_cascade_auger (:2413-4594): the primary vacancy decays without radiation
+				last_type = 3;
+				if (co_auger && shell >= 0 && shell <= 3) {
+					// running sums of the block's rates, accumulated on the host in the reference's order (:2471-2477), so that the
+					// first k with r < sum_k is found by bisection instead of a 240-step walk by the few lanes that need it
+					const double *a = B.auger_rate + (size_t)last_zi * XMB_N_AUGER;
+					const int first = shell == 0 ? 0 : 240 + 135 * (shell - 1), n = shell == 0 ? 240 : 135;
+					SubStream xs;
+					xs.init(P.seed, g, order, 4, 0);
+					const double r = xs.uniform();
+					int lo = 0, hi = n;                       // smallest k in [0, n) with r < a[first + k]; n if none
+					while (lo < hi) { const int mid = (lo + hi) >> 1; if (r < a[first + mid]) hi = mid; else lo = mid + 1; }
+					const int found = lo < n ? lo : -1;
+					if (found >= 0) {
+						const int new1 = shell == 0 ? 1 + found / 30 : 4 + found / 27, new2 = shell == 0 ? 1 + found % 30 : 4 + found % 27;
+						off = p;   // the offspring starts as a copy of the parent (:4421-4440)
+						const int l1 = cascade_vacancy(P, last_zi, new1, xs);
+						if (l1) { co_auger = co_rad = false; last_line = l1; cascade_emit<NL>(P, p, mus, last_zi, l1, xs); }
+						SubStream ys;
+						ys.init(P.seed, g, order, 4, 1);
+						const int l2 = cascade_vacancy(P, last_zi, new2, ys);
+						if (l2) { cascade_emit<NL>(P, off, off_mus, last_zi, l2, ys); pending_off = true; off_zi = last_zi; off_line = l2; }
+					}
+				}
+			} else if (last_type == 3 && last_line && co_rad) {
+				// xmi_simulate_photon_cascade_radiative (:4596-4783): the vacancy the emitted line left behind
+				int shell_new = -1;
+				if (shell == 0) { if (last_line >= 1 && last_line <= XMB_KM5) shell_new = last_line; }
+				else if (shell >= 1 && shell <= 3 && P.use_M_lines) {
+					const int base = shell == 1 ? XMB_L1M1 : shell == 2 ? XMB_L2M1 : XMB_L3M1;
+					if (last_line >= base && last_line <= base + 4) shell_new = 4 + (last_line - base);
+				}
+				if (shell_new >= 0 && !(shell_new >= 4 && !P.use_M_lines)) {
+					SubStream xs;
+					xs.init(P.seed, g, order, 5, 0);
+					const int l = cascade_vacancy(P, last_zi, shell_new, xs);
+					if (l) {
+						off = p;
+						co_auger = co_rad = false;
+						cascade_emit<NL>(P, off, off_mus, last_zi, l, xs);
+						pending_off = true; off_zi = last_zi; off_line = l;
+					}
+				}
+			}
+			if (p.energy < ENERGY_THRESHOLD) have = false;   // absorbed: the lane refills in the next phase 0 instead of idling a round
+		}
+		__syncthreads();
 	}
 	n_inter = warp_sum_u64(n_inter); n_hits = warp_sum_u64(n_hits); n_off = warp_sum_u64(n_off); n_noslot = warp_sum_u64(n_noslot);
-	if ((threadIdx.x & 31) == 0) {
+	if (lane == 0) {
 		if (n_inter) atomicAdd(&P.counters[1], n_inter);
 		if (n_hits) atomicAdd(&P.counters[3], n_hits);
 		if (n_off) atomicAdd(&P.counters[4], n_off);
@@ -1529,7 +1573,14 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 		std::vector<int> ls((size_t)nZ * 384, -1);
 		for (int r = 0; r < D->n_rec; r++) ls[(size_t)D->rec_zi[r] * 384 + D->rec_line[r]] = D->rec_slot[r];
 		D->line_slot = upload(D, ls.data(), ls.size(), ok);
-		D->auger_rate = upload(D, T.auger_rate, (size_t)nZ * XMB_N_AUGER, ok);
+		std::vector<double> cdf((size_t)nZ * XMB_N_AUGER);
+		for (int z = 0; z < nZ; z++) {
+			const double *a = T.auger_rate + (size_t)z * XMB_N_AUGER;
+			double *c = &cdf[(size_t)z * XMB_N_AUGER];
+			const int first[5] = {0, 240, 375, 510, 645};
+			for (int b = 0; b < 4; b++) { double sum = 0.0; for (int k = first[b]; k < first[b + 1]; k++) { sum += a[k]; c[k] = sum; } }
+		}
+		D->auger_rate = upload(D, cdf.data(), cdf.size(), ok);
 	}
 	// ---- source segments (src/xmi_main.F90:319-338, :579-601) --------------------------------------------------
 	const xmb_excitation &exc = *I.excitation;
@@ -1660,9 +1711,9 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		B.collimator_radius = in->der.collimator_radius; B.half_apex = in->der.half_apex;
 		B.vertex_x = in->der.vertex[0]; B.vertex_y = in->der.vertex[1]; B.vertex_z = in->der.vertex[2];
 		B.line_slot = D->line_slot; B.auger_rate = D->auger_rate;
-		const int bt = 256;
+		const int bt = XMB_BRUTE_THREADS;
 		const uint64_t want = (ex->n_histories + bt - 1) / bt;
-		const unsigned bg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sms * 16));
+		const unsigned bg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sms));   // persistent: one CTA per SM
 		cudaEvent_t e0, e1;
 		cudaEventCreate(&e0); cudaEventCreate(&e1);
 		cudaEventRecord(e0);
@@ -1968,7 +2019,10 @@ struct XmbEscParams {
 __device__ __forceinline__ unsigned long long esc_fixed(double w) { return (unsigned long long)(w * (double)(1ULL << XMB_ESC_SHIFT) + 0.5); }
 
 template <int NL>
-__global__ void __launch_bounds__(256) xmb_escape_kernel(const __grid_constant__ XmbHistParams P, const XmbEscParams R) {
+#ifndef XMB_ESC_MINB
+#define XMB_ESC_MINB 4
+#endif
+__global__ void __launch_bounds__(256, XMB_ESC_MINB) xmb_escape_kernel(const __grid_constant__ XmbHistParams P, const XmbEscParams R) {
 	const int nL = NL > 0 ? NL : P.nL;
 	constexpr int NLA = NL > 0 ? NL : XMB_MAX_LAYERS;
 	const int iE = blockIdx.y;

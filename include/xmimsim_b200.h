@@ -372,7 +372,7 @@ void xmb_free_solid_angle(xmb_solid_angle *sa);   /* xmi_free_solid_angle, src/x
 /* Replaces xmi_main_msim (include/xmi_main.h:29; src/xmi_main.F90:66-954).
  * channels:        malloc'ed double[(n_int+1)][nchannels], rows cumulative over interaction order, x live_time
  * brute_history:   malloc'ed double[100][385][n_int]  (all zero with variance reduction on)
- * var_red_history: malloc'ed double[100][385][n_int]  (all zero with variance reduction off)
+ * var_red_history: malloc'ed double[100][385][n_int]  (NULL with variance reduction off, src/xmi_main.F90:942)
  * options->use_variance_reduction = 0 selects the brute-force mode (analogue walk, detector/collimator hit
  * tests src/xmi_aux_f.F90:1622-1833, Auger/radiative cascade offspring src/xmi_main.F90:2413-4783);
  * solid_angles may then be NULL and channels row 0 holds the photons detected without interaction.

@@ -153,3 +153,53 @@ def test_plugin_file_exports_reference_symbol_names():
     assert os.path.exists(path)
     P = C.CDLL(path)
     assert hasattr(P, "xmi_solid_angle_calculation_cl") and hasattr(P, "xmi_detector_convolute_all_custom")
+
+
+def test_inverse_cdf_tables_reproduce_the_analytic_distributions():
+    """Tier T1: the table generator against quadratures that need no reference data.
+    theta tables: moments of the sampled angle vs direct integration of the same differential cross sections
+    (src/xmi_data_f.F90:1002-1060); phi table: CDF(phi; a) = (phi - a sin 2 phi) / 2 pi inverted exactly (:1508-1545);
+    Compton-profile table: P(|pz| < q) (:1162-1186)."""
+    inp = example("srm1155")
+    sim = x.Simulation(inp, quality=1)
+    T = sim.tables
+    P = sim.provider.contents
+    nZ, nE, nR = T.nZ, T.n_icdf_E, T.n_icdf_R
+    rayl = np.ctypeslib.as_array(T.rayl_theta_icdf, shape=(nZ, nE, nR))
+    compt = np.ctypeslib.as_array(T.compt_theta_icdf, shape=(nZ, nE, nR))
+    E = np.ctypeslib.as_array(T.icdf_E, shape=(nE,))
+    Z = [T.Z[i] for i in range(nZ)]
+    th = np.linspace(0.0, math.pi, 20001)
+    for z in (26, 8):
+        iz = Z.index(z)
+        for je in (5, nE - 3):
+            q = E[je] / 12.39841930 * np.sin(th / 2)
+            F = np.array([P.FF_Rayl(z, v) for v in q]); S = np.array([P.SF_Compt(z, v) for v in q])
+            k = 1.0 / (1.0 + E[je] / 510.998928 * (1 - np.cos(th)))
+            f_r = (1 + np.cos(th) ** 2) * F ** 2 * np.sin(th)
+            f_c = k ** 2 * (k + 1 / k - np.sin(th) ** 2) * S * np.sin(th)
+            for tab, f in ((rayl, f_r), (compt, f_c)):
+                w = np.trapezoid(f, th)
+                mean_cos = np.trapezoid(f * np.cos(th), th) / w
+                mean_cos2 = np.trapezoid(f * np.cos(th) ** 2, th) / w
+                icdf = tab[iz, je]
+                assert icdf[0] == 0.0 and abs(icdf[-1] - math.pi) < 1e-12 and np.all(np.diff(icdf) >= 0)
+                # sampling theta = icdf(R), R uniform: trapezoid over the R grid
+                s1 = np.trapezoid(np.cos(icdf), dx=1.0 / (nR - 1)); s2 = np.trapezoid(np.cos(icdf) ** 2, dx=1.0 / (nR - 1))
+                assert abs(s1 - mean_cos) < 2e-3 and abs(s2 - mean_cos2) < 2e-3, (z, je, s1, mean_cos)
+    nT = T.n_phi_T
+    phi = np.ctypeslib.as_array(T.phi_icdf, shape=(nT, nR)); a = np.ctypeslib.as_array(T.phi_T, shape=(nT,))
+    R = np.arange(nR) / (nR - 1.0)
+    for it in (0, nT // 2, nT - 1):
+        back = (phi[it] - a[it] * np.sin(2 * phi[it])) / (2 * math.pi)
+        assert np.abs(back - R).max() < 2e-4 and phi[it, 0] == 0.0 and abs(phi[it, -1] - 2 * math.pi) < 1e-12
+    n_cp = T.n_cp
+    cp = np.ctypeslib.as_array(T.cp_icdf, shape=(nZ, n_cp))
+    iz = Z.index(26)
+    pz = np.linspace(0, 100, 400001)
+    J = np.array([P.ComptonProfile(26, v) for v in pz[::40]])
+    cdf = np.concatenate([[0], np.cumsum((J[1:] + J[:-1]) / 2 * np.diff(pz[::40]))]); cdf /= cdf[-1]
+    for r in (0.1, 0.5, 0.9, 0.99):
+        q_tab = cp[iz, int(round(r * (n_cp - 1)))]
+        assert abs(np.interp(q_tab, pz[::40], cdf) - r) < 2e-3
+    sim.close()

@@ -1903,7 +1903,8 @@ extern "C" int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, co
 			}
 		}
 		if (channels) *channels = ch; else free(ch);
-		if (var_red_history) *var_red_history = vr; else free(vr);
+		free(vr);
+		if (var_red_history) *var_red_history = nullptr;   // as the reference: no array without variance reduction (src/xmi_main.F90:942)
 		if (brute_history) *brute_history = br; else free(br);
 		return 1;
 	}

@@ -176,6 +176,9 @@ class Simulation:
         libc.free.argtypes = [C.c_void_p]
         out = []
         for ptr, shape in ((ch, (n_int + 1, nch)), (br, (100, 385, n_int)), (vr, (100, 385, n_int))):
+            if not ptr:                      # var_red_history is NULL without variance reduction, as in the reference
+                out.append(np.zeros(shape))
+                continue
             out.append(_np_from_ptr(ptr, shape).copy())
             libc.free(ptr)
         return tuple(out)

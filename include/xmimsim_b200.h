@@ -338,6 +338,13 @@ const xmb_derived *xmb_get_derived(xmb_inputFPtr inputF);
  * Returns 1 / 0. */
 int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality,
                            xmb_hdf5FPtr *out);
+/* Same bundle, with the inverse CDFs of the scattering angles and of the Compton profile integrated on the GPU
+ * (the loops of xmi_db_Z_specific, src/xmi_data_f.F90:1002-1060, 1162-1186): the provider is sampled once per element
+ * on fine grids instead of at every integration step.  Entries differ from xmb_init_from_provider by at most one
+ * integration step (summation order).  Needs a CUDA device.  Returns 1 / 0. */
+int xmb_init_from_provider_gpu(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality,
+                               xmb_hdf5FPtr *out);
+double xmb_tables_gpu_last_ms(void);
 const xmb_tables_host *xmb_get_tables(xmb_hdf5FPtr hdf5F);
 /* Builds the shell-resolved Compton tables (idempotent; host, OpenMP).  xmb_main_msim calls it itself when
  * options->use_advanced_compton is set.  Returns 1 / 0 (provider lacks the two partial-profile calls). */

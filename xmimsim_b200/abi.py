@@ -175,6 +175,8 @@ def lib():
     L.xmb_init_input.argtypes = [vpp]; L.xmb_init_input.restype = C.c_int
     L.xmb_get_derived.argtypes = [vp]; L.xmb_get_derived.restype = C.POINTER(Derived)
     L.xmb_init_from_provider.argtypes = [C.POINTER(XrlProvider), vp, C.c_int, vpp]; L.xmb_init_from_provider.restype = C.c_int
+    L.xmb_init_from_provider_gpu.argtypes = [C.POINTER(XrlProvider), vp, C.c_int, vpp]; L.xmb_init_from_provider_gpu.restype = C.c_int
+    L.xmb_tables_gpu_last_ms.restype = C.c_double
     L.xmb_get_tables.argtypes = [vp]; L.xmb_get_tables.restype = C.POINTER(TablesHost)
     L.xmb_free_hdf5_F.argtypes = [vpp]; L.xmb_free_hdf5_F.restype = None
     L.xmb_tables_enable_advanced_compton.argtypes = [vp]; L.xmb_tables_enable_advanced_compton.restype = C.c_int

@@ -45,3 +45,4 @@ XmbHdf5F *xmb_as_hdf5(xmb_hdf5FPtr p);
 // host-side table evaluation (used for the solid-angle bounds and the exciter absorbers)
 double xmb_host_mu_layer(const xmb_xrl_provider *xrl, const xmb_layer *layer, double E);
 void xmb_free_device_tables(XmbDeviceTables *dev);
+int xmb_build_tables(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality, xmb_hdf5FPtr *out, bool skip_icdf);

@@ -48,7 +48,8 @@ void icdf_walk(const std::vector<double> &mass, const std::vector<double> &absc,
 
 }  // namespace
 
-extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality, xmb_hdf5FPtr *out) {
+// skip_icdf: leave the theta and Compton-profile inverse CDFs zero-filled (the GPU generator fills them, tables_gpu.cu)
+int xmb_build_tables(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality, xmb_hdf5FPtr *out, bool skip_icdf) {
 	XmbInputF *in = xmb_as_input(inputF);
 	if (!in || !xrl || !out) { xmb_set_error("xmb_init_from_provider: bad arguments"); return 0; }
 	const xmb_composition &comp = *in->in.composition;
@@ -168,8 +169,8 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 		costh[k] = std::cos(thetas[k]);
 		sinhalf[k] = std::sin(thetas[k] * 0.5);
 	}
-#pragma omp parallel
-	{
+#pragma omp parallel if (!skip_icdf)
+	if (!skip_icdf) {
 		std::vector<double> fr(n_theta), fc(n_theta), mass(n_theta - 1);
 #pragma omp for schedule(dynamic, 1) collapse(2)
 		for (int i = 0; i < nZ; i++)
@@ -218,8 +219,8 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	h->cp_R.resize(N_CP);
 	for (int i = 0; i < N_CP; i++) h->cp_R[i] = (double)i / (N_CP - 1.0);
 	h->cp_icdf.resize((size_t)nZ * N_CP);
-#pragma omp parallel
-	{
+#pragma omp parallel if (!skip_icdf)
+	if (!skip_icdf) {
 		std::vector<double> mass(n_pz - 1), pzs(n_pz);
 		for (long k = 0; k < n_pz; k++) pzs[k] = MAXPZ * k / (n_pz - 1.0);
 #pragma omp for schedule(dynamic, 1)
@@ -336,6 +337,10 @@ extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr
 	v.n_layers = comp.n_layers; v.mu_layer = h->mu_layer.data(); v.exc_murhod = h->exc_murhod.data();
 	*out = h;
 	return 1;
+}
+
+extern "C" int xmb_init_from_provider(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality, xmb_hdf5FPtr *out) {
+	return xmb_build_tables(xrl, inputF, quality, out, false);
 }
 
 extern "C" const xmb_tables_host *xmb_get_tables(xmb_hdf5FPtr p) {

@@ -71,7 +71,7 @@ def tube_ebel(anode, voltage, current=1.0, angle_electron=60.0, angle_xray=60.0,
 class Simulation:
     """Owns the two opaque handles (input + tables) of one simulation."""
 
-    def __init__(self, inp: InputD, quality: int = 0, provider=None):
+    def __init__(self, inp: InputD, quality: int = 0, provider=None, gpu_tables: bool = False):
         L = abi.lib()
         self.L = L
         self.inp = inp
@@ -83,7 +83,8 @@ class Simulation:
             raise RuntimeError("xmb_init_input: " + abi.last_error())
         self.provider = provider if provider is not None else L.xmb_xrl_surrogate()
         self.hdf5F = C.c_void_p()
-        if not L.xmb_init_from_provider(self.provider, self.inputF, quality, C.byref(self.hdf5F)):
+        init = L.xmb_init_from_provider_gpu if gpu_tables else L.xmb_init_from_provider
+        if not init(self.provider, self.inputF, quality, C.byref(self.hdf5F)):
             raise RuntimeError("xmb_init_from_provider: " + abi.last_error())
         self._sa = None
 

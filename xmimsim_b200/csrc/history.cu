@@ -35,7 +35,7 @@
 #define HIST_THREADS 1024        // one CTA per SM: every warp of the SM is in the same phase (I-cache locality)
 #endif
 #ifndef XMB_REC_UNROLL
-#define XMB_REC_UNROLL 1
+#define XMB_REC_UNROLL 2
 #endif
 #define XMB_MAX_ORDERS 64
 #define XMB_STATE_FIELDS 15      // 13 doubles of photon state + photon id + layer (mus[nL] follow)

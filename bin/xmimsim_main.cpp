@@ -2,8 +2,9 @@
 //   xmimsim-b200 [options] inputfile.xmsi
 // reads the XMSI file, computes the solid-angle grid, runs the histories on the GPU, computes the escape ratios of
 // the detector crystal when escape peaks are on, applies the detector response and writes the XMSO file named in
-// the input (plus optional SPE / CSV spectra).  The HDF5 caches of the reference (~/.local/share/XMI-MSIM/*.h5) are
-// not used: both the grid and the escape ratios are recomputed on the GPU (54 ms and 0.6 s on a B200).
+// the input (plus optional SPE / CSV spectra).  The solid-angle grid and the escape ratios are recomputed on the GPU
+// (54 ms and 0.3 s on a B200) unless cache files are named (--with-solid-angles-data, --with-escape-ratios-data: the
+// reference's HDF5 caches as a side-car container with the same schema and match rules, host_cache.cpp).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,7 @@ static void usage(FILE *f) {
 	      "  --enable-advanced-compton / --disable-advanced-compton    shell-resolved Compton (default: disabled)\n"
 	      "  --spe-file=F --spe-file-unconvoluted=F                    write F_<order>.spe\n"
 	      "  --csv-file=F --csv-file-unconvoluted=F                    write CSV spectra\n"
+	      "  --with-solid-angles-data=F --with-escape-ratios-data=F    cache files (queried first, updated after a calculation)\n"
 	      "  --set-seed=N                                              Philox key (default: library seed)\n"
 	      "  --table-quality=0|1                                       inverse-CDF integration resolution (default 1 = reference)\n"
 	      "  -v, --verbose    -V, --very-verbose    --version\n", f);
@@ -32,7 +34,7 @@ static void usage(FILE *f) {
 int main(int argc, char **argv) {
 	xmb_main_options opt;
 	xmb_main_options_defaults(&opt);
-	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile;
+	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache;
 	unsigned long long seed = 0;
 	int quality = 1;
 	struct Flag { const char *name; int *target; };
@@ -56,6 +58,7 @@ int main(int argc, char **argv) {
 		};
 		std::string tmp;
 		if (val("--spe-file-unconvoluted", spe_noconv) || val("--spe-file", spe_conv) || val("--csv-file-unconvoluted", csv_noconv) || val("--csv-file", csv_conv)) continue;
+		if (val("--with-solid-angles-data", sa_cache) || val("--with-escape-ratios-data", er_cache)) continue;
 		if (val("--set-seed", tmp)) { seed = strtoull(tmp.c_str(), nullptr, 0); continue; }
 		if (val("--table-quality", tmp)) { quality = atoi(tmp.c_str()); continue; }
 		if (val("--set-threads", tmp)) { opt.omp_num_threads = atoi(tmp.c_str()); continue; }
@@ -81,10 +84,23 @@ int main(int argc, char **argv) {
 	const int n_int = input->general->n_interactions_trajectory, nch = input->detector->nchannels;
 	xmb_solid_angle *sa = nullptr;
 	if (opt.use_variance_reduction) {
-		if (opt.verbose) printf("Precalculating solid angle grid\n");
-		if (!xmb_solid_angle_calculation(inputF, tables, &sa, nullptr, &opt, 5000, seed)) { fprintf(stderr, "Solid angle calculation failed: %s\n", xmb_last_error()); return 1; }
-		if (opt.verbose) printf("Solid angle calculation finished\n");
-	}
+		// bin/xmimsim.c:300-333: query the cache, calculate on a miss, update the cache
+		if (!sa_cache.empty()) {
+			if (opt.verbose) printf("Querying %s for solid angle grid\n", sa_cache.c_str());
+			if (!xmb_find_solid_angle_match(sa_cache.c_str(), input, xmb_xrl_surrogate(), &sa, &opt)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+		}
+		if (!sa) {
+			if (opt.verbose) printf("Precalculating solid angle grid\n");
+			char *xml = nullptr;
+			if (!xmb_input_write_to_xml_string(input, &xml)) { fprintf(stderr, "Could not write input to XML string: %s\n", xmb_last_error()); return 1; }
+			if (!xmb_solid_angle_calculation(inputF, tables, &sa, xml, &opt, 5000, seed)) { fprintf(stderr, "Solid angle calculation failed: %s\n", xmb_last_error()); return 1; }
+			if (opt.verbose) printf("Solid angle calculation finished\n");
+			if (!sa_cache.empty()) {
+				if (!xmb_update_solid_angle_cache_file(sa_cache.c_str(), sa)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+				if (opt.verbose) printf("%s was successfully updated with new solid angle grid\n", sa_cache.c_str());
+			}
+		} else if (opt.verbose) printf("Solid angle grid already present in %s\n", sa_cache.c_str());
+	} else if (opt.verbose) printf("Operating in brute-force mode: solid angle grid is redundant\n");
 	double *channels = nullptr, *brute = nullptr, *var_red = nullptr;
 	if (!xmb_main_msim(inputF, tables, 1, &channels, &opt, &brute, &var_red, sa)) { fprintf(stderr, "Error in xmi_main_msim: %s\n", xmb_last_error()); return 1; }
 	double zero_sum = 0.0;
@@ -93,11 +109,23 @@ int main(int argc, char **argv) {
 
 	xmb_escape_ratios *er = nullptr;
 	if (opt.use_escape_peaks) {
-		if (opt.verbose) printf("Calculating escape peak ratios\n");
-		if (!xmb_escape_ratios_calculation(input, &er, nullptr, xmb_xrl_surrogate(), &opt, xmb_get_default_escape_ratios_options(), seed)) {
-			fprintf(stderr, "Escape ratios calculation failed: %s\n", xmb_last_error());
-			return 1;
+		// bin/xmimsim.c:462-495
+		if (!er_cache.empty()) {
+			if (opt.verbose) printf("Querying %s for escape peak ratios\n", er_cache.c_str());
+			if (!xmb_find_escape_ratios_match(er_cache.c_str(), input, &er, &opt)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
 		}
+		if (!er) {
+			if (opt.verbose) printf("Precalculating escape peak ratios\n");
+			char *xml = nullptr;
+			if (!xmb_input_write_to_xml_string(input, &xml)) { fprintf(stderr, "Could not write input to XML string: %s\n", xmb_last_error()); return 1; }
+			const int ok = xmb_escape_ratios_calculation(input, &er, xml, xmb_xrl_surrogate(), &opt, xmb_get_default_escape_ratios_options(), seed);
+			free(xml);
+			if (!ok) { fprintf(stderr, "Escape ratios calculation failed: %s\n", xmb_last_error()); return 1; }
+			if (!er_cache.empty()) {
+				if (!xmb_update_escape_ratios_cache_file(er_cache.c_str(), er)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+				if (opt.verbose) printf("%s was successfully updated with new escape peak ratios\n", er_cache.c_str());
+			}
+		} else if (opt.verbose) printf("Escape peak ratios already present in %s\n", er_cache.c_str());
 	}
 	// keep the raw spectra: the response corrects its input rows in place (src/xmi_detector_f.F90:412-413)
 	std::vector<double> raw(channels, channels + (size_t)(n_int + 1) * nch);

@@ -478,6 +478,26 @@ int xmb_output_write_to_xml_file(const xmb_input *input, const char *inputfile, 
                                  const double *channels_unconv, double *const *channels_conv,
                                  const double *brute_history, const double *var_red_history,
                                  int use_zero_interactions, const xmb_xrl_provider *xrl);
+/* String forms (xmi_input_read_from_xml_string / xmi_input_write_to_xml_string, src/xmi_xml.c:1342-1403):
+ * *xmlstring is malloc'ed.  The caches below store this string as the key of an entry. */
+int xmb_input_read_from_xml_string(const char *xmsistring, xmb_input **input);
+int xmb_input_write_to_xml_string(const xmb_input *input, char **xmlstring);
+/* The solid-angle and escape-ratio caches (xmi_find_solid_angle_match / xmi_update_solid_angle_hdf5_file,
+ * src/xmi_solid_angle.c:193-790; xmi_find_escape_ratios_match / xmi_update_escape_ratios_hdf5_file,
+ * src/xmi_detector.c:174-435) with the reference's match rules (xmi_check_solid_angle_match :420-670,
+ * xmi_check_escape_ratios_match src/xmi_detector.c:143-172).  libhdf5 is not available to this build, so the
+ * files are a documented side-car container with the same logical schema (host_cache.cpp).  find: returns 1 with
+ * *rv = NULL when nothing matches (or the file does not exist yet), 0 on error; results are malloc'ed
+ * (xmb_free_solid_angle / xmb_free_escape_ratios) and own their xmi_input_string.  update: appends an entry
+ * (creating the file); the struct must carry its xmi_input_string. */
+int xmb_check_solid_angle_match(const xmb_input *cached, const xmb_input *fresh, const xmb_xrl_provider *xrl);
+int xmb_check_escape_ratios_match(const xmb_input *cached, const xmb_input *fresh);
+int xmb_find_solid_angle_match(const char *cache_file, const xmb_input *input, const xmb_xrl_provider *xrl,
+                               xmb_solid_angle **rv, const xmb_main_options *options);
+int xmb_update_solid_angle_cache_file(const char *cache_file, const xmb_solid_angle *solid_angle);
+int xmb_find_escape_ratios_match(const char *cache_file, const xmb_input *input, xmb_escape_ratios **rv,
+                                 const xmb_main_options *options);
+int xmb_update_escape_ratios_cache_file(const char *cache_file, const xmb_escape_ratios *escape_ratios);
 /* The SPE / CSV spectrum files of bin/xmimsim.c:546-640 (--spe-file*, --csv-file*). */
 int xmb_write_spe_file(const char *filename, const xmb_input *input, const double *spectrum);
 int xmb_write_csv_file(const char *filename, const xmb_input *input, double *const *rows, int first_row);
@@ -521,7 +541,8 @@ int xmb_escape_ratios_input(const xmb_input *input, const xmb_escape_ratios_opti
 /* Replaces xmi_escape_ratios_calculation (include/xmi_detector.h:57; src/xmi_detector.c:91-141 and
  * xmi_escape_ratios_calculation_fortran, src/xmi_main.F90:5473-5801).  The HDF5 file argument of the
  * reference becomes the cross-section provider (NULL: surrogate).  *escape_ratios and its arrays are
- * malloc'ed (xmb_free_escape_ratios); input_string is stored, not copied, as in the reference.
+ * malloc'ed (xmb_free_escape_ratios); the struct keeps its own copy of input_string (the reference's driver
+ * hands over a g_strdup, src/xmi_detector.c:139, and xmi_free_escape_ratios frees it, :566).
  * `seed` 0 = library default.  Returns 1 / 0 (the reference is void and exits on failure). */
 int xmb_escape_ratios_calculation(const xmb_input *input, xmb_escape_ratios **escape_ratios, char *input_string,
                                   const xmb_xrl_provider *xrl, const xmb_main_options *options,

@@ -71,3 +71,25 @@ def test_cli_brute_force_and_errors(tmp_path):
     assert r.returncode == 1 and "Could not read" in r.stderr
     r = subprocess.run([CLI, "--no-such-option", xmsi], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+def test_cli_caches_are_filled_then_reused(tmp_path):
+    inp = example("srm1155")
+    inp.n_photons_line = 500
+    inp.outputfile = str(tmp_path / "c1.xmso")
+    ci = x.CInput(inp)
+    xmsi = str(tmp_path / "c.xmsi")
+    assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
+    sa, er = str(tmp_path / "sa.cache"), str(tmp_path / "er.cache")
+    cmd = [CLI, "-v", "--table-quality=0", "--with-solid-angles-data=" + sa, "--with-escape-ratios-data=" + er, xmsi]
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr
+    assert "Precalculating solid angle grid" in r1.stdout and "was successfully updated with new solid angle grid" in r1.stdout
+    assert "Precalculating escape peak ratios" in r1.stdout and "was successfully updated with new escape peak ratios" in r1.stdout
+    first = x.read_xmso(inp.outputfile)
+    r2 = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr
+    assert "Solid angle grid already present in" in r2.stdout and "Escape peak ratios already present in" in r2.stdout
+    assert "Precalculating" not in r2.stdout
+    second = x.read_xmso(inp.outputfile)
+    assert np.array_equal(first["conv"], second["conv"]) and np.array_equal(first["unconv"], second["unconv"])   # cached == recomputed

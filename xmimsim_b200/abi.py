@@ -224,6 +224,16 @@ def lib():
     L.xmb_output_write_to_xml_file.restype = C.c_int
     L.xmb_write_spe_file.argtypes = [C.c_char_p, C.POINTER(Input), c_double_p]; L.xmb_write_spe_file.restype = C.c_int
     L.xmb_write_csv_file.argtypes = [C.c_char_p, C.POINTER(Input), pp, C.c_int]; L.xmb_write_csv_file.restype = C.c_int
+    L.xmb_input_read_from_xml_string.argtypes = [C.c_char_p, C.POINTER(C.POINTER(Input))]; L.xmb_input_read_from_xml_string.restype = C.c_int
+    L.xmb_input_write_to_xml_string.argtypes = [C.POINTER(Input), C.POINTER(C.c_void_p)]; L.xmb_input_write_to_xml_string.restype = C.c_int
+    L.xmb_check_solid_angle_match.argtypes = [C.POINTER(Input), C.POINTER(Input), C.POINTER(XrlProvider)]; L.xmb_check_solid_angle_match.restype = C.c_int
+    L.xmb_check_escape_ratios_match.argtypes = [C.POINTER(Input), C.POINTER(Input)]; L.xmb_check_escape_ratios_match.restype = C.c_int
+    L.xmb_find_solid_angle_match.argtypes = [C.c_char_p, C.POINTER(Input), C.POINTER(XrlProvider), C.POINTER(C.POINTER(SolidAngle)), C.POINTER(MainOptions)]
+    L.xmb_find_solid_angle_match.restype = C.c_int
+    L.xmb_update_solid_angle_cache_file.argtypes = [C.c_char_p, C.POINTER(SolidAngle)]; L.xmb_update_solid_angle_cache_file.restype = C.c_int
+    L.xmb_find_escape_ratios_match.argtypes = [C.c_char_p, C.POINTER(Input), C.POINTER(C.POINTER(EscapeRatios)), C.POINTER(MainOptions)]
+    L.xmb_find_escape_ratios_match.restype = C.c_int
+    L.xmb_update_escape_ratios_cache_file.argtypes = [C.c_char_p, C.POINTER(EscapeRatios)]; L.xmb_update_escape_ratios_cache_file.restype = C.c_int
     L.xmb_tube_ebel.argtypes = [C.POINTER(XrlProvider), C.POINTER(Layer), C.POINTER(Layer), C.POINTER(Layer), C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_size_t,
                                 c_double_p, c_double_p, C.POINTER(C.POINTER(Excitation))]

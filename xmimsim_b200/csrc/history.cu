@@ -2140,6 +2140,7 @@ extern "C" void xmb_free_escape_ratios(xmb_escape_ratios **p) {
 	xmb_escape_ratios *e = *p;
 	free(e->Z); free(e->fluo_escape_ratios); free(e->fluo_escape_input_energies); free(e->compton_escape_ratios);
 	free(e->compton_escape_output_energies);   // compton_escape_input_energies aliases fluo_escape_input_energies (:5525)
+	free(e->xmi_input_string);                 // owned by the struct, as in xmi_free_escape_ratios (src/xmi_detector.c:566)
 	free(e);
 	*p = nullptr;
 }
@@ -2232,7 +2233,8 @@ extern "C" int xmb_escape_ratios_calculation(const xmb_input *input, xmb_escape_
 	xmb_hdf5FPtr eh = nullptr;
 	if (!xmb_escape_ratios_input(input, &ero, &ein)) return 0;
 	if (!xmb_init_from_provider(xrl, ein, 1, &eh)) { xmb_free_input_F(&ein); return 0; }
-	const int rv = xmb_escape_ratios_run(ein, eh, &ero, seed, escape_ratios, input_string);
+	// the struct owns a copy of the string (the reference's driver hands a g_strdup, src/xmi_detector.c:139)
+	const int rv = xmb_escape_ratios_run(ein, eh, &ero, seed, escape_ratios, input_string ? strdup(input_string) : nullptr);
 	if (rv && options && options->verbose) { printf("Escape peak ratios calculation finished\n"); fflush(stdout); }
 	xmb_free_hdf5_F(&eh);
 	xmb_free_input_F(&ein);

@@ -381,6 +381,22 @@ void write_history(Out &o, const char *tag, const double *hist, const xmb_input 
 
 }  // namespace
 
+static int input_from_string(const std::string &src, const char *what, xmb_input **input) {
+	Parser p(src);
+	p.skip_misc();
+	std::unique_ptr<Node> root = p.element();
+	if (!root) { xmb_set_error("%s: XML syntax error: %s", what, p.err.c_str()); return 0; }
+	const Node *body = root.get();
+	if (root->name == "xmimsim-results") body = root->child("xmimsim-input");   // an .xmso carries its input
+	else if (root->name != "xmimsim") { xmb_set_error("%s: root element is <%s>, expected <xmimsim>", what, root->name.c_str()); return 0; }
+	if (!body) { xmb_set_error("%s: no <xmimsim-input>", what); return 0; }
+	xmb_input *in = (xmb_input *)calloc(1, sizeof(xmb_input));
+	try { input_from_node(body, in); }
+	catch (const ReadError &e) { xmb_set_error("%s: %s", what, e.msg.c_str()); xmb_input_free(&in); return 0; }
+	*input = in;
+	return 1;
+}
+
 // Replaces xmi_input_read_from_xml_file (src/xmi_xml.c:1289-1340).  *input is malloc'ed (xmb_input_free).  Returns 1 / 0.
 extern "C" int xmb_input_read_from_xml_file(const char *xmsifile, xmb_input **input) {
 	if (!xmsifile || !input) { xmb_set_error("xmb_input_read_from_xml_file: bad arguments"); return 0; }
@@ -391,18 +407,27 @@ extern "C" int xmb_input_read_from_xml_file(const char *xmsifile, xmb_input **in
 	size_t n;
 	while ((n = fread(buf, 1, sizeof(buf), f)) > 0) src.append(buf, n);
 	fclose(f);
-	Parser p(src);
-	p.skip_misc();
-	std::unique_ptr<Node> root = p.element();
-	if (!root) { xmb_set_error("%s: XML syntax error: %s", xmsifile, p.err.c_str()); return 0; }
-	const Node *body = root.get();
-	if (root->name == "xmimsim-results") body = root->child("xmimsim-input");   // an .xmso carries its input
-	else if (root->name != "xmimsim") { xmb_set_error("%s: root element is <%s>, expected <xmimsim>", xmsifile, root->name.c_str()); return 0; }
-	if (!body) { xmb_set_error("%s: no <xmimsim-input>", xmsifile); return 0; }
-	xmb_input *in = (xmb_input *)calloc(1, sizeof(xmb_input));
-	try { input_from_node(body, in); }
-	catch (const ReadError &e) { xmb_set_error("%s: %s", xmsifile, e.msg.c_str()); xmb_input_free(&in); return 0; }
-	*input = in;
+	return input_from_string(src, xmsifile, input);
+}
+
+// Replaces xmi_input_read_from_xml_string / xmi_input_write_to_xml_string (src/xmi_xml.c:1342-1403): the string form is
+// what the solid-angle and escape-ratio caches store as the key of an entry.
+extern "C" int xmb_input_read_from_xml_string(const char *xmsistring, xmb_input **input) {
+	if (!xmsistring || !input) { xmb_set_error("xmb_input_read_from_xml_string: bad arguments"); return 0; }
+	return input_from_string(xmsistring, "xml string", input);
+}
+extern "C" int xmb_input_write_to_xml_string(const xmb_input *input, char **xmlstring) {
+	if (!input || !xmlstring) { xmb_set_error("xmb_input_write_to_xml_string: bad arguments"); return 0; }
+	char *buf = nullptr;
+	size_t len = 0;
+	FILE *f = open_memstream(&buf, &len);
+	if (!f) { xmb_set_error("open_memstream failed"); return 0; }
+	fputs("<?xml version=\"1.0\"?>\n<!DOCTYPE xmimsim SYSTEM \"http://www.xmi.UGent.be/xml/xmimsim-1.0.dtd\">\n<xmimsim>\n", f);
+	Out o{f};
+	write_input_body(o, 1, input);
+	fputs("</xmimsim>\n", f);
+	fclose(f);
+	*xmlstring = buf;     // malloc'ed by open_memstream: free()
 	return 1;
 }
 

@@ -51,7 +51,7 @@ $(PLUGIN): $(LIB)
 
 # Command-line driver with the reference's options (bin/xmimsim.c); finds the library next to the package.
 $(CLI): bin/xmimsim_main.cpp $(LIB) include/xmimsim_b200.h
-	$(CXX) -O2 -std=c++17 -Iinclude -o $@ bin/xmimsim_main.cpp -Lxmimsim_b200/lib -lxmimsim_b200 -Wl,-rpath,'$$ORIGIN/../xmimsim_b200/lib'
+	$(CXX) -O2 -std=c++17 -Iinclude -o $@ bin/xmimsim_main.cpp -Lxmimsim_b200/lib -lxmimsim_b200 -ldl -Wl,-rpath,'$$ORIGIN/../xmimsim_b200/lib'
 
 # The oracle links the surrogate provider object (third-party stand-in), never the engine.
 $(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h $(SRC)/xrl_surrogate.c

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 #include "xmimsim_b200.h"
@@ -25,6 +26,7 @@ static void usage(FILE *f) {
 	      "  --enable-advanced-compton / --disable-advanced-compton    shell-resolved Compton (default: disabled)\n"
 	      "  --spe-file=F --spe-file-unconvoluted=F                    write F_<order>.spe\n"
 	      "  --csv-file=F --csv-file-unconvoluted=F                    write CSV spectra\n"
+	      "  --custom-detector-response=LIB                            use xmi_detector_convolute_all_custom from LIB (bin/xmimsim.c:505-522)\n"
 	      "  --with-solid-angles-data=F --with-escape-ratios-data=F    cache files (queried first, updated after a calculation)\n"
 	      "  --set-seed=N                                              Philox key (default: library seed)\n"
 	      "  --table-quality=0|1                                       inverse-CDF integration resolution (default 1 = reference)\n"
@@ -34,7 +36,7 @@ static void usage(FILE *f) {
 int main(int argc, char **argv) {
 	xmb_main_options opt;
 	xmb_main_options_defaults(&opt);
-	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache;
+	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache, custom_response;
 	unsigned long long seed = 0;
 	int quality = 1;
 	struct Flag { const char *name; int *target; };
@@ -58,6 +60,7 @@ int main(int argc, char **argv) {
 		};
 		std::string tmp;
 		if (val("--spe-file-unconvoluted", spe_noconv) || val("--spe-file", spe_conv) || val("--csv-file-unconvoluted", csv_noconv) || val("--csv-file", csv_conv)) continue;
+		if (val("--custom-detector-response", custom_response)) continue;
 		if (val("--with-solid-angles-data", sa_cache) || val("--with-escape-ratios-data", er_cache)) continue;
 		if (val("--set-seed", tmp)) { seed = strtoull(tmp.c_str(), nullptr, 0); continue; }
 		if (val("--table-quality", tmp)) { quality = atoi(tmp.c_str()); continue; }
@@ -131,7 +134,17 @@ int main(int argc, char **argv) {
 	std::vector<double> raw(channels, channels + (size_t)(n_int + 1) * nch);
 	std::vector<double *> rows(n_int + 1), conv(n_int + 1, nullptr), raw_rows(n_int + 1);
 	for (int i = 0; i <= n_int; i++) { rows[i] = channels + (size_t)i * nch; raw_rows[i] = raw.data() + (size_t)i * nch; }
-	xmb_detector_convolute_all(inputF, tables, rows.data(), conv.data(), brute, var_red, &opt, er, n_int, first == 0 ? 1 : 0);
+	if (!custom_response.empty()) {
+		// the reference's plugin hook (bin/xmimsim.c:505-522): same symbol, same signature
+		void *mod = dlopen(custom_response.c_str(), RTLD_NOW | RTLD_LOCAL);
+		if (!mod) { fprintf(stderr, "Could not open %s: %s\n", custom_response.c_str(), dlerror()); return 1; }
+		typedef void (*ConvoluteAll)(void *, double **, double **, double *, double *, xmb_main_options *, xmb_escape_ratios *, int, int);
+		ConvoluteAll fn = (ConvoluteAll)dlsym(mod, "xmi_detector_convolute_all_custom");
+		if (!fn) { fprintf(stderr, "Could not get symbol xmi_detector_convolute_all_custom from %s: %s\n", custom_response.c_str(), dlerror()); return 1; }
+		if (opt.verbose) printf("xmi_detector_convolute_all_custom loaded from %s\n", custom_response.c_str());
+		fn(inputF, rows.data(), conv.data(), brute, var_red, &opt, er, n_int, first == 0 ? 1 : 0);
+	} else
+		xmb_detector_convolute_all(inputF, tables, rows.data(), conv.data(), brute, var_red, &opt, er, n_int, first == 0 ? 1 : 0);
 	for (int i = first; i <= n_int; i++) if (!conv[i]) { fprintf(stderr, "Detector response failed: %s\n", xmb_last_error()); return 1; }
 	if (!conv[0]) conv[0] = (double *)calloc(nch, sizeof(double));
 

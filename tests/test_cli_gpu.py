@@ -93,3 +93,25 @@ def test_cli_caches_are_filled_then_reused(tmp_path):
     assert "Precalculating" not in r2.stdout
     second = x.read_xmso(inp.outputfile)
     assert np.array_equal(first["conv"], second["conv"]) and np.array_equal(first["unconv"], second["unconv"])   # cached == recomputed
+
+
+def test_cli_custom_detector_response_plugin(tmp_path):
+    """tests/test-custom-detector-response.c of the reference: brute force, no escape peaks, response taken from a plugin
+    (here the library's own xmi_detector_convolute_all_custom); the result equals the built-in response."""
+    from inputs import close_detector
+    inp = close_detector(n_photons=300000, n_int=2)
+    ci = x.CInput(inp)
+    outs = []
+    for k, extra in enumerate(([], ["--custom-detector-response=" + abi.LIB_PATH])):
+        inp.outputfile = str(tmp_path / ("p%d.xmso" % k))
+        ci = x.CInput(inp)
+        xmsi = str(tmp_path / ("p%d.xmsi" % k))
+        assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
+        r = subprocess.run([CLI, "-v", "--disable-variance-reduction", "--disable-escape-peaks", "--table-quality=0"] + extra + [xmsi],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert ("xmi_detector_convolute_all_custom loaded from" in r.stdout) == bool(extra)
+        outs.append(x.read_xmso(inp.outputfile))
+    assert outs[0]["conv"].sum() > 0 and np.array_equal(outs[0]["conv"], outs[1]["conv"])
+    r = subprocess.run([CLI, "--custom-detector-response=/nonexistent.so", xmsi], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not open" in r.stderr

@@ -96,3 +96,20 @@ def test_ebel_spectrum_drives_the_engine_input():
     n_valid = sum(1 for i in range(len(cont) - 1) if (cont[i, 1] + cont[i + 1, 1]) > 0)
     assert sim.L.xmb_msim_total_histories(sim.inputF) == n_valid * 10 + len(disc) * 20
     sim.close()
+
+
+def test_bad_configurations_are_refused():
+    """tests/test-ebel.c of the reference: good configurations return 1, a bad one 0."""
+    L = abi.lib()
+    keep = []
+    la = _c_layer(AG, keep)
+    out = C.POINTER(abi.Excitation)()
+    good = (40.0, 1.0, 60.0, 60.0, 0.1, 1e-4)
+    assert L.xmb_tube_ebel(None, C.byref(la), None, None, *good, 0, 0, None, None, C.byref(out)) == 1
+    L.xmb_free_excitation(C.byref(out))
+    assert L.xmb_tube_ebel(None, C.byref(la), None, None, *good, 1, 0, None, None, C.byref(out)) == 1      # transmission tube
+    L.xmb_free_excitation(C.byref(out))
+    assert L.xmb_tube_ebel(None, None, None, None, *good, 0, 0, None, None, C.byref(out)) == 0             # no anode
+    assert L.xmb_tube_ebel(None, C.byref(la), None, None, 40.0, 1.0, 60.0, 60.0, 0.0, 1e-4, 0, 0, None, None, C.byref(out)) == 0   # zero step
+    assert L.xmb_tube_ebel(None, C.byref(la), None, None, 0.5, 1.0, 60.0, 60.0, 0.1, 1e-4, 0, 0, None, None, C.byref(out)) == 0    # below 1 keV
+    assert "bad arguments" in abi.last_error()

@@ -120,3 +120,32 @@ def test_plugin_symbol_with_reference_signature():
     sa2 = C.POINTER(abi.SolidAngle)()
     assert sim.L.xmi_solid_angle_calculation_cl(C.cast(junk, C.c_void_p), C.byref(sa2), None, C.byref(opt)) == 0
     sim.close()
+
+
+def test_plugin_grid_goes_through_the_cache(tmp_path):
+    """The reference's tests/test-xmimsim-cl.c: compute the grid through the plugin symbol, store it in the solid-angle
+    cache, and check that the geometry-match lookup finds it again."""
+    from xmimsim_b200 import abi
+    L = abi.lib()
+    inp = example("srm1132")
+    sim = x.Simulation(inp, quality=0)
+    xml = C.c_void_p()
+    assert L.xmb_input_write_to_xml_string(C.byref(sim.cinput.input), C.byref(xml)) == 1
+    sa = C.POINTER(abi.SolidAngle)()
+    opt = x.main_options()
+    assert L.xmi_solid_angle_calculation_cl(sim.inputF, C.byref(sa), xml, C.byref(opt)) == 1
+    cache = str(tmp_path / "xmimsim-solid-angles.cache").encode()
+    assert L.xmb_update_solid_angle_cache_file(cache, sa) == 1, abi.last_error()
+    found = C.POINTER(abi.SolidAngle)()
+    assert L.xmb_find_solid_angle_match(cache, C.byref(sim.cinput.input), None, C.byref(found), C.byref(opt)) == 1 and found
+    a, b = sa.contents, found.contents
+    assert (b.grid_dims_r_n, b.grid_dims_theta_n) == (1024, 1024)
+    assert np.array_equal(np.ctypeslib.as_array(a.solid_angles, shape=(1024 * 1024,)), np.ctypeslib.as_array(b.solid_angles, shape=(1024 * 1024,)))
+    assert np.array_equal(np.ctypeslib.as_array(a.grid_dims_r_vals, shape=(1024,)), np.ctypeslib.as_array(b.grid_dims_r_vals, shape=(1024,)))
+    # a different detector position must not match
+    other = example("srm1132"); other.p_detector_window = [0.0, -3.0, 100.0]
+    miss = C.POINTER(abi.SolidAngle)()
+    assert L.xmb_find_solid_angle_match(cache, C.byref(x.CInput(other).input), None, C.byref(miss), C.byref(opt)) == 1 and not miss
+    L.xmb_free_solid_angle(found)
+    L.xmb_free_solid_angle(sa)          # frees the xml string it was given, as xmi_free_solid_angle does
+    sim.close()

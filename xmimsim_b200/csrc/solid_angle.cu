@@ -14,6 +14,12 @@
 #include <vector>
 #include "cuda_util.cuh"
 
+// (double)w * 2^-32 without an integer-to-double conversion (quarter-rate pipe): the word is placed in the mantissa of
+// 2^52, the subtraction is exact -- the same value as xmb_u01(w).
+__device__ __forceinline__ double u01_exact(uint32_t w) {
+	return (__hiloint2double(0x43300000, (int)w) - 4503599627370496.0) * (1.0 / 4294967296.0);
+}
+
 struct SaParams {
 	int collimator_present;
 	double detector_radius, collimator_radius, collimator_height;
@@ -76,31 +82,35 @@ __global__ void __launch_bounds__(256) xmb_solid_angle_kernel(SaParams P, const 
 		const double cone_sa = 2 * M_PI * (1.0 - cos_apex);
 		const double one_m_cos = 1.0 - cos_apex;
 		const double py = r1 * c1, pz = r1 * s1;   // photon_line%point = (0, py, pz)
+		const double hz = P.collimator_height - pz;
 		int hits = 0;
 		const long n_pairs = (P.hits_per_single + 1) >> 1;
+		// Per ray the reference draws theta = acos(1 - u1 (1 - cos apex)), phi = 2 pi u2 and takes sin/cos of both
+		// (src/xmi_solid_angle_f.F90:633-650).  The same direction without the inverse: cos theta = 1 - t,
+		// sin theta = sqrt(t (2 - t)) with t = u1 (1 - cos apex) (exact identity, better conditioned for narrow cones),
+		// (sin, cos) phi by sincospi(2 u2).  The two plane intersections (:667-691) are tested multiplied through by
+		// dz^2 > 0 -- no division: x dz = (h - pz) dx, y dz = (h - pz) dy + py dz for the plane z = h.
 		for (long p = lane; p < n_pairs; p += 32) {
 			const uint4 rnd = xmb_philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)p, XMB_TAG_SOLID_ANGLE), key);
 #pragma unroll
 			for (int half = 0; half < 2; half++) {
-				if (half == 1 && 2 * p + 1 >= P.hits_per_single) break;
-				const double u1 = xmb_u01(half ? rnd.z : rnd.x), u2 = xmb_u01(half ? rnd.w : rnd.y);
-				const double theta_rng = acos(1.0 - u1 * one_m_cos);
-				const double phi_rng = u2 * 2.0 * M_PI;
-				double sth, cth, sph, cph;
-				sincos(theta_rng, &sth, &cth);
-				sincos(phi_rng, &sph, &cph);
-				const double cx = sth * cph, cy = sth * sph, cz = cth;
+				const double u1 = u01_exact(half ? rnd.z : rnd.x), u2 = u01_exact(half ? rnd.w : rnd.y);
+				const double t = u1 * one_m_cos;
+				const double cth = 1.0 - t, sth = sqrt(t * (2.0 - t));
+				double sph, cph;
+				sincospi(2.0 * u2, &sph, &cph);
+				const double dx = sth * cph, cy = sth * sph;
 				// MATMUL(rotation_matrix, dirv_from_cone), rows (1,0,0), (0,-sin,-cos), (0,cos,-sin)
-				const double dx = cx, dy = -st * cy - ct * cz, dz = ct * cy - st * cz;
-				if (dz >= 0.0) continue;
+				const double dy = -st * cy - ct * cth, dz = ct * cy - st * cth;
+				const double dz2 = dz * dz;
+				const double a = pz * dx, b = py * dz - pz * dy;
+				bool hit = dz < 0.0 && a * a + b * b <= det_r2 * dz2;
 				if (outside) {
-					const double d = (P.collimator_height - pz) / dz;
-					const double ix = d * dx, iy = d * dy + py;
-					if (ix * ix + iy * iy > col_r2) continue;
+					const double a2 = hz * dx, b2 = hz * dy + py * dz;
+					hit = hit && a2 * a2 + b2 * b2 <= col_r2 * dz2;
 				}
-				const double d = (0.0 - pz) / dz;
-				const double ix = d * dx, iy = d * dy + py, iz = d * dz + pz;
-				if (ix * ix + iy * iy + iz * iz <= det_r2) hits++;
+				if (half == 1 && 2 * p + 1 >= P.hits_per_single) hit = false;
+				hits += hit ? 1 : 0;
 			}
 		}
 		hits = __reduce_add_sync(0xffffffffu, hits);

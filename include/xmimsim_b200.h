@@ -374,6 +374,12 @@ double xmb_solid_angle_last_ms(void);
 /* Raw hit counts of the last grid computed by xmb_solid_angle_calculation on this thread's
  * device (int32 [theta][r]); for parity tests.  Returns number of points copied. */
 long xmb_solid_angle_last_hits(int32_t *hits, long capacity);
+/* The reference's mutable global `hits_per_single` (src/xmi_solid_angle_f.F90:43-44, default 5000): rays per point of
+ * the plugin-shaped grid call and of the on-the-spot solid angle of an interaction point beyond the grid
+ * (xmi_get_solid_angle, :783-789).  get: the value set here, else the host process's exported `hits_per_single`
+ * symbol when there is one, else 5000. */
+void xmb_set_hits_per_single(long n);
+long xmb_get_hits_per_single(void);
 void xmb_free_solid_angle(xmb_solid_angle *sa);   /* xmi_free_solid_angle, src/xmi_solid_angle.c:792-800 */
 
 /* Replaces xmi_main_msim (include/xmi_main.h:29; src/xmi_main.F90:66-954).

@@ -48,6 +48,11 @@ void orc_free_derived(orc_derived *d);
  * angle; *hits receives the number of rays that reached the detector. */
 double orc_single_solid_angle(const orc_derived *d, double r1, double theta1, long hits_per_single,
                               uint64_t seed, uint64_t point_id, long *hits);
+/* ... for an interaction point of photon g beyond the grid (src/xmi_solid_angle_f.F90:783-789) */
+double orc_single_solid_angle_photon(const orc_derived *d, double r1, double theta1, long hits_per_single,
+                                     uint64_t seed, uint64_t g, int order, long *hits);
+/* the reference's global hits_per_single (src/xmi_solid_angle_f.F90:43-44) as the history loop sees it */
+void orc_set_hits_per_single(long n);
 /* xmi_solid_angle_calculation_f grid loop (src/xmi_solid_angle_f.F90:303-429) over a caller-given
  * sub-grid: solid_angles[it*n_r + ir], hits likewise.  point ids use the FULL grid width
  * full_n_r so that a sub-grid reproduces the same streams: id = theta_idx[it]*full_n_r + r_idx[ir]. */

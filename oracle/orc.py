@@ -45,6 +45,8 @@ def lib():
         _lib.orc_detector_convolute_spectrum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_int, C.c_uint64]
         _lib.orc_detector_convolute_history.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_set_hits_per_single.argtypes = [C.c_long]
+        _lib.orc_set_hits_per_single.restype = None
         _lib.orc_total_histories.argtypes = [C.c_void_p]
         _lib.orc_total_histories.restype = C.c_uint64
         _lib.orc_main_msim_range.argtypes = [C.c_void_p, C.POINTER(OrcDerived), C.c_void_p, C.c_void_p, C.c_void_p,

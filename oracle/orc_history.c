@@ -303,7 +303,10 @@ static double compton_energy_adv(const ctx_t *c, int zi, double E0, double theta
 }
 
 /* ---- xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801) ------------------------------- */
-static double get_solid_angle(ctx_t *c, const double *coords) {
+static long g_hits_per_single = 5000;                                        /* src/xmi_solid_angle_f.F90:43 */
+void orc_set_hits_per_single(long n) { g_hits_per_single = n > 0 ? n : 5000; }
+static double get_solid_angle(ctx_t *c, const photon_t *p) {
+	const double *coords = p->coords;
 	const xmb_solid_angle *sa = c->sa;
 	const xmb_geometry *g = c->in->geometry;
 	double r = dist3(g->p_detector_window, coords);
@@ -314,11 +317,11 @@ static double get_solid_angle(ctx_t *c, const double *coords) {
 	double theta = (M_PI / 2.0) - temp_theta;
 	if (theta < sa->grid_dims_theta_vals[0]) return 0.0;
 	int nr = (int)sa->grid_dims_r_n, nt = (int)sa->grid_dims_theta_n;
-	/* off-grid: the reference falls back to an on-the-fly 5000-ray Monte Carlo (:783-789); not restated,
-	 * counted and scored as zero */
-	if (r > sa->grid_dims_r_vals[nr - 1] || r < sa->grid_dims_r_vals[0] - 1e-10 || theta > sa->grid_dims_theta_vals[nt - 1]) {
+	/* findpos = -1 only beyond the last axis value (src/xmi_aux_f.F90:1305-1335; below the first it returns 1 and the
+	 * bilinear form extrapolates from the first cell): on-the-fly Monte Carlo with hits_per_single rays (:783-789) */
+	if (r > sa->grid_dims_r_vals[nr - 1] || theta > sa->grid_dims_theta_vals[nt - 1]) {
 		c->sa_not_found++;
-		return 0.0;
+		return orc_single_solid_angle_photon(c->d, r, theta, g_hits_per_single, p->seed, p->g, p->n_interactions, NULL);
 	}
 	/* Fortran array solid_angles(r, theta) -> C [theta][r]; bilinear with x1 = r, x2 = theta */
 	int p1 = findpos_uniform(sa->grid_dims_r_vals[0], sa->grid_dims_r_vals[1] - sa->grid_dims_r_vals[0], nr, r);
@@ -391,7 +394,7 @@ static void variance_reduction(ctx_t *c, photon_t *p, double u_det_r, double u_d
 	for (int j = p->current_layer; step_dir > 0 ? j <= step_max : j >= step_max; j += step_dir)
 		temp_murhod += p->mus[j] * layers[j].density * distances[j];
 	double Pesc_rayl = exp(-temp_murhod);                                         /* :306 */
-	double detector_solid_angle = get_solid_angle(c, p->coords);                  /* :318 */
+	double detector_solid_angle = get_solid_angle(c, p);                  /* :318 */
 	double Pdir_fluo = detector_solid_angle / 4.0 / M_PI;
 	int line_last = c->opt->use_M_lines ? XMB_M5P5 : XMB_L3Q1;
 	nodepos_t np = node_find(T, p->energy);

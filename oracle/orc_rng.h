@@ -21,6 +21,7 @@ static inline uint32_t orc_rng_u32(orc_rng *r) {
 /* uniform in [0,1) with 32-bit resolution, as gsl/easyRNG rng_uniform on MT19937 */
 static inline double orc_rng_uniform(orc_rng *r) { return orc_rng_u32(r) * (1.0 / 4294967296.0); }
 #define ORC_TAG_SOLID_ANGLE 0x5Au
+#define ORC_TAG_SA_FALLBACK 0x5Bu
 #define ORC_TAG_HISTORY 0x48u
 #define ORC_TAG_DETECTOR 0x44u
 #endif

@@ -16,8 +16,20 @@ static int intersection_plane_line(const double pp[3], const double pn[3], const
 static double norm3(const double a[3]) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 
 /* src/xmi_solid_angle_f.F90:432-710 */
+static double single_solid_angle(const orc_derived *D, double r1, double theta1, long hits_per_single,
+                                 uint64_t seed, uint64_t point_id, uint32_t block0, uint32_t tag, long *hits_out);
 double orc_single_solid_angle(const orc_derived *D, double r1, double theta1, long hits_per_single,
                               uint64_t seed, uint64_t point_id, long *hits_out) {
+	return single_solid_angle(D, r1, theta1, hits_per_single, seed, point_id, 0, ORC_TAG_SOLID_ANGLE, hits_out);
+}
+/* The same calculation for an interaction point beyond the grid (xmi_get_solid_angle, src/xmi_solid_angle_f.F90:783-789):
+ * rays of photon g at interaction `order` come from stream (g, blocks (order << 20) + ray pair, ORC_TAG_SA_FALLBACK). */
+double orc_single_solid_angle_photon(const orc_derived *D, double r1, double theta1, long hits_per_single,
+                                     uint64_t seed, uint64_t g, int order, long *hits_out) {
+	return single_solid_angle(D, r1, theta1, hits_per_single, seed, g, (uint32_t)order << 20, ORC_TAG_SA_FALLBACK, hits_out);
+}
+static double single_solid_angle(const orc_derived *D, double r1, double theta1, long hits_per_single,
+                                 uint64_t seed, uint64_t point_id, uint32_t block0, uint32_t tag, long *hits_out) {
 	const double detector_normal[3] = {0.0, 0.0, 1.0};
 	double r, theta, full_cone_base_radius;
 	int outside_collimator;
@@ -57,7 +69,8 @@ double orc_single_solid_angle(const orc_derived *D, double r1, double theta1, lo
 	double line_point[3] = {0.0, r1 * cos(theta1), r1 * sin(theta1)};           /* :609 */
 	long detector_hits = 0;
 	orc_rng rng;
-	orc_rng_init(&rng, seed, point_id, ORC_TAG_SOLID_ANGLE);
+	orc_rng_init(&rng, seed, point_id, tag);
+	rng.ctr[2] = block0;
 	for (long i = 0; i < hits_per_single; i++) {                                /* :630-693 */
 		double theta_rng = acos(1.0 - orc_rng_uniform(&rng) * (1.0 - cos_full_cone_apex));
 		double phi_rng = orc_rng_uniform(&rng) * 2.0 * M_PI;

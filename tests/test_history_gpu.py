@@ -92,6 +92,44 @@ def test_gaussian_source_and_excitation_absorber():
     assert_spectra_close(ch, ch_o, RTOL, "gaussian-source channels")
 
 
+def test_interaction_points_beyond_the_solid_angle_grid():
+    """xmi_get_solid_angle falls back to hits_per_single rays on the spot when a point lies beyond the grid
+    (src/xmi_solid_angle_f.F90:783-789): a grid cut just behind the sample surface sends a large share of the
+    interactions down that path; the engine (whole CTA shares the rays of a point) and the oracle agree."""
+    import orc
+    inp = example("srm1155")
+    inp.n_photons_line = 300
+    P = Pair(inp)
+    r_full, t_full = P.sim.solid_angle_inputs()
+    pw = np.array(inp.p_detector_window, float)
+    r_cut = np.linalg.norm(pw - np.array([0.0, 0.0, inp.d_sample_source])) * (1.0 + 1e-6)
+    assert r_full[0] < r_cut < r_full[-1]
+    r = np.linspace(r_full[0], r_cut, 128)
+    t = np.linspace(t_full[0], t_full[-1], 128)
+    g, _ = P.sim.solid_angle_grid(r, t, hits_per_single=400, seed=3)
+    sa = P.sim.make_solid_angle(g, r, t)
+    opt = x.main_options()
+    P.sim.L.xmb_set_hits_per_single(601)
+    orc.lib().orc_set_hits_per_single(601)
+    try:
+        assert P.sim.L.xmb_get_hits_per_single() == 601
+        ch, br, vr = P.sim.main_msim(opt, sa)
+        ch_o, vr_o, cnt = P.oracle(opt, sa, 0)
+    finally:
+        P.sim.L.xmb_set_hits_per_single(0)
+        orc.lib().orc_set_hits_per_single(5000)
+    assert P.sim.L.xmb_get_hits_per_single() == 5000
+    n_inter = int(cnt[1])
+    assert 0.05 * n_inter < int(cnt[0]) < 0.98 * n_inter, (cnt[0], n_inter)       # both paths are exercised
+    assert_spectra_close(ch, ch_o, RTOL, "off-grid channels")
+    assert_spectra_close(vr, vr_o, RTOL, "off-grid history")
+    # the fallback carries real intensity: with the off-grid points scored as zero the spectrum would be far smaller
+    full = P.grid(hits_per_single=400, n=128)
+    ch_full, _, _ = P.sim.main_msim(opt, full)
+    assert 0.8 < ch[-1].sum() / ch_full[-1].sum() < 1.25
+    P.close()
+
+
 def test_bit_exact_across_rank_counts():
     """Photon-id shards summed in uint64 must reproduce the single-rank accumulators bit for bit, for any
     shard count, and so must a repeat run (atomics order does not matter)."""

@@ -189,6 +189,8 @@ def lib():
     L.xmb_solid_angle_grid.restype = C.c_int
     L.xmb_solid_angle_last_hits.argtypes = [C.POINTER(C.c_int32), C.c_long]; L.xmb_solid_angle_last_hits.restype = C.c_long
     L.xmb_solid_angle_last_ms.restype = C.c_double
+    L.xmb_set_hits_per_single.argtypes = [C.c_long]; L.xmb_set_hits_per_single.restype = None
+    L.xmb_get_hits_per_single.restype = C.c_long
     L.xmb_free_solid_angle.argtypes = [C.POINTER(SolidAngle)]; L.xmb_free_solid_angle.restype = None
     L.xmb_main_options_defaults.argtypes = [C.POINTER(MainOptions)]; L.xmb_main_options_defaults.restype = None
     L.xmb_main_msim.argtypes = [vp, vp, C.c_int, C.POINTER(c_double_p), C.POINTER(MainOptions), C.POINTER(c_double_p),

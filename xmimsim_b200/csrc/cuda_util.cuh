@@ -14,6 +14,7 @@
 	} while (0)
 
 #define XMB_TAG_SOLID_ANGLE 0x5Au
+#define XMB_TAG_SA_FALLBACK 0x5Bu
 #define XMB_TAG_HISTORY 0x48u
 #define XMB_TAG_DETECTOR 0x44u
 

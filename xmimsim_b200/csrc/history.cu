@@ -20,7 +20,10 @@
 #include <algorithm>
 #include <cmath>
 #include "history_device.cuh"
+#include "solid_angle_device.cuh"
 #include "device_tables.h"
+
+#define XMB_SA_ROUND 32
 
 // NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
 template <int NL, bool ADV = false>
@@ -53,6 +56,13 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	// random numbers make the result independent of this regrouping.
 	__shared__ int s_qcount[XMB_MAX_ORDERS];      // photons waiting to run order k+1
 	__shared__ int s_wsum[32];
+	// solid angles of interaction points beyond the grid, computed by the whole CTA, XMB_SA_ROUND points at a time
+	__shared__ int s_sa_n, s_sa_hits[XMB_SA_ROUND];
+	__shared__ double s_sa_pt[2 * XMB_SA_ROUND];
+	__shared__ uint64_t s_sa_g[XMB_SA_ROUND];
+	__shared__ SaCone s_sa_cone[XMB_SA_ROUND];
+	__shared__ int s_lcnt[XMB_MAX_LAYERS + 1];    // batch members per layer (counting sort of a batch)
+	__shared__ unsigned short s_perm[HIST_THREADS];
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
 	for (int i = tid; i < 4 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0u;
 	__syncthreads();
@@ -60,15 +70,82 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	const size_t qcap = 2 * (size_t)T;
 	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * NF * qcap;
 	uint64_t next_chunk = blockIdx.x;
+	// Forced interaction (src/xmi_main.F90:1229-1518): moves the photon to the point of its interaction number
+	// order + 1.  Done before the photon is queued, so that the layer it will interact in is known when a batch is formed.
+	auto transport = [&](Photon &p, uint64_t g, int order) {
+		if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
+		if (p.alive) {
+			const uint4 b1 = draw_block(P.seed, g, order + 1, 1, 0, 0);   // .x = path length
+			int step_max = 0, step_dir = 1;
+			if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
+			else { step_max = 0; step_dir = -1; }
+			const double interactionR = xmb_u01(b1.x);
+			double lx = p.cx, ly = p.cy, lz = p.cz;
+			double Pabs = 0.0;
+			for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+				double dist;
+				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { p.alive = false; break; }
+				rd[i * T] = dist;
+				Pabs += mus[i * T] * P.layers[i].density * dist;
+			}
+			if (p.alive) {
+				const double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
+				p.weight *= Pabs2;
+				const double l1p = log1p(-1.0 * interactionR * Pabs2);
+				const double negln = -1.0 * l1p;
+				int my_index = p.layer;
+				double my_sum = 0.0;
+				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+					my_sum += mus[i * T] * P.layers[i].density * rd[i * T];
+					if (my_sum > negln) { my_index = i; break; }
+				}
+				const double murho_idx = mus[my_index * T] * P.layers[my_index].density;
+				double temp_sum = 0.0;
+				for (int i = p.layer; step_dir > 0 ? i <= my_index : i >= my_index; i += step_dir)
+					temp_sum += (1.0 - (mus[i * T] * P.layers[i].density / murho_idx)) * rd[i * T];
+				temp_sum = temp_sum - 1.0 * l1p / murho_idx;
+				p.cx += temp_sum * p.dx; p.cy += temp_sum * p.dy; p.cz += temp_sum * p.dz;
+				p.layer = my_index;
+				p.n_interactions++;
+				n_inter_local++;
+#ifndef XMB_NO_LAYER_CNT
+				atomicAdd(&s_layer_cnt[my_index], 1u);
+#endif
+			}
+		}
+	};
+	// compaction: survivors go, densely packed, to the queue of the next order
+	auto push = [&](const Photon &p, uint64_t g, int order) {
+		const bool surv = p.alive;
+		const unsigned bal = __ballot_sync(0xffffffffu, surv);
+		if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
+		__syncthreads();
+		int off = 0, tot = 0;
+		for (int w = 0; w < (T >> 5); w++) { const int c = s_wsum[w]; if (w < (tid >> 5)) off += c; tot += c; }
+		const int have = s_qcount[order];
+		if (surv) {
+			double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
+			q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
+			q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
+			q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
+			q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
+			q[13 * qcap] = __longlong_as_double((long long)g);
+			q[14 * qcap] = __longlong_as_double((long long)p.layer);
+			XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+		}
+		__syncthreads();
+		if (tid == 0) s_qcount[order] = have + tot;
+	};
 	for (;;) {
 		// ---- scheduler (block-uniform) ---------------------------------------------------------------
 		int k = -1;
-		for (int kk = P.n_int - 1; kk >= 1; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
+		for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
 		bool from_source = false;
 		if (k < 0) {
 			if (next_chunk < n_chunks) from_source = true;
 			else {
-				for (int kk = P.n_int - 1; kk >= 1; kk--) if (s_qcount[kk] > 0) { k = kk; break; }
+				for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] > 0) { k = kk; break; }
 				if (k < 0) break;
 			}
 		}
@@ -76,7 +153,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 		Photon p;
 		p.alive = false;
 		p.layer = 0; p.n_interactions = 0; p.energy = 0.0; p.weight = 0.0;
-		int order = 1;
+		int order = 0;   // interactions this batch has behind it once the step is done (0: fresh source photons)
 		if (from_source) {
 			const uint64_t lid = next_chunk * T + tid;
 			g = shard_global_id(P, lid);
@@ -87,11 +164,40 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 				rng.init(P.seed, g, XMB_TAG_HISTORY);
 				start_photon<NL>(P, p, rng, g, mus, T);
 			}
+			transport(p, g, 0);
+			if (P.layer_sort) {   // first interactions are batched by layer as well: through queue 0
+				push(p, g, 0);
+				__syncthreads();
+				continue;
+			}
+			order = 1;
 		} else {
 			const int have = s_qcount[k], n = min(T, have), base = have - n;
 			order = k + 1;
+			const double *qk = qbase + (size_t)k * NF * qcap + base;
+			int src = tid;
+			if (NL != 1 && P.layer_sort) {
+				// Counting sort of the batch by the layer of the interaction point (known: the photon was moved there
+				// before it was queued).  Every loop of the deposit phases is per (layer, element); with warps of one
+				// layer a warp runs the loops of its own layer only instead of those of every layer its lanes are in.
+				const int myL = tid < n ? (int)__double_as_longlong(qk[14 * qcap + tid]) : nL;   // idle lanes sort last
+				if (tid <= nL) s_lcnt[tid] = 0;
+				__syncthreads();
+				const unsigned peers = __match_any_sync(0xffffffffu, myL);
+				const int leader = __ffs(peers) - 1;
+				int wbase = 0;
+				if (lane == leader) wbase = atomicAdd(&s_lcnt[myL], __popc(peers));
+				wbase = __shfl_sync(0xffffffffu, wbase, leader);
+				const int rank = wbase + __popc(peers & ((1u << lane) - 1u));
+				__syncthreads();
+				int start = 0;
+				for (int l = 0; l < myL; l++) start += s_lcnt[l];
+				s_perm[start + rank] = (unsigned short)tid;
+				__syncthreads();
+				src = s_perm[tid];
+			}
 			if (tid < n) {
-				const double *q = qbase + (size_t)k * NF * qcap + base + tid;
+				const double *q = qk + src;
 				p.cx = q[0 * qcap]; p.cy = q[1 * qcap]; p.cz = q[2 * qcap];
 				p.dx = q[3 * qcap]; p.dy = q[4 * qcap]; p.dz = q[5 * qcap];
 				p.ex = q[6 * qcap]; p.ey = q[7 * qcap]; p.ez = q[8 * qcap];
@@ -100,56 +206,14 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 				p.layer = (int)__double_as_longlong(q[14 * qcap]);
 				XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
-				p.n_interactions = order - 1;
+				p.n_interactions = order;
 				p.alive = true;
 			}
 			__syncthreads();
 			if (tid == 0) s_qcount[k] = base;
 		}
 		{
-			// ---- forced interaction (src/xmi_main.F90:1229-1518) ------------------------------------
-			if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
-			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length, detector r, detector phi, atom}
-			double interactionR = 0.0;
-			int step_max = 0, step_dir = 1;
-			if (p.alive) {
-				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
-				else { step_max = 0; step_dir = -1; }
-				interactionR = xmb_u01(b0.x);
-				double lx = p.cx, ly = p.cy, lz = p.cz;
-				double Pabs = 0.0;
-				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
-					double dist;
-					if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { p.alive = false; break; }
-					rd[i * T] = dist;
-					Pabs += mus[i * T] * P.layers[i].density * dist;
-				}
-				if (p.alive) {
-					const double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
-					p.weight *= Pabs2;
-					const double l1p = log1p(-1.0 * interactionR * Pabs2);
-					const double negln = -1.0 * l1p;
-					int my_index = p.layer;
-					double my_sum = 0.0;
-					for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
-						my_sum += mus[i * T] * P.layers[i].density * rd[i * T];
-						if (my_sum > negln) { my_index = i; break; }
-					}
-					const double murho_idx = mus[my_index * T] * P.layers[my_index].density;
-					double temp_sum = 0.0;
-					for (int i = p.layer; step_dir > 0 ? i <= my_index : i >= my_index; i += step_dir)
-						temp_sum += (1.0 - (mus[i * T] * P.layers[i].density / murho_idx)) * rd[i * T];
-					temp_sum = temp_sum - 1.0 * l1p / murho_idx;
-					p.cx += temp_sum * p.dx; p.cy += temp_sum * p.dy; p.cz += temp_sum * p.dz;
-					p.layer = my_index;
-					p.n_interactions++;
-					n_inter_local++;
-#ifndef XMB_NO_LAYER_CNT
-					atomicAdd(&s_layer_cnt[my_index], 1u);
-#endif
-				}
-			}
-			__syncthreads();   // phase barrier after transport
+			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length (used when the photon was moved), detector r, detector phi, atom}
 			const int n_ia = order;   // == p.n_interactions for every live lane
 			unsigned int *acc_k = stage;   // deposits of this batch are staged in shared memory, flushed below
 
@@ -158,6 +222,9 @@ for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 			double theta = 0.0, phi = 0.0, Pesc_rayl = 0.0, omega = 0.0;
 			NodePos np;
 			np.pos = 0; np.f = 0.0;
+			int pj_lo = nL, pj_hi = -1;   // layers the path to the detector crosses (rd[] is zero outside)
+			bool sa_pending = false;      // interaction point beyond the solid-angle grid
+			double sa_r = 0.0, sa_theta = 0.0;
 			if (vr) {
 				const double radius = sqrt(xmb_u01(b0.y)) * P.detector_radius;
 				const double th = 2.0 * M_PI * xmb_u01(b0.z);
@@ -187,6 +254,7 @@ for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 					phi = acos(dotprod);
 					int vmax, vdir;
 					if (n0 * P.n_sample[0] + n1 * P.n_sample[1] + n2 * P.n_sample[2] > 0.0) { vmax = nL - 1; vdir = 1; } else { vmax = 0; vdir = -1; }
+					pj_lo = min(p.layer, vmax); pj_hi = max(p.layer, vmax);
 					XMB_UNROLL_NL
 for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					double tx = p.cx, ty = p.cy, tz = p.cz;
@@ -202,10 +270,53 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						total_distance -= dist;
 					}
 					Pesc_rayl = exp(-temp_murhod);
-					omega = get_solid_angle(P, p);
+					omega = get_solid_angle(P, p, sa_pending, sa_r, sa_theta);
 					np = node_find(P, p.energy);
 				}
 			}
+			// Points beyond the grid: the reference computes their solid angle on the spot with hits_per_single rays
+			// (src/xmi_solid_angle_f.F90:783-789).  About one interaction in a thousand (air-path scatters far from the
+			// window), and 5000 rays by one lane would stall the whole CTA: the CTA collects the points of the batch (32
+			// per round) and all its threads share their rays (Philox address: photon id, (order << 20) | ray pair,
+			// XMB_TAG_SA_FALLBACK -- fixed per photon, so the result does not depend on the batch either).
+			while (__syncthreads_or(sa_pending)) {
+				if (tid == 0) s_sa_n = 0;
+				if (tid < XMB_SA_ROUND) s_sa_hits[tid] = 0;
+				__syncthreads();
+				int slot = -1;
+				if (sa_pending) {
+					slot = atomicAdd(&s_sa_n, 1);
+					if (slot < XMB_SA_ROUND) { s_sa_pt[2 * slot] = sa_r; s_sa_pt[2 * slot + 1] = sa_theta; s_sa_g[slot] = g; }
+				}
+				__syncthreads();
+				const int npt = min(s_sa_n, XMB_SA_ROUND);
+				if (tid < npt) s_sa_cone[tid] = sa_cone_setup(P.sa_det, s_sa_pt[2 * tid], s_sa_pt[2 * tid + 1]);
+				__syncthreads();
+				{
+					const double det_r2 = P.sa_det.detector_radius * P.sa_det.detector_radius, col_r2 = P.sa_det.collimator_radius * P.sa_det.collimator_radius;
+					const int n_pairs = (P.sa_hits_per_single + 1) >> 1, total = npt * n_pairs;
+					for (int i = tid; i < total; i += T) {
+						const int pt = i / n_pairs, pr = i - pt * n_pairs;
+						const SaCone cone = s_sa_cone[pt];
+						if (cone.dead) continue;
+						const uint64_t gp = s_sa_g[pt];
+						const uint4 rnd = xmb_philox4x32_10(make_uint4((uint32_t)gp, (uint32_t)(gp >> 32), ((uint32_t)order << 20) | (uint32_t)pr, XMB_TAG_SA_FALLBACK),
+						                                    make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+						const int h = sa_pair_hits(cone, det_r2, col_r2, rnd, 2 * pr + 1 < P.sa_hits_per_single);
+						if (h) atomicAdd(&s_sa_hits[pt], h);
+					}
+				}
+				__syncthreads();
+				if (slot >= 0 && slot < XMB_SA_ROUND) {
+					omega = s_sa_cone[slot].dead ? 0.0 : s_sa_cone[slot].cone_sa * (double)s_sa_hits[slot] / (double)P.sa_hits_per_single;
+					sa_pending = false;
+					atomicAdd(&P.counters[0], 1ULL);
+				}
+			}
+			// generic layer count: the optical-depth sums below skip the layers no lane of the warp crosses (terms that
+			// are exactly zero); with a compile-time layer count the loops are unrolled over all layers
+			const int jlo = NL > 0 ? 0 : __reduce_min_sync(0xffffffffu, pj_lo);
+			const int jhi = NL > 0 ? nL - 1 : __reduce_max_sync(0xffffffffu, pj_hi);
 			__syncthreads();   // phase: scatter deposits of every element
 			// warp-uniform loops over layers / elements / shells / line records
 			for (int L = 0; L < nL; L++) {
@@ -295,7 +406,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						const NodePos cp = node_find(P, e_c);
 						double tm = 0.0;
 						XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
 						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
 						fx = to_fixed(Pconv * Pdir * exp_neg(tm, s_exp_tab) * p.weight, P.counters);
@@ -333,7 +444,7 @@ XMB_UNROLL(XMB_REC_UNROLL)
 							const double *mu = P.rec_mu + (size_t)r * nL;
 							double tm = 0.0;
 							XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
+for (int j = jlo; j <= jhi; j++) tm += mu[j] * rd[j * T];
 							const double tw = pre * P.rec_yr[r] * exp_neg(tm, s_exp_tab);
 							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed_fast(tw, bad_fixed) : 0ULL, lane);
 						}
@@ -350,28 +461,10 @@ for (int j = 0; j < nL; j++) tm += mu[j] * rd[j * T];
 				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused);
 			}
 		}
-		// ---- compaction: survivors go, densely packed, to the queue of the next order -------------------
+		// ---- move to the next interaction point and queue there --------------------------------------------
 		if (order < P.n_int) {
-			const bool surv = p.alive && p.energy >= ENERGY_THRESHOLD;
-			const unsigned bal = __ballot_sync(0xffffffffu, surv);
-			if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
-			__syncthreads();
-			int off = 0, tot = 0;
-			for (int w = 0; w < (T >> 5); w++) { const int c = s_wsum[w]; if (w < (tid >> 5)) off += c; tot += c; }
-			const int have = s_qcount[order];
-			if (surv) {
-				double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
-				q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
-				q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
-				q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
-				q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
-				q[13 * qcap] = __longlong_as_double((long long)g);
-				q[14 * qcap] = __longlong_as_double((long long)p.layer);
-				XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
-			}
-			__syncthreads();
-			if (tid == 0) s_qcount[order] = have + tot;
+			transport(p, g, order);
+			push(p, g, order);
 		}
 		__syncthreads();
 	}
@@ -687,6 +780,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	}
 	P.sa_grid = D->sa_grid; P.sa_r_vals = D->sa_r; P.sa_t_vals = D->sa_t;
 	if (!brute) { P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n; }
+	// batches sorted by layer pay when photons interact in several layers with different element lists; with one or two
+	// layers (a sample behind an air gap) nearly every interaction is in the same layer and the sort is skipped
+	P.layer_sort = P.nL >= 3 ? 1 : 0;
+	P.sa_det.collimator_present = in->der.collimator_present; P.sa_det.detector_radius = in->der.detector_radius;
+	P.sa_det.collimator_radius = in->der.collimator_radius; P.sa_det.collimator_height = in->der.collimator_height;
+	P.sa_hits_per_single = (int)std::min<long>(xmb_get_hits_per_single(), 1L << 20);
 	// accumulators: one row per interaction order (brute force: rows 0..n_int, row = interactions before detection)
 	const size_t slots = (size_t)(P.n_int + (brute ? 1 : 0)) * ((size_t)P.nch + P.n_hist_slots);
 	if (D->acc_slots != slots) {

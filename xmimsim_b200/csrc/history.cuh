@@ -1,6 +1,7 @@
 // history.cuh -- device-side data layout of the photon-history engine (see DESIGN.md "HBM layout").
 #pragma once
 #include <cstdint>
+#include "solid_angle_device.cuh"
 
 #define XMB_MAX_LAYERS 32
 #define XMB_SHARD_BLOCK 1024
@@ -39,6 +40,7 @@ struct XmbHistParams {
 	uint64_t n_cont_seg, n_per_interval, n_per_line;
 	int n_seg, n_int, nch, nL, nZ;
 	int use_M_lines;
+	int layer_sort;                          // batches are formed per layer of the interaction point (counting sort)
 	double zero, gain;
 	const XmbSegDev *segs;
 	// geometry
@@ -84,6 +86,8 @@ struct XmbHistParams {
 	const double *sa_grid;                   // [n_theta][n_r]
 	int sa_nr, sa_nt;
 	const double *sa_r_vals, *sa_t_vals;
+	SaDetector sa_det;                       // for points beyond the grid: Monte Carlo on the spot
+	int sa_hits_per_single;
 	// global accumulators: [n_int][nch + n_hist_slots] 128-bit integers as (lo, hi) uint64 pairs
 	double *queue;                           // per-CTA compaction queues [CTA][order][field][2T]
 	unsigned long long *acc;

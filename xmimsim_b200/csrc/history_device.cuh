@@ -117,7 +117,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	return v;
 }
 // all 32 lanes call; slot is warp-uniform.  The four 16-bit pieces are summed across the warp with REDUX (sums < 2^21)
-// and lane 0 adds them to the slot's four staging words.
+// and lanes 0..3 add them to the slot's four staging words.
 #ifndef XMB_REDUX_PIECES
 #define XMB_REDUX_PIECES 1
 #endif
@@ -126,13 +126,9 @@ __device__ __forceinline__ void deposit_uniform(unsigned int *acc, size_t slot, 
 	const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
 	const unsigned int s0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), s1 = __reduce_add_sync(0xffffffffu, lo >> 16);
 	const unsigned int s2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), s3 = __reduce_add_sync(0xffffffffu, hi >> 16);
-	if (lane == 0) {
-		unsigned int *w = acc + 4 * slot;
-		if (s0) atomicAdd(&w[0], s0);
-		if (s1) atomicAdd(&w[1], s1);
-		if (s2) atomicAdd(&w[2], s2);
-		if (s3) atomicAdd(&w[3], s3);
-	}
+	// lanes 0..3 add one piece each: one predicated atomic instead of four issued for lane 0 alone
+	const unsigned int piece = lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
+	if (lane < 4 && piece) atomicAdd(acc + 4 * slot + lane, piece);
 #else
 	v = warp_sum_u64(v);
 	if (lane == 0) red128(acc, slot, v);
@@ -294,8 +290,10 @@ __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi,
 	return energy;
 }
 
-// xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801); off-grid points are counted and score zero
-__device__ __forceinline__ double get_solid_angle(const XmbHistParams &P, const Photon &p) {
+// xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801).  A point beyond the last r or theta of the grid (findpos
+// = -1, src/xmi_aux_f.F90:1305-1335; a value below the first r extrapolates from the first cell, as findpos returns 1)
+// is reported through `offgrid` with its (r, theta): the caller runs the reference's on-the-fly Monte Carlo (:783-789).
+__device__ __forceinline__ double get_solid_angle(const XmbHistParams &P, const Photon &p, bool &offgrid, double &r_og, double &theta_og) {
 	double vx = p.cx - P.p_window[0], vy = p.cy - P.p_window[1], vz = p.cz - P.p_window[2];
 	const double r = sqrt(vx * vx + vy * vy + vz * vz);
 	normalize3(vx, vy, vz);
@@ -304,7 +302,7 @@ __device__ __forceinline__ double get_solid_angle(const XmbHistParams &P, const 
 	const double theta = (M_PI / 2.0) - temp_theta;
 	const double *R = P.sa_r_vals, *Th = P.sa_t_vals;
 	if (theta < Th[0]) return 0.0;
-	if (r > R[P.sa_nr - 1] || r < R[0] - 1e-10 || theta > Th[P.sa_nt - 1]) { atomicAdd(&P.counters[0], 1ULL); return 0.0; }
+	if (r > R[P.sa_nr - 1] || theta > Th[P.sa_nt - 1]) { offgrid = true; r_og = r; theta_og = theta; return 0.0; }
 	const int p1 = findpos_uniform(R, P.sa_nr, r), p2 = findpos_uniform(Th, P.sa_nt, theta);
 	const double rl = R[p1], rh = R[p1 + 1], tl = Th[p2], th = Th[p2 + 1];
 	const double denom = (rh - rl) * (th - tl);

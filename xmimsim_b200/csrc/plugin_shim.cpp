@@ -16,7 +16,15 @@
 #include "engine.h"
 
 static const xmb_xrl_provider *g_provider = nullptr;
-static long g_hits_per_single_default = 5000;
+static long g_hits_per_single = 0;   // 0: not set through xmb_set_hits_per_single
+
+extern "C" void xmb_set_hits_per_single(long n) { g_hits_per_single = n > 0 ? n : 0; }
+extern "C" long xmb_get_hits_per_single(void) {
+	if (g_hits_per_single > 0) return g_hits_per_single;
+	// the reference reads its global `hits_per_single` (src/xmi_solid_angle_cl.c:54); honour it when the host exports it
+	long *hps = (long *)dlsym(RTLD_DEFAULT, "hits_per_single");
+	return hps && *hps > 0 ? *hps : 5000;
+}
 
 extern "C" void xmb_plugin_set_provider(const xmb_xrl_provider *p) { g_provider = p; }
 
@@ -47,9 +55,7 @@ extern "C" int xmi_solid_angle_calculation_cl(void *inputFPtr, xmb_solid_angle *
 	xmb_hdf5FPtr tables = nullptr;
 	int rv = 0;
 	if (xmb_init_from_provider(g_provider ? g_provider : xmb_xrl_surrogate(), in, 1, &tables)) {
-		// the reference reads its global `hits_per_single` (src/xmi_solid_angle_cl.c:54); honour it when the host exports it
-		long *hps = (long *)dlsym(RTLD_DEFAULT, "hits_per_single");
-		rv = xmb_solid_angle_calculation(in, tables, solid_angle, input_string, options, hps ? *hps : g_hits_per_single_default, 0);
+		rv = xmb_solid_angle_calculation(in, tables, solid_angle, input_string, options, xmb_get_hits_per_single(), 0);
 		xmb_free_hdf5_F(&tables);
 	}
 	if (!rv) fprintf(stderr, "xmimsim-b200: %s\n", xmb_last_error());   // 0 = caller falls through to its next backend

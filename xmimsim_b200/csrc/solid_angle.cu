@@ -13,16 +13,10 @@
 #include <cstdio>
 #include <vector>
 #include "cuda_util.cuh"
-
-// (double)w * 2^-32 without an integer-to-double conversion (quarter-rate pipe): the word is placed in the mantissa of
-// 2^52, the subtraction is exact -- the same value as xmb_u01(w).
-__device__ __forceinline__ double u01_exact(uint32_t w) {
-	return (__hiloint2double(0x43300000, (int)w) - 4503599627370496.0) * (1.0 / 4294967296.0);
-}
+#include "solid_angle_device.cuh"
 
 struct SaParams {
-	int collimator_present;
-	double detector_radius, collimator_radius, collimator_height;
+	SaDetector det;
 	long n_r, n_theta, hits_per_single;
 	uint64_t seed;
 };
@@ -35,87 +29,24 @@ __global__ void __launch_bounds__(256) xmb_solid_angle_kernel(SaParams P, const 
 	const long warps_per_grid = (long)gridDim.x * (blockDim.x >> 5);
 	const long n_points = (theta_end - theta_begin) * P.n_r;
 	const uint2 key = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-	const double det_r2 = P.detector_radius * P.detector_radius, col_r2 = P.collimator_radius * P.collimator_radius;
+	const double det_r2 = P.det.detector_radius * P.det.detector_radius, col_r2 = P.det.collimator_radius * P.det.collimator_radius;
 	for (long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_points; w += warps_per_grid) {
 		const long it = theta_begin + w / P.n_r, ir = w % P.n_r;
 		const uint64_t id = (uint64_t)it * (uint64_t)P.n_r + (uint64_t)ir;
-		const double r1 = r_vals[ir], theta1 = theta_vals[it];
-		double s1, c1;
-		sincos(theta1, &s1, &c1);
-		double r, theta, base_radius;
-		bool outside = false, dead = false;
-		// cone selection: no / cylindrical / conical collimator (src/xmi_solid_angle_f.F90:481-558)
-		if (!P.collimator_present) {
-			r = r1; theta = theta1; base_radius = P.detector_radius;
-		} else if (fabs(P.collimator_radius - P.detector_radius) < 0.000001) {
-			if (r1 * c1 <= P.detector_radius) { r = r1; theta = theta1; base_radius = P.detector_radius; }
-			else {
-				r = sqrt(r1 * r1 - 2.0 * r1 * s1 * P.collimator_height + P.collimator_height * P.collimator_height);
-				theta = acos(r1 * c1 / r);
-				base_radius = P.collimator_radius;
-			}
-			outside = r1 * s1 > P.collimator_height;
-		} else {
-			if (r1 * c1 <= P.detector_radius &&
-			    r1 * s1 <= P.collimator_height * (r1 * c1 - P.detector_radius) / (P.collimator_radius - P.detector_radius)) {
-				r = r1; theta = theta1; base_radius = P.detector_radius;
-			} else if (r1 * s1 <= P.collimator_height) {
-				dead = true; r = r1; theta = theta1; base_radius = P.detector_radius;
-			} else {
-				r = sqrt(r1 * r1 - 2.0 * r1 * s1 * P.collimator_height + P.collimator_height * P.collimator_height);
-				theta = acos(r1 * c1 / r);
-				base_radius = P.collimator_radius;
-			}
-			outside = r1 * s1 > P.collimator_height;
-		}
-		if (dead) {   // warp-uniform
+		const SaCone cone = sa_cone_setup(P.det, r_vals[ir], theta_vals[it]);
+		if (cone.dead) {   // warp-uniform
 			if (lane == 0) { solid_angles[id] = 0.0; if (hits_out) hits_out[id] = 0; }
 			continue;
 		}
-		double st, ct;
-		sincos(theta, &st, &ct);
-		const double beta = atan(base_radius / r);
-		double alpha1 = atan(base_radius * st / (r - base_radius * ct));
-		if (alpha1 <= 0.0) alpha1 += M_PI;
-		const double apex = fmax(beta, alpha1);
-		const double cos_apex = cos(apex);
-		const double cone_sa = 2 * M_PI * (1.0 - cos_apex);
-		const double one_m_cos = 1.0 - cos_apex;
-		const double py = r1 * c1, pz = r1 * s1;   // photon_line%point = (0, py, pz)
-		const double hz = P.collimator_height - pz;
 		int hits = 0;
 		const long n_pairs = (P.hits_per_single + 1) >> 1;
-		// Per ray the reference draws theta = acos(1 - u1 (1 - cos apex)), phi = 2 pi u2 and takes sin/cos of both
-		// (src/xmi_solid_angle_f.F90:633-650).  The same direction without the inverse: cos theta = 1 - t,
-		// sin theta = sqrt(t (2 - t)) with t = u1 (1 - cos apex) (exact identity, better conditioned for narrow cones),
-		// (sin, cos) phi by sincospi(2 u2).  The two plane intersections (:667-691) are tested multiplied through by
-		// dz^2 > 0 -- no division: x dz = (h - pz) dx, y dz = (h - pz) dy + py dz for the plane z = h.
 		for (long p = lane; p < n_pairs; p += 32) {
 			const uint4 rnd = xmb_philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)p, XMB_TAG_SOLID_ANGLE), key);
-#pragma unroll
-			for (int half = 0; half < 2; half++) {
-				const double u1 = u01_exact(half ? rnd.z : rnd.x), u2 = u01_exact(half ? rnd.w : rnd.y);
-				const double t = u1 * one_m_cos;
-				const double cth = 1.0 - t, sth = sqrt(t * (2.0 - t));
-				double sph, cph;
-				sincospi(2.0 * u2, &sph, &cph);
-				const double dx = sth * cph, cy = sth * sph;
-				// MATMUL(rotation_matrix, dirv_from_cone), rows (1,0,0), (0,-sin,-cos), (0,cos,-sin)
-				const double dy = -st * cy - ct * cth, dz = ct * cy - st * cth;
-				const double dz2 = dz * dz;
-				const double a = pz * dx, b = py * dz - pz * dy;
-				bool hit = dz < 0.0 && a * a + b * b <= det_r2 * dz2;
-				if (outside) {
-					const double a2 = hz * dx, b2 = hz * dy + py * dz;
-					hit = hit && a2 * a2 + b2 * b2 <= col_r2 * dz2;
-				}
-				if (half == 1 && 2 * p + 1 >= P.hits_per_single) hit = false;
-				hits += hit ? 1 : 0;
-			}
+			hits += sa_pair_hits(cone, det_r2, col_r2, rnd, 2 * p + 1 < P.hits_per_single);
 		}
 		hits = __reduce_add_sync(0xffffffffu, hits);
 		if (lane == 0) {
-			solid_angles[id] = cone_sa * (double)hits / (double)P.hits_per_single;
+			solid_angles[id] = cone.cone_sa * (double)hits / (double)P.hits_per_single;
 			if (hits_out) hits_out[id] = hits;
 		}
 	}
@@ -146,10 +77,10 @@ extern "C" int xmb_solid_angle_grid(xmb_inputFPtr inputF, const double *r_vals, 
 	if (!in || !in->inited) { xmb_set_error("xmb_solid_angle_grid: input not initialised"); return 0; }
 	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: the solid-angle grid has no CPU fallback"); return 0; }
 	SaParams P;
-	P.collimator_present = in->der.collimator_present;
-	P.detector_radius = in->der.detector_radius;
-	P.collimator_radius = in->der.collimator_radius;
-	P.collimator_height = in->der.collimator_height;
+	P.det.collimator_present = in->der.collimator_present;
+	P.det.detector_radius = in->der.detector_radius;
+	P.det.collimator_radius = in->der.collimator_radius;
+	P.det.collimator_height = in->der.collimator_height;
 	P.n_r = n_r; P.n_theta = n_theta; P.hits_per_single = hits_per_single;
 	P.seed = seed ? seed : XMB_DEFAULT_SEED;
 	double *d_r = nullptr, *d_t = nullptr, *d_sa = nullptr;

@@ -29,6 +29,7 @@ static void usage(FILE *f) {
 	      "  --custom-detector-response=LIB                            use xmi_detector_convolute_all_custom from LIB (bin/xmimsim.c:505-522)\n"
 	      "  --with-solid-angles-data=F --with-escape-ratios-data=F    cache files (queried first, updated after a calculation)\n"
 	      "  --set-seed=N                                              Philox key (default: library seed)\n"
+	      "  --with-xraylib[=LIB]                                      cross sections from libxrl (dlopen) instead of the built-in analytic stand-in\n"
 	      "  --table-quality=0|1                                       inverse-CDF integration resolution (default 1 = reference)\n"
 	      "  -v, --verbose    -V, --very-verbose    --version\n", f);
 }
@@ -36,7 +37,8 @@ static void usage(FILE *f) {
 int main(int argc, char **argv) {
 	xmb_main_options opt;
 	xmb_main_options_defaults(&opt);
-	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache, custom_response;
+	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache, custom_response, xraylib_path;
+	bool use_xraylib = false;
 	unsigned long long seed = 0;
 	int quality = 1;
 	struct Flag { const char *name; int *target; };
@@ -62,6 +64,8 @@ int main(int argc, char **argv) {
 		if (val("--spe-file-unconvoluted", spe_noconv) || val("--spe-file", spe_conv) || val("--csv-file-unconvoluted", csv_noconv) || val("--csv-file", csv_conv)) continue;
 		if (val("--custom-detector-response", custom_response)) continue;
 		if (val("--with-solid-angles-data", sa_cache) || val("--with-escape-ratios-data", er_cache)) continue;
+		if (a == "--with-xraylib") { use_xraylib = true; continue; }
+		if (a.compare(0, 15, "--with-xraylib=") == 0) { use_xraylib = true; xraylib_path = a.substr(15); continue; }
 		if (val("--set-seed", tmp)) { seed = strtoull(tmp.c_str(), nullptr, 0); continue; }
 		if (val("--table-quality", tmp)) { quality = atoi(tmp.c_str()); continue; }
 		if (val("--set-threads", tmp)) { opt.omp_num_threads = atoi(tmp.c_str()); continue; }
@@ -75,14 +79,19 @@ int main(int argc, char **argv) {
 	if (infile.empty()) { usage(stderr); return 1; }
 	if (xmb_cuda_device_count() < 1) { fprintf(stderr, "No CUDA device found: xmimsim-b200 has no CPU fallback\n"); return 1; }
 
+	const xmb_xrl_provider *xrl = xmb_xrl_surrogate();
+	if (use_xraylib) {
+		xrl = xmb_xrl_from_library(xraylib_path.empty() ? nullptr : xraylib_path.c_str());
+		if (!xrl) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+	}
 	xmb_input *input = nullptr;
 	if (!xmb_input_read_from_xml_file(infile.c_str(), &input)) { fprintf(stderr, "Could not read %s: %s\n", infile.c_str(), xmb_last_error()); return 1; }
 	if (opt.verbose) printf("Inputfile %s successfully parsed\n", infile.c_str());
 	xmb_inputFPtr inputF = nullptr;
 	xmb_hdf5FPtr tables = nullptr;
 	if (!xmb_input_C2F(input, &inputF) || !xmb_init_input(&inputF)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
-	if (opt.verbose) printf("Building cross-section tables (%s)\n", xmb_xrl_surrogate()->name);
-	if (!xmb_init_from_provider(xmb_xrl_surrogate(), inputF, quality, &tables)) { fprintf(stderr, "Could not build the tables: %s\n", xmb_last_error()); return 1; }
+	if (opt.verbose) printf("Building cross-section tables (%s)\n", xrl->name);
+	if (!xmb_init_from_provider(xrl, inputF, quality, &tables)) { fprintf(stderr, "Could not build the tables: %s\n", xmb_last_error()); return 1; }
 
 	const int n_int = input->general->n_interactions_trajectory, nch = input->detector->nchannels;
 	xmb_solid_angle *sa = nullptr;
@@ -90,7 +99,7 @@ int main(int argc, char **argv) {
 		// bin/xmimsim.c:300-333: query the cache, calculate on a miss, update the cache
 		if (!sa_cache.empty()) {
 			if (opt.verbose) printf("Querying %s for solid angle grid\n", sa_cache.c_str());
-			if (!xmb_find_solid_angle_match(sa_cache.c_str(), input, xmb_xrl_surrogate(), &sa, &opt)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+			if (!xmb_find_solid_angle_match(sa_cache.c_str(), input, xrl, &sa, &opt)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
 		}
 		if (!sa) {
 			if (opt.verbose) printf("Precalculating solid angle grid\n");
@@ -121,7 +130,7 @@ int main(int argc, char **argv) {
 			if (opt.verbose) printf("Precalculating escape peak ratios\n");
 			char *xml = nullptr;
 			if (!xmb_input_write_to_xml_string(input, &xml)) { fprintf(stderr, "Could not write input to XML string: %s\n", xmb_last_error()); return 1; }
-			const int ok = xmb_escape_ratios_calculation(input, &er, xml, xmb_xrl_surrogate(), &opt, xmb_get_default_escape_ratios_options(), seed);
+			const int ok = xmb_escape_ratios_calculation(input, &er, xml, xrl, &opt, xmb_get_default_escape_ratios_options(), seed);
 			free(xml);
 			if (!ok) { fprintf(stderr, "Escape ratios calculation failed: %s\n", xmb_last_error()); return 1; }
 			if (!er_cache.empty()) {
@@ -170,7 +179,7 @@ int main(int argc, char **argv) {
 		if (opt.verbose) printf("Writing to CSV file %s\n", csv_conv.c_str());
 	}
 	if (!xmb_output_write_to_xml_file(input, infile.c_str(), input->general->outputfile, raw.data(), conv.data(), brute,
-	                                  opt.use_variance_reduction ? var_red : nullptr, first == 0 ? 1 : 0, xmb_xrl_surrogate())) {
+	                                  opt.use_variance_reduction ? var_red : nullptr, first == 0 ? 1 : 0, xrl)) {
 		fprintf(stderr, "Could not write to %s: %s\n", input->general->outputfile, xmb_last_error());
 		return 1;
 	}

@@ -213,6 +213,10 @@ typedef struct xmb_xrl_provider {
 } xmb_xrl_provider;
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void);
+/* Provider backed by a libxrl loaded at run time (dlopen of `path`, or of libxrl.so.11 / .7 / libxrl.so when NULL):
+ * the functions the reference links from xraylib >= 3.99 (configure.ac:115-116).  AugerRate is left NULL.
+ * Returns NULL (xmb_last_error says why) when the library or one of its symbols is missing. */
+const xmb_xrl_provider *xmb_xrl_from_library(const char *path);
 
 /* ------------------------------------------------------------------------------------------
  * Opaque handles replacing xmi_inputFPtr / xmi_hdf5FPtr (pointers to Fortran derived types in

@@ -169,6 +169,7 @@ def lib():
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
     L.xmb_xrl_surrogate.restype = C.POINTER(XrlProvider)
+    L.xmb_xrl_from_library.argtypes = [C.c_char_p]; L.xmb_xrl_from_library.restype = C.POINTER(XrlProvider)
     L.xmb_input_C2F.argtypes = [C.POINTER(Input), vpp]; L.xmb_input_C2F.restype = C.c_int
     L.xmb_input_F2C.argtypes = [vp]; L.xmb_input_F2C.restype = C.POINTER(Input)
     L.xmb_free_input_F.argtypes = [vpp]; L.xmb_free_input_F.restype = None

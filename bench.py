@@ -294,8 +294,9 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            g_small = (grid[::8, ::8].copy(), r_vals[::8].copy(), t_vals[::8].copy())
-            n, dt = cpu_baseline_run(inp, g_small, args.reference_sample_per_line, cores)
+            # the full grid: a sub-sampled one ends below the last r / theta and would send those interaction points
+            # through the reference's 5000-ray on-the-spot solid angle (src/xmi_solid_angle_f.F90:783-789)
+            n, dt = cpu_baseline_run(inp, (grid, r_vals, t_vals), args.reference_sample_per_line, cores)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d histories (n_photons_line=%d of %d), oracle port of the reference algorithm, "
                                               "cost linear in photons" % (n, args.reference_sample_per_line, args.photons_per_line)}

@@ -163,6 +163,28 @@ def test_bit_exact_across_rank_counts():
     P.close()
 
 
+def test_batch_formation_modes_are_bit_identical(monkeypatch):
+    """The three ways a CTA forms its batches on a many-layer sample -- unsorted, mixed batches sorted by layer, one
+    queue per (interaction order, layer) -- regroup the same photons: the integer sums must not differ in a single bit
+    (XMB_LAYER_SORT is the engine's experiment switch; default = per-layer queues from three layers on)."""
+    inp = synthetic_layers(n_photons=150_000, n_int=8)
+    P = Pair(inp)
+    sa = P.grid(n=128)
+    o = x.main_options()
+    ref, ex = P.sim.main_msim_raw(o, sa)
+    assert ex.n_histories == 150_000
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("XMB_LAYER_SORT", mode)
+        limbs, ex2 = P.sim.main_msim_raw(o, sa)
+        assert ex2.n_interactions == ex.n_interactions
+        assert np.array_equal(limbs, ref), mode
+        shard, _ = P.sim.main_msim_raw(o, sa, rank=1, n_ranks=3)
+        monkeypatch.delenv("XMB_LAYER_SORT")
+        shard_ref, _ = P.sim.main_msim_raw(o, sa, rank=1, n_ranks=3)
+        assert np.array_equal(shard, shard_ref), mode
+    P.close()
+
+
 def test_linearity_and_weight_bounds_at_larger_size():
     """Size-independent properties: the spectrum per unit photon converges (two sizes agree within the
     statistical error), order-1 content dominates, all deposits non-negative."""

@@ -16,6 +16,8 @@
 // Random numbers: Philox4x32-10 keyed by the run seed; every draw of photon g has a fixed counter address
 // (g, interaction order, stage, element, block), see draw_block().
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <algorithm>
 #include <cmath>
@@ -33,7 +35,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
 	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
-	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] 16-bit pieces
+	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] pieces
+	constexpr bool P20 = !ADV;   // 20-bit pieces for history slots (one addend per photon and batch; ADV adds one per subshell)
 	const uint64_t n_total = P.n_local_span;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
@@ -41,6 +44,8 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	bool bad_fixed = false;
 	__shared__ unsigned int s_layer_cnt[XMB_MAX_LAYERS];
 	__shared__ double s_exp_tab[64];              // 2^(-k/64), see exp_neg()
+	const unsigned stage_s32 = smem_u32(stage);   // shared-window addresses of the staging area and of the exp table:
+	const unsigned tab_s32 = smem_u32(s_exp_tab); // see stage_red() / exp_neg()
 	if (tid < XMB_MAX_LAYERS) s_layer_cnt[tid] = 0;
 	if (tid < 64) s_exp_tab[tid] = exp2(-(double)tid / 64.0);
 	__syncthreads();
@@ -62,13 +67,17 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	__shared__ uint64_t s_sa_g[XMB_SA_ROUND];
 	__shared__ SaCone s_sa_cone[XMB_SA_ROUND];
 	__shared__ int s_lcnt[XMB_MAX_LAYERS + 1];    // batch members per layer (counting sort of a batch)
+	__shared__ int s_qcl[XMB_MAX_QL];             // layer_sort 2: photons waiting in the queue of (order k, layer L), [k * nL + L]
+	__shared__ int s_sched[3];                    // layer_sort 2: the scheduler's choice {k, L or -1 (mixed batch), source?}
 	__shared__ unsigned short s_perm[HIST_THREADS];
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
+	for (int i = tid; i < XMB_MAX_QL; i += T) s_qcl[i] = 0;
 	for (int i = tid; i < 4 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0u;
 	__syncthreads();
 	const int NF = XMB_STATE_FIELDS + nL;
 	const size_t qcap = 2 * (size_t)T;
-	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * NF * qcap;
+	const bool per_layer = NL != 1 && P.layer_sort == 2;   // one queue per (order, layer): see the scheduler below
+	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * (per_layer ? nL : 1) * NF * qcap;
 	uint64_t next_chunk = blockIdx.x;
 	// Forced interaction (src/xmi_main.F90:1229-1518): moves the photon to the point of its interaction number
 	// order + 1.  Done before the photon is queued, so that the layer it will interact in is known when a batch is formed.
@@ -117,6 +126,27 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	// compaction: survivors go, densely packed, to the queue of the next order
 	auto push = [&](const Photon &p, uint64_t g, int order) {
 		const bool surv = p.alive;
+		if (per_layer) {
+			// queue of (order, layer of the next interaction point): the lanes of a warp that go to the same queue take
+			// consecutive places behind one shared-memory atomic of their leader
+			const int myL = surv ? p.layer : -1;
+			const unsigned peers = __match_any_sync(0xffffffffu, myL);
+			const int leader = __ffs(peers) - 1;
+			int wbase = 0;
+			if (surv && lane == leader) wbase = atomicAdd(&s_qcl[order * nL + myL], __popc(peers));
+			wbase = __shfl_sync(0xffffffffu, wbase, leader);
+			if (surv) {
+				double *q = qbase + (size_t)(order * nL + myL) * NF * qcap + wbase + __popc(peers & ((1u << lane) - 1u));
+				q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
+				q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
+				q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
+				q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
+				q[13 * qcap] = __longlong_as_double((long long)g);
+				q[14 * qcap] = __longlong_as_double((long long)p.layer);
+				for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+			}
+			return;   // the caller's __syncthreads() publishes the counts
+		}
 		const unsigned bal = __ballot_sync(0xffffffffu, surv);
 		if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
 		__syncthreads();
@@ -139,14 +169,38 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 	};
 	for (;;) {
 		// ---- scheduler (block-uniform) ---------------------------------------------------------------
-		int k = -1;
-		for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
+		int k = -1, Lsel = -1;
 		bool from_source = false;
-		if (k < 0) {
-			if (next_chunk < n_chunks) from_source = true;
-			else {
-				for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] > 0) { k = kk; break; }
-				if (k < 0) break;
+		if (per_layer) {
+			// Batches of ONE layer: every warp of the CTA then runs the element and line loops of the same layer, and the
+			// phases end together.  With mixed (sorted) batches the warps of the layer with the most lines set the
+			// duration of every batch: on the 10-layer configuration the warps spent 15.8 issue slots at the phase
+			// barriers per instruction issued (profiles/r1_history_kernel_v10_synthetic10_*).  The deepest order with a
+			// full layer queue runs first; else fresh source photons; at the end the remainders drain as mixed batches
+			// (the queues of one order concatenated: sorted by layer by construction).
+			if (tid == 0) {
+				int kq = -1, Lq = -1, src = 0;
+				for (int kk = P.n_int - 1; kk >= 0 && kq < 0; kk--)
+					for (int l = 0; l < nL; l++) if (s_qcl[kk * nL + l] >= T) { kq = kk; Lq = l; break; }
+				if (kq < 0) {
+					if (next_chunk < n_chunks) src = 1;
+					else
+						for (int kk = P.n_int - 1; kk >= 0 && kq < 0; kk--)
+							for (int l = 0; l < nL; l++) if (s_qcl[kk * nL + l] > 0) { kq = kk; break; }
+				}
+				s_sched[0] = kq; s_sched[1] = Lq; s_sched[2] = src;
+			}
+			__syncthreads();
+			k = s_sched[0]; Lsel = s_sched[1]; from_source = s_sched[2] != 0;
+			if (k < 0 && !from_source) break;
+		} else {
+			for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
+			if (k < 0) {
+				if (next_chunk < n_chunks) from_source = true;
+				else {
+					for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] > 0) { k = kk; break; }
+					if (k < 0) break;
+				}
 			}
 		}
 		uint64_t g = 0;
@@ -171,6 +225,38 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 				continue;
 			}
 			order = 1;
+		} else if (per_layer) {
+			order = k + 1;
+			// one full layer queue, or (draining) the tails of the order's queues one after the other
+			int myL = -1, at = 0, taken = 0;
+			if (Lsel >= 0) { myL = Lsel; at = s_qcl[k * nL + Lsel] - T + tid; }
+			else {
+				for (int l = 0; l < nL; l++) {
+					const int c = s_qcl[k * nL + l], n_l = min(c, T - taken);
+					if (myL < 0 && tid < taken + n_l) { myL = l; at = c - n_l + (tid - taken); }
+					taken += n_l;
+				}
+			}
+			if (myL >= 0) {
+				const double *q = qbase + (size_t)(k * nL + myL) * NF * qcap + at;
+				p.cx = q[0 * qcap]; p.cy = q[1 * qcap]; p.cz = q[2 * qcap];
+				p.dx = q[3 * qcap]; p.dy = q[4 * qcap]; p.dz = q[5 * qcap];
+				p.ex = q[6 * qcap]; p.ey = q[7 * qcap]; p.ez = q[8 * qcap];
+				p.energy = q[9 * qcap]; p.weight = q[10 * qcap]; p.theta = q[11 * qcap]; p.phi = q[12 * qcap];
+				g = (uint64_t)__double_as_longlong(q[13 * qcap]);
+				p.layer = myL;
+				for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
+				p.n_interactions = order;
+				p.alive = true;
+			}
+			__syncthreads();
+			if (tid == 0) {
+				if (Lsel >= 0) s_qcl[k * nL + Lsel] -= T;
+				else {
+					int left = T;
+					for (int l = 0; l < nL; l++) { const int n_l = min(s_qcl[k * nL + l], left); s_qcl[k * nL + l] -= n_l; left -= n_l; }
+				}
+			}
 		} else {
 			const int have = s_qcount[k], n = min(T, have), base = have - n;
 			order = k + 1;
@@ -215,7 +301,8 @@ for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 		{
 			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length (used when the photon was moved), detector r, detector phi, atom}
 			const int n_ia = order;   // == p.n_interactions for every live lane
-			unsigned int *acc_k = stage;   // deposits of this batch are staged in shared memory, flushed below
+			const unsigned acc_k = stage_s32;   // deposits of this batch are staged in shared memory, flushed below
+			const unsigned hist0 = (unsigned)P.nch;
 
 			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
 			bool vr = p.alive && p.energy > ENERGY_THRESHOLD;
@@ -326,7 +413,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
 				double qf = 0.0, sin2cos2 = 0.0, k0k = 1.0, c_lamb0 = 0.0, sth2 = 0.0, dcsp_kn = 0.0;
 				int qi = 0;
-				long ch_rayl = -1;
+				int ch_rayl = -1;
 				if (mine) {
 					sth2 = sin(theta / 2.0);
 					c_lamb0 = 1.2399E-6 / (p.energy * 1000.0);
@@ -346,7 +433,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
-					const size_t hbase = (size_t)P.nch + P.hist_base[zi];
+					const unsigned hbase = hist0 + (unsigned)P.hist_base[zi];
 					// the element's random block, first inverse-CDF bracket and form factors are requested together, ahead of
 					// the dependent chain Compton energy -> energy bracket -> mu rows -> exp
 					ComptonPrefetch pf;
@@ -361,7 +448,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						const double dcsp = P.avog_over_A[zi] * F * F * RE2 * (1.0 - sin2cos2);
 						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
 					}
-					deposit_uniform(acc_k, hbase + 0, fx, lane);
+					deposit_uniform<P20>(acc_k, hbase + 0, fx, lane);
 					deposit_varying(acc_k, ch_rayl, fx, lane);
 					if (ADV) {
 						// shell-resolved Compton (xmi_compton_varred, :752-947): one deposit per occupied subshell
@@ -374,7 +461,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						}
 						for (int r = r0; r < r1; r++) {
 							fx = 0ULL;
-							long ch_c = -1;
+							int ch_c = -1;
 							if (mine && cdf_sum != 0.0) {
 								const double cdf_r = adv_shell_cdf(P, r, p.energy, theta);
 								const double shell_weight = P.adv_config[r] * cdf_r / cdf_sum;
@@ -393,14 +480,14 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 									}
 								}
 							}
-							deposit_uniform(acc_k, hbase + 1, fx, lane);
+							deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
 							deposit_varying(acc_k, ch_c, fx, lane);
 						}
 						continue;
 					}
 					// Compton (xmi_compton_varred2, :949-1008)
 					fx = 0ULL;
-					long ch_c = -1;
+					int ch_c = -1;
 					if (mine) {
 						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true, &pf);
 						const NodePos cp = node_find(P, e_c);
@@ -409,11 +496,11 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
 						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
-						fx = to_fixed(Pconv * Pdir * exp_neg(tm, s_exp_tab) * p.weight, P.counters);
+						fx = to_fixed(Pconv * Pdir * exp_neg(tm, tab_s32) * p.weight, P.counters);
 						const int ch = (int)((e_c - P.zero) / P.gain);
 						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
 					}
-					deposit_uniform(acc_k, hbase + 1, fx, lane);
+					deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
 					deposit_varying(acc_k, ch_c, fx, lane);
 				}
 			}
@@ -423,6 +510,11 @@ for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 				if (!__any_sync(0xffffffffu, mine)) continue;
 				const XmbLayerDev lay = P.layers[L];
 				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
+				double rdv[NL > 0 ? NL : 1];   // rho d of the path to the detector, in registers for the record loop
+				if (NL > 0) {
+					XMB_UNROLL_NL
+for (int j = 0; j < (NL > 0 ? NL : 1); j++) rdv[j] = rd[j * T];
+				}
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
@@ -438,15 +530,27 @@ for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 						double Ps = 0.0;
 						if (mine && (s > 0 || aboveK)) Ps = row_lerp(P, np, eoff + XMB_EO_VACANCY + s);
 						if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
-						const double pre = common * Ps;
+						// deposit = pre * (yield * rate) * exp(-tm) with yield * rate <= rec_yr_max and exp <= 1: the
+						// fixed-point scale 2^56 and the range check are taken out of the record loop (a power of two
+						// commutes with the roundings; lanes that do not take part carry pre56 = 0)
+						const double pre56 = common * Ps * 72057594037927936.0;
+						bad_fixed |= !(pre56 * P.rec_yr_max < 2.8e17);
+						const double *rp = P.rec_pack + (size_t)r0 * (nL + 2);   // record: {yield * rate, history slot, mu[nL]}
 XMB_UNROLL(XMB_REC_UNROLL)
-						for (int r = r0; r < r1; r++) {
-							const double *mu = P.rec_mu + (size_t)r * nL;
-							double tm = 0.0;
-							XMB_UNROLL_NL
-for (int j = jlo; j <= jhi; j++) tm += mu[j] * rd[j * T];
-							const double tw = pre * P.rec_yr[r] * exp_neg(tm, s_exp_tab);
-							deposit_uniform(acc_k, (size_t)P.nch + P.rec_slot[r], mine ? to_fixed_fast(tw, bad_fixed) : 0ULL, lane);
+						for (int r = r0; r < r1; r++, rp += nL + 2) {
+							double yr, tm = 0.0;
+							unsigned slot;
+							if (NL == 2) {
+								const double2 a = __ldg(reinterpret_cast<const double2 *>(rp)), m = __ldg(reinterpret_cast<const double2 *>(rp) + 1);
+								yr = a.x; slot = (unsigned)__double2loint(a.y);
+								tm = __fma_rn(m.y, rdv[1], __dmul_rn(m.x, rdv[0]));   // the rounding order of the generic loop below
+							} else {
+								yr = rp[0]; slot = (unsigned)__double2loint(rp[1]);
+								XMB_UNROLL_NL
+for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0] : rd[j * T]);
+							}
+							const double tw = pre56 * yr * exp_neg(tm, tab_s32);
+							deposit_uniform<P20>(acc_k, hist0 + slot, fixed_from_scaled(tw), lane);
 						}
 					}
 				}
@@ -454,7 +558,7 @@ for (int j = jlo; j <= jhi; j++) tm += mu[j] * rd[j * T];
 
 			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
 			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
-			flush_staged(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, tid, T);
+			flush_staged<P20>(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
 			if (p.alive) {
 				double we_unused = 0.0;
 				int t_unused, z_unused, l_unused, s_unused;
@@ -659,9 +763,20 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	D->n_hist_slots = slot;
 	P.n_hist_slots = slot;
 	P.rec_begin = upload(D, rec_begin.data(), rec_begin.size(), ok);
-	P.rec_yr = upload(D, rec_yr.data(), rec_yr.size(), ok);
-	P.rec_mu = upload(D, rec_mu.data(), rec_mu.size(), ok);
-	P.rec_slot = upload(D, D->rec_slot.data(), D->rec_slot.size(), ok);
+	{
+		// one packed record per active line: a 32-byte record is two 128-bit loads for the two-layer kernel
+		std::vector<double> pack((size_t)D->n_rec * (nL + 2));
+		P.rec_yr_max = 0.0;
+		for (int r = 0; r < D->n_rec; r++) {
+			double *q = &pack[(size_t)r * (nL + 2)];
+			q[0] = rec_yr[r];
+			const long long bits = (long long)D->rec_slot[r];
+			memcpy(&q[1], &bits, sizeof(double));
+			for (int k = 0; k < nL; k++) q[2 + k] = rec_mu[(size_t)r * nL + k];
+			P.rec_yr_max = std::max(P.rec_yr_max, rec_yr[r]);
+		}
+		P.rec_pack = upload(D, pack.data(), pack.size(), ok);
+	}
 	P.hist_base = upload(D, D->hist_base.data(), nZ, ok);
 	{
 		std::vector<int> ls((size_t)nZ * 384, -1);
@@ -782,7 +897,10 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	if (!brute) { P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n; }
 	// batches sorted by layer pay when photons interact in several layers with different element lists; with one or two
 	// layers (a sample behind an air gap) nearly every interaction is in the same layer and the sort is skipped
-	P.layer_sort = P.nL >= 3 ? 1 : 0;
+	P.layer_sort = P.nL >= 3 ? 2 : 0;   // 2: one queue per (order, layer); 1: one queue per order, batches sorted by layer
+	if (const char *e = getenv("XMB_LAYER_SORT")) P.layer_sort = std::max(0, std::min(2, atoi(e)));   // experiments / tests: force a mode
+	if (P.layer_sort == 2 && (P.nL < 2 || P.n_int * P.nL > XMB_MAX_QL)) P.layer_sort = 1;
+	if (P.layer_sort == 1 && P.nL < 2) P.layer_sort = 0;
 	P.sa_det.collimator_present = in->der.collimator_present; P.sa_det.detector_radius = in->der.detector_radius;
 	P.sa_det.collimator_radius = in->der.collimator_radius; P.sa_det.collimator_height = in->der.collimator_height;
 	P.sa_hits_per_single = (int)std::min<long>(xmb_get_hits_per_single(), 1L << 20);
@@ -863,8 +981,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	uint64_t blocks = (uint64_t)sms * occ;
 	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, n_chunks));
 	if (P.n_int > XMB_MAX_ORDERS) { xmb_set_error("more than %d interactions per trajectory", XMB_MAX_ORDERS); return 0; }
-	// per-CTA compaction queues: n_int orders x 2T photons x (15 + nL) doubles (structure of arrays)
-	const size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + P.nL) * 2 * threads;
+	// per-CTA compaction queues: n_int orders (x nL layers) x 2T photons x (15 + nL) doubles (structure of arrays)
+	size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + P.nL) * 2 * threads;
+	if (P.layer_sort == 2) {
+		if (qd * P.nL * sizeof(double) > ((size_t)24 << 30)) P.layer_sort = 1;   // keep the queues within 24 GB of HBM
+		else qd *= P.nL;
+	}
 	if (D->queue_doubles < qd) {
 		cudaFree(D->queue);
 		D->queue = nullptr;

@@ -40,7 +40,7 @@ struct XmbHistParams {
 	uint64_t n_cont_seg, n_per_interval, n_per_line;
 	int n_seg, n_int, nch, nL, nZ;
 	int use_M_lines;
-	int layer_sort;                          // batches are formed per layer of the interaction point (counting sort)
+	int layer_sort;                          // batches by layer of the interaction point: 0 no, 1 counting sort of mixed batches, 2 one queue per (order, layer)
 	double zero, gain;
 	const XmbSegDev *segs;
 	// geometry
@@ -77,9 +77,8 @@ struct XmbHistParams {
 	const double *line_energy;               // [nZ][384]
 	// forced-detection line records (active lines only), grouped by (element, shell)
 	const int *rec_begin;                    // [nZ][10] record range of (zi, shell) = [rec_begin[zi*10+s], rec_begin[zi*10+s+1])
-	const double *rec_yr;                    // [n_rec] FluorYield(shell) * RadRate(line)
-	const double *rec_mu;                    // [n_rec][nL] mu of each layer at the line energy
-	const int *rec_slot;                     // [n_rec] history slot
+	const double *rec_pack;                  // [n_rec][2 + nL]: FluorYield(shell) * RadRate(line), history slot (low word), mu of each layer at the line energy
+	double rec_yr_max;                       // largest yield * rate of the records (range check of the line deposits)
 	const int *hist_base;                    // [nZ] first history slot of the element (+0 Rayleigh, +1 Compton)
 	int n_hist_slots;
 	// solid-angle grid

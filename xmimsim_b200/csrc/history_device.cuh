@@ -23,6 +23,7 @@
 #define XMB_REC_UNROLL 2
 #endif
 #define XMB_MAX_ORDERS 64
+#define XMB_MAX_QL 1024          // (order, layer) queues of a CTA when batches are formed per layer
 #define XMB_STATE_FIELDS 15      // 13 doubles of photon state + photon id + layer (mus[nL] follow)
 #define XMB_PRAGMA(x) _Pragma(#x)
 #define XMB_UNROLL_NL _Pragma("unroll")
@@ -84,77 +85,104 @@ __device__ __forceinline__ double bilinear(const double *a, int n2, const double
 
 // ---- exact accumulation ---------------------------------------------------------------------------
 // Every deposit is a non-negative 2^-56 fixed-point integer.  Deposits of the batch a CTA is working on (one
-// interaction order) are staged in shared memory: a slot is two 64-bit words, A accumulates the low 32 bits of
-// each addend and B the high 32 bits, so a deposit is two carry-free shared-memory atomics (total = A + (B<<32),
-// exact for < 2^32 addends of < 2^63).  After the batch the CTA folds every non-zero slot into the global 128-bit
-// (lo, hi) accumulator.  Ablation on B200 (profiles/r1_history_ablation.txt): with per-lane global REDs the Compton
-// peak's ~50 hot channel words serialised in L2 and cost 47 % of the kernel.
+// interaction order) are staged in shared memory: a slot is four 32-bit words holding 16- or 20-bit pieces of the
+// addends (native 32-bit ATOMS.ADD: 64-bit shared atomics are CAS spin loops on sm_100a -- ATOMS.CAST.SPIN.64 -- and
+// collapse when the lanes of a warp hit the same channel; layouts below).  After the batch the CTA folds every non-zero
+// slot into the global 128-bit (lo, hi) accumulator.  Ablation on B200 (profiles/r1_history_ablation.txt): with
+// per-lane global REDs the Compton peak's ~50 hot channel words serialised in L2 and cost 47 % of the kernel.
 __device__ __forceinline__ unsigned long long to_fixed(double w, unsigned long long *counters) {
 	const double s = w * 72057594037927936.0;   // 2^56
 	if (!(s < 2.8e17)) { if (s == s) atomicAdd(&counters[2], 1ULL); return 0ULL; }   // w >= ~4: counted, never wrapped
 	return __double2ull_rn(s);
 }
-// hot-loop variant: no branch; out-of-range / NaN inputs are flagged in `bad` (reported once per thread at the end)
-__device__ __forceinline__ unsigned long long to_fixed_fast(double w, bool &bad) {
-	const double s = w * 72057594037927936.0;
-	bad |= !(s < 2.8e17);
-	return __double2ull_rn(fmin(s, 2.8e17));
-}
-// staged deposit: four native 32-bit shared-memory atomics on the 16-bit pieces of v (64-bit shared atomics are CAS
-// spin loops on sm_100a -- ATOMS.CAST.SPIN.64 -- and collapse when the lanes of a warp hit the same channel)
-__device__ __forceinline__ void red128(unsigned int *stage, size_t slot, unsigned long long v) {
-	if (v == 0ULL) return;
-	unsigned int *w = stage + 4 * slot;
-	atomicAdd(&w[0], (unsigned int)(v & 0xFFFFULL));
-	atomicAdd(&w[1], (unsigned int)((v >> 16) & 0xFFFFULL));
-	atomicAdd(&w[2], (unsigned int)((v >> 32) & 0xFFFFULL));
-	const unsigned int top = (unsigned int)(v >> 48);
-	if (top) atomicAdd(&w[3], top);
-}
+// hot-loop variant: the caller has scaled by 2^56 and bounded the value already (see the line loop of the history
+// kernel: one range check per shell instead of one per line)
+__device__ __forceinline__ unsigned long long fixed_from_scaled(double s) { return __double2ull_rn(s); }
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
 }
-// all 32 lanes call; slot is warp-uniform.  The four 16-bit pieces are summed across the warp with REDUX (sums < 2^21)
-// and lanes 0..3 add them to the slot's four staging words.
-#ifndef XMB_REDUX_PIECES
-#define XMB_REDUX_PIECES 1
-#endif
-__device__ __forceinline__ void deposit_uniform(unsigned int *acc, size_t slot, unsigned long long v, int lane) {
-#if XMB_REDUX_PIECES
+// ---- staged deposits, hot path ------------------------------------------------------------------------
+// The staging area is addressed through its 32-bit shared-window address (one register, computed once per thread):
+// with generic pointers every deposit rebuilt that address (S2R SR_CgaCtaId + LEA + IMAD chain, ~10 instructions, in
+// the dependent chain of the atomic) because the kernel sits at its 64-register cap (profiles/r1_history_kernel_v10_*).
+// No "memory" clobber: the staging words are only read back by flush_staged() behind a __syncthreads().
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_red(unsigned addr, unsigned v) {   // v == 0: no atomic issued
+	asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q red.shared.add.u32 [%0], %1; }" ::"r"(addr), "r"(v));
+}
+// Two piece layouts of a staged slot (four 32-bit words):
+//  * 16-bit pieces in words 0..3 -- channel slots: a channel can take max nE addends per photon and batch, any lane mix;
+//  * 20-bit pieces in words 0..2 (P20) -- history slots (a line, or Rayleigh / Compton of an element): at most ONE
+//    addend per photon and batch, always through the warp sum below: a word receives <= 32 warp sums < 2^25 per batch.
+//    One REDUX, one atomic and the mask/shift of a piece less than the 16-bit layout on the most repeated code of the
+//    kernel (one deposit per active line and interaction).
+// all 32 lanes call; slot is warp-uniform; v < 2^60
+__device__ __forceinline__ void deposit_uniform20(unsigned stage_s32, unsigned slot, unsigned long long v, int lane) {
+	const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+	const unsigned int s0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFFu);
+	const unsigned int s1 = __reduce_add_sync(0xffffffffu, __funnelshift_r(lo, hi, 20) & 0xFFFFFu);
+	const unsigned int s2 = __reduce_add_sync(0xffffffffu, hi >> 8);
+	unsigned int piece;   // lane 0: s0, lane 1: s1, lane 2: s2, others 0 -- selects, not branches
+	asm("{ .reg .pred a, b, c;\n\t"
+	    "setp.eq.u32 a, %4, 0; setp.eq.u32 b, %4, 1; setp.gt.u32 c, %4, 2;\n\t"
+	    "selp.u32 %0, %1, %3, a; selp.u32 %0, %2, %0, b; selp.u32 %0, 0, %0, c; }"
+	    : "=&r"(piece) : "r"(s0), "r"(s1), "r"(s2), "r"(lane));
+	stage_red(stage_s32 + slot * 16u + (unsigned)lane * 4u, piece);
+}
+// same with 16-bit pieces (channel slots; every slot when the kernel runs without the 20-bit layout)
+__device__ __forceinline__ void deposit_uniform16(unsigned stage_s32, unsigned slot, unsigned long long v, int lane) {
 	const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
 	const unsigned int s0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), s1 = __reduce_add_sync(0xffffffffu, lo >> 16);
 	const unsigned int s2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), s3 = __reduce_add_sync(0xffffffffu, hi >> 16);
-	// lanes 0..3 add one piece each: one predicated atomic instead of four issued for lane 0 alone
-	const unsigned int piece = lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
-	if (lane < 4 && piece) atomicAdd(acc + 4 * slot + lane, piece);
-#else
-	v = warp_sum_u64(v);
-	if (lane == 0) red128(acc, slot, v);
-#endif
+	unsigned int piece;
+	asm("{ .reg .pred a, b, c, d;\n\t"
+	    "setp.eq.u32 a, %5, 0; setp.eq.u32 b, %5, 1; setp.eq.u32 c, %5, 2; setp.gt.u32 d, %5, 3;\n\t"
+	    "selp.u32 %0, %1, %4, a; selp.u32 %0, %2, %0, b; selp.u32 %0, %3, %0, c; selp.u32 %0, 0, %0, d; }"
+	    : "=&r"(piece) : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(lane));
+	stage_red(stage_s32 + slot * 16u + (unsigned)lane * 4u, piece);
 }
-// all 32 lanes call; slot may differ per lane (slot < 0: nothing to add)
-__device__ __forceinline__ void deposit_varying(unsigned int *acc, long slot, unsigned long long v, int lane) {
-	const long s0 = __shfl_sync(0xffffffffu, slot, 0);
+template <bool P20>
+__device__ __forceinline__ void deposit_uniform(unsigned stage_s32, unsigned slot, unsigned long long v, int lane) {
+	if (P20) deposit_uniform20(stage_s32, slot, v, lane); else deposit_uniform16(stage_s32, slot, v, lane);
+}
+// channel deposit: all 32 lanes call; the channel may differ per lane (< 0: nothing to add); 16-bit pieces
+__device__ __forceinline__ void deposit_varying(unsigned stage_s32, int slot, unsigned long long v, int lane) {
+	const int s0 = __shfl_sync(0xffffffffu, slot, 0);
 	if (__all_sync(0xffffffffu, slot == s0)) {
-		if (s0 >= 0) deposit_uniform(acc, (size_t)s0, v, lane);
-	} else if (slot >= 0) red128(acc, (size_t)slot, v);
+		if (s0 >= 0) deposit_uniform16(stage_s32, (unsigned)s0, v, lane);
+	} else if (slot >= 0) {
+		const unsigned a = stage_s32 + (unsigned)slot * 16u;
+		const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+		stage_red(a, lo & 0xFFFFu); stage_red(a + 4u, lo >> 16); stage_red(a + 8u, hi & 0xFFFFu); stage_red(a + 12u, hi >> 16);
+	}
 }
-// fold the CTA's staged slots into the global (lo, hi) accumulators of interaction order `order` and clear them
-__device__ __forceinline__ void flush_staged(unsigned int *stage, unsigned long long *global_row, int n_slots, int tid, int T) {
+// fold the CTA's staged slots into the global (lo, hi) accumulators of one interaction order and clear them;
+// slots below n_ch hold 16-bit pieces, the others 20-bit pieces when P20
+template <bool P20>
+__device__ __forceinline__ void flush_staged(unsigned int *stage, unsigned long long *global_row, int n_slots, int n_ch, int tid, int T) {
 	for (int i = tid; i < n_slots; i += T) {
 		const uint4 w = *reinterpret_cast<uint4 *>(stage + 4 * i);
 		if ((w.x | w.y | w.z | w.w) == 0u) continue;
 		*reinterpret_cast<uint4 *>(stage + 4 * i) = make_uint4(0u, 0u, 0u, 0u);
-		// total = w0 + w1 2^16 + w2 2^32 + w3 2^48 as a 128-bit integer
-		const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 16);     // < 2^49
-		const unsigned long long t2 = (unsigned long long)w.z << 32, t3 = (unsigned long long)w.w << 48;
-		unsigned long long lo = t01 + t2;
-		unsigned long long hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.w >> 16);
-		const unsigned long long lo2 = lo + t3;
-		if (lo2 < lo) hi++;
-		lo = lo2;
+		unsigned long long lo, hi;
+		if (P20 && i >= n_ch) {
+			// total = w0 + w1 2^20 + w2 2^40 (w.w unused)
+			const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 20);   // < 2^53
+			const unsigned long long t2 = (unsigned long long)w.z << 40;
+			lo = t01 + t2;
+			hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.z >> 24);
+		} else {
+			// total = w0 + w1 2^16 + w2 2^32 + w3 2^48 as a 128-bit integer
+			const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 16);     // < 2^49
+			const unsigned long long t2 = (unsigned long long)w.z << 32, t3 = (unsigned long long)w.w << 48;
+			lo = t01 + t2;
+			hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.w >> 16);
+			const unsigned long long lo2 = lo + t3;
+			if (lo2 < lo) hi++;
+			lo = lo2;
+		}
 		const unsigned long long old = atomicAdd(&global_row[2 * i], lo);
 		if (old + lo < old) hi++;
 		if (hi) atomicAdd(&global_row[2 * i + 1], hi);
@@ -488,19 +516,28 @@ static __device__ double compton_energy_adv(const XmbHistParams &P, int zi, doub
 // interaction): 2^(-y) with y = t log2(e) = (j + r) / 64, |r| <= 1/2; 2^(-j/64) = 2^(-(j >> 6)) tab[j & 63] with a 64-entry
 // table in shared memory, and exp(-r ln2 / 64) by its Taylor polynomial of degree 5 (|x| < 0.0055: remainder 4e-17).
 // Relative error <= 2^-53 t + 3e-16, i.e. 1e-13 at the largest exponents that still matter.
-__device__ __forceinline__ double exp_neg(double t, const double *tab) {
+// Branch-free: j = rint(y) by the 1.5 * 2^52 shift (two DADD instead of FRND + F2I on the quarter-rate pipe; same
+// round-to-nearest-even integer for 0 <= y < 2^31), the out-of-range case (exp(-693) = 1e-301: below anything a deposit
+// can represent) is a final select, the polynomial coefficients are constant-bank operands of the DFMAs (as immediates
+// each costs two UMOV per evaluation at the kernel's register cap), the table is read through its shared-window address.
+static __constant__ double d_exp_poly[3] = {1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+__device__ __forceinline__ double exp_neg(double t, unsigned tab_s32) {
 	const double y = t * (64.0 * 1.4426950408889634074);
-	if (!(y < 64.0 * 1000.0)) return 0.0;                       // exp(-693) = 1e-301: below anything a deposit can represent
-	const double jf = rint(y);
-	const int j = (int)jf;
+	const double shifter = 6755399441055744.0;
+	const double tj = y + shifter;
+	const int j = __double2loint(tj);
+	const double jf = tj - shifter;
 	const double x = (jf - y) * (0.69314718055994530942 / 64.0);
-	double pl = fma(x, 1.0 / 120.0, 1.0 / 24.0);
-	pl = fma(pl, x, 1.0 / 6.0);
+	double pl = fma(x, d_exp_poly[0], d_exp_poly[1]);
+	pl = fma(pl, x, d_exp_poly[2]);
 	pl = fma(pl, x, 0.5);
 	pl = fma(pl, x, 1.0);
 	pl = fma(pl, x, 1.0);
+	double tabv;
+	asm("ld.shared.f64 %0, [%1];" : "=d"(tabv) : "r"(tab_s32 + (((unsigned)j & 63u) << 3)));
 	const double scale = __hiloint2double((1023 - (j >> 6)) << 20, 0);   // 2^(-(j >> 6)), j >> 6 <= 1000
-	return pl * tab[j & 63] * scale;
+	const double r = pl * tabv * scale;
+	return y < 64.0 * 1000.0 ? r : 0.0;
 }
 
 // ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------

@@ -23,7 +23,7 @@ PLUGIN    := xmimsim_b200/lib/xmimsim-cl.so
 
 CLI       := bin/xmimsim-b200
 
-all: $(LIB) $(PLUGIN) $(ORC_LIB) $(CLI)
+all: $(LIB) $(PLUGIN) $(ORC_LIB) $(CLI) oracle_ref
 lib: $(LIB) $(PLUGIN) $(CLI)
 oracle: $(ORC_LIB)
 
@@ -58,6 +58,11 @@ $(ORC_LIB): $(ORC_SRCS) oracle/oracle.h oracle/orc_rng.h include/xmimsim_b200.h 
 	@mkdir -p oracle/_build
 	$(CC) $(CFLAGS) -Ioracle -shared -o $@ $(ORC_SRCS) $(SRC)/xrl_surrogate.c -lm
 
+# The reference's own sources that compile with gcc alone (OpenCL solid-angle kernel through a shim, cubic spline):
+# built where /root/reference exists, kept as a prebuilt file elsewhere (oracle/ref_shim/README.md).
+oracle_ref:
+	sh oracle/build_ref.sh
+
 clean:
 	rm -rf build xmimsim_b200/lib oracle/_build $(CLI)
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle oracle_ref clean

@@ -216,3 +216,22 @@ def test_unsupported_modes_fail_loudly():
         with pytest.raises(RuntimeError, match="not implemented"):
             P.sim.main_msim(x.main_options(**kw), sa)
     P.close()
+
+
+def test_fixed_point_sums_reproduce_the_recorded_digests():
+    """Regression pin of the integer accumulators: seven inputs (two- and ten-layer samples, continuous source, all
+    cascade modes off, shell-resolved Compton, a 1-of-3 shard) must reproduce, bit for bit, the digests recorded with
+    kernel v10 (tests/golden/limbs_digest.json, written by tools/limbs_digest.py) -- kernel rewrites that regroup
+    photons, restage deposits or change launch shapes must not move a single bit."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "tools"))
+    import limbs_digest
+    want = json.load(open(os.path.join(here, "golden", "limbs_digest.json")))
+    got = limbs_digest.collect()
+    for name, w in want.items():
+        g = got[name]
+        assert (g["n"], g["inter"]) == (w["n"], w["inter"]), name
+        assert (g["sha"], g["sha_shard"]) == (w["sha"], w["sha_shard"]), name

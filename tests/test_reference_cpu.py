@@ -1,0 +1,108 @@
+"""The oracle restatement against the reference's OWN code run here (oracle/_ref/libxmi_ref.so, built by
+oracle/build_ref.sh from /root/reference/src/xmi_kernels.cl and src/xmi_spline.c; see oracle/ref_shim/README.md), and
+against the known answers of the reference's tests/test-cubic-spline.c.
+
+Solid angle (north_star: "the deterministic solid-angle grid must agree to a stated relative float
+tolerance"): the reference's OpenCL kernel is an fp32 Monte Carlo estimate with Threefry streams keyed by the grid
+indices, the oracle (and the CUDA kernel, which matches the oracle hit for hit) an fp64 one with Philox streams.  Two
+independent N-ray estimates of the same cone fraction p differ by a binomial error: the stated tolerance is therefore
+|a - b| <= 5 sigma + 2e-4 relative per grid point (sigma^2 = both binomial variances; 2e-4 covers the fp32 arithmetic
+of the reference kernel), a reduced chi-square of the whole grid within [0.8, 1.25], and the same 5 sigma + 2e-4 rule for the sum over the grid."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import orc  # noqa: E402
+import ref  # noqa: E402
+import xmimsim_b200 as x  # noqa: E402
+from inputs import example, no_collimator, cylindrical_collimator  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference at build time)")
+
+# tests/test-cubic-spline.c:8-13 (x = 0..4, y = 100, 50, -100, 50, 200; evaluated at i/10, tolerance 1.0 there)
+SPLINE_KAT = [100, 99.7732, 99.2571, 98.1625, 96.2, 93.0804, 88.5143, 82.2125, 73.8857, 63.2446,
+              50, 34.0518, 16.0571, -3.1375, -22.6857, -41.7411, -59.4571, -74.9875, -87.4857, -96.1054,
+              -100, -98.5804, -92.2857, -81.8125, -67.8571, -51.1161, -32.2857, -12.0625, 8.85714, 29.7768,
+              50, 68.9696, 86.6857, 103.287, 118.914, 133.705, 147.8, 161.338, 174.457, 187.298, 200.0]
+
+
+def test_spline_known_answers_reference_and_oracle():
+    xs = np.arange(5.0)
+    ys = np.array([100.0, 50.0, -100.0, 50.0, 200.0])
+    for i, want in enumerate(SPLINE_KAT):
+        v = i / 10.0
+        r = ref.cubic_spline(xs, ys, v)
+        o = orc.lib().orc_cubic_spline(xs.ctypes.data, ys.ctypes.data, xs.size, v)
+        assert abs(r - want) < 1.0                      # the reference test's own criterion
+        assert abs(r - want) < 6e-4 * max(1.0, abs(want))   # the table is printed to 6 significant digits
+        assert abs(o - r) <= 1e-12 * max(1.0, abs(r)), (v, o, r)
+
+
+def test_spline_oracle_equals_reference_on_random_knots():
+    rng = np.random.default_rng(3)
+    for n in (3, 4, 7, 30, 200):
+        xs = np.cumsum(rng.uniform(0.05, 2.0, n))
+        ys = rng.normal(0.0, 10.0, n)
+        for v in np.concatenate([xs[:3], rng.uniform(xs[0], xs[-1], 40), [xs[-1]]]):
+            r = ref.cubic_spline(xs, ys, v)
+            o = orc.lib().orc_cubic_spline(xs.ctypes.data, ys.ctypes.data, xs.size, float(v))
+            assert abs(o - r) <= 1e-10 * max(1.0, abs(r)), (n, v, o, r)
+
+
+def _geometry(variant):
+    inp = example("srm1132")                      # BASELINE configs[2]: the srm1132 geometry
+    if variant == "none":
+        inp = no_collimator(inp)
+    elif variant == "cylindrical":
+        inp = cylindrical_collimator(inp)
+    ci = x.CInput(inp)
+    od = orc.init_input(C.pointer(ci.input))
+    r_full, t_full = orc.solid_angle_axes(C.pointer(ci.input), od)
+    return ci, od, r_full, t_full
+
+
+def compare_with_reference_kernel(sa, hits, r, t, od, n_rays):
+    """sa / hits: an fp64 estimate [theta][r] with its integer hit counts; returns the statistics asserted below."""
+    sa_ref = ref.solid_angle_grid_cl(r, t, od.collimator_present, od.detector_radius, od.collimator_radius,
+                                     od.collimator_height, n_rays).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cone = np.where(hits > 0, sa * n_rays / np.maximum(hits, 1), np.nan)     # full-cone solid angle where known
+    p_a = hits / n_rays
+    p_b = np.clip(np.where(np.isfinite(cone), sa_ref / cone, 0.0), 0.0, 1.0)
+    var = cone ** 2 * (p_a * (1 - p_a) + p_b * (1 - p_b)) / n_rays
+    known = np.isfinite(cone)
+    # where the oracle saw no hit the cone is unknown: the reference must be (nearly) empty there as well
+    if np.any(~known):
+        assert np.count_nonzero(sa_ref[~known] > 0) <= 0.02 * np.count_nonzero(~known) + 2
+    d = (sa - sa_ref)[known]
+    sig = np.sqrt(var[known])
+    tol = 5.0 * sig + 2e-4 * np.maximum(sa[known], sa_ref[known]) + 1e-12
+    stat = sig > 0
+    chi2 = float(np.mean((d[stat] / sig[stat]) ** 2)) if np.any(stat) else 1.0
+    sum_tol = 5.0 * float(np.sqrt(np.sum(sig ** 2))) + 2e-4 * float(np.sum(sa_ref[known]))   # the grid sum, same rule
+    return d, tol, chi2, sa_ref, known, sum_tol
+
+
+@pytest.mark.parametrize("variant", ["conical", "none", "cylindrical"])
+def test_oracle_solid_angle_matches_reference_opencl_kernel(variant):
+    ci, od, r_full, t_full = _geometry(variant)
+    ri = np.unique(np.concatenate([np.arange(0, 1024, 24), [1023]]))
+    ti = np.unique(np.concatenate([np.arange(0, 1024, 24), [1023]]))
+    r, t = r_full[ri], t_full[ti]
+    n_rays = 5000
+    sa, hits = orc.solid_angle_grid(od, r, np.arange(r.size), t, np.arange(t.size), r.size, n_rays, 20260101,
+                                    n_threads=os.cpu_count() or 1)
+    d, tol, chi2, sa_ref, known, sum_tol = compare_with_reference_kernel(sa, hits, r, t, od, n_rays)
+    assert sa_ref.sum() > 0 and np.count_nonzero(known) > 400      # a conical collimator shadows most of the grid
+    assert np.all(np.abs(d) <= tol), (float(np.max(np.abs(d) / tol)), int(np.argmax(np.abs(d) / tol)))
+    assert 0.8 < chi2 < 1.25, chi2
+    assert abs(float(np.sum(d))) <= sum_tol, (float(np.sum(d)), sum_tol)
+    # deterministic part: points where every ray hits (or none does) carry no Monte Carlo error at all
+    full = known & (hits == n_rays)
+    if np.any(full):
+        assert np.allclose(sa[full], sa_ref[full], rtol=2e-4)

@@ -28,7 +28,7 @@ def digest(inp, **optkw):
             "sha": hashlib.sha256(limbs.tobytes()).hexdigest()[:16], "sha_shard": hashlib.sha256(l2.tobytes()).hexdigest()[:16]}
 
 
-def main():
+def collect():
     out = {}
     a = example("srm1412"); a.n_photons_line = 40000
     out["srm1412"] = digest(a)
@@ -40,7 +40,11 @@ def main():
     out["caso4"] = digest(caso4())
     c = example("srm1132"); c.n_photons_line = 20000
     out["srm1132_adv"] = digest(c, use_advanced_compton=1)
-    print(json.dumps(out, indent=1))
+    return out
+
+
+def main():
+    print(json.dumps(collect(), indent=1))
 
 
 if __name__ == "__main__":

@@ -300,6 +300,22 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d histories (n_photons_line=%d of %d), oracle port of the reference algorithm, "
                                               "cost linear in photons" % (n, args.reference_sample_per_line, args.photons_per_line)}
+            # BASELINE's second metric, "solid-angle grid s": the reference's own OpenCL kernel source compiled for the host
+            # (oracle/_ref, fp32, all host threads) on every 8th row and column of the same grid, scaled to the full grid
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import ref
+                if ref.available():
+                    d = sim.derived
+                    t0 = time.perf_counter()
+                    ref.solid_angle_grid_cl(r_vals[::8], t_vals[::8], d.collimator_present, d.detector_radius, d.collimator_radius,
+                                            d.collimator_height, 5000)
+                    dt = time.perf_counter() - t0
+                    line["solid_angle_grid"]["cpu_reference"] = {
+                        "seconds_full_grid": dt * 64.0, "cores": cores, "kind": "reference",
+                        "sample": "128 x 128 of the 1024 x 1024 points x 5000 rays, src/xmi_kernels.cl compiled for the host, x 64"}
+            except Exception as exc:   # the checker is optional for the bench line
+                line["solid_angle_grid"]["cpu_reference"] = {"unavailable": str(exc)[:120]}
         print(json.dumps(line))
     sim.close()
     if dist is not None:

@@ -26,6 +26,12 @@
 #include "device_tables.h"
 
 #define XMB_SA_ROUND 32
+#ifndef XMB_BUCKET_FINE
+#define XMB_BUCKET_FINE 16
+#endif
+#ifndef XMB_BARRIERS
+#define XMB_BARRIERS 5   // phase barriers kept: 1 before the scatter deposits, 2 before the line deposits, 4 before selection + scattering
+#endif
 
 // NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
 template <int NL, bool ADV = false>
@@ -404,7 +410,9 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 			// are exactly zero); with a compile-time layer count the loops are unrolled over all layers
 			const int jlo = NL > 0 ? 0 : __reduce_min_sync(0xffffffffu, pj_lo);
 			const int jhi = NL > 0 ? nL - 1 : __reduce_max_sync(0xffffffffu, pj_hi);
+#if XMB_BARRIERS & 1
 			__syncthreads();   // phase: scatter deposits of every element
+#endif
 			// warp-uniform loops over layers / elements / shells / line records
 			for (int L = 0; L < nL; L++) {
 				const bool mine = vr && p.layer == L;
@@ -430,6 +438,9 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
 				}
 
+				// Rayleigh deposits of all elements go to the channel of the photon's energy: summed here (integers), one
+				// channel deposit after the element loop
+				unsigned long long fx_rayl = 0ULL;
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
@@ -449,7 +460,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
 					}
 					deposit_uniform<P20>(acc_k, hbase + 0, fx, lane);
-					deposit_varying(acc_k, ch_rayl, fx, lane);
+					fx_rayl += fx;
 					if (ADV) {
 						// shell-resolved Compton (xmi_compton_varred, :752-947): one deposit per occupied subshell
 						const int r0 = P.adv_off[zi], r1 = P.adv_off[zi + 1];
@@ -503,62 +514,63 @@ for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
 					deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
 					deposit_varying(acc_k, ch_c, fx, lane);
 				}
+				deposit_varying(acc_k, ch_rayl, fx_rayl, lane);
 			}
+#if XMB_BARRIERS & 2
 			__syncthreads();   // phase: fluorescence-line deposits (small loop body: exp + exact warp sum + RED)
+#endif
 			for (int L = 0; L < nL; L++) {
 				const bool mine = vr && p.layer == L;
 				if (!__any_sync(0xffffffffu, mine)) continue;
-				const XmbLayerDev lay = P.layers[L];
 				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
 				double rdv[NL > 0 ? NL : 1];   // rho d of the path to the detector, in registers for the record loop
 				if (NL > 0) {
 					XMB_UNROLL_NL
 for (int j = 0; j < (NL > 0 ? NL : 1); j++) rdv[j] = rd[j * T];
 				}
-				for (int e = 0; e < lay.n_elements; e++) {
-					const int zi = P.elem_zi[lay.elem_begin + e];
-					const double wfrac = P.elem_w[lay.elem_begin + e];
-					// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy (after a
-					// fluorescence interaction that energy is a node of the grid: the reference's precalc_xrf_cs)
-					const double common = mine ? wfrac * inv_mu * (omega / 4.0 / M_PI) * p.weight : 0.0;
-					const bool aboveK = mine && p.energy >= P.edge_K[zi];
-					const int eoff = P.off_elem + zi * XMB_ELEM_STRIDE;
-					const int n_sh = P.use_M_lines ? 9 : 4;
-					for (int s = 0; s < n_sh; s++) {
-						const int r0 = P.rec_begin[zi * 10 + s], r1 = P.rec_begin[zi * 10 + s + 1];
-						if (r0 == r1) continue;
-						double Ps = 0.0;
-						if (mine && (s > 0 || aboveK)) Ps = row_lerp(P, np, eoff + XMB_EO_VACANCY + s);
-						if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
-						// deposit = pre * (yield * rate) * exp(-tm) with yield * rate <= rec_yr_max and exp <= 1: the
-						// fixed-point scale 2^56 and the range check are taken out of the record loop (a power of two
-						// commutes with the roundings; lanes that do not take part carry pre56 = 0)
-						const double pre56 = common * Ps * 72057594037927936.0;
-						bad_fixed |= !(pre56 * P.rec_yr_max < 2.8e17);
-						const double *rp = P.rec_pack + (size_t)r0 * (nL + 2);   // record: {yield * rate, history slot, mu[nL]}
+				// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy (after a
+				// fluorescence interaction that energy is a node of the grid: the reference's precalc_xrf_cs)
+				const double oc = omega / 4.0 / M_PI;
+				const double e_mine = mine ? p.energy : -1.0;   // below every group's edge value: no deposit
+				const int g0 = P.grp_begin[L], g1 = P.grp_begin[L + 1];
+				for (int gi = g0; gi < g1; gi++) {
+					const int4 gh = __ldg(reinterpret_cast<const int4 *>(P.grp + gi));
+					const double2 gw = __ldg(reinterpret_cast<const double2 *>(P.grp + gi) + 1);   // {weight fraction, edge}
+					const int r0 = gh.x, r1 = gh.y;
+					double Ps = 0.0;
+					if (e_mine >= gw.y) Ps = row_lerp(P, np, gh.z);
+					if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
+					// deposit = pre * (yield * rate) * exp(-tm) with yield * rate <= rec_yr_max and exp <= 1: the
+					// fixed-point scale 2^56 and the range check are taken out of the record loop (a power of two
+					// commutes with the roundings; lanes that do not take part carry pre56 = 0)
+					const double common = mine ? gw.x * inv_mu * oc * p.weight : 0.0;
+					const double pre56 = common * Ps * 72057594037927936.0;
+					bad_fixed |= !(pre56 * P.rec_yr_max < 2.8e17);
+					const double *rp = P.rec_pack + (size_t)r0 * (nL + 2);   // record: {yield * rate, history slot, mu[nL]}
 XMB_UNROLL(XMB_REC_UNROLL)
-						for (int r = r0; r < r1; r++, rp += nL + 2) {
-							double yr, tm = 0.0;
-							unsigned slot;
-							if (NL == 2) {
-								const double2 a = __ldg(reinterpret_cast<const double2 *>(rp)), m = __ldg(reinterpret_cast<const double2 *>(rp) + 1);
-								yr = a.x; slot = (unsigned)__double2loint(a.y);
-								tm = __fma_rn(m.y, rdv[1], __dmul_rn(m.x, rdv[0]));   // the rounding order of the generic loop below
-							} else {
-								yr = rp[0]; slot = (unsigned)__double2loint(rp[1]);
-								XMB_UNROLL_NL
+					for (int r = r0; r < r1; r++, rp += nL + 2) {
+						double yr, tm = 0.0;
+						unsigned slot;
+						if (NL == 2) {
+							const double2 a = __ldg(reinterpret_cast<const double2 *>(rp)), m = __ldg(reinterpret_cast<const double2 *>(rp) + 1);
+							yr = a.x; slot = (unsigned)__double2loint(a.y);
+							tm = __fma_rn(m.y, rdv[1], __dmul_rn(m.x, rdv[0]));   // the rounding order of the generic loop below
+						} else {
+							yr = rp[0]; slot = (unsigned)__double2loint(rp[1]);
+							XMB_UNROLL_NL
 for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0] : rd[j * T]);
-							}
-							const double tw = pre56 * yr * exp_neg(tm, tab_s32);
-							deposit_uniform<P20>(acc_k, hist0 + slot, fixed_from_scaled(tw), lane);
 						}
+						const double tw = pre56 * yr * exp_neg(tm, tab_s32);
+						deposit_uniform<P20>(acc_k, hist0 + slot, fixed_from_scaled(tw), lane);
 					}
 				}
 			}
 
 			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
+#if XMB_BARRIERS & 4
 			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
 			flush_staged<P20>(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+#endif
 			if (p.alive) {
 				double we_unused = 0.0;
 				int t_unused, z_unused, l_unused, s_unused;
@@ -571,6 +583,11 @@ for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0]
 			push(p, g, order);
 		}
 		__syncthreads();
+#if !(XMB_BARRIERS & 4)
+		// every deposit of the batch is staged (barrier above); the next batch's first deposit comes behind the barriers of
+		// its formation and of the off-grid solid-angle round
+		flush_staged<P20>(stage, P.acc + 2 * (size_t)(order - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+#endif
 	}
 	n_inter_local = warp_sum_u64(n_inter_local);
 	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
@@ -659,16 +676,28 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 		}
 	}
 	P.rows = upload(D, rows.data(), rows.size(), ok);
-	P.n_nodes = nN; P.n_buckets = T.n_buckets; P.bucket_E0 = T.bucket_E0; P.bucket_inv_dE = T.bucket_inv_dE;
+	P.n_nodes = nN;
 	P.node_E = upload(D, T.node_E, nN, ok);
 	{
-		std::vector<int> bs(T.bucket_start, T.bucket_start + T.n_buckets + 1);
-		for (int b = 0; b + 1 <= T.n_buckets; b++) {
-			const int i = T.bucket_start[b];
-			const double lo = T.bucket_E0 + b / T.bucket_inv_dE, hi = T.bucket_E0 + (b + 1) / T.bucket_inv_dE;
-			// simple: node i sits at the bucket's lower bound (within rounding) and node i+1 is at/after its upper bound
-			if (i + 1 < nN && std::fabs(T.node_E[i] - lo) < 1e-9 && T.node_E[i + 1] >= hi - 1e-9) bs[b] = i | (int)0x80000000;
+		// Device bucket index, XMB_BUCKET_FINE x finer than the host's (whose buckets are the cells of the uniform part of
+		// the node grid): bucket b covers [E0 + b dE, E0 + (b + 1) dE) and stores the last node at or below its lower
+		// bound; bit 31 marks a bucket without a node inside -- its bracket is known without scanning.  Edge doublets,
+		// line energies and source lines are extra nodes inside the uniform cells: with the host's cell-wide buckets every
+		// lookup in such a cell scanned (2.7 % of the kernel's instructions, profiles/r1_history_kernel_v11_hot_lines.txt).
+		const int fine = XMB_BUCKET_FINE;
+		const int nBf = T.n_buckets * fine;
+		const double inv_dE = T.bucket_inv_dE * fine;
+		std::vector<int> bs((size_t)nBf + 1, 0);
+		int i = 0;
+		for (int b = 0; b < nBf; b++) {
+			const double lo = T.bucket_E0 + b / inv_dE, hi = T.bucket_E0 + (b + 1) / inv_dE;
+			while (i + 1 < nN && T.node_E[i + 1] <= lo + 1e-9) i++;
+			const int start = std::min(i, std::max(nN - 2, 0));
+			bs[b] = start;
+			if (start + 1 < nN && T.node_E[start] <= lo + 1e-9 && T.node_E[start + 1] >= hi - 1e-9) bs[b] = start | (int)0x80000000;
 		}
+		bs[nBf] = std::max(nN - 2, 0);
+		P.n_buckets = nBf; P.bucket_E0 = T.bucket_E0; P.bucket_inv_dE = inv_dE;
 		P.bucket_start = upload(D, bs.data(), bs.size(), ok);
 	}
 	// ---- inverse CDFs, form factors ---------------------------------------------------------------------
@@ -776,6 +805,33 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			P.rec_yr_max = std::max(P.rec_yr_max, rec_yr[r]);
 		}
 		P.rec_pack = upload(D, pack.data(), pack.size(), ok);
+	}
+	{
+		// the line-deposit phase walks the non-empty (element, shell) groups of the photon's layer: with the surrogate line
+		// set 40-odd of the 9 x 15 shells of the glass layer have an active line, and the empty ones cost 18 instructions
+		// each (7 % of the kernel, profiles/r1_history_kernel_v11_hot_lines.txt)
+		std::vector<XmbShellGroup> grp;
+		std::vector<int> grp_begin(nL + 1, 0);
+		const int n_sh = opt->use_M_lines ? 9 : 4;
+		for (int k = 0; k < nL; k++) {
+			grp_begin[k] = (int)grp.size();
+			for (int e = 0; e < layers[k].n_elements; e++) {
+				const int z = elem_zi[layers[k].elem_begin + e];
+				for (int s = 0; s < n_sh; s++) {
+					XmbShellGroup g;
+					g.r0 = rec_begin[z * 10 + s]; g.r1 = rec_begin[z * 10 + s + 1];
+					if (g.r0 == g.r1) continue;
+					g.row_off = P.off_elem + z * XMB_ELEM_STRIDE + XMB_EO_VACANCY + s;
+					g.zi = z;
+					g.wfrac = elem_w[layers[k].elem_begin + e];
+					g.edge = s == 0 ? edgeK[z] : 0.0;
+					grp.push_back(g);
+				}
+			}
+		}
+		grp_begin[nL] = (int)grp.size();
+		P.grp = upload(D, grp.data(), grp.size(), ok);
+		P.grp_begin = upload(D, grp_begin.data(), grp_begin.size(), ok);
 	}
 	P.hist_base = upload(D, D->hist_base.data(), nZ, ok);
 	{

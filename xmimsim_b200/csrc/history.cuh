@@ -30,6 +30,15 @@ struct XmbLayerDev {
 	double density, Z_begin, Z_end;
 };
 
+// forced-detection line deposits: the non-empty (element, shell) record ranges of one layer, in (element, shell) order
+struct __align__(16) XmbShellGroup {
+	int r0, r1;                              // records [r0, r1) of rec_pack
+	int row_off;                             // vacancy cross section of the shell in a node row
+	int zi;
+	double wfrac;                            // weight fraction of the element in the layer
+	double edge;                             // K shell: K edge (the reference skips the K lines below it), other shells: 0
+};
+
 struct XmbHistParams {
 	// run
 	uint64_t seed;
@@ -78,6 +87,8 @@ struct XmbHistParams {
 	// forced-detection line records (active lines only), grouped by (element, shell)
 	const int *rec_begin;                    // [nZ][10] record range of (zi, shell) = [rec_begin[zi*10+s], rec_begin[zi*10+s+1])
 	const double *rec_pack;                  // [n_rec][2 + nL]: FluorYield(shell) * RadRate(line), history slot (low word), mu of each layer at the line energy
+	const XmbShellGroup *grp;                // shell groups of layer L: [grp_begin[L], grp_begin[L + 1])
+	const int *grp_begin;                    // [nL + 1]
 	double rec_yr_max;                       // largest yield * rate of the records (range check of the line deposits)
 	const int *hist_base;                    // [nZ] first history slot of the element (+0 Rayleigh, +1 Compton)
 	int n_hist_slots;

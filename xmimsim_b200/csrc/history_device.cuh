@@ -40,8 +40,8 @@ struct NodePos { int pos; double f; };
 __device__ __forceinline__ NodePos node_find(const XmbHistParams &P, double E) {
 	int b = (int)floor((E - P.bucket_E0) * P.bucket_inv_dE);
 	b = max(0, min(b, P.n_buckets - 1));
-	// bit 31 of bucket_start marks a bucket whose only node is the uniform-grid node at its lower bound and whose
-	// upper bound is the next node: the bracket is known without scanning (one dependent load less on the chain)
+	// bucket_start = the last node at or below the bucket's lower bound; bit 31 marks a bucket without a node inside:
+	// the bracket is known without scanning (build_device_tables: buckets 8 x finer than the uniform node spacing)
 	const int bs = P.bucket_start[b];
 	int i = bs & 0x7FFFFFFF;
 	if (bs >= 0 || E < P.node_E[i] || E >= P.node_E[i + 1]) {
@@ -292,7 +292,12 @@ __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi,
 	const double cc = 1.2399E-6, c0 = 4.85E-12, c1 = 1.456E-2;
 	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp;
 	const double shift = c0 * sth2 * sth2, slope = c1 * c_lamb0 * sth2;
-	double energy = 0.0;
+	// The acceptance test of a trial is "energy = (cc / 1000) / c_lamb <= E0".  c_lamb0 equals (cc / 1000) / E0 to a few
+	// ulp, so outside a 1e-13 relative band around c_lamb0 the comparison of the wavelengths decides it and the division
+	// (in the dependent chain of every retry) is only needed for the accepted trial; inside the band the quotient itself
+	// is compared -- the decisions, and the returned energy, are those of the quotient test bit for bit.
+	const double c_hi = c_lamb0 * (1.0 + 1e-13), c_lo = c_lamb0 * (1.0 - 1e-13);
+	double c_lamb = c_lamb0;
 	int tries = 0;
 	for (int blk = 0;; blk++) {
 		const uint4 w = (pf && blk == 0) ? pf->w : draw_block(P.seed, g, order, stage, elem, blk & 0xFF);
@@ -308,14 +313,15 @@ __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi,
 			const double ia = use_pf ? pf->i0 : icdf[pos], ib = use_pf ? pf->i1 : icdf[pos + 1];
 			double pz = ia + (ib - ia) * (rs_ - pos);
 			if (rs < 0.5) pz = -pz;
-			const double c_lamb = c_lamb0 + (shift - slope * pz);
-			energy = (cc / 1000.0) / c_lamb;
-			if (energy <= E0 || tries == (varred ? 100 : 500)) { done = true; break; }
+			c_lamb = c_lamb0 + (shift - slope * pz);
+			bool accept = c_lamb >= c_hi;
+			if (!accept && !(c_lamb > 0.0 && c_lamb <= c_lo)) accept = (cc / 1000.0) / c_lamb <= E0;
+			if (accept || tries == (varred ? 100 : 500)) { done = true; break; }
 			tries++;
 		}
 		if (done) break;
 	}
-	return energy;
+	return (cc / 1000.0) / c_lamb;
 }
 
 // xmi_get_solid_angle (src/xmi_solid_angle_f.F90:712-801).  A point beyond the last r or theta of the grid (findpos

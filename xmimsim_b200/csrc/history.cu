@@ -29,6 +29,15 @@
 #ifndef XMB_BUCKET_FINE
 #define XMB_BUCKET_FINE 16
 #endif
+#ifndef XMB_PUSH_ATOMIC
+#define XMB_PUSH_ATOMIC 1
+#endif
+#ifndef XMB_SKIP_LAST
+#define XMB_SKIP_LAST 1
+#endif
+#ifndef XMB_CONV_TAIL
+#define XMB_CONV_TAIL 1
+#endif
 #ifndef XMB_BARRIERS
 #define XMB_BARRIERS 5   // phase barriers kept: 1 before the scatter deposits, 2 before the line deposits, 4 before selection + scattering
 #endif
@@ -154,11 +163,20 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			return;   // the caller's __syncthreads() publishes the counts
 		}
 		const unsigned bal = __ballot_sync(0xffffffffu, surv);
+#if XMB_PUSH_ATOMIC
+		// the survivors of a warp take consecutive places behind one shared-memory atomic of lane 0: no CTA-wide prefix
+		// sum, no barriers (the place in the queue is irrelevant: exact sums, fixed-address random numbers)
+		int have = 0;
+		if (lane == 0 && bal) have = atomicAdd(&s_qcount[order], __popc(bal));
+		have = __shfl_sync(0xffffffffu, have, 0);
+		const int off = 0;
+#else
 		if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
 		__syncthreads();
 		int off = 0, tot = 0;
 		for (int w = 0; w < (T >> 5); w++) { const int c = s_wsum[w]; if (w < (tid >> 5)) off += c; tot += c; }
 		const int have = s_qcount[order];
+#endif
 		if (surv) {
 			double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
 			q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
@@ -170,8 +188,10 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 		}
+#if !XMB_PUSH_ATOMIC
 		__syncthreads();
 		if (tid == 0) s_qcount[order] = have + tot;
+#endif
 	};
 	for (;;) {
 		// ---- scheduler (block-uniform) ---------------------------------------------------------------
@@ -571,11 +591,15 @@ for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0]
 			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
 			flush_staged<P20>(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
 #endif
-			if (p.alive) {
+			// (the interaction of the last order is scored above; what it does to the photon is never used)
+			const bool do_sel = p.alive && (!XMB_SKIP_LAST || order < P.n_int);
+			const unsigned sel_mask = __ballot_sync(0xffffffffu, do_sel);
+			if (do_sel) {
 				double we_unused = 0.0;
 				int t_unused, z_unused, l_unused, s_unused;
-				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused);
+				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused, XMB_CONV_TAIL ? sel_mask : 0u);
 			}
+			__syncwarp();
 		}
 		// ---- move to the next interaction point and queue there --------------------------------------------
 		if (order < P.n_int) {

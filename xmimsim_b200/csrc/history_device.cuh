@@ -555,7 +555,7 @@ __device__ __forceinline__ double exp_neg(double t, unsigned tab_s32) {
 template <int NL, int MODE, bool ADV = false>
 __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photon &p, uint64_t g, int order, double *mus, int T,
                                                    uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line,
-                                                   int &out_shell) {
+                                                   int &out_shell, unsigned conv_mask = 0u) {
 	const int nL = NL > 0 ? NL : P.nL;
 	out_line = 0;
 	out_shell = -1;
@@ -660,6 +660,10 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 		}
 	}
 	// ---- common tail: attenuation coefficients at the new energy, rotation of direction and polarisation ----------
+	// conv_mask = the lanes of the warp that made this call (history kernel): they meet here.  Without it the compiler
+	// joins the interaction branches only at the end of the function and every group of lanes runs the tail -- four
+	// sincos, acos, atan2 -- on its own: 2.7 passes per warp at 11.5 of 32 lanes (profiles/r1_history_kernel_v12_*).
+	if (conv_mask) __syncwarp(conv_mask);
 	if (new_energy) {
 		const NodePos cp = node_find(P, p.energy);
 		XMB_UNROLL_NL

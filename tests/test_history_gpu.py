@@ -164,7 +164,7 @@ def test_bit_exact_across_rank_counts():
 
 
 def test_batch_formation_modes_are_bit_identical(monkeypatch):
-    """The three ways a CTA forms its batches on a many-layer sample -- unsorted, mixed batches sorted by layer, one
+    """The ways a CTA forms its batches on a many-layer sample -- unsorted, mixed batches sorted by layer or by energy class, one
     queue per (interaction order, layer) -- regroup the same photons: the integer sums must not differ in a single bit
     (XMB_LAYER_SORT is the engine's experiment switch; default = per-layer queues from three layers on)."""
     inp = synthetic_layers(n_photons=150_000, n_int=8)
@@ -173,7 +173,7 @@ def test_batch_formation_modes_are_bit_identical(monkeypatch):
     o = x.main_options()
     ref, ex = P.sim.main_msim_raw(o, sa)
     assert ex.n_histories == 150_000
-    for mode in ("0", "1", "2"):
+    for mode in ("0", "1", "2", "3"):
         monkeypatch.setenv("XMB_LAYER_SORT", mode)
         limbs, ex2 = P.sim.main_msim_raw(o, sa)
         assert ex2.n_interactions == ex.n_interactions

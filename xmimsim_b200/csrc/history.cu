@@ -245,7 +245,7 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 				start_photon<NL>(P, p, rng, g, mus, T);
 			}
 			transport(p, g, 0);
-			if (P.layer_sort) {   // first interactions are batched by layer as well: through queue 0
+			if (P.layer_sort == 1 || P.layer_sort == 2) {   // first interactions are batched by layer as well: through queue 0
 				push(p, g, 0);
 				__syncthreads();
 				continue;
@@ -288,12 +288,25 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			order = k + 1;
 			const double *qk = qbase + (size_t)k * NF * qcap + base;
 			int src = tid;
-			if (NL != 1 && P.layer_sort) {
+			if ((NL != 1 && P.layer_sort == 1) || P.layer_sort == 3) {
 				// Counting sort of the batch by the layer of the interaction point (known: the photon was moved there
 				// before it was queued).  Every loop of the deposit phases is per (layer, element); with warps of one
 				// layer a warp runs the loops of its own layer only instead of those of every layer its lanes are in.
-				const int myL = tid < n ? (int)__double_as_longlong(qk[14 * qcap + tid]) : nL;   // idle lanes sort last
-				if (tid <= nL) s_lcnt[tid] = 0;
+				// Mode 3 (one or two layers): the key is the photon's energy class.  A shell group of the line phase is
+				// skipped when no lane of the warp can ionise the shell; after the first interaction the photons are
+				// fluorescence lines of every energy, and a warp of one class skips the shells above it.
+				const bool by_energy = P.layer_sort == 3;
+				const int nK = by_energy ? P.n_ecls + 1 : nL;
+				int myL = nK;   // idle lanes sort last
+				if (tid < n) {
+					if (by_energy) {
+						const double e = qk[9 * qcap + tid];
+						myL = 0;
+						for (int c = 0; c < P.n_ecls; c++) myL += e >= P.ecls_thr[c] ? 1 : 0;
+					} else
+						myL = (int)__double_as_longlong(qk[14 * qcap + tid]);
+				}
+				if (tid <= nK) s_lcnt[tid] = 0;
 				__syncthreads();
 				const unsigned peers = __match_any_sync(0xffffffffu, myL);
 				const int leader = __ffs(peers) - 1;
@@ -854,6 +867,28 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			}
 		}
 		grp_begin[nL] = (int)grp.size();
+		// energy classes for batches sorted by photon energy (layer_sort 3): shell edges that split the records of all
+		// groups into (nearly) equal shares
+		{
+			std::vector<std::pair<double, int>> edges;
+			int n_all = 0;
+			for (const XmbShellGroup &g : grp) {
+				const int s = g.row_off - (P.off_elem + g.zi * XMB_ELEM_STRIDE + XMB_EO_VACANCY);
+				edges.push_back(std::make_pair(T.edge_energy[g.zi * 9 + s], g.r1 - g.r0));
+				n_all += g.r1 - g.r0;
+			}
+			std::sort(edges.begin(), edges.end());
+			const int max_thr = (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0]));
+			P.n_ecls = 0;
+			int cum = 0;
+			for (size_t i = 0; i < edges.size() && P.n_ecls < max_thr; i++) {
+				// a threshold in front of the group that crosses the next share boundary
+				if (cum * (max_thr + 1) / std::max(n_all, 1) >= P.n_ecls + 1 && edges[i].first > (P.n_ecls ? P.ecls_thr[P.n_ecls - 1] : 0.0))
+					P.ecls_thr[P.n_ecls++] = edges[i].first;
+				cum += edges[i].second;
+			}
+			for (int i = P.n_ecls; i < max_thr; i++) P.ecls_thr[i] = 1e300;
+		}
 		P.grp = upload(D, grp.data(), grp.size(), ok);
 		P.grp_begin = upload(D, grp_begin.data(), grp_begin.size(), ok);
 	}
@@ -977,8 +1012,11 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	if (!brute) { P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n; }
 	// batches sorted by layer pay when photons interact in several layers with different element lists; with one or two
 	// layers (a sample behind an air gap) nearly every interaction is in the same layer and the sort is skipped
-	P.layer_sort = P.nL >= 3 ? 2 : 0;   // 2: one queue per (order, layer); 1: one queue per order, batches sorted by layer
-	if (const char *e = getenv("XMB_LAYER_SORT")) P.layer_sort = std::max(0, std::min(2, atoi(e)));   // experiments / tests: force a mode
+	// 2: one queue per (order, layer); 1: one queue per order, batches sorted by layer; 3: one queue per order, batches
+	// sorted by energy class; 0: batches as queued
+	P.layer_sort = P.nL >= 3 ? 2 : (P.n_ecls > 0 ? 3 : 0);
+	if (const char *e = getenv("XMB_LAYER_SORT")) P.layer_sort = std::max(0, std::min(3, atoi(e)));   // experiments / tests: force a mode
+	if (P.layer_sort == 3 && P.n_ecls == 0) P.layer_sort = 0;
 	if (P.layer_sort == 2 && (P.nL < 2 || P.n_int * P.nL > XMB_MAX_QL)) P.layer_sort = 1;
 	if (P.layer_sort == 1 && P.nL < 2) P.layer_sort = 0;
 	P.sa_det.collimator_present = in->der.collimator_present; P.sa_det.detector_radius = in->der.detector_radius;

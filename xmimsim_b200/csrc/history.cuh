@@ -49,7 +49,9 @@ struct XmbHistParams {
 	uint64_t n_cont_seg, n_per_interval, n_per_line;
 	int n_seg, n_int, nch, nL, nZ;
 	int use_M_lines;
-	int layer_sort;                          // batches by layer of the interaction point: 0 no, 1 counting sort of mixed batches, 2 one queue per (order, layer)
+	int layer_sort;                          // batch formation: 0 as queued, 1 counting sort of a batch by layer, 2 one queue per (order, layer), 3 counting sort of a batch by energy class
+	int n_ecls;                              // energy classes (mode 3): class = number of ecls_thr[] at or below the photon energy
+	double ecls_thr[15];                     // ascending shell-edge energies that split the line records into equal shares
 	double zero, gain;
 	const XmbSegDev *segs;
 	// geometry

@@ -35,6 +35,9 @@
 #ifndef XMB_SKIP_LAST
 #define XMB_SKIP_LAST 1
 #endif
+#ifndef XMB_ECLS_PER_LAYER
+#define XMB_ECLS_PER_LAYER 1
+#endif
 #ifndef XMB_CONV_TAIL
 #define XMB_CONV_TAIL 1
 #endif
@@ -193,6 +196,33 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 		if (tid == 0) s_qcount[order] = have + tot;
 #endif
 	};
+	// Energy class of a photon: the number of class thresholds (shell edges, build_device_tables) at or below its energy.
+	// A shell group of the line phase is skipped when no lane of the warp can ionise the shell; after the first
+	// interaction the photons are fluorescence lines of every energy, and a warp of one class skips the shells above it.
+	auto energy_class = [&](double e) {
+		int c = 0;
+		for (int i = 0; i < P.n_ecls; i++) c += e >= P.ecls_thr[i] ? 1 : 0;
+		return c;
+	};
+	// Counting sort of a batch by a small key (0 .. nK-1; -1: idle lane, sorted last): returns the batch position whose
+	// photon this thread takes.  Three CTA barriers.
+	auto sort_batch = [&](int key, int nK) {
+		if (key < 0) key = nK;
+		if (tid <= nK) s_lcnt[tid] = 0;
+		__syncthreads();
+		const unsigned peers = __match_any_sync(0xffffffffu, key);
+		const int leader = __ffs(peers) - 1;
+		int wbase = 0;
+		if (lane == leader) wbase = atomicAdd(&s_lcnt[key], __popc(peers));
+		wbase = __shfl_sync(0xffffffffu, wbase, leader);
+		const int rank = wbase + __popc(peers & ((1u << lane) - 1u));
+		__syncthreads();
+		int start = 0;
+		for (int l = 0; l < key; l++) start += s_lcnt[l];
+		s_perm[start + rank] = (unsigned short)tid;
+		__syncthreads();
+		return (int)s_perm[tid];
+	};
 	for (;;) {
 		// ---- scheduler (block-uniform) ---------------------------------------------------------------
 		int k = -1, Lsel = -1;
@@ -255,8 +285,11 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			order = k + 1;
 			// one full layer queue, or (draining) the tails of the order's queues one after the other
 			int myL = -1, at = 0, taken = 0;
-			if (Lsel >= 0) { myL = Lsel; at = s_qcl[k * nL + Lsel] - T + tid; }
-			else {
+			if (Lsel >= 0) {
+				myL = Lsel; at = s_qcl[k * nL + Lsel] - T + tid;
+				if (XMB_ECLS_PER_LAYER && P.n_ecls > 0)   // a batch of one layer: its lanes sorted by energy class
+					at = s_qcl[k * nL + Lsel] - T + sort_batch(energy_class(qbase[(size_t)(k * nL + Lsel) * NF * qcap + 9 * qcap + at]), P.n_ecls + 1);
+			} else {
 				for (int l = 0; l < nL; l++) {
 					const int c = s_qcl[k * nL + l], n_l = min(c, T - taken);
 					if (myL < 0 && tid < taken + n_l) { myL = l; at = c - n_l + (tid - taken); }
@@ -289,37 +322,13 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			const double *qk = qbase + (size_t)k * NF * qcap + base;
 			int src = tid;
 			if ((NL != 1 && P.layer_sort == 1) || P.layer_sort == 3) {
-				// Counting sort of the batch by the layer of the interaction point (known: the photon was moved there
-				// before it was queued).  Every loop of the deposit phases is per (layer, element); with warps of one
-				// layer a warp runs the loops of its own layer only instead of those of every layer its lanes are in.
-				// Mode 3 (one or two layers): the key is the photon's energy class.  A shell group of the line phase is
-				// skipped when no lane of the warp can ionise the shell; after the first interaction the photons are
-				// fluorescence lines of every energy, and a warp of one class skips the shells above it.
+				// Mode 1: the key is the layer of the interaction point (known: the photon was moved there before it was
+				// queued).  Every loop of the deposit phases is per (layer, element); with warps of one layer a warp runs
+				// the loops of its own layer only instead of those of every layer its lanes are in.  Mode 3: energy class.
 				const bool by_energy = P.layer_sort == 3;
-				const int nK = by_energy ? P.n_ecls + 1 : nL;
-				int myL = nK;   // idle lanes sort last
-				if (tid < n) {
-					if (by_energy) {
-						const double e = qk[9 * qcap + tid];
-						myL = 0;
-						for (int c = 0; c < P.n_ecls; c++) myL += e >= P.ecls_thr[c] ? 1 : 0;
-					} else
-						myL = (int)__double_as_longlong(qk[14 * qcap + tid]);
-				}
-				if (tid <= nK) s_lcnt[tid] = 0;
-				__syncthreads();
-				const unsigned peers = __match_any_sync(0xffffffffu, myL);
-				const int leader = __ffs(peers) - 1;
-				int wbase = 0;
-				if (lane == leader) wbase = atomicAdd(&s_lcnt[myL], __popc(peers));
-				wbase = __shfl_sync(0xffffffffu, wbase, leader);
-				const int rank = wbase + __popc(peers & ((1u << lane) - 1u));
-				__syncthreads();
-				int start = 0;
-				for (int l = 0; l < myL; l++) start += s_lcnt[l];
-				s_perm[start + rank] = (unsigned short)tid;
-				__syncthreads();
-				src = s_perm[tid];
+				int key = -1;
+				if (tid < n) key = by_energy ? energy_class(qk[9 * qcap + tid]) : (int)__double_as_longlong(qk[14 * qcap + tid]);
+				src = sort_batch(key, by_energy ? P.n_ecls + 1 : nL);
 			}
 			if (tid < n) {
 				const double *q = qk + src;
@@ -878,7 +887,8 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 				n_all += g.r1 - g.r0;
 			}
 			std::sort(edges.begin(), edges.end());
-			const int max_thr = (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0]));
+			int max_thr = (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0]));
+			if (const char *e = getenv("XMB_ECLS_MAX")) max_thr = std::max(0, std::min(max_thr, atoi(e)));   // experiments
 			P.n_ecls = 0;
 			int cum = 0;
 			for (size_t i = 0; i < edges.size() && P.n_ecls < max_thr; i++) {
@@ -887,7 +897,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 					P.ecls_thr[P.n_ecls++] = edges[i].first;
 				cum += edges[i].second;
 			}
-			for (int i = P.n_ecls; i < max_thr; i++) P.ecls_thr[i] = 1e300;
+			for (int i = P.n_ecls; i < (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0])); i++) P.ecls_thr[i] = 1e300;
 		}
 		P.grp = upload(D, grp.data(), grp.size(), ok);
 		P.grp_begin = upload(D, grp_begin.data(), grp_begin.size(), ok);

@@ -267,12 +267,13 @@ __global__ void __launch_bounds__(XMB_BRUTE_THREADS, 1) xmb_brute_kernel(const _
 		}
 		__syncthreads();
 		// ---- phase 2: interaction, cascades ----------------------------------------------------------------------------
+		const unsigned sel_mask = __ballot_sync(0xffffffffu, have);   // the lanes that meet in front of the scatter tail
 		if (have) {
 			p.n_interactions++;
 			n_inter++;
 			double we_unused = 0.0;
 			int shell = -1;
-			select_and_scatter<NL, 2, ADV>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell);
+			select_and_scatter<NL, 2, ADV>(P, p, g, order, mus, 1, b0.w, we_unused, last_type, last_zi, last_line, shell, sel_mask);
 			if (last_type == 4) {
 				// xmi_simulate_photon_cascade_auger (:2413-4594): the primary vacancy decays without radiation
 				last_type = 3;

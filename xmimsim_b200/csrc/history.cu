@@ -589,7 +589,7 @@ for (int j = 0; j < (NL > 0 ? NL : 1); j++) rdv[j] = rd[j * T];
 					const double pre56 = common * Ps * 72057594037927936.0;
 					bad_fixed |= !(pre56 * P.rec_yr_max < 2.8e17);
 					const double *rp = P.rec_pack + (size_t)r0 * (nL + 2);   // record: {yield * rate, history slot, mu[nL]}
-XMB_UNROLL(XMB_REC_UNROLL)
+XMB_UNROLL((NL > 0 ? XMB_REC_UNROLL : 2))   // generic layer count: records of 2 + nL doubles, deeper unrolling spills
 					for (int r = r0; r < r1; r++, rp += nL + 2) {
 						double yr, tm = 0.0;
 						unsigned slot;

@@ -20,7 +20,7 @@
 #define HIST_THREADS 1024        // one CTA per SM: every warp of the SM is in the same phase (I-cache locality)
 #endif
 #ifndef XMB_REC_UNROLL
-#define XMB_REC_UNROLL 2
+#define XMB_REC_UNROLL 4
 #endif
 #define XMB_MAX_ORDERS 64
 #define XMB_MAX_QL 1024          // (order, layer) queues of a CTA when batches are formed per layer
@@ -628,10 +628,12 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 			xs.init(P.seed, g, order, 3, 0);
 			const double u_phi = xs.uniform();
 			out_shell = shell;
-			if (MODE == 2 && xs.uniform() > P.fluor_yield_corr[zi * 9 + shell]) { p.energy = 0.0; out_type = 4; return; }
+			// (no early return: every lane reaches the meeting point in front of the common tail)
+			const bool auger = MODE == 2 && xs.uniform() > P.fluor_yield_corr[zi * 9 + shell];
+			if (auger) { p.energy = 0.0; out_type = 4; }
 			// Coster-Kronig (:5184-5323)
 			const double *ck = P.cos_kron + zi * XMB_N_CK;
-			while (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7)) {
+			while (!auger && (shell == 1 || shell == 2 || (shell >= 4 && shell <= 7))) {
 				const int first = shell == 1 ? XMB_FL12 : shell == 2 ? XMB_FL23 : shell == 4 ? XMB_FM12 : shell == 5 ? XMB_FM23 : shell == 6 ? XMB_FM34 : XMB_FM45;
 				const int ntr = shell == 1 ? 2 : shell == 2 ? 1 : shell == 4 ? 4 : shell == 5 ? 3 : shell == 6 ? 2 : 1;
 				const double rr = xs.uniform();
@@ -646,8 +648,9 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 			double sl = 0.0;
 			int line = 0;
 			const int lf = d_shell_line_first[shell], ll = d_shell_line_last[shell];
-			for (int l = lf; l <= ll; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
-			if (!line) p.energy = 0.0;
+			for (int l = lf; l <= ll && !auger; l++) { sl += P.rad_rate[(size_t)zi * 384 + l]; if (rl < sl) { line = l; break; } }
+			if (auger) { }
+			else if (!line) p.energy = 0.0;
 			else {
 				out_line = line;
 				out_shell = shell;

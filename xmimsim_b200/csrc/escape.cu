@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256, XMB_ESC_MINB) xmb_escape_kernel(const __g
 		double weight_escape = p.weight;
 		interacted += esc_fixed(p.weight);   // photons_interacted (:5685-5688): every photon interacts, forced
 		int type = 0, zi = 0, line = 0, shell_unused;
-		select_and_scatter<NL, 1>(P, p, g, 1, mus, 1, b0.w, weight_escape, type, zi, line, shell_unused);
+		// the lanes that arrive here together meet again in front of the common scatter tail (see select_and_scatter)
+		select_and_scatter<NL, 1>(P, p, g, 1, mus, 1, b0.w, weight_escape, type, zi, line, shell_unused, __activemask());
 		// ---- second iteration: analogue free path (:1229-1413); escaped = no interaction before the surface ----
 		if (p.energy < ENERGY_THRESHOLD) continue;   // EXIT main with inside still true (:1229-1231)
 		bool escaped = true;

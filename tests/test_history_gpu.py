@@ -1,6 +1,8 @@
 """GPU parity of the photon-history engine against the CPU oracle on identical inputs, tables and
 Philox streams (tier T0 of SURVEY.md 8c), plus size-independent properties at larger sizes."""
 import copy
+import os
+import warnings
 
 import numpy as np
 import pytest
@@ -25,8 +27,33 @@ def run_both(inp, options=None, seed=11, grid_n=None, hits=400):
     sa = P.grid(hits_per_single=hits, n=grid_n)
     ch, br, vr = P.sim.main_msim(options, sa)
     ch_o, vr_o, cnt = P.oracle(options, sa, 0)   # seed 0 -> default key on both sides
+    if _differs(ch, ch_o) or _differs(vr, vr_o):
+        # About one run of this file in fifteen has shown one comparison off by a large factor, with kernels v11 .. v15
+        # alike, while the engine reproduced its sums bit for bit in 80 fresh simulations and 180 repetitions and the
+        # oracle did in 40 (tools/flaky_hunt*.py, tools/repeat_check.py): a transient outside the engine.  Both sides are
+        # therefore run a second time: the ENGINE must reproduce its first output exactly (a difference is a failure of
+        # the product and is reported as such), and the comparison is made against the second oracle run.
+        ch2, br2, vr2 = P.sim.main_msim(options, sa)
+        ch_o2, vr_o2, cnt2 = P.oracle(options, sa, 0)
+        note = ("parity retry: engine repeat identical=%s, oracle repeat identical=%s, first err=%.3e, second err=%.3e"
+                % (np.array_equal(ch, ch2) and np.array_equal(vr, vr2), np.array_equal(ch_o, ch_o2) and np.array_equal(vr_o, vr_o2),
+                   np.abs(ch - ch_o).max() / max(np.abs(ch_o).max(), 1e-300), np.abs(ch2 - ch_o2).max() / max(np.abs(ch_o2).max(), 1e-300)))
+        warnings.warn(note)
+        try:
+            os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_retries.log"), "a") as f:
+                f.write(note + "\n")
+        except OSError:
+            pass
+        assert np.array_equal(ch, ch2) and np.array_equal(vr, vr2), "engine output not reproducible: " + note
+        ch_o, vr_o, cnt = ch_o2, vr_o2, cnt2
     P.close()
     return ch, br, vr, ch_o, vr_o, cnt
+
+
+def _differs(a, b):
+    scale = np.abs(b).max()
+    return bool(scale > 0 and np.abs(a - b).max() > RTOL * scale)
 
 
 @pytest.mark.parametrize("name,n_line", [("srm1155", 1500), ("srm1412", 1500), ("srm1132", 1500), ("In", 1500)])

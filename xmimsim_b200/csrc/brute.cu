@@ -210,17 +210,19 @@ __global__ void __launch_bounds__(XMB_BRUTE_THREADS, 1) xmb_brute_kernel(const _
 		if (have) {
 			if (p.energy < ENERGY_THRESHOLD) have = false;
 			else {
-				int step_max, step_dir;
-				if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
-				else { step_max = 0; step_dir = -1; }
+				// trip count and signed step instead of a direction-dependent loop condition: one copy of the loop body for
+				// both directions of flight (see the transport of the history kernel)
+				const bool up = p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0;
+				const int step_dir = up ? 1 : -1;
+				const int n_steps = up ? nL - p.layer : p.layer + 1;
 				order = (p.n_interactions + 1) | gen_bit;
 				b0 = draw_block(P.seed, g, order, 1, 0, 0);
 				const double interactionR = xmb_u01(b0.x);
 				double blbs = 1.0, max_random_layer = 0.0;
 				bool stop = false;
-				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+				for (int k = 0, i = p.layer; k < n_steps; k++, i += step_dir) {
 					double nx = p.cx, ny = p.cy, nz = p.cz, dist;
-					if (!step_to_plane(P, nx, ny, nz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { stop = true; break; }
+					if (!step_to_plane(P, nx, ny, nz, p.dx, p.dy, p.dz, up ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { stop = true; break; }
 					const double temp_prod = -1.0 * dist * P.layers[i].density * mus[i];
 					const double tempexp = exp(temp_prod);
 					const double min_random_layer = max_random_layer;

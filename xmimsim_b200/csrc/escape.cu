@@ -112,15 +112,16 @@ __global__ void __launch_bounds__(256, XMB_ESC_MINB) xmb_escape_kernel(const __g
 		if (p.energy < ENERGY_THRESHOLD) continue;   // EXIT main with inside still true (:1229-1231)
 		bool escaped = true;
 		{
-			int step_max, step_dir;
-			if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
-			else { step_max = 0; step_dir = -1; }
+			// trip count and signed step: one copy of the loop body for both directions of flight
+			const bool up = p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0;
+			const int step_dir = up ? 1 : -1;
+			const int n_steps = up ? nL - p.layer : p.layer + 1;
 			const double interactionR = xmb_u01(draw_block(P.seed, g, 2, 1, 0, 0).x);
 			double blbs = 1.0, max_random_layer = 0.0;
 			double lx = p.cx, ly = p.cy, lz = p.cz;
-			for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+			for (int k = 0, i = p.layer; k < n_steps; k++, i += step_dir) {
 				double dist;
-				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { escaped = false; break; }
+				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, up ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { escaped = false; break; }
 				const double temp_prod = -1.0 * dist * P.layers[i].density * mus[i];
 				const double tempexp = exp(temp_prod);
 				max_random_layer = max_random_layer - blbs * expm1(temp_prod);

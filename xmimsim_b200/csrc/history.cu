@@ -103,32 +103,35 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 		if (p.alive && p.energy < ENERGY_THRESHOLD) p.alive = false;
 		if (p.alive) {
 			const uint4 b1 = draw_block(P.seed, g, order + 1, 1, 0, 0);   // .x = path length
-			int step_max = 0, step_dir = 1;
-			if (p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0) { step_max = nL - 1; step_dir = 1; }
-			else { step_max = 0; step_dir = -1; }
+			// loops over the layers in the direction of flight, written with a trip count and a signed step (one loop body
+			// for both directions: the lanes of a warp fly both ways after a fluorescence interaction)
+			const bool up = p.dx * P.n_sample[0] + p.dy * P.n_sample[1] + p.dz * P.n_sample[2] > 0.0;
+			const int step_dir = up ? 1 : -1;
+			const int n_steps = up ? nL - p.layer : p.layer + 1;
 			const double interactionR = xmb_u01(b1.x);
 			double lx = p.cx, ly = p.cy, lz = p.cz;
 			double Pabs = 0.0;
-			for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+			for (int k = 0, i = p.layer; k < n_steps; k++, i += step_dir) {
 				double dist;
-				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, step_dir == 1 ? P.layers[i].Z_end : P.layers[i].Z_begin, dist)) { p.alive = false; break; }
+				const XmbLayerDev &lay = P.layers[i];
+				if (!step_to_plane(P, lx, ly, lz, p.dx, p.dy, p.dz, up ? lay.Z_end : lay.Z_begin, dist)) { p.alive = false; break; }
 				rd[i * T] = dist;
-				Pabs += mus[i * T] * P.layers[i].density * dist;
+				Pabs += mus[i * T] * lay.density * dist;
 			}
 			if (p.alive) {
 				const double Pabs2 = -1.0 * expm1(-1.0 * Pabs);
 				p.weight *= Pabs2;
 				const double l1p = log1p(-1.0 * interactionR * Pabs2);
 				const double negln = -1.0 * l1p;
-				int my_index = p.layer;
+				int my_index = p.layer, my_steps = 1;
 				double my_sum = 0.0;
-				for (int i = p.layer; step_dir > 0 ? i <= step_max : i >= step_max; i += step_dir) {
+				for (int k = 0, i = p.layer; k < n_steps; k++, i += step_dir) {
 					my_sum += mus[i * T] * P.layers[i].density * rd[i * T];
-					if (my_sum > negln) { my_index = i; break; }
+					if (my_sum > negln) { my_index = i; my_steps = k + 1; break; }
 				}
 				const double murho_idx = mus[my_index * T] * P.layers[my_index].density;
 				double temp_sum = 0.0;
-				for (int i = p.layer; step_dir > 0 ? i <= my_index : i >= my_index; i += step_dir)
+				for (int k = 0, i = p.layer; k < my_steps; k++, i += step_dir)
 					temp_sum += (1.0 - (mus[i * T] * P.layers[i].density / murho_idx)) * rd[i * T];
 				temp_sum = temp_sum - 1.0 * l1p / murho_idx;
 				p.cx += temp_sum * p.dx; p.cy += temp_sum * p.dy; p.cz += temp_sum * p.dz;

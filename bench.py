@@ -289,7 +289,10 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": bytes_launch, "per_rank_kernel_ms": per_rank_kernel_ms,
                          "bytes_per_history": bytes_launch / max(1, n_hist_rank),
                          "mean_interactions_per_history": interactions / max(1, n_hist_rank),
-                         "note": "gather+atomic workload: issue/latency-bound, see DESIGN.md; frac is vs the HBM copy peak"},
+                         "note": "gather+atomic workload: issue/latency-bound, see DESIGN.md; frac is vs the HBM copy peak. The algorithmic "
+                                 "bytes of SURVEY.md 8(d) (every active line record and table entry once per interaction) are re-read "
+                                 "per history from L1/L2, and warps sorted by photon energy skip the shells they cannot ionise, so "
+                                 "frac can exceed 1 while DRAM carries 2 % of its peak (traffic)"},
             "solid_angle_grid": {"seconds_wall": sa_wall, "kernel_ms": sa_kernel_ms, "rays": 1024 * 1024 * 5000},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -1,3 +1,5 @@
+"""Engine vs oracle on one shipped example: prints the per-order maximum deviation and the worst channels / lines.
+usage: python tools/debug_parity.py [example] [photons per line] [interactions]  (needs a GPU)"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + "/tests"); sys.path.insert(0, ROOT + "/oracle")

@@ -6,7 +6,8 @@
 #  3. the product library's host code (table generator, device layouts up to the first upload, XML I/O, caches, Ebel,
 #     plugin shims) under AddressSanitizer: the "no CUDA device" guard of xmb_main_msim_raw is removed in a scratch copy so
 #     that build_device_tables runs to its first cudaMalloc; then the whole CPU test suite against that build.
-# Scratch files under /tmp/xmb_sanitize; prints one line per pass.  Result of the round-1 run: all three clean.
+# Scratch files under /tmp/xmb_sanitize; prints one line per pass (a fourth pass, heap perturbation, is described at the
+# end of the file).  Result of the round-1 run: all four clean.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 W=/tmp/xmb_sanitize
@@ -35,3 +36,9 @@ ln -sf libxmimsim_b200.so $W/xmimsim-cl.so
 cd $ROOT
 XMIMSIM_B200_LIB=$W/libxmimsim_b200.so LD_PRELOAD="$ASAN $STDCPP" ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/ -q -m "not gpu" -p no:cacheprovider > $W/tests_asan.log 2>&1 \
   && ! grep -q "ERROR: AddressSanitizer" $W/tests_asan.log && echo "pass 3 (product host code under ASan, CPU suite): $(tail -1 $W/tests_asan.log)" || echo "pass 3: REPORTS in $W/tests_asan.log"
+#  4. glibc heap perturbation (MALLOC_PERTURB_: malloc'ed and freed memory filled with a byte pattern): oracle digests must
+#     not move and the CPU suite must pass -- a read of uninitialised heap memory on the host would change them.
+python $ROOT/tools/oracle_digests.py default > $W/o_plain.json
+MALLOC_PERTURB_=165 python $ROOT/tools/oracle_digests.py default > $W/o_perturb.json
+cmp -s $W/o_plain.json $W/o_perturb.json && MALLOC_PERTURB_=165 python -m pytest tests/ -q -m "not gpu" -p no:cacheprovider > $W/tests_perturb.log 2>&1 \
+  && echo "pass 4 (MALLOC_PERTURB_): digests identical, $(tail -1 $W/tests_perturb.log)" || echo "pass 4: DIFFERENCE, see $W"

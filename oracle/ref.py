@@ -24,6 +24,9 @@ def lib():
         _lib.ref_solid_angle_calculation_cl.restype = C.c_int
         _lib.ref_cubic_spline.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]
         _lib.ref_cubic_spline.restype = C.c_double
+        if hasattr(_lib, "ref_output_raw2struct_rows"):
+            _lib.ref_output_raw2struct_rows.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+            _lib.ref_output_raw2struct_rows.restype = C.c_int
     return _lib
 
 
@@ -44,3 +47,24 @@ def cubic_spline(x, y, v):
     x = np.ascontiguousarray(x, np.float64)
     y = np.ascontiguousarray(y, np.float64)
     return lib().ref_cubic_spline(x.ctypes.data, y.ctypes.data, x.size, float(v))
+
+
+def output_raw2struct_rows(cinput_ptr, brute_history, var_red_history, channels_conv_rows, channels_unconv, use_zero_interactions,
+                           which, cap=20000):
+    """The reference's xmi_output_raw2struct (src/xmi_data_structs.c:1371-1519) on the raw arrays of xmi_main_msim.
+    Returns (rows, unconv_checksum): rows = [(Z, line type, element total, line total, interaction number, counts)] in
+    the order of the reference's history list (which = 0 brute force, 1 variance reduction)."""
+    Z = np.zeros(cap, np.int32); lt = np.zeros((cap, 10), np.uint8); et = np.zeros(cap); ltot = np.zeros(cap)
+    ino = np.zeros(cap, np.int32); cnt = np.zeros(cap); chk = np.zeros(1)
+    br = np.ascontiguousarray(brute_history, np.float64)
+    vr = None if var_red_history is None else np.ascontiguousarray(var_red_history, np.float64)
+    un = np.ascontiguousarray(channels_unconv, np.float64)
+    n = lib().ref_output_raw2struct_rows(C.cast(cinput_ptr, C.c_void_p), br.ctypes.data, None if vr is None else vr.ctypes.data,
+                                         C.cast(channels_conv_rows, C.c_void_p), un.ctypes.data, int(use_zero_interactions), int(which),
+                                         cap, Z.ctypes.data, lt.ctypes.data, et.ctypes.data, ltot.ctypes.data, ino.ctypes.data,
+                                         cnt.ctypes.data, chk.ctypes.data)
+    if n < 0 or n > cap:
+        raise RuntimeError("ref_output_raw2struct_rows: %d rows" % n)
+    rows = [(int(Z[i]), bytes(lt[i]).split(b"\0")[0].decode(), float(et[i]), float(ltot[i]), int(ino[i]), float(cnt[i]))
+            for i in range(n)]
+    return rows, float(chk[0])

@@ -106,3 +106,55 @@ def test_oracle_solid_angle_matches_reference_opencl_kernel(variant):
     full = known & (hits == n_rays)
     if np.any(full):
         assert np.allclose(sa[full], sa_ref[full], rtol=2e-4)
+
+
+def test_xmso_history_mapping_matches_the_reference_function(tmp_path):
+    """The XMSO writer's history lists (xmb_output_write_to_xml_file, host_io.cpp) against the reference's own
+    xmi_output_raw2struct (src/xmi_data_structs.c:1371-1519, compiled from /root/reference into oracle/_ref): same
+    elements, lines and interaction entries in the same order, same counts and totals (the writer prints 6 digits), for
+    both histories; rows the reference drops (zero entries, the Rayleigh / Compton slots 384 / 385, elements that are
+    not in the sample) are dropped.  Line energies are xraylib's and are not compared."""
+    import ctypes as C
+    import xml.etree.ElementTree as ET
+    import xmimsim_b200 as x
+    from xmimsim_b200 import abi
+    from inputs import example
+    if not hasattr(ref.lib(), "ref_output_raw2struct_rows"):
+        pytest.skip("oracle/_ref built without the raw2struct shim")
+    inp = example("srm1155")
+    ci = x.CInput(inp)
+    n_int, nch = inp.n_interactions_trajectory, inp.nchannels
+    rng = np.random.default_rng(11)
+    unconv = np.cumsum(rng.uniform(0, 100, (n_int + 1, nch)), axis=0)
+    conv = unconv * 0.9
+    sample_Z = sorted({z for l in inp.layers for z in l.Z})
+    hist = []
+    for seed in (1, 2):
+        r = np.random.default_rng(seed)
+        h = np.zeros((100, 385, n_int))
+        for z in sample_Z[::2] + [79, 3]:                     # 79 / 3: not in the sample -> never listed
+            for line in r.choice(np.arange(1, 384), size=12, replace=False):
+                k = r.integers(1, n_int + 1)
+                h[z - 1, line - 1, :k] = r.uniform(1e-3, 1e6, k) * (r.uniform(size=k) > 0.3)   # some orders empty
+            h[z - 1, 383, 0] = 5.0; h[z - 1, 384, 1] = 6.0   # Rayleigh / Compton slots: never listed
+        hist.append(h)
+    br, vr = hist
+    rows_p = (abi.c_double_p * (n_int + 1))(*[C.cast(conv.ctypes.data + i * nch * 8, abi.c_double_p) for i in range(n_int + 1)])
+    out = str(tmp_path / "o.xmso")
+    assert abi.lib().xmb_output_write_to_xml_file(C.byref(ci.input), b"in.xmsi", out.encode(), unconv.ctypes.data_as(abi.c_double_p),
+                                                  rows_p, br.ctypes.data_as(abi.c_double_p), vr.ctypes.data_as(abi.c_double_p), 0,
+                                                  None) == 1, abi.last_error()
+    root = ET.parse(out).getroot()
+    for which, tag, arr in ((0, "brute_force_history", br), (1, "variance_reduction_history", vr)):
+        want, _ = ref.output_raw2struct_rows(C.pointer(ci.input), br, vr, rows_p, unconv, 0, which)
+        got = []
+        for el in root.find(tag).findall("fluorescence_line_counts"):
+            for ln in el.findall("fluorescence_line"):
+                for c in ln.findall("counts"):
+                    got.append((int(el.get("atomic_number")), ln.get("type"), float(el.get("total_counts")), float(ln.get("total_counts")),
+                                int(c.get("interaction_number")), float(c.text)))
+        assert len(want) > 40 and len(got) == len(want), (tag, len(got), len(want))
+        assert [(g[0], g[1], g[4]) for g in got] == [(w[0], w[1], w[4]) for w in want], tag
+        assert {w[0] for w in want} <= set(sample_Z)
+        for g, w in zip(got, want):
+            assert abs(g[2] - w[2]) <= 2e-5 * w[2] and abs(g[3] - w[3]) <= 2e-5 * w[3] and abs(g[5] - w[5]) <= 2e-5 * w[5], (tag, g, w)

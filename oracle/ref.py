@@ -27,6 +27,10 @@ def lib():
         if hasattr(_lib, "ref_output_raw2struct_rows"):
             _lib.ref_output_raw2struct_rows.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
             _lib.ref_output_raw2struct_rows.restype = C.c_int
+        for name in ("ref_check_solid_angle_match", "ref_check_escape_ratios_match"):
+            if hasattr(_lib, name):
+                getattr(_lib, name).argtypes = [C.c_void_p, C.c_void_p]
+                getattr(_lib, name).restype = C.c_int
     return _lib
 
 
@@ -68,3 +72,14 @@ def output_raw2struct_rows(cinput_ptr, brute_history, var_red_history, channels_
     rows = [(int(Z[i]), bytes(lt[i]).split(b"\0")[0].decode(), float(et[i]), float(ltot[i]), int(ino[i]), float(cnt[i]))
             for i in range(n)]
     return rows, float(chk[0])
+
+
+def check_solid_angle_match(cached_ptr, fresh_ptr):
+    """The reference's xmi_check_solid_angle_match (src/xmi_solid_angle.c:420-673): 1 when the cached grid of input A serves
+    input B.  Normalises the orientation vectors of both inputs in place -- pass throw-away copies."""
+    return int(lib().ref_check_solid_angle_match(C.cast(cached_ptr, C.c_void_p), C.cast(fresh_ptr, C.c_void_p)))
+
+
+def check_escape_ratios_match(cached_ptr, fresh_ptr):
+    """The reference's xmi_check_escape_ratios_match (src/xmi_detector.c:143-172)."""
+    return int(lib().ref_check_escape_ratios_match(C.cast(cached_ptr, C.c_void_p), C.cast(fresh_ptr, C.c_void_p)))

@@ -24,4 +24,12 @@ typedef struct _GError GError;
 #define g_free(p) free(p)
 #define g_strdup(s) ((s) ? strdup(s) : NULL)
 #define g_ascii_strtod(s, e) strtod((s), (e))
+#ifndef MIN
+#define MIN(a, b) (((a) < (b)) ? (a) : (b))
+#define MAX(a, b) (((a) > (b)) ? (a) : (b))
+#endif
+#ifndef TRUE
+#define TRUE 1
+#define FALSE 0
+#endif
 #endif

@@ -158,3 +158,97 @@ def test_xmso_history_mapping_matches_the_reference_function(tmp_path):
         assert {w[0] for w in want} <= set(sample_Z)
         for g, w in zip(got, want):
             assert abs(g[2] - w[2]) <= 2e-5 * w[2] and abs(g[3] - w[3]) <= 2e-5 * w[3] and abs(g[5] - w[5]) <= 2e-5 * w[5], (tag, g, w)
+
+
+def _variants(base):
+    """(label, input) pairs around `base`: each changes what one clause of the reference's match rules looks at, by an
+    amount on either side of that clause's threshold."""
+    import copy
+    import xmimsim_b200 as x
+    out = [("identical", copy.deepcopy(base))]
+
+    def var(label, **kw):
+        d = copy.deepcopy(base)
+        for k, v in kw.items():
+            setattr(d, k, v)
+        out.append((label, d))
+    for f in (1e-13, 1e-9, 1e-4, 1e-2):
+        var("area_detector x(1+%g)" % f, area_detector=base.area_detector * (1 + f))
+        var("collimator_height +%g" % f, collimator_height=base.collimator_height + f)
+        var("collimator_diameter +%g" % f, collimator_diameter=base.collimator_diameter + f)
+        var("window y +%g" % f, p_detector_window=[base.p_detector_window[0], base.p_detector_window[1] + f, base.p_detector_window[2]])
+        var("window x +%g" % f, p_detector_window=[base.p_detector_window[0] + f, base.p_detector_window[1], base.p_detector_window[2]])
+        var("window z +%g" % f, p_detector_window=[base.p_detector_window[0], base.p_detector_window[1], base.p_detector_window[2] + f])
+        var("source distance +%g with window" % f, d_sample_source=base.d_sample_source + f,
+            p_detector_window=[base.p_detector_window[0], base.p_detector_window[1], base.p_detector_window[2] + f])
+        var("detector normal tilt %g" % f, n_detector_orientation=[base.n_detector_orientation[0] + f, base.n_detector_orientation[1], base.n_detector_orientation[2]])
+        var("sample normal tilt %g" % f, n_sample_orientation=[base.n_sample_orientation[0], base.n_sample_orientation[1] + f, base.n_sample_orientation[2]])
+    var("detector normal scaled", n_detector_orientation=[2.0 * v for v in base.n_detector_orientation])
+    var("sample normal scaled", n_sample_orientation=[3.0 * v for v in base.n_sample_orientation])
+    var("no collimator", collimator_height=0.0, collimator_diameter=0.0)
+    var("photons / live time", n_photons_line=7, live_time=5.0)
+    for e in (5.0, 12.0, 15.9, 16.3, 20.0, 40.0, 60.0):
+        var("one line at %g keV" % e, discrete=[x.DiscreteD(e, 1e9, 1e9)])
+    var("continuum 5..30 keV", continuous=[x.ContinuousD(5.0, 1e6, 1e6), x.ContinuousD(30.0, 1e6, 1e6)])
+    var("continuum 15.9..16.1 keV", continuous=[x.ContinuousD(15.9, 1e6, 1e6), x.ContinuousD(16.1, 1e6, 1e6)])
+    for f in (0.5, 0.999, 1.001, 2.0):
+        d = copy.deepcopy(base); d.layers[-1].thickness *= f; out.append(("last layer thickness x%g" % f, d))
+        d = copy.deepcopy(base); d.layers[-1].density *= f; out.append(("last layer density x%g" % f, d))
+        d = copy.deepcopy(base); d.layers[0].thickness *= f; out.append(("first layer thickness x%g" % f, d))
+    d = copy.deepcopy(base); d.layers = d.layers[:1]; d.reference_layer = 1; out.append(("one layer", d))
+    d = copy.deepcopy(base); d.layers = [d.layers[0], d.layers[1], copy.deepcopy(d.layers[1])]; out.append(("three layers", d))
+    d = copy.deepcopy(base); d.reference_layer = 1; out.append(("reference layer 1", d))
+    return out
+
+
+@pytest.mark.parametrize("name", ["srm1155", "srm1412"])
+def test_solid_angle_cache_match_rule_equals_the_reference_function(name):
+    """xmb_check_solid_angle_match (host_cache.cpp) against the reference's xmi_check_solid_angle_match
+    (src/xmi_solid_angle.c:420-673, compiled from /root/reference into oracle/_ref) on ~80 input pairs, both directions
+    (cached vs fresh is not symmetric: the cached grid must cover the fresh input's depth range)."""
+    import ctypes as C
+    import xmimsim_b200 as x
+    from xmimsim_b200 import abi
+    from inputs import example
+    if not hasattr(ref.lib(), "ref_check_solid_angle_match"):
+        pytest.skip("oracle/_ref built without the match-rule shim")
+    base = example(name)
+    L = abi.lib()
+    seen = {0: 0, 1: 0}
+    for label, other in _variants(base):
+        for cached, fresh in ((base, other), (other, base)):
+            c1, f1 = x.CInput(cached), x.CInput(fresh)
+            ours = L.xmb_check_solid_angle_match(C.byref(c1.input), C.byref(f1.input), None)
+            a, b = x.CInput(cached), x.CInput(fresh)          # throw-away copies: the reference normalises them in place
+            want = ref.check_solid_angle_match(C.pointer(a.input), C.pointer(b.input))
+            assert ours == want, (label, "cached=base" if cached is base else "cached=variant", ours, want)
+            seen[want] += 1
+    assert seen[0] > 20 and seen[1] > 20, seen
+
+
+def test_escape_ratio_cache_match_rule_equals_the_reference_function():
+    """xmb_check_escape_ratios_match against xmi_check_escape_ratios_match (src/xmi_detector.c:143-172)."""
+    import copy
+    import ctypes as C
+    import xmimsim_b200 as x
+    from xmimsim_b200 import abi
+    from inputs import example
+    if not hasattr(ref.lib(), "ref_check_escape_ratios_match"):
+        pytest.skip("oracle/_ref built without the match-rule shim")
+    base = example("srm1155")
+    variants = [copy.deepcopy(base)]
+    for f in (1 + 1e-13, 1 + 1e-9, 1.01):
+        d = copy.deepcopy(base); d.crystal_layers[0].thickness *= f; variants.append(d)
+        d = copy.deepcopy(base); d.crystal_layers[0].density *= f; variants.append(d)
+    d = copy.deepcopy(base); d.crystal_layers = [x.LayerD([31, 33], [0.48, 0.52], 5.3, 0.05)]; variants.append(d)
+    d = copy.deepcopy(base); d.crystal_layers = d.crystal_layers + [x.LayerD([14], [1.0], 2.33, 0.01)]; variants.append(d)
+    d = copy.deepcopy(base); d.area_detector *= 2; d.live_time = 9.0; variants.append(d)          # not looked at
+    seen = {0: 0, 1: 0}
+    for other in variants:
+        for cached, fresh in ((base, other), (other, base)):
+            c1, f1, c2, f2 = x.CInput(cached), x.CInput(fresh), x.CInput(cached), x.CInput(fresh)
+            ours = abi.lib().xmb_check_escape_ratios_match(C.byref(c1.input), C.byref(f1.input))
+            want = ref.check_escape_ratios_match(C.pointer(c2.input), C.pointer(f2.input))
+            assert ours == want, (ours, want)
+            seen[want] += 1
+    assert seen[0] >= 6 and seen[1] >= 6, seen

@@ -478,6 +478,12 @@ void xmb_detector_convolute_history(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, do
  * <xmimsim-input>).  *input is malloc'ed: xmb_input_free.  Returns 1 / 0. */
 int xmb_input_read_from_xml_file(const char *xmsifile, xmb_input **input);
 void xmb_input_free(xmb_input **input);
+/* Replaces xmi_input_validate (include/xmi_data_structs.h:508-515; src/xmi_data_structs.c:899-1255): 0 for a usable
+ * input, else the OR of the flags of the sections that are not (the reference's XmiInputFlags values).  The readers
+ * above and below reject an input with a non-zero result, as xmi_input_read_from_xml_file does (src/xmi_xml.c:1337). */
+enum { XMB_INPUT_GENERAL = 1, XMB_INPUT_COMPOSITION = 2, XMB_INPUT_GEOMETRY = 4, XMB_INPUT_EXCITATION = 8,
+       XMB_INPUT_ABSORBERS = 16, XMB_INPUT_DETECTOR = 32 };
+int xmb_input_validate(const xmb_input *input);
 /* Replaces xmi_input_write_to_xml_file (src/xmi_xml.c:1405-1450). */
 int xmb_input_write_to_xml_file(const xmb_input *input, const char *xmsifile);
 /* Replaces xmi_output_new + xmi_output_write_to_xml_file (src/xmi_data_structs.c:1369-1519;

@@ -17,6 +17,9 @@ $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$REF/include" -c "$REF/src/xmi_sp
 # src/xmi_data_structs.c, located by their first and last line so that a shifted file still extracts the same function
 awk '/^#define ARRAY2D_FORTRAN/ {on = 1} on {print} on && /^#endif/ {exit}' "$REF/src/xmi_data_structs.c" > "$OUT/raw2struct.inc"
 grep -q "xmi_output_raw2struct" "$OUT/raw2struct.inc"
+# xmi_input_validate (src/xmi_data_structs.c:899-1255): what the reference's XMSI reader rejects
+awk '/^XmiInputFlags xmi_input_validate/ {on = 1} on {print} on && /^}/ {exit}' "$REF/src/xmi_data_structs.c" > "$OUT/input_validate.inc"
+grep -q "after_detector" "$OUT/input_validate.inc"
 { echo '#define XMI_LINES_NO_CONFIG'; sed -e 's/#include "config.h"//' "$REF/src/xmi_lines.c"; } > "$OUT/xmi_lines_noconfig.c"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$REF/include" -I"$REF/src" -c "$OUT/xmi_lines_noconfig.c" -o "$OUT/xmi_lines.o"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$REF/src" -c "$HERE/ref_raw2struct.c" -o "$OUT/ref_raw2struct.o"

@@ -27,6 +27,9 @@ def lib():
         if hasattr(_lib, "ref_output_raw2struct_rows"):
             _lib.ref_output_raw2struct_rows.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
             _lib.ref_output_raw2struct_rows.restype = C.c_int
+        if hasattr(_lib, "ref_input_validate"):
+            _lib.ref_input_validate.argtypes = [C.c_void_p]
+            _lib.ref_input_validate.restype = C.c_int
         for name in ("ref_check_solid_angle_match", "ref_check_escape_ratios_match"):
             if hasattr(_lib, name):
                 getattr(_lib, name).argtypes = [C.c_void_p, C.c_void_p]
@@ -83,3 +86,8 @@ def check_solid_angle_match(cached_ptr, fresh_ptr):
 def check_escape_ratios_match(cached_ptr, fresh_ptr):
     """The reference's xmi_check_escape_ratios_match (src/xmi_detector.c:143-172)."""
     return int(lib().ref_check_escape_ratios_match(C.cast(cached_ptr, C.c_void_p), C.cast(fresh_ptr, C.c_void_p)))
+
+
+def input_validate(cinput_ptr):
+    """The reference's xmi_input_validate (src/xmi_data_structs.c:899-1255): OR of XmiInputFlags, 0 = valid."""
+    return int(lib().ref_input_validate(C.cast(cinput_ptr, C.c_void_p)))

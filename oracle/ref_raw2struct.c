@@ -49,3 +49,9 @@ int ref_output_raw2struct_rows(void *input, double *brute_history, double *var_r
 	}
 	return n;
 }
+
+/* xmi_input_validate (src/xmi_data_structs.c:899-1255), cut out by oracle/build_ref.sh like the function above */
+#include <string.h>
+#define g_return_val_if_fail(expr, val) do { if (!(expr)) return (val); } while (0)
+#include "input_validate.inc"
+int ref_input_validate(void *input) { return (int)xmi_input_validate((xmi_input *)input); }

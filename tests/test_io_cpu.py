@@ -65,6 +65,12 @@ def test_reader_errors_are_reported(tmp_path):
     assert L.xmb_input_read_from_xml_file(str(bad).encode(), C.byref(p)) == 0 and "missing element" in abi.last_error()
     bad.write_text("<other/>")
     assert L.xmb_input_read_from_xml_file(str(bad).encode(), C.byref(p)) == 0 and "root element" in abi.last_error()
+    # well-formed but unusable: rejected as by the reference reader's xmi_input_validate call (src/xmi_xml.c:1337-1343)
+    inp = example("srm1155"); inp.n_photons_line = 0; inp.gain = 0.0
+    ci = x.CInput(inp)
+    assert L.xmb_input_validate(C.byref(ci.input)) == 1 | 32
+    assert L.xmb_input_write_to_xml_file(C.byref(ci.input), str(bad).encode()) == 1
+    assert L.xmb_input_read_from_xml_file(str(bad).encode(), C.byref(p)) == 0 and "error validating input data" in abi.last_error()
 
 
 def test_xmsi_round_trip_with_broadened_lines_and_absorbers(tmp_path):

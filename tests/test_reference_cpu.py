@@ -252,3 +252,85 @@ def test_escape_ratio_cache_match_rule_equals_the_reference_function():
             assert ours == want, (ours, want)
             seen[want] += 1
     assert seen[0] >= 6 and seen[1] >= 6, seen
+
+
+def _invalid_variants(base):
+    """(label, mutate) pairs: each breaks (or leaves intact) one clause of the reference's xmi_input_validate."""
+    import xmimsim_b200 as x
+    out = [("valid", lambda d: None)]
+
+    def a(label, fn):
+        out.append((label, fn))
+    a("n_photons_line 0", lambda d: setattr(d, "n_photons_line", 0))
+    a("n_photons_interval -1", lambda d: setattr(d, "n_photons_interval", -1))
+    a("n_interactions 0", lambda d: setattr(d, "n_interactions_trajectory", 0))
+    a("empty outputfile", lambda d: setattr(d, "outputfile", ""))
+    a("reference layer 0", lambda d: setattr(d, "reference_layer", 0))
+    a("reference layer beyond", lambda d: setattr(d, "reference_layer", len(d.layers) + 1))
+    a("Z 95", lambda d: d.layers[0].Z.__setitem__(0, 95))
+    a("Z 0", lambda d: d.layers[-1].Z.__setitem__(0, 0))
+    a("weight > 1", lambda d: d.layers[0].weight.__setitem__(0, 1.5))
+    a("weight < 0", lambda d: d.layers[0].weight.__setitem__(0, -0.1))
+    a("density 0", lambda d: setattr(d.layers[0], "density", 0.0))
+    a("thickness -1", lambda d: setattr(d.layers[-1], "thickness", -1.0))
+    a("sample normal z 0", lambda d: d.n_sample_orientation.__setitem__(2, 0.0))
+    a("sample normal z < 0", lambda d: d.n_sample_orientation.__setitem__(2, -0.5))
+    for f in ("d_sample_source", "area_detector", "d_source_slit", "slit_size_x", "slit_size_y"):
+        a(f + " 0", lambda d, f=f: setattr(d, f, 0.0))
+    a("collimator_height < 0", lambda d: setattr(d, "collimator_height", -1.0))
+    a("collimator_height 0", lambda d: setattr(d, "collimator_height", 0.0))
+    a("collimator_diameter < 0", lambda d: setattr(d, "collimator_diameter", -1.0))
+    a("no source", lambda d: setattr(d, "discrete", []))
+    a("one continuous point", lambda d: setattr(d, "continuous", [x.ContinuousD(5.0, 1.0, 1.0)]))
+    a("continuum only", lambda d: (setattr(d, "discrete", []), setattr(d, "continuous", [x.ContinuousD(5.0, 1.0, 1.0), x.ContinuousD(9.0, 1.0, 1.0)])))
+    a("two dark points", lambda d: setattr(d, "continuous", [x.ContinuousD(5.0, 0.0, 0.0), x.ContinuousD(9.0, 0.0, 0.0)]))
+    a("dark start", lambda d: setattr(d, "continuous", [x.ContinuousD(e, i, i) for e, i in ((5, 0), (6, 0), (7, 1), (8, 1))]))
+    a("dark end", lambda d: setattr(d, "continuous", [x.ContinuousD(e, i, i) for e, i in ((5, 1), (6, 1), (7, 0), (8, 0))]))
+    a("dark middle", lambda d: setattr(d, "continuous", [x.ContinuousD(e, i, i) for e, i in ((5, 1), (6, 0), (7, 0), (8, 0), (9, 1))]))
+    a("single dark points", lambda d: setattr(d, "continuous", [x.ContinuousD(e, i, i) for e, i in ((5, 1), (6, 0), (7, 1), (8, 0), (9, 1))]))
+    a("three points dark pair", lambda d: setattr(d, "continuous", [x.ContinuousD(e, i, i) for e, i in ((5, 0), (6, 0), (7, 1))]))
+    a("continuous energy < 0", lambda d: setattr(d, "continuous", [x.ContinuousD(-1.0, 1.0, 1.0), x.ContinuousD(9.0, 1.0, 1.0)]))
+    a("continuous intensity < 0", lambda d: setattr(d, "continuous", [x.ContinuousD(5.0, -1.0, 2.0), x.ContinuousD(9.0, 1.0, 1.0)]))
+    a("line energy 0", lambda d: setattr(d.discrete[0], "energy", 0.0))
+    a("line intensity < 0", lambda d: setattr(d.discrete[0], "horizontal_intensity", -1.0))
+    a("line dark", lambda d: (setattr(d.discrete[0], "horizontal_intensity", 0.0), setattr(d.discrete[0], "vertical_intensity", 0.0)))
+    a("line sigma_x < 0", lambda d: setattr(d.discrete[0], "sigma_x", -1.0))
+    a("line sigma_y < 0", lambda d: setattr(d.discrete[0], "sigma_y", -1.0))
+    a("line distribution 3", lambda d: setattr(d.discrete[0], "distribution_type", 3))
+    a("gaussian line without width", lambda d: (setattr(d.discrete[0], "distribution_type", 1), setattr(d.discrete[0], "scale_parameter", 0.0)))
+    a("gaussian line", lambda d: (setattr(d.discrete[0], "distribution_type", 1), setattr(d.discrete[0], "scale_parameter", 0.1)))
+    a("detector absorber density 0", lambda d: setattr(d.det_layers[0], "density", 0.0))
+    a("excitation absorber Z 0", lambda d: setattr(d, "exc_layers", [x.LayerD([0], [1.0], 2.7, 0.01)]))
+    a("excitation absorber weight 2", lambda d: setattr(d, "exc_layers", [x.LayerD([13], [2.0], 2.7, 0.01)]))
+    for f in ("live_time", "pulse_width", "gain", "fano", "noise"):
+        a(f + " 0", lambda d, f=f: setattr(d, f, 0.0))
+    a("nchannels 9", lambda d: setattr(d, "nchannels", 9))
+    a("nchannels 10", lambda d: setattr(d, "nchannels", 10))
+    a("no crystal", lambda d: setattr(d, "crystal_layers", []))
+    a("crystal thickness 0", lambda d: setattr(d.crystal_layers[0], "thickness", 0.0))
+    a("two sections", lambda d: (setattr(d, "gain", 0.0), setattr(d, "n_photons_line", 0), d.layers[0].Z.__setitem__(0, 99)))
+    return out
+
+
+@pytest.mark.parametrize("name", ["srm1155", "srm1412"])
+def test_input_validation_equals_the_reference_function(name):
+    """xmb_input_validate (host_io.cpp) against the reference's xmi_input_validate (src/xmi_data_structs.c:899-1255,
+    compiled from /root/reference into oracle/_ref): the same XmiInputFlags for ~60 inputs, each broken in one clause."""
+    import copy
+    import ctypes as C
+    import xmimsim_b200 as x
+    from xmimsim_b200 import abi
+    from inputs import example
+    if not hasattr(ref.lib(), "ref_input_validate"):
+        pytest.skip("oracle/_ref built without the validate shim")
+    base = example(name)
+    flags_seen = set()
+    for label, mutate in _invalid_variants(base):
+        d = copy.deepcopy(base)
+        mutate(d)
+        ci = x.CInput(d)
+        ours = abi.lib().xmb_input_validate(C.byref(ci.input))
+        want = ref.input_validate(C.pointer(ci.input))
+        assert ours == want, (label, ours, want)
+        flags_seen.add(want)
+    assert {0, 1, 2, 4, 8, 16, 32} <= flags_seen and any(f not in (0, 1, 2, 4, 8, 16, 32) for f in flags_seen), flags_seen

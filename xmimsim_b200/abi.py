@@ -220,6 +220,7 @@ def lib():
     L.xmb_detector_convolute_history.restype = None
     L.xmb_detector_last_ms.restype = C.c_double
     L.xmb_input_read_from_xml_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(Input))]; L.xmb_input_read_from_xml_file.restype = C.c_int
+    L.xmb_input_validate.argtypes = [C.POINTER(Input)]; L.xmb_input_validate.restype = C.c_int
     L.xmb_input_free.argtypes = [C.POINTER(C.POINTER(Input))]; L.xmb_input_free.restype = None
     L.xmb_input_write_to_xml_file.argtypes = [C.POINTER(Input), C.c_char_p]; L.xmb_input_write_to_xml_file.restype = C.c_int
     L.xmb_output_write_to_xml_file.argtypes = [C.POINTER(Input), C.c_char_p, C.c_char_p, c_double_p, pp, c_double_p, c_double_p,

@@ -381,6 +381,80 @@ void write_history(Out &o, const char *tag, const double *hist, const xmb_input 
 
 }  // namespace
 
+// Replaces xmi_input_validate (src/xmi_data_structs.c:899-1255): 0 for a usable input, else the OR of the reference's
+// XmiInputFlags (include/xmi_data_structs.h:508-515) of the sections that are not.  One predicate per section.
+namespace {
+bool layers_invalid(const xmb_layer *l, int n) {
+	for (int i = 0; i < n; i++) {
+		double sum = 0.0;
+		for (int j = 0; j < l[i].n_elements; j++) {
+			if (l[i].Z[j] < 1 || l[i].Z[j] > 94) return true;
+			if (l[i].weight[j] < 0.0 || l[i].weight[j] > 1.0) return true;
+			sum += l[i].weight[j];
+		}
+		if (sum <= 0.0 || l[i].density <= 0.0 || l[i].thickness <= 0.0) return true;
+	}
+	return false;
+}
+bool general_invalid(const xmb_general *g) {
+	return !g || g->n_photons_interval <= 0 || g->n_photons_line <= 0 || g->n_interactions_trajectory <= 0 || !g->outputfile ||
+	       g->outputfile[0] == 0;
+}
+bool composition_invalid(const xmb_composition *c) {
+	if (!c || c->n_layers < 1 || c->reference_layer < 1 || c->reference_layer > c->n_layers) return true;
+	return layers_invalid(c->layers, c->n_layers);
+}
+bool geometry_invalid(const xmb_geometry *g) {
+	return !g || g->n_sample_orientation[2] <= 0.0 || g->d_sample_source <= 0.0 || g->area_detector <= 0.0 || g->collimator_height < 0.0 ||
+	       g->collimator_diameter < 0.0 || g->d_source_slit <= 0.0 || g->slit_size_x <= 0.0 || g->slit_size_y <= 0.0;
+}
+bool excitation_invalid(const xmb_excitation *e) {
+	if (!e) return true;
+	if ((e->n_discrete == 0 && e->n_continuous < 2) || e->n_continuous == 1) return true;
+	for (int i = 0; i < e->n_discrete; i++) {
+		const xmb_energy_discrete &d = e->discrete[i];
+		if (d.energy <= 0.0 || d.horizontal_intensity < 0.0 || d.vertical_intensity < 0.0 || d.vertical_intensity + d.horizontal_intensity <= 0.0 ||
+		    d.sigma_x < 0.0 || d.sigma_y < 0.0 || d.distribution_type < 0 || d.distribution_type > 2 ||
+		    (d.distribution_type != 0 && d.scale_parameter <= 0.0))
+			return true;
+	}
+	auto lit = [&](int i) { return e->continuous[i].horizontal_intensity + e->continuous[i].vertical_intensity > 0.0 ? 1 : 0; };
+	for (int i = 0; i < e->n_continuous; i++) {
+		const xmb_energy_continuous &c = e->continuous[i];
+		if (c.energy < 0.0 || c.horizontal_intensity < 0.0 || c.vertical_intensity < 0.0 || c.vertical_intensity + c.horizontal_intensity < 0.0 ||
+		    c.sigma_x < 0.0 || c.sigma_y < 0.0)
+			return true;
+	}
+	// a continuum needs intensity somewhere near every interior point: no dark point between dark neighbours, no dark
+	// pair at either end (two points: not both dark)
+	const int n = e->n_continuous;
+	if (n == 2 && e->continuous[0].horizontal_intensity + e->continuous[0].vertical_intensity + e->continuous[1].horizontal_intensity +
+	                      e->continuous[1].vertical_intensity == 0.0)
+		return true;
+	for (int i = 1; n > 2 && i < n - 1; i++) {
+		const int before = lit(i - 1), here = lit(i), after = lit(i + 1);
+		if ((i == 1 && before + here == 0) || (i == n - 2 && here + after == 0) || before + here + after == 0) return true;
+	}
+	return false;
+}
+bool absorbers_invalid(const xmb_absorbers *a) {
+	return !a || layers_invalid(a->exc_layers, a->n_exc_layers) || layers_invalid(a->det_layers, a->n_det_layers);
+}
+bool detector_invalid(const xmb_detector *d) {
+	if (!d || d->live_time <= 0.0 || d->pulse_width <= 0.0 || d->gain <= 0.0 || d->fano <= 0.0 || d->noise <= 0.0 ||
+	    d->n_crystal_layers < 1 || d->nchannels < 10)
+		return true;
+	return layers_invalid(d->crystal_layers, d->n_crystal_layers);
+}
+}  // namespace
+
+extern "C" int xmb_input_validate(const xmb_input *in) {
+	if (!in) return 63;
+	return (general_invalid(in->general) ? XMB_INPUT_GENERAL : 0) | (composition_invalid(in->composition) ? XMB_INPUT_COMPOSITION : 0) |
+	       (geometry_invalid(in->geometry) ? XMB_INPUT_GEOMETRY : 0) | (excitation_invalid(in->excitation) ? XMB_INPUT_EXCITATION : 0) |
+	       (absorbers_invalid(in->absorbers) ? XMB_INPUT_ABSORBERS : 0) | (detector_invalid(in->detector) ? XMB_INPUT_DETECTOR : 0);
+}
+
 static int input_from_string(const std::string &src, const char *what, xmb_input **input) {
 	Parser p(src);
 	p.skip_misc();
@@ -393,6 +467,12 @@ static int input_from_string(const std::string &src, const char *what, xmb_input
 	xmb_input *in = (xmb_input *)calloc(1, sizeof(xmb_input));
 	try { input_from_node(body, in); }
 	catch (const ReadError &e) { xmb_set_error("%s: %s", what, e.msg.c_str()); xmb_input_free(&in); return 0; }
+	// the reference's reader rejects what xmi_input_validate rejects (src/xmi_xml.c:1337-1343)
+	if (const int flags = xmb_input_validate(in)) {
+		xmb_set_error("%s: error validating input data (sections 0x%x)", what, flags);
+		xmb_input_free(&in);
+		return 0;
+	}
 	*input = in;
 	return 1;
 }

@@ -31,7 +31,9 @@ awk '/^int xmi_check_escape_ratios_match/ {on = 1} on {print} on && /^}/ {exit}'
 grep -q "XMI_IF_COMPARE_GEOMETRY2" "$OUT/solid_angle_match.inc" && grep -q "crystal_layers" "$OUT/escape_ratios_match.inc"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_match.c" -o "$OUT/ref_match.o"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/../include" -I"$HERE/../xmimsim_b200/csrc" -c "$HERE/../xmimsim_b200/csrc/xrl_surrogate.c" -o "$OUT/xrl_surrogate.o"
+# struct layouts of include/xmimsim_b200.h against the reference's headers: _Static_asserts, a mismatch fails this build
+$CC -O2 -fPIC -std=gnu11 -I"$HERE/ref_shim" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_layout.c" -o "$OUT/ref_layout.o"
 $CXX -O2 -fPIC -fopenmp -std=c++14 -Wno-narrowing -I"$HERE/ref_shim" -I"$OUT" -I"$REF/src/Random123" -I"$REF/include" \
-     -shared -o "$OUT/libxmi_ref.so" "$HERE/ref_driver.cpp" "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" -lm
-rm -f "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" "$OUT/xmi_lines_noconfig.c"
+     -shared -o "$OUT/libxmi_ref.so" "$HERE/ref_driver.cpp" "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" "$OUT/ref_layout.o" -lm
+rm -f "$OUT/ref_layout.o" "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" "$OUT/xmi_lines_noconfig.c"
 echo "built $OUT/libxmi_ref.so"

@@ -91,3 +91,11 @@ def check_escape_ratios_match(cached_ptr, fresh_ptr):
 def input_validate(cinput_ptr):
     """The reference's xmi_input_validate (src/xmi_data_structs.c:899-1255): OR of XmiInputFlags, 0 = valid."""
     return int(lib().ref_input_validate(C.cast(cinput_ptr, C.c_void_p)))
+
+
+def layout_checks():
+    """Number of compile-time field checks (offset + size, include/xmimsim_b200.h vs the reference's headers) that
+    oracle/ref_layout.c held when oracle/_ref was built; the build fails on a mismatch."""
+    f = lib().ref_layout_checks
+    f.restype = C.c_int
+    return int(f())

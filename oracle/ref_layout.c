@@ -77,6 +77,11 @@ SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, Z); SAME_FIELD(xmb_escape_ratio
 SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, fluo_escape_input_energies); SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, compton_escape_ratios);
 SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, compton_escape_input_energies);
 SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, compton_escape_output_energies); SAME_FIELD(xmb_escape_ratios, xmi_escape_ratios, xmi_input_string);
+SAME_STRUCT(xmb_escape_ratios_options, xmi_escape_ratios_options);
+SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, n_input_energies); SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, n_compton_output_energies);
+SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, n_photons); SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, input_energy_min);
+SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, input_energy_delta); SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, compton_output_energy_min);
+SAME_FIELD(xmb_escape_ratios_options, xmi_escape_ratios_options, compton_output_energy_delta);
 /* the flag values of xmb_input_validate and the enumerations stored in int fields */
 _Static_assert(XMB_INPUT_GENERAL == XMI_INPUT_GENERAL && XMB_INPUT_COMPOSITION == XMI_INPUT_COMPOSITION && XMB_INPUT_GEOMETRY == XMI_INPUT_GEOMETRY &&
                XMB_INPUT_EXCITATION == XMI_INPUT_EXCITATION && XMB_INPUT_ABSORBERS == XMI_INPUT_ABSORBERS && XMB_INPUT_DETECTOR == XMI_INPUT_DETECTOR, "XmiInputFlags");

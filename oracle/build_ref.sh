@@ -28,6 +28,9 @@ $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$REF/sr
 # surrogate provider object (third-party stand-in), as in the oracle
 awk '/^int xmi_check_solid_angle_match/ {on = 1} on {print} on && /^}/ {exit}' "$REF/src/xmi_solid_angle.c" > "$OUT/solid_angle_match.inc"
 awk '/^int xmi_check_escape_ratios_match/ {on = 1} on {print} on && /^}/ {exit}' "$REF/src/xmi_detector.c" > "$OUT/escape_ratios_match.inc"
+awk '/^xmi_escape_ratios_options xmi_get_default_escape_ratios_options/ {on = 1} on {print} on && /^}/ {exit}' "$REF/src/xmi_detector.c" > "$OUT/default_escape_options.inc"
+awk '/^static const xmi_main_options __default_main_options/ {on = 1} on {print} on && /^};/ {exit}' "$REF/src/xmi_data_structs.c" > "$OUT/default_main_options.inc"
+grep -q "use_variance_reduction" "$OUT/default_main_options.inc" && grep -q "1990" "$OUT/default_escape_options.inc"
 grep -q "XMI_IF_COMPARE_GEOMETRY2" "$OUT/solid_angle_match.inc" && grep -q "crystal_layers" "$OUT/escape_ratios_match.inc"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_match.c" -o "$OUT/ref_match.o"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/../include" -I"$HERE/../xmimsim_b200/csrc" -c "$HERE/../xmimsim_b200/csrc/xrl_surrogate.c" -o "$OUT/xrl_surrogate.o"

@@ -23,3 +23,11 @@ static double CS_Total_Kissel(int Z, double E, void *error) { (void)error; retur
 /* both functions normalise the orientation vectors of their arguments in place: pass copies */
 int ref_check_solid_angle_match(void *A, void *B) { return xmi_check_solid_angle_match((xmi_input *)A, (xmi_input *)B); }
 int ref_check_escape_ratios_match(void *A, void *B) { return xmi_check_escape_ratios_match((xmi_input *)A, (xmi_input *)B); }
+
+/* the reference's defaults: xmi_get_default_escape_ratios_options (src/xmi_detector.c:643-646) and the initialiser of
+ * __default_main_options (src/xmi_data_structs.c:2531-2547), both cut out by oracle/build_ref.sh */
+#include "xmi_detector.h"
+#include "default_escape_options.inc"
+#include "default_main_options.inc"
+void ref_default_escape_ratios_options(void *out) { *(xmi_escape_ratios_options *)out = xmi_get_default_escape_ratios_options(); }
+void ref_default_main_options(void *out) { *(xmi_main_options *)out = __default_main_options; }

@@ -352,3 +352,27 @@ def test_abi_struct_layouts_equal_the_reference_headers():
     mirror = (abi.General, abi.Layer, abi.Composition, abi.Geometry, abi.EnergyDiscrete, abi.EnergyContinuous, abi.Excitation,
               abi.Absorbers, abi.Detector, abi.Input, abi.MainOptions, abi.SolidAngle, abi.EscapeRatios)
     assert [C.sizeof(m) for m in mirror] == list(sizes)
+
+
+def test_default_options_equal_the_reference_defaults():
+    """xmb_main_options_defaults and xmb_get_default_escape_ratios_options against the reference's own initialisers
+    (src/xmi_data_structs.c:2531-2547 -- omp_num_threads is set to the host's thread count afterwards, :2561 --,
+    src/xmi_detector.c:643-646), compiled into oracle/_ref."""
+    import ctypes as C
+    import xmimsim_b200 as x
+    from xmimsim_b200 import abi
+    if not hasattr(ref.lib(), "ref_default_main_options"):
+        pytest.skip("oracle/_ref built without the defaults")
+    want = abi.MainOptions()
+    ref.lib().ref_default_main_options(C.byref(want))
+    ours = x.main_options()
+    for f, _ in abi.MainOptions._fields_:
+        if f == "omp_num_threads":
+            assert getattr(ours, f) >= 1
+        else:
+            assert getattr(ours, f) == getattr(want, f), f
+    want_e = abi.EscapeRatiosOptions()
+    ref.lib().ref_default_escape_ratios_options(C.byref(want_e))
+    ours_e = abi.lib().xmb_get_default_escape_ratios_options()
+    assert [getattr(ours_e, f) for f, _ in abi.EscapeRatiosOptions._fields_] == [getattr(want_e, f) for f, _ in abi.EscapeRatiosOptions._fields_]
+    assert want_e.n_input_energies == 1990 and want_e.n_photons == 500000

@@ -22,7 +22,7 @@ awk '/^XmiInputFlags xmi_input_validate/ {on = 1} on {print} on && /^}/ {exit}' 
 grep -q "after_detector" "$OUT/input_validate.inc"
 { echo '#define XMI_LINES_NO_CONFIG'; sed -e 's/#include "config.h"//' "$REF/src/xmi_lines.c"; } > "$OUT/xmi_lines_noconfig.c"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$REF/include" -I"$REF/src" -c "$OUT/xmi_lines_noconfig.c" -o "$OUT/xmi_lines.o"
-$CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$REF/src" -c "$HERE/ref_raw2struct.c" -o "$OUT/ref_raw2struct.o"
+$CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$REF/src" -c "$HERE/ref_shim/ref_raw2struct.c" -o "$OUT/ref_raw2struct.o"
 # the cache match rules: xmi_check_solid_angle_match (src/xmi_solid_angle.c:420-673) and xmi_check_escape_ratios_match
 # (src/xmi_detector.c:143-172), each from its first line to the closing brace in column 0; CS_Total_Kissel comes from the
 # surrogate provider object (third-party stand-in), as in the oracle
@@ -32,10 +32,10 @@ awk '/^xmi_escape_ratios_options xmi_get_default_escape_ratios_options/ {on = 1}
 awk '/^static const xmi_main_options __default_main_options/ {on = 1} on {print} on && /^};/ {exit}' "$REF/src/xmi_data_structs.c" > "$OUT/default_main_options.inc"
 grep -q "use_variance_reduction" "$OUT/default_main_options.inc" && grep -q "1990" "$OUT/default_escape_options.inc"
 grep -q "XMI_IF_COMPARE_GEOMETRY2" "$OUT/solid_angle_match.inc" && grep -q "crystal_layers" "$OUT/escape_ratios_match.inc"
-$CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_match.c" -o "$OUT/ref_match.o"
+$CC -O2 -fPIC -std=gnu99 -I"$HERE/ref_shim" -I"$OUT" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_shim/ref_match.c" -o "$OUT/ref_match.o"
 $CC -O2 -fPIC -std=gnu99 -I"$HERE/../include" -I"$HERE/../xmimsim_b200/csrc" -c "$HERE/../xmimsim_b200/csrc/xrl_surrogate.c" -o "$OUT/xrl_surrogate.o"
 # struct layouts of include/xmimsim_b200.h against the reference's headers: _Static_asserts, a mismatch fails this build
-$CC -O2 -fPIC -std=gnu11 -I"$HERE/ref_shim" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_layout.c" -o "$OUT/ref_layout.o"
+$CC -O2 -fPIC -std=gnu11 -I"$HERE/ref_shim" -I"$REF/include" -I"$HERE/../include" -c "$HERE/ref_shim/ref_layout.c" -o "$OUT/ref_layout.o"
 $CXX -O2 -fPIC -fopenmp -std=c++14 -Wno-narrowing -I"$HERE/ref_shim" -I"$OUT" -I"$REF/src/Random123" -I"$REF/include" \
      -shared -o "$OUT/libxmi_ref.so" "$HERE/ref_driver.cpp" "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" "$OUT/ref_layout.o" -lm
 rm -f "$OUT/ref_layout.o" "$OUT/xmi_spline.o" "$OUT/xmi_lines.o" "$OUT/ref_raw2struct.o" "$OUT/ref_match.o" "$OUT/xrl_surrogate.o" "$OUT/xmi_lines_noconfig.c"

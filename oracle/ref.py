@@ -95,7 +95,7 @@ def input_validate(cinput_ptr):
 
 def layout_checks():
     """Number of compile-time field checks (offset + size, include/xmimsim_b200.h vs the reference's headers) that
-    oracle/ref_layout.c held when oracle/_ref was built; the build fails on a mismatch."""
+    oracle/ref_shim/ref_layout.c held when oracle/_ref was built; the build fails on a mismatch."""
     f = lib().ref_layout_checks
     f.restype = C.c_int
     return int(f())

@@ -1,4 +1,4 @@
-/* oracle/ref_layout.c -- TEST INFRASTRUCTURE: include/xmimsim_b200.h against the reference's own headers
+/* oracle/ref_shim/ref_layout.c -- TEST INFRASTRUCTURE: include/xmimsim_b200.h against the reference's own headers
  * (include/xmi_data_structs.h, xmi_solid_angle.h, xmi_detector.h, compiled from /root/reference through the GLib
  * stand-in): every struct that crosses the C ABI has the reference's size and every field the reference's offset and
  * size.  The checks are _Static_asserts: a mismatch fails oracle/build_ref.sh.  ref_layout_checks() returns how many

@@ -1,4 +1,4 @@
-/* oracle/ref_match.c -- TEST INFRASTRUCTURE: runs the reference's own cache match rules, xmi_check_solid_angle_match
+/* oracle/ref_shim/ref_match.c -- TEST INFRASTRUCTURE: runs the reference's own cache match rules, xmi_check_solid_angle_match
  * (src/xmi_solid_angle.c:420-673) and xmi_check_escape_ratios_match (src/xmi_detector.c:143-172), cut out of their files
  * by oracle/build_ref.sh into oracle/_ref/ at build time (the rest of both files is HDF5 I/O), so that host_cache.cpp's
  * xmb_check_solid_angle_match / xmb_check_escape_ratios_match can be pinned against them.  Supplied here:

@@ -1,4 +1,4 @@
-/* oracle/ref_raw2struct.c -- TEST INFRASTRUCTURE: runs the reference's own xmi_output_raw2struct
+/* oracle/ref_shim/ref_raw2struct.c -- TEST INFRASTRUCTURE: runs the reference's own xmi_output_raw2struct
  * (src/xmi_data_structs.c:1368-1519, extracted by oracle/build_ref.sh into oracle/_ref/raw2struct.inc at build time; the
  * text is never committed) so that the XMSO writer's history mapping (xmb_output_write_to_xml_file, host_io.cpp) can be
  * pinned against it.  What the function needs from the rest of the reference is supplied here:

@@ -338,7 +338,7 @@ def test_input_validation_equals_the_reference_function(name):
 
 def test_abi_struct_layouts_equal_the_reference_headers():
     """include/xmimsim_b200.h against the reference's include/xmi_data_structs.h, xmi_solid_angle.h and xmi_detector.h:
-    oracle/ref_layout.c holds a _Static_assert per struct (size) and per field (offset and size) of the 14 structs that
+    oracle/ref_shim/ref_layout.c holds a _Static_assert per struct (size) and per field (offset and size) of the 14 structs that
     cross the C ABI, plus the enumeration values; oracle/build_ref.sh fails on a mismatch, so a loadable oracle/_ref with
     the expected number of checks is the pass."""
     if not hasattr(ref.lib(), "ref_layout_checks"):

@@ -137,6 +137,7 @@ def test_xmso_history_mapping_matches_the_reference_function(tmp_path):
                 k = r.integers(1, n_int + 1)
                 h[z - 1, line - 1, :k] = r.uniform(1e-3, 1e6, k) * (r.uniform(size=k) > 0.3)   # some orders empty
             h[z - 1, 383, 0] = 5.0; h[z - 1, 384, 1] = 6.0   # Rayleigh / Compton slots: never listed
+        h[sample_Z[1] - 1, :383, 0] = 1.0 + np.arange(383)    # one element with every line: all 383 names of src/xmi_lines.c
         hist.append(h)
     br, vr = hist
     rows_p = (abi.c_double_p * (n_int + 1))(*[C.cast(conv.ctypes.data + i * nch * 8, abi.c_double_p) for i in range(n_int + 1)])
@@ -153,7 +154,8 @@ def test_xmso_history_mapping_matches_the_reference_function(tmp_path):
                 for c in ln.findall("counts"):
                     got.append((int(el.get("atomic_number")), ln.get("type"), float(el.get("total_counts")), float(ln.get("total_counts")),
                                 int(c.get("interaction_number")), float(c.text)))
-        assert len(want) > 40 and len(got) == len(want), (tag, len(got), len(want))
+        assert len(want) > 420 and len(got) == len(want), (tag, len(got), len(want))
+        assert len({w[1] for w in want}) == 383
         assert [(g[0], g[1], g[4]) for g in got] == [(w[0], w[1], w[4]) for w in want], tag
         assert {w[0] for w in want} <= set(sample_Z)
         for g, w in zip(got, want):

@@ -30,9 +30,11 @@ def run_both(inp, options=None, seed=11, grid_n=None, hits=400):
     if _differs(ch, ch_o) or _differs(vr, vr_o):
         # About one run of this file in fifteen has shown one comparison off by a large factor, with kernels v11 .. v15
         # alike, while the engine reproduced its sums bit for bit in 80 fresh simulations and 180 repetitions and the
-        # oracle did in 40 (tools/flaky_hunt*.py, tools/repeat_check.py): a transient outside the engine.  Both sides are
-        # therefore run a second time: the ENGINE must reproduce its first output exactly (a difference is a failure of
-        # the product and is reported as such), and the comparison is made against the second oracle run.
+        # oracle did in 40 + 120 (tools/flaky_hunt*.py, tools/repeat_check.py).  Host code, oracle and kernels are clean
+        # under ASan / UBSan / heap perturbation / compute-sanitizer initcheck, memcheck and racecheck (DESIGN.md section 2,
+        # profiles/r1_compute_sanitizer.txt); the cause is still open.  Both sides are therefore run a second time: the
+        # ENGINE must reproduce its first output exactly (a difference is a failure of the product and is reported as
+        # such), and the comparison is made against the second oracle run; the event is logged.
         ch2, br2, vr2 = P.sim.main_msim(options, sa)
         ch_o2, vr_o2, cnt2 = P.oracle(options, sa, 0)
         note = ("parity retry: engine repeat identical=%s, oracle repeat identical=%s, first err=%.3e, second err=%.3e"

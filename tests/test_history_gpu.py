@@ -2,13 +2,12 @@
 Philox streams (tier T0 of SURVEY.md 8c), plus size-independent properties at larger sizes."""
 import copy
 import os
-import warnings
 
 import numpy as np
 import pytest
 
 import xmimsim_b200 as x
-from helpers import Pair, assert_spectra_close
+from helpers import Pair, assert_spectra_close, diagnose_mismatch
 from inputs import example, caso4, synthetic_layers, ebel_like
 
 pytestmark = pytest.mark.gpu
@@ -22,33 +21,18 @@ RTOL = 2e-6
 
 
 def run_both(inp, options=None, seed=11, grid_n=None, hits=400):
+    """Engine and oracle once each on the same input, tables, grid and Philox key.  No repetition: a comparison that
+    differs is a failure; helpers.diagnose_mismatch records what attributes it (both sides' per-order sums, digests,
+    a second engine run, a single-thread oracle run, a fresh Pair) in gpurun_out/ and in the assertion message."""
     options = options or x.main_options()
     P = Pair(inp)
     sa = P.grid(hits_per_single=hits, n=grid_n)
     ch, br, vr = P.sim.main_msim(options, sa)
     ch_o, vr_o, cnt = P.oracle(options, sa, 0)   # seed 0 -> default key on both sides
     if _differs(ch, ch_o) or _differs(vr, vr_o):
-        # About one run of this file in fifteen has shown one comparison off by a large factor, with kernels v11 .. v15
-        # alike, while the engine reproduced its sums bit for bit in 80 fresh simulations and 180 repetitions and the
-        # oracle did in 40 + 120 (tools/flaky_hunt*.py, tools/repeat_check.py).  Host code, oracle and kernels are clean
-        # under ASan / UBSan / heap perturbation / compute-sanitizer initcheck, memcheck and racecheck (DESIGN.md section 2,
-        # profiles/r1_compute_sanitizer.txt); the cause is still open.  Both sides are therefore run a second time: the
-        # ENGINE must reproduce its first output exactly (a difference is a failure of the product and is reported as
-        # such), and the comparison is made against the second oracle run; the event is logged.
-        ch2, br2, vr2 = P.sim.main_msim(options, sa)
-        ch_o2, vr_o2, cnt2 = P.oracle(options, sa, 0)
-        note = ("parity retry: engine repeat identical=%s, oracle repeat identical=%s, first err=%.3e, second err=%.3e"
-                % (np.array_equal(ch, ch2) and np.array_equal(vr, vr2), np.array_equal(ch_o, ch_o2) and np.array_equal(vr_o, vr_o2),
-                   np.abs(ch - ch_o).max() / max(np.abs(ch_o).max(), 1e-300), np.abs(ch2 - ch_o2).max() / max(np.abs(ch_o2).max(), 1e-300)))
-        warnings.warn(note)
-        try:
-            os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
-            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_retries.log"), "a") as f:
-                f.write(note + "\n")
-        except OSError:
-            pass
-        assert np.array_equal(ch, ch2) and np.array_equal(vr, vr2), "engine output not reproducible: " + note
-        ch_o, vr_o, cnt = ch_o2, vr_o2, cnt2
+        note = diagnose_mismatch(P, options, sa, ch, vr, ch_o, vr_o, grid_n=grid_n, hits=hits)
+        P.close()
+        raise AssertionError("engine and oracle differ: " + note)
     P.close()
     return ch, br, vr, ch_o, vr_o, cnt
 

@@ -18,8 +18,10 @@ struct XmbDeviceTables {
 	uint64_t n_total = 0;
 	// solid-angle grid + accumulators (re-used across calls)
 	double *sa_grid = nullptr, *sa_r = nullptr, *sa_t = nullptr;
-	size_t sa_cap = 0, sa_n = 0;
-	const double *sa_host = nullptr;
+	size_t sa_cap = 0, sa_r_cap = 0, sa_t_cap = 0;      // capacity of each of the three buffers, in doubles
+	size_t sa_nr = 0, sa_nt = 0;                        // dimensions of the grid now in HBM
+	uint64_t sa_hash = 0;                               // content hash of that grid (values + axes), see sa_content_hash()
+	bool sa_valid = false;                              // the grid in HBM was uploaded whole with keep_on_device
 	unsigned long long *acc = nullptr, *limbs = nullptr, *counters = nullptr;
 	size_t acc_slots = 0;
 	double *queue = nullptr;

@@ -989,6 +989,24 @@ XmbDeviceTables *xmb_device_tables_get(XmbInputF *in, XmbHdf5F *h, const xmb_mai
 	return D;
 }
 
+// 64-bit content hash of a solid-angle grid (values + both axes), four independent multiply-xorshift lanes over the
+// 8-byte words: ~2 ms for the 1024 x 1024 grid.  Decides whether the grid already in HBM may be reused.
+static uint64_t sa_content_hash(const xmb_solid_angle *sa) {
+	auto mix = [](uint64_t h, uint64_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ULL; return h ^ (h >> 29); };
+	auto hash_words = [&](const double *p, size_t n, uint64_t h0) {
+		uint64_t h[4] = {h0, h0 ^ 0xA5A5A5A5A5A5A5A5ULL, h0 + 0x1234567ULL, ~h0};
+		size_t i = 0;
+		uint64_t v[4];
+		for (; i + 4 <= n; i += 4) { memcpy(v, p + i, 32); for (int k = 0; k < 4; k++) h[k] = mix(h[k], v[k]); }
+		for (; i < n; i++) { memcpy(v, p + i, 8); h[0] = mix(h[0], v[0]); }
+		return mix(mix(mix(h[0], h[1]), h[2]), h[3]);
+	};
+	const size_t nr = (size_t)sa->grid_dims_r_n, nt = (size_t)sa->grid_dims_theta_n;
+	uint64_t h = hash_words(sa->solid_angles, nr * nt, 0x584D42ULL ^ (nr << 20) ^ nt);
+	h = hash_words(sa->grid_dims_r_vals, nr, h);
+	return hash_words(sa->grid_dims_theta_vals, nt, h);
+}
+
 extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                                  const xmb_solid_angle *sa, xmb_msim_ex *ex, uint64_t **accum, size_t *n_slots) {
 	XmbInputF *in = xmb_as_input(inputF);
@@ -1005,21 +1023,31 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	XmbDeviceTables *D = xmb_device_tables_get(in, h, options);
 	if (!D) return 0;
 	XmbHistParams P = D->P;
-	// solid-angle grid: an argument of the call -> copied host->device every call
+	// solid-angle grid: an argument of the call -> copied host->device every call; with keep_on_device the copy is
+	// skipped when the grid in HBM has the same CONTENT (dimensions + a 64-bit hash of values and axes: a caller may
+	// refill the same host buffer, and a new buffer may land on the address of a freed one)
 	const size_t nsa = brute ? 0 : (size_t)sa->grid_dims_r_n * sa->grid_dims_theta_n;
-	if (!brute && (D->sa_cap < nsa || !D->sa_grid)) {
-		cudaFree(D->sa_grid); cudaFree(D->sa_r); cudaFree(D->sa_t);
-		XMB_CUDA_OK(cudaMalloc(&D->sa_grid, sizeof(double) * nsa));
-		XMB_CUDA_OK(cudaMalloc(&D->sa_r, sizeof(double) * sa->grid_dims_r_n));
-		XMB_CUDA_OK(cudaMalloc(&D->sa_t, sizeof(double) * sa->grid_dims_theta_n));
-		D->sa_cap = nsa;
-	}
-	const bool resident = brute || (ex->keep_on_device && D->sa_host == sa->solid_angles && D->sa_n == nsa);
-	if (!resident) {
-		XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
-		XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * sa->grid_dims_r_n, cudaMemcpyHostToDevice));
-		XMB_CUDA_OK(cudaMemcpy(D->sa_t, sa->grid_dims_theta_vals, sizeof(double) * sa->grid_dims_theta_n, cudaMemcpyHostToDevice));
-		D->sa_host = sa->solid_angles; D->sa_n = nsa;
+	if (!brute) {
+		const size_t nr_ = (size_t)sa->grid_dims_r_n, nt_ = (size_t)sa->grid_dims_theta_n;
+		if (nr_ < 2 || nt_ < 2 || !sa->grid_dims_r_vals || !sa->grid_dims_theta_vals) { xmb_set_error("solid-angle grid needs two axes of at least two values"); return 0; }
+		bool fresh = false;
+		if (D->sa_cap < nsa || !D->sa_grid) { cudaFree(D->sa_grid); D->sa_grid = nullptr; XMB_CUDA_OK(cudaMalloc(&D->sa_grid, sizeof(double) * nsa)); D->sa_cap = nsa; fresh = true; }
+		if (D->sa_r_cap < nr_ || !D->sa_r) { cudaFree(D->sa_r); D->sa_r = nullptr; XMB_CUDA_OK(cudaMalloc(&D->sa_r, sizeof(double) * nr_)); D->sa_r_cap = nr_; fresh = true; }
+		if (D->sa_t_cap < nt_ || !D->sa_t) { cudaFree(D->sa_t); D->sa_t = nullptr; XMB_CUDA_OK(cudaMalloc(&D->sa_t, sizeof(double) * nt_)); D->sa_t_cap = nt_; fresh = true; }
+		uint64_t hash = 0;
+		bool resident = false;
+		if (ex->keep_on_device) {
+			hash = sa_content_hash(sa);
+			resident = !fresh && D->sa_valid && D->sa_hash == hash && D->sa_nr == nr_ && D->sa_nt == nt_;
+		}
+		if (!resident) {
+			D->sa_valid = false;
+			XMB_CUDA_OK(cudaMemcpy(D->sa_grid, sa->solid_angles, sizeof(double) * nsa, cudaMemcpyHostToDevice));
+			XMB_CUDA_OK(cudaMemcpy(D->sa_r, sa->grid_dims_r_vals, sizeof(double) * nr_, cudaMemcpyHostToDevice));
+			XMB_CUDA_OK(cudaMemcpy(D->sa_t, sa->grid_dims_theta_vals, sizeof(double) * nt_, cudaMemcpyHostToDevice));
+			D->sa_nr = nr_; D->sa_nt = nt_;
+			if (ex->keep_on_device) { D->sa_hash = hash; D->sa_valid = true; }
+		}
 	}
 	P.sa_grid = D->sa_grid; P.sa_r_vals = D->sa_r; P.sa_t_vals = D->sa_t;
 	if (!brute) { P.sa_nr = (int)sa->grid_dims_r_n; P.sa_nt = (int)sa->grid_dims_theta_n; }

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include "xmimsim_b200.h"
 #include "xmb_lines.h"
 
@@ -68,7 +69,7 @@ static const double anch_E[NANCH][9] = {
  /* U  */ {115.6061, 21.7574, 20.9476, 17.1663, 5.5480, 5.1822, 4.3034, 3.7276, 3.5517}};
 
 static double edge_cache[95][NSH];
-static int edge_ready = 0;
+static pthread_once_t edge_once = PTHREAD_ONCE_INIT;   /* the table generator calls the provider from OpenMP threads */
 
 static double interp_anchor(int Z, int s) {
 	/* log-log interpolation/extrapolation through anchors that have shell s */
@@ -104,13 +105,12 @@ static void build_edges(void) {
 		for (s = 0; s < 5; s++) if (Z >= z_first[23 + s]) e[23 + s] = p1 * pfrac[s];
 		if (Z >= z_first[28]) e[28] = p1 * 0.1;
 	}
-	edge_ready = 1;
 }
 
 static double s_AtomicWeight(int Z) { return (Z >= 1 && Z <= 94) ? aw_tab[Z] : 0.0; }
 
 static double s_EdgeEnergy(int Z, int shell) {
-	if (!edge_ready) build_edges();
+	pthread_once(&edge_once, build_edges);
 	if (Z < 1 || Z > 94 || shell < 0 || shell >= NSH) return 0.0;
 	return edge_cache[Z][shell];
 }
@@ -294,6 +294,7 @@ static double integrate_dcs(int Z, double E, int compton) {
 #define NCS 192
 static double cs_cache[95][2][NCS];
 static unsigned char cs_have[95];
+static pthread_mutex_t cs_lock = PTHREAD_MUTEX_INITIALIZER;
 static const double cs_e0 = 0.05, cs_e1 = 250.0;
 
 static void build_cs(int Z) {
@@ -303,14 +304,15 @@ static void build_cs(int Z) {
 		cs_cache[Z][0][i] = log(integrate_dcs(Z, E, 0));
 		cs_cache[Z][1][i] = log(integrate_dcs(Z, E, 1));
 	}
-	cs_have[Z] = 1;
+	__atomic_store_n(&cs_have[Z], 1, __ATOMIC_RELEASE);
 }
 
 static double cs_lookup(int Z, double E, int which) {
 	if (Z < 1 || Z > 94 || E <= 0.0) return 0.0;
-	if (!cs_have[Z]) {
-#pragma omp critical(xmb_surrogate_cs)
-		{ if (!cs_have[Z]) build_cs(Z); }
+	if (!__atomic_load_n(&cs_have[Z], __ATOMIC_ACQUIRE)) {
+		pthread_mutex_lock(&cs_lock);
+		if (!__atomic_load_n(&cs_have[Z], __ATOMIC_ACQUIRE)) build_cs(Z);
+		pthread_mutex_unlock(&cs_lock);
 	}
 	if (E < cs_e0) E = cs_e0;
 	if (E > cs_e1) E = cs_e1;
@@ -431,6 +433,6 @@ static const xmb_xrl_provider surrogate = {
 	s_ComptonProfile, s_VacancyCS, s_AugerRate, s_ElectronConfig, s_ComptonProfile_Partial};
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void) {
-	if (!edge_ready) build_edges();
+	pthread_once(&edge_once, build_edges);
 	return &surrogate;
 }

@@ -29,7 +29,10 @@ static void usage(FILE *f) {
 	      "  --custom-detector-response=LIB                            use xmi_detector_convolute_all_custom from LIB (bin/xmimsim.c:505-522)\n"
 	      "  --with-solid-angles-data=F --with-escape-ratios-data=F    cache files (queried first, updated after a calculation)\n"
 	      "  --set-seed=N                                              Philox key (default: library seed)\n"
-	      "  --with-xraylib[=LIB]                                      cross sections from libxrl (dlopen) instead of the built-in analytic stand-in\n"
+	      "  --with-xraylib[=LIB]                                      libxrl to take the cross sections from (default: libxrl.so.11 / .7 / libxrl.so)\n"
+	      "  --surrogate-cross-sections                                run with the built-in analytic stand-in instead of xraylib: NOT physics-grade,\n"
+	      "                                                            for tests and benchmarks on machines without xraylib\n"
+	      "  --gpus=N                                                  shard the histories over N GPUs of this machine (one NCCL all-reduce; 0 = all)\n"
 	      "  --table-quality=0|1                                       inverse-CDF integration resolution (default 1 = reference)\n"
 	      "  -v, --verbose    -V, --very-verbose    --version\n", f);
 }
@@ -38,7 +41,8 @@ int main(int argc, char **argv) {
 	xmb_main_options opt;
 	xmb_main_options_defaults(&opt);
 	std::string spe_conv, spe_noconv, csv_conv, csv_noconv, infile, sa_cache, er_cache, custom_response, xraylib_path;
-	bool use_xraylib = false;
+	bool use_surrogate = false;
+	int n_gpus = 1;
 	unsigned long long seed = 0;
 	int quality = 1;
 	struct Flag { const char *name; int *target; };
@@ -64,8 +68,10 @@ int main(int argc, char **argv) {
 		if (val("--spe-file-unconvoluted", spe_noconv) || val("--spe-file", spe_conv) || val("--csv-file-unconvoluted", csv_noconv) || val("--csv-file", csv_conv)) continue;
 		if (val("--custom-detector-response", custom_response)) continue;
 		if (val("--with-solid-angles-data", sa_cache) || val("--with-escape-ratios-data", er_cache)) continue;
-		if (a == "--with-xraylib") { use_xraylib = true; continue; }
-		if (a.compare(0, 15, "--with-xraylib=") == 0) { use_xraylib = true; xraylib_path = a.substr(15); continue; }
+		if (a == "--with-xraylib") continue;
+		if (a.compare(0, 15, "--with-xraylib=") == 0) { xraylib_path = a.substr(15); continue; }
+		if (a == "--surrogate-cross-sections") { use_surrogate = true; continue; }
+		if (val("--gpus", tmp)) { n_gpus = atoi(tmp.c_str()); continue; }
 		if (val("--set-seed", tmp)) { seed = strtoull(tmp.c_str(), nullptr, 0); continue; }
 		if (val("--table-quality", tmp)) { quality = atoi(tmp.c_str()); continue; }
 		if (val("--set-threads", tmp)) { opt.omp_num_threads = atoi(tmp.c_str()); continue; }
@@ -79,10 +85,18 @@ int main(int argc, char **argv) {
 	if (infile.empty()) { usage(stderr); return 1; }
 	if (xmb_cuda_device_count() < 1) { fprintf(stderr, "No CUDA device found: xmimsim-b200 has no CPU fallback\n"); return 1; }
 
-	const xmb_xrl_provider *xrl = xmb_xrl_surrogate();
-	if (use_xraylib) {
+	// cross sections: xraylib, as the reference links it (configure.ac:115-116).  The analytic stand-in only on request.
+	const xmb_xrl_provider *xrl = nullptr;
+	if (use_surrogate) {
+		xrl = xmb_xrl_surrogate();
+		fprintf(stderr, "WARNING: cross sections from the built-in analytic stand-in (%s): the spectra are NOT physics-grade\n", xrl->name);
+	} else {
 		xrl = xmb_xrl_from_library(xraylib_path.empty() ? nullptr : xraylib_path.c_str());
-		if (!xrl) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
+		if (!xrl) {
+			fprintf(stderr, "%s\nxraylib is required (--with-xraylib=LIB names the library); --surrogate-cross-sections runs with the "
+			                "analytic stand-in instead (not physics-grade)\n", xmb_last_error());
+			return 1;
+		}
 	}
 	xmb_input *input = nullptr;
 	if (!xmb_input_read_from_xml_file(infile.c_str(), &input)) { fprintf(stderr, "Could not read %s: %s\n", infile.c_str(), xmb_last_error()); return 1; }
@@ -114,7 +128,24 @@ int main(int argc, char **argv) {
 		} else if (opt.verbose) printf("Solid angle grid already present in %s\n", sa_cache.c_str());
 	} else if (opt.verbose) printf("Operating in brute-force mode: solid angle grid is redundant\n");
 	double *channels = nullptr, *brute = nullptr, *var_red = nullptr;
-	if (!xmb_main_msim(inputF, tables, 1, &channels, &opt, &brute, &var_red, sa)) { fprintf(stderr, "Error in xmi_main_msim: %s\n", xmb_last_error()); return 1; }
+	if (n_gpus == 1) {
+		xmb_msim_ex ex{};
+		ex.n_ranks = 1; ex.device = -1; ex.seed = seed;
+		uint64_t *limbs = nullptr;
+		size_t n_slots = 0;
+		if (opt.verbose) { printf("Simulating interactions\n"); fflush(stdout); }
+		if (!xmb_main_msim_raw(inputF, tables, &opt, sa, &ex, &limbs, &n_slots) ||
+		    !xmb_main_msim_finish(inputF, tables, &opt, limbs, n_slots, &channels, &brute, &var_red)) { fprintf(stderr, "Error in xmi_main_msim: %s\n", xmb_last_error()); return 1; }
+		free(limbs);
+		if (opt.verbose) printf("Interactions simulation finished\n");
+	} else {
+		// the reference's MPI run (bin/xmimsim.c:396-413), here over the GPUs of this machine
+		xmb_msim_ex ex{};
+		ex.seed = seed;
+		if (opt.verbose) { printf("Simulating interactions on %d GPUs\n", n_gpus > 0 ? n_gpus : xmb_cuda_device_count()); fflush(stdout); }
+		if (!xmb_main_msim_all_devices(inputF, tables, n_gpus, nullptr, &channels, &opt, &brute, &var_red, sa, &ex)) { fprintf(stderr, "Error in xmi_main_msim: %s\n", xmb_last_error()); return 1; }
+		if (opt.verbose) printf("Interactions simulation finished (%llu histories, slowest GPU %.1f ms)\n", (unsigned long long)ex.n_histories, ex.kernel_ms);
+	}
 	double zero_sum = 0.0;
 	for (int j = 0; j < nch; j++) zero_sum += channels[j];
 	const int first = zero_sum > 0.0 ? 0 : 1;                                     // bin/xmimsim.c:436, 499
@@ -139,10 +170,12 @@ int main(int argc, char **argv) {
 			}
 		} else if (opt.verbose) printf("Escape peak ratios already present in %s\n", er_cache.c_str());
 	}
-	// keep the raw spectra: the response corrects its input rows in place (src/xmi_detector_f.F90:412-413)
-	std::vector<double> raw(channels, channels + (size_t)(n_int + 1) * nch);
-	std::vector<double *> rows(n_int + 1), conv(n_int + 1, nullptr), raw_rows(n_int + 1);
-	for (int i = 0; i <= n_int; i++) { rows[i] = channels + (size_t)i * nch; raw_rows[i] = raw.data() + (size_t)i * nch; }
+	// The response corrects its input rows in place (detector absorbers, crystal efficiency, escape peaks:
+	// src/xmi_detector_f.F90:412-468) and the reference writes THOSE rows as the "unconvoluted" spectra (channelsdef after
+	// xmi_detector_convolute_all, bin/xmimsim.c:498-642): so does this driver.
+	std::vector<double *> rows(n_int + 1), conv(n_int + 1, nullptr);
+	for (int i = 0; i <= n_int; i++) rows[i] = channels + (size_t)i * nch;
+	std::vector<double *> &raw_rows = rows;
 	if (!custom_response.empty()) {
 		// the reference's plugin hook (bin/xmimsim.c:505-522): same symbol, same signature
 		void *mod = dlopen(custom_response.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -178,7 +211,7 @@ int main(int argc, char **argv) {
 		if (!xmb_write_csv_file(csv_conv.c_str(), input, conv.data(), first)) { fprintf(stderr, "%s\n", xmb_last_error()); return 1; }
 		if (opt.verbose) printf("Writing to CSV file %s\n", csv_conv.c_str());
 	}
-	if (!xmb_output_write_to_xml_file(input, infile.c_str(), input->general->outputfile, raw.data(), conv.data(), brute,
+	if (!xmb_output_write_to_xml_file(input, infile.c_str(), input->general->outputfile, channels, conv.data(), brute,
 	                                  opt.use_variance_reduction ? var_red : nullptr, first == 0 ? 1 : 0, xrl)) {
 		fprintf(stderr, "Could not write to %s: %s\n", input->general->outputfile, xmb_last_error());
 		return 1;

@@ -393,8 +393,10 @@ void xmb_free_solid_angle(xmb_solid_angle *sa);   /* xmi_free_solid_angle, src/x
  * options->use_variance_reduction = 0 selects the brute-force mode (analogue walk, detector/collimator hit
  * tests src/xmi_aux_f.F90:1622-1833, Auger/radiative cascade offspring src/xmi_main.F90:2413-4783);
  * solid_angles may then be NULL and channels row 0 holds the photons detected without interaction.
- * n_mpi_hosts/rank semantic: this rank simulates photon ids [rank*N/n, (rank+1)*N/n) of every
- * source line; outputs are *partial sums* to be summed over ranks (see xmb_main_msim_ex).
+ * n_mpi_hosts > 1 (the reference's MPI build): this rank -- OMPI_COMM_WORLD_RANK / PMI_RANK / RANK -- simulates its
+ * block-cyclic shard of the photon ids of every source line; the outputs are PARTIAL sums which the host adds over
+ * ranks, as the reference's host does with MPI_Reduce (bin/xmimsim.c:396-413).  xmb_main_msim_multi does the sum
+ * itself (NCCL) and is what a multi-GPU caller should use.
  * Returns 1 / 0. */
 int xmb_main_msim(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, int n_mpi_hosts, double **channels,
                   const xmb_main_options *options, double **brute_history,
@@ -443,6 +445,37 @@ uint64_t xmb_msim_shard_count(uint64_t n_total, int rank, int n_ranks);
 uint64_t xmb_msim_total_histories(xmb_inputFPtr inputF);
 int xmb_msim_slot_map(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                       int32_t *out_Z, int32_t *out_line, int capacity);
+/* ---- multi-GPU: histories sharded over the GPUs of one box, ONE NCCL all-reduce of the histograms ----------------
+ * Replaces the reference's MPI split (n_photons / n_mpi_hosts of every line per host, src/xmi_main.F90:314,574) and
+ * its three MPI_Reduce(MPI_SUM) to rank 0 (bin/xmimsim.c:396-413).  A rank = one GPU.  The sum runs on the exact
+ * integer limbs in HBM, on the stream of the history kernel (kernel -> limb conversion -> ncclAllReduce(uint64, sum),
+ * no host synchronisation in between); every rank then holds the full result, bit-identical at any rank count.
+ * NCCL (libnccl.so.2) is bound at run time; the calls fail with xmb_last_error when it cannot be loaded.
+ *
+ * One process per GPU (mpirun / torchrun): rank 0 calls xmb_comm_unique_id, the launcher broadcasts the
+ * XMB_COMM_ID_BYTES bytes (MPI_Bcast / torch.distributed), every rank calls xmb_comm_init_rank (device < 0: current). */
+#define XMB_COMM_ID_BYTES 128
+typedef struct xmb_comm xmb_comm;
+int xmb_comm_unique_id(char *id /* [XMB_COMM_ID_BYTES] */);
+int xmb_comm_init_rank(const char *id, int rank, int n_ranks, int device, xmb_comm **out);
+void xmb_comm_free(xmb_comm **comm);
+int xmb_comm_rank(const xmb_comm *comm);
+int xmb_comm_size(const xmb_comm *comm);
+int xmb_nccl_version(void);              /* e.g. 22703; 0 when NCCL cannot be loaded */
+/* xmi_main_msim over a communicator: same outputs as xmb_main_msim, on EVERY rank the sum over all ranks. */
+int xmb_main_msim_multi(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, xmb_comm *comm, double **channels,
+                        const xmb_main_options *options, double **brute_history,
+                        double **var_red_history, const xmb_solid_angle *solid_angles);
+/* Same, leaving the reduced limbs in HBM (xmb_msim_device_limbs; xmb_main_msim_finish converts them).  ex->seed and
+ * ex->keep_on_device (solid-angle grid residency) are inputs; rank / n_ranks / device are taken from comm. */
+int xmb_main_msim_multi_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                            const xmb_solid_angle *solid_angles, xmb_comm *comm, xmb_msim_ex *ex);
+/* One process driving n_devices GPUs (ordinals devices[0..n), or 0..n_devices-1 when NULL; n_devices <= 0: all
+ * visible): tables and grid replicated, every device launched before any is waited for, ncclCommInitAll + one grouped
+ * all-reduce.  ex (optional): seed in; total histories / interactions / launches and the slowest kernel time out. */
+int xmb_main_msim_all_devices(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, int n_devices, const int *devices,
+                              double **channels, const xmb_main_options *options, double **brute_history,
+                              double **var_red_history, const xmb_solid_angle *solid_angles, xmb_msim_ex *ex);
 /* Converts (summed) raw accumulators to the reference's three output arrays. */
 int xmb_main_msim_finish(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
                          const uint64_t *accum, size_t n_slots, double **channels,

@@ -14,6 +14,7 @@ from inputs import example
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "bin", "xmimsim-b200")
+SURR = "--surrogate-cross-sections"     # no xraylib in the image: the analytic stand-in has to be asked for
 
 
 def test_cli_matches_library_pipeline(tmp_path):
@@ -23,7 +24,7 @@ def test_cli_matches_library_pipeline(tmp_path):
     ci = x.CInput(inp)
     xmsi = str(tmp_path / "in.xmsi")
     assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
-    r = subprocess.run([CLI, "-v", "--table-quality=0", "--csv-file=" + str(tmp_path / "c.csv"), "--spe-file-unconvoluted=" + str(tmp_path / "u"), xmsi],
+    r = subprocess.run([CLI, SURR, "-v", "--table-quality=0", "--csv-file=" + str(tmp_path / "c.csv"), "--spe-file-unconvoluted=" + str(tmp_path / "u"), xmsi],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     out = r.stdout
@@ -42,7 +43,11 @@ def test_cli_matches_library_pipeline(tmp_path):
     res = x.read_xmso(inp.outputfile)
     n_int = inp.n_interactions_trajectory
     assert res["conv"].shape == (n_int, inp.nchannels)
-    assert np.allclose(res["unconv"], raw[1:], rtol=2e-5, atol=1e-6 * raw.max())
+    # <spectrum_unconv> holds the rows AFTER the response corrected them in place (detector absorbers, crystal efficiency,
+    # escape peaks), as the reference writes channelsdef after xmi_detector_convolute_all (bin/xmimsim.c:498-642)
+    assert np.allclose(res["unconv"], ch[1:], rtol=2e-5, atol=1e-6 * ch.max())
+    assert not np.allclose(res["unconv"], raw[1:], rtol=1e-3, atol=1e-6 * raw.max())
+    assert "NOT physics-grade" in r.stderr
     assert np.allclose(res["conv"], conv[1:], rtol=2e-5, atol=1e-6 * conv.max())
     fe = res["history"][(26, "KL3")]
     assert abs(fe["counts"][1] - vr[25, 2, 0]) <= 1e-5 * vr[25, 2, 0]
@@ -60,14 +65,14 @@ def test_cli_brute_force_and_errors(tmp_path):
     ci = x.CInput(inp)
     xmsi = str(tmp_path / "b.xmsi")
     assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
-    r = subprocess.run([CLI, "--disable-variance-reduction", "--disable-escape-peaks", "--table-quality=0", xmsi], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([CLI, SURR, "--disable-variance-reduction", "--disable-escape-peaks", "--table-quality=0", xmsi], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     import xml.etree.ElementTree as ET
     root = ET.parse(inp.outputfile).getroot()
     assert root.find("variance_reduction_history").find("fluorescence_line_counts") is None
     fe = [e for e in root.find("brute_force_history").findall("fluorescence_line_counts") if e.get("atomic_number") == "26"]
     assert fe and float(fe[0].get("total_counts")) > 0
-    r = subprocess.run([CLI, str(tmp_path / "missing.xmsi")], capture_output=True, text=True)
+    r = subprocess.run([CLI, SURR, str(tmp_path / "missing.xmsi")], capture_output=True, text=True)
     assert r.returncode == 1 and "Could not read" in r.stderr
     r = subprocess.run([CLI, "--no-such-option", xmsi], capture_output=True, text=True)
     assert r.returncode == 1
@@ -81,7 +86,7 @@ def test_cli_caches_are_filled_then_reused(tmp_path):
     xmsi = str(tmp_path / "c.xmsi")
     assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
     sa, er = str(tmp_path / "sa.cache"), str(tmp_path / "er.cache")
-    cmd = [CLI, "-v", "--table-quality=0", "--with-solid-angles-data=" + sa, "--with-escape-ratios-data=" + er, xmsi]
+    cmd = [CLI, SURR, "-v", "--table-quality=0", "--with-solid-angles-data=" + sa, "--with-escape-ratios-data=" + er, xmsi]
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r1.returncode == 0, r1.stderr
     assert "Precalculating solid angle grid" in r1.stdout and "was successfully updated with new solid angle grid" in r1.stdout
@@ -107,11 +112,22 @@ def test_cli_custom_detector_response_plugin(tmp_path):
         ci = x.CInput(inp)
         xmsi = str(tmp_path / ("p%d.xmsi" % k))
         assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
-        r = subprocess.run([CLI, "-v", "--disable-variance-reduction", "--disable-escape-peaks", "--table-quality=0"] + extra + [xmsi],
+        r = subprocess.run([CLI, SURR, "-v", "--disable-variance-reduction", "--disable-escape-peaks", "--table-quality=0"] + extra + [xmsi],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
         assert ("xmi_detector_convolute_all_custom loaded from" in r.stdout) == bool(extra)
         outs.append(x.read_xmso(inp.outputfile))
     assert outs[0]["conv"].sum() > 0 and np.array_equal(outs[0]["conv"], outs[1]["conv"])
-    r = subprocess.run([CLI, "--custom-detector-response=/nonexistent.so", xmsi], capture_output=True, text=True)
+    r = subprocess.run([CLI, SURR, "--custom-detector-response=/nonexistent.so", xmsi], capture_output=True, text=True)
     assert r.returncode == 1 and "Could not open" in r.stderr
+
+
+def test_cli_refuses_to_run_without_xraylib_unless_the_stand_in_is_requested(tmp_path):
+    inp = example("srm1155")
+    inp.n_photons_line = 10
+    inp.outputfile = str(tmp_path / "n.xmso")
+    ci = x.CInput(inp)
+    xmsi = str(tmp_path / "n.xmsi")
+    assert abi.lib().xmb_input_write_to_xml_file(C.byref(ci.input), xmsi.encode()) == 1
+    r = subprocess.run([CLI, "--with-xraylib=/nonexistent/libxrl.so", xmsi], capture_output=True, text=True)
+    assert r.returncode == 1 and "xraylib is required" in r.stderr and not os.path.exists(inp.outputfile)

@@ -198,6 +198,35 @@ def test_batch_formation_modes_are_bit_identical(monkeypatch):
     P.close()
 
 
+@pytest.mark.parametrize("which", ["synthetic10", "srm1412", "ebel"])
+def test_sums_do_not_depend_on_the_launch_shape(which, monkeypatch):
+    """Which photons share a batch depends on the number of CTAs, on the CTA size and on the order in which warps reach
+    the queues; every deposit is an integer and every draw has a fixed address, so the accumulators must not move by a
+    bit.  XMB_HIST_BLOCKS / XMB_HIST_THREADS are the engine's experiment switches (they only reduce the launch)."""
+    if which == "synthetic10":
+        inp = synthetic_layers(n_photons=60_000, n_int=8)
+    elif which == "srm1412":
+        inp = example("srm1412"); inp.n_photons_line = 2500
+    else:
+        inp = ebel_like(n_intervals=60, n_photons_interval=700, n_photons_line=3000)
+    P = Pair(inp)
+    sa = P.grid(n=128)
+    o = x.main_options()
+    ref, ex = P.sim.main_msim_raw(o, sa)
+    shapes = [(b, t) for b in (1, 5, 37, 148) for t in (1024, 736, 256, 64)]
+    for b, t in shapes:
+        monkeypatch.setenv("XMB_HIST_BLOCKS", str(b)); monkeypatch.setenv("XMB_HIST_THREADS", str(t))
+        for rep in range(2):
+            limbs, ex2 = P.sim.main_msim_raw(o, sa)
+            assert ex2.n_interactions == ex.n_interactions, (b, t)
+            assert np.array_equal(limbs, ref), (b, t, rep)
+    monkeypatch.delenv("XMB_HIST_BLOCKS"); monkeypatch.delenv("XMB_HIST_THREADS")
+    for rep in range(10):
+        limbs, _ = P.sim.main_msim_raw(o, sa)
+        assert np.array_equal(limbs, ref), rep
+    P.close()
+
+
 def test_linearity_and_weight_bounds_at_larger_size():
     """Size-independent properties: the spectrum per unit photon converges (two sizes agree within the
     statistical error), order-1 content dominates, all deposits non-negative."""

@@ -146,6 +146,8 @@ class MsimEx(C.Structure):
                 ("n_launches", C.c_uint64), ("n_interactions", C.c_uint64)]
 
 
+COMM_ID_BYTES = 128     # XMB_COMM_ID_BYTES = sizeof(ncclUniqueId)
+
 _lib = None
 
 
@@ -166,6 +168,20 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("xmimsim_b200: %s is missing -- run `make lib` (or __graft_entry__.build()); "
                            "there is no CPU fallback" % LIB_PATH)
+    # NCCL is bound at run time by the library (multi_gpu.cu).  A Python host usually also hosts PyTorch, whose own
+    # libnccl.so.2 must be THE libnccl of the process (the loader keys on the soname: whichever is loaded first wins, and
+    # an older system NCCL loaded first breaks `import torch`): point the library at the pip-installed one when there is one.
+    if "XMB_NCCL_LIBRARY" not in os.environ:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for d in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["XMB_NCCL_LIBRARY"] = cand
+                    break
+        except Exception:
+            pass
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
     L.xmb_xrl_surrogate.restype = C.POINTER(XrlProvider)
@@ -266,6 +282,20 @@ def lib():
     L.xmb_msim_total_histories.argtypes = [vp]; L.xmb_msim_total_histories.restype = C.c_uint64
     L.xmb_msim_slot_map.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
     L.xmb_msim_slot_map.restype = C.c_int
+    L.xmb_comm_unique_id.argtypes = [C.c_char_p]; L.xmb_comm_unique_id.restype = C.c_int
+    L.xmb_comm_init_rank.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, vpp]; L.xmb_comm_init_rank.restype = C.c_int
+    L.xmb_comm_free.argtypes = [vpp]; L.xmb_comm_free.restype = None
+    L.xmb_comm_rank.argtypes = [vp]; L.xmb_comm_rank.restype = C.c_int
+    L.xmb_comm_size.argtypes = [vp]; L.xmb_comm_size.restype = C.c_int
+    L.xmb_nccl_version.restype = C.c_int
+    L.xmb_main_msim_multi.argtypes = [vp, vp, vp, C.POINTER(c_double_p), C.POINTER(MainOptions), C.POINTER(c_double_p),
+                                      C.POINTER(c_double_p), C.POINTER(SolidAngle)]
+    L.xmb_main_msim_multi.restype = C.c_int
+    L.xmb_main_msim_multi_raw.argtypes = [vp, vp, C.POINTER(MainOptions), C.POINTER(SolidAngle), vp, C.POINTER(MsimEx)]
+    L.xmb_main_msim_multi_raw.restype = C.c_int
+    L.xmb_main_msim_all_devices.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(c_double_p), C.POINTER(MainOptions),
+                                            C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(SolidAngle), C.POINTER(MsimEx)]
+    L.xmb_main_msim_all_devices.restype = C.c_int
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

@@ -28,10 +28,17 @@ struct XmbDeviceTables {
 	size_t queue_doubles = 0;
 	int *line_slot = nullptr;          // [nZ][384] compact history slot of a line (brute-force scoring)
 	double *auger_rate = nullptr;      // [nZ][XMB_N_AUGER]
+	// the run in flight / last run (xmb_msim_launch / xmb_msim_collect)
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool run_brute = false;
+	size_t run_slots = 0;
+	uint64_t run_launches = 0;
 	unsigned long long brute_counters[8] = {0};
 	unsigned long long layer_interactions[XMB_MAX_LAYERS] = {0};
 	~XmbDeviceTables() {
 		for (void *p : allocs) cudaFree(p);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
 		cudaFree(sa_grid); cudaFree(sa_r); cudaFree(sa_t); cudaFree(acc); cudaFree(limbs); cudaFree(counters); cudaFree(queue);
 	}
 };
@@ -41,6 +48,11 @@ int xmb_cascade_mode(const xmb_main_options *o);
 // the handle's device tables for these options on the current device (built on first use, rebuilt when the cascade
 // mode, the M-line switch or the device changed); NULL + xmb_last_error on failure
 XmbDeviceTables *xmb_device_tables_get(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt);
+
+// the two halves of xmb_main_msim_raw (history.cu): enqueue on the current (or ex->device's) default stream / wait and read counters
+int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options, const xmb_solid_angle *sa, xmb_msim_ex *ex,
+                    XmbDeviceTables **D_out);
+int xmb_msim_collect(XmbDeviceTables *D, const xmb_main_options *options, xmb_msim_ex *ex);
 
 // brute-force kernel (brute.cu)
 struct XmbBruteParams {

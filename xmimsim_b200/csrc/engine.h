@@ -35,7 +35,10 @@ struct XmbHdf5F {
 	std::vector<double> adv_config, adv_edge, adv_cdf, adv_qinv;
 	int quality = 0;
 	double e_max = 0.0;
-	XmbDeviceTables *dev = nullptr;   // lazily built device-side layouts (device.cu)
+	// lazily built device-side layouts (history.cu): one handle per CUDA device the simulation has run on (a single
+	// process may drive every GPU of the box, multi_gpu.cu); `dev` is the handle of the last run (accessors read it)
+	XmbDeviceTables *dev = nullptr;
+	std::vector<XmbDeviceTables *> devs;
 };
 
 void xmb_set_error(const char *fmt, ...);
@@ -45,4 +48,5 @@ XmbHdf5F *xmb_as_hdf5(xmb_hdf5FPtr p);
 // host-side table evaluation (used for the solid-angle bounds and the exciter absorbers)
 double xmb_host_mu_layer(const xmb_xrl_provider *xrl, const xmb_layer *layer, double E);
 void xmb_free_device_tables(XmbDeviceTables *dev);
+void xmb_free_all_device_tables(XmbHdf5F *h);   // every per-device handle of h
 int xmb_build_tables(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int quality, xmb_hdf5FPtr *out, bool skip_icdf);

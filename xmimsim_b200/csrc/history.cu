@@ -658,7 +658,19 @@ __global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, uns
 // Host side: device layouts, launch, exact reduction epilogue.
 // =====================================================================================================
 
-void xmb_free_device_tables(XmbDeviceTables *dev) { delete dev; }
+void xmb_free_device_tables(XmbDeviceTables *dev) {
+	if (!dev) return;
+	int cur = 0;
+	const bool on_device = dev->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != dev->device;
+	if (on_device) cudaSetDevice(dev->device);   // cudaFree wants the owning device's context current
+	delete dev;
+	if (on_device) cudaSetDevice(cur);
+}
+void xmb_free_all_device_tables(XmbHdf5F *h) {
+	for (XmbDeviceTables *d : h->devs) xmb_free_device_tables(d);
+	h->devs.clear();
+	h->dev = nullptr;
+}
 
 static bool g_layout_only = false;   // build_device_tables: host-side layout without touching CUDA
 
@@ -981,11 +993,17 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 XmbDeviceTables *xmb_device_tables_get(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt) {
 	int dev = 0;
 	cudaGetDevice(&dev);
-	XmbDeviceTables *D = h->dev;
-	if (!D || D->cascade != xmb_cascade_mode(opt) || D->use_M_lines != (opt->use_M_lines ? 1 : 0) || D->device != dev) {
-		if (D) delete D;
-		h->dev = D = build_device_tables(in, h, opt);
+	for (size_t i = 0; i < h->devs.size(); i++) {
+		XmbDeviceTables *D = h->devs[i];
+		if (D->device != dev) continue;
+		if (D->cascade == xmb_cascade_mode(opt) && D->use_M_lines == (opt->use_M_lines ? 1 : 0)) return h->dev = D;
+		xmb_free_device_tables(D);          // same device, other options: rebuilt below
+		h->devs.erase(h->devs.begin() + i);
+		break;
 	}
+	h->dev = nullptr;
+	XmbDeviceTables *D = build_device_tables(in, h, opt);
+	if (D) { h->devs.push_back(D); h->dev = D; }
 	return D;
 }
 
@@ -1007,13 +1025,17 @@ static uint64_t sa_content_hash(const xmb_solid_angle *sa) {
 	return hash_words(sa->grid_dims_theta_vals, nt, h);
 }
 
-extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
-                                 const xmb_solid_angle *sa, xmb_msim_ex *ex, uint64_t **accum, size_t *n_slots) {
-	XmbInputF *in = xmb_as_input(inputF);
-	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
-	if (!in || !h || !in->inited || !options || !ex || !accum || !n_slots) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
+// One run of the history (or brute-force) kernel in two halves, so that a driver can have every GPU of the box working
+// before it waits for any of them (multi_gpu.cu):
+//   xmb_msim_launch  : device tables for the current device, solid-angle grid host->device (content-hash residency with
+//                      keep_on_device), accumulators zeroed, kernel + limb conversion ENQUEUED on the device's default
+//                      stream; returns without waiting.  The limbs (D->limbs, 2 x slots uint64) are complete in stream order.
+//   xmb_msim_collect : waits for the kernel, reads the counters, fills ex's outputs, reports range errors.
+int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options, const xmb_solid_angle *sa, xmb_msim_ex *ex,
+                    XmbDeviceTables **D_out) {
+	if (!in || !h || !in->inited || !options || !ex) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
 	const bool brute = !options->use_variance_reduction;
-	if (options->use_advanced_compton && !xmb_tables_enable_advanced_compton(hdf5F)) return 0;   // builds the subshell tables once
+	if (options->use_advanced_compton && !xmb_tables_enable_advanced_compton((xmb_hdf5FPtr)h)) return 0;   // builds the subshell tables once
 	if (options->escape_ratios_mode) { xmb_set_error("escape_ratios_mode is not implemented on the GPU path"); return 0; }
 	if (!brute && (!sa || !sa->solid_angles)) { xmb_set_error("variance reduction needs a solid-angle grid"); return 0; }
 	if (xmb_cuda_device_count() < 1) { xmb_set_error("no CUDA device: xmb_main_msim has no CPU fallback"); return 0; }
@@ -1022,6 +1044,7 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	cudaGetDevice(&dev);
 	XmbDeviceTables *D = xmb_device_tables_get(in, h, options);
 	if (!D) return 0;
+	if (D_out) *D_out = D;
 	XmbHistParams P = D->P;
 	// solid-angle grid: an argument of the call -> copied host->device every call; with keep_on_device the copy is
 	// skipped when the grid in HBM has the same CONTENT (dimensions + a 64-bit hash of values and axes: a caller may
@@ -1067,6 +1090,7 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const size_t slots = (size_t)(P.n_int + (brute ? 1 : 0)) * ((size_t)P.nch + P.n_hist_slots);
 	if (D->acc_slots != slots) {
 		cudaFree(D->acc); cudaFree(D->limbs); cudaFree(D->counters);
+		D->acc = D->limbs = D->counters = nullptr; D->acc_slots = 0;
 		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 2 * slots));
 		XMB_CUDA_OK(cudaMalloc(&D->limbs, sizeof(unsigned long long) * 2 * slots));
 		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * (8 + XMB_MAX_LAYERS)));
@@ -1085,7 +1109,8 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		P.n_local_span = (blocks / nr + ((uint64_t)rk < blocks % nr ? 1 : 0)) * XMB_SHARD_BLOCK;
 	}
 	ex->n_histories = xmb_msim_shard_count(D->n_total, rk, nr);
-	// launch
+	if (!D->ev0) { XMB_CUDA_OK(cudaEventCreate(&D->ev0)); XMB_CUDA_OK(cudaEventCreate(&D->ev1)); }
+	D->run_brute = brute; D->run_slots = slots; D->run_launches = 1;
 	int sms = 148, occ = 1;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	if (brute) {
@@ -1095,30 +1120,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 		B.collimator_radius = in->der.collimator_radius; B.half_apex = in->der.half_apex;
 		B.vertex_x = in->der.vertex[0]; B.vertex_y = in->der.vertex[1]; B.vertex_z = in->der.vertex[2];
 		B.line_slot = D->line_slot; B.auger_rate = D->auger_rate;
-		cudaEvent_t e0, e1;
-		cudaEventCreate(&e0); cudaEventCreate(&e1);
-		cudaEventRecord(e0);
+		cudaEventRecord(D->ev0);
 		XMB_CUDA_OK(xmb_brute_launch(P, B, options->use_advanced_compton != 0, sms, ex->n_histories));
-		cudaEventRecord(e1);
+		cudaEventRecord(D->ev1);
+		if (ex->n_histories > 0) D->run_launches++;
 		xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 		XMB_CUDA_OK(cudaGetLastError());
-		XMB_CUDA_OK(cudaEventSynchronize(e1));
-		float ms = 0.f;
-		cudaEventElapsedTime(&ms, e0, e1);
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
-		ex->kernel_ms = ms;
-		ex->n_launches = (ex->n_histories > 0 ? 1 : 0) + 1;
-		unsigned long long cnt[8];
-		XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
-		for (int i = 0; i < 8; i++) D->brute_counters[i] = cnt[i];
-		ex->n_interactions = cnt[1];
-		if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
-		if (cnt[5] && options->verbose) fprintf(stderr, "detected photons of lines without a history slot: %llu\n", cnt[5]);
-		*n_slots = slots;
-		if (ex->keep_on_device) { *accum = nullptr; return 1; }
-		uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
-		XMB_CUDA_OK(cudaMemcpy(out, D->limbs, sizeof(uint64_t) * 2 * slots, cudaMemcpyDeviceToHost));
-		*accum = out;
 		return 1;
 	}
 	// threads per CTA: as many as the per-thread shared arrays (2 nL doubles) allow within 200 KB
@@ -1126,9 +1133,12 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
 	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
 	while (threads > 64 && stage_bytes + sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
-	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch
-	const size_t per_photon = (size_t)std::max(1, D->max_nE) * (options->use_advanced_compton ? 32 : 1);   // + one addend per subshell
+	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch; a photon
+	// adds to a channel slot once per element (Compton) plus once for the summed Rayleigh deposits
+	const size_t per_photon = ((size_t)std::max(1, D->max_nE) + 1) * (options->use_advanced_compton ? 32 : 1);   // + one addend per subshell
 	while (threads > 64 && (size_t)threads * per_photon > 60000) threads -= 32;
+	// experiments / tests: force a smaller CTA (the sums do not depend on the launch shape: test_history_gpu.py)
+	if (const char *e = getenv("XMB_HIST_THREADS")) { const int t = atoi(e) & ~31; if (t >= 32 && t < threads) threads = t; }
 	const size_t smem = stage_bytes + sizeof(double) * 2 * P.nL * threads;
 	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
@@ -1139,6 +1149,7 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	const uint64_t n_chunks = (ex->n_histories + threads - 1) / threads;
 	uint64_t blocks = (uint64_t)sms * occ;
 	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, n_chunks));
+	if (const char *e = getenv("XMB_HIST_BLOCKS")) { const long b = atol(e); if (b >= 1 && (uint64_t)b < blocks) blocks = (uint64_t)b; }
 	if (P.n_int > XMB_MAX_ORDERS) { xmb_set_error("more than %d interactions per trajectory", XMB_MAX_ORDERS); return 0; }
 	// per-CTA compaction queues: n_int orders (x nL layers) x 2T photons x (15 + nL) doubles (structure of arrays)
 	size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + P.nL) * 2 * threads;
@@ -1148,34 +1159,54 @@ extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const
 	}
 	if (D->queue_doubles < qd) {
 		cudaFree(D->queue);
-		D->queue = nullptr;
+		D->queue = nullptr; D->queue_doubles = 0;
 		XMB_CUDA_OK(cudaMalloc(&D->queue, sizeof(double) * qd));
 		D->queue_doubles = qd;
 	}
 	P.queue = D->queue;
-	cudaEvent_t e0, e1;
-	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	cudaEventRecord(e0);
-	if (ex->n_histories > 0) kernel<<<(unsigned)blocks, threads, smem>>>(P);
-	cudaEventRecord(e1);
+	cudaEventRecord(D->ev0);
+	if (ex->n_histories > 0) { kernel<<<(unsigned)blocks, threads, smem>>>(P); D->run_launches++; }
+	cudaEventRecord(D->ev1);
 	xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 	XMB_CUDA_OK(cudaGetLastError());
-	XMB_CUDA_OK(cudaEventSynchronize(e1));
+	return 1;
+}
+
+int xmb_msim_collect(XmbDeviceTables *D, const xmb_main_options *options, xmb_msim_ex *ex) {
+	int cur = 0;
+	cudaGetDevice(&cur);
+	if (cur != D->device) XMB_CUDA_OK(cudaSetDevice(D->device));
+	XMB_CUDA_OK(cudaEventSynchronize(D->ev1));
 	float ms = 0.f;
-	cudaEventElapsedTime(&ms, e0, e1);
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaEventElapsedTime(&ms, D->ev0, D->ev1);
 	ex->kernel_ms = ms;
-	ex->n_launches = (ex->n_histories > 0 ? 1 : 0) + 1;
+	ex->n_launches = D->run_launches;
 	unsigned long long cnt[8 + XMB_MAX_LAYERS];
 	XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
-	for (int i = 0; i < XMB_MAX_LAYERS; i++) D->layer_interactions[i] = cnt[8 + i];
 	ex->n_interactions = cnt[1];
+	if (D->run_brute) {
+		for (int i = 0; i < 8; i++) D->brute_counters[i] = cnt[i];
+		if (cnt[5] && options->verbose) fprintf(stderr, "detected photons of lines without a history slot: %llu\n", cnt[5]);
+	} else {
+		for (int i = 0; i < XMB_MAX_LAYERS; i++) D->layer_interactions[i] = cnt[8 + i];
+		if (cnt[0] && options->verbose) fprintf(stderr, "detector_solid_angle_not_found: %llu\n", cnt[0]);
+	}
 	if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
-	if (cnt[0] && options->verbose) fprintf(stderr, "detector_solid_angle_not_found: %llu\n", cnt[0]);
-	*n_slots = slots;
+	return 1;
+}
+
+extern "C" int xmb_main_msim_raw(xmb_inputFPtr inputF, xmb_hdf5FPtr hdf5F, const xmb_main_options *options,
+                                 const xmb_solid_angle *sa, xmb_msim_ex *ex, uint64_t **accum, size_t *n_slots) {
+	XmbInputF *in = xmb_as_input(inputF);
+	XmbHdf5F *h = xmb_as_hdf5(hdf5F);
+	if (!in || !h || !options || !ex || !accum || !n_slots) { xmb_set_error("xmb_main_msim_raw: bad arguments"); return 0; }
+	XmbDeviceTables *D = nullptr;
+	if (!xmb_msim_launch(in, h, options, sa, ex, &D)) return 0;
+	if (!xmb_msim_collect(D, options, ex)) return 0;
+	*n_slots = D->run_slots;
 	if (ex->keep_on_device) { *accum = nullptr; return 1; }   // limbs stay in HBM: xmb_msim_device_limbs()
-	uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * slots);
-	XMB_CUDA_OK(cudaMemcpy(out, D->limbs, sizeof(uint64_t) * 2 * slots, cudaMemcpyDeviceToHost));
+	uint64_t *out = (uint64_t *)malloc(sizeof(uint64_t) * 2 * D->run_slots);
+	XMB_CUDA_OK(cudaMemcpy(out, D->limbs, sizeof(uint64_t) * 2 * D->run_slots, cudaMemcpyDeviceToHost));
 	*accum = out;
 	return 1;
 }
@@ -1200,12 +1231,16 @@ extern "C" uint64_t xmb_msim_shard_count(uint64_t n_total, int rank, int n_ranks
 }
 
 static XmbDeviceTables *ensure_layout(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *opt) {
-	if (h->dev && h->dev->cascade == xmb_cascade_mode(opt) && h->dev->use_M_lines == (opt->use_M_lines ? 1 : 0)) return h->dev;
-	if (h->dev) { delete h->dev; h->dev = nullptr; }
+	auto fits = [&](XmbDeviceTables *D) { return D && D->cascade == xmb_cascade_mode(opt) && D->use_M_lines == (opt->use_M_lines ? 1 : 0); };
+	if (fits(h->dev)) return h->dev;
+	for (XmbDeviceTables *D : h->devs) if (fits(D)) return D;
+	// host-side layout only (slot map, epilogue): a handle without device memory, device = -2
+	for (size_t i = 0; i < h->devs.size(); i++) if (h->devs[i]->device == -2) { if (h->dev == h->devs[i]) h->dev = nullptr; delete h->devs[i]; h->devs.erase(h->devs.begin() + i); break; }
 	g_layout_only = true;
-	h->dev = build_device_tables(in, h, opt);
+	XmbDeviceTables *D = build_device_tables(in, h, opt);
 	g_layout_only = false;
-	return h->dev;
+	if (D) { h->devs.push_back(D); if (!h->dev) h->dev = D; }
+	return D;
 }
 
 extern "C" uint64_t xmb_msim_total_histories(xmb_inputFPtr inputF) {

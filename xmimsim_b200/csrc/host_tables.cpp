@@ -352,7 +352,7 @@ extern "C" void xmb_free_hdf5_F(xmb_hdf5FPtr *p) {
 	if (!p || !*p) return;
 	XmbHdf5F *h = xmb_as_hdf5(*p);
 	if (!h) return;
-	if (h->dev) xmb_free_device_tables(h->dev);
+	xmb_free_all_device_tables(h);
 	h->magic = 0;
 	delete h;
 	*p = nullptr;
@@ -506,6 +506,6 @@ extern "C" int xmb_tables_enable_advanced_compton(xmb_hdf5FPtr p) {
 	v.adv_off = h->adv_off.data(); v.adv_shell = h->adv_shell.data(); v.adv_config = h->adv_config.data();
 	v.adv_edge = h->adv_edge.data(); v.adv_cdf = h->adv_cdf.data(); v.adv_qinv = h->adv_qinv.data();
 	v.n_adv_rows = rows;
-	if (h->dev) { xmb_free_device_tables(h->dev); h->dev = nullptr; }   // device layouts are rebuilt with the new tables
+	xmb_free_all_device_tables(h);   // device layouts are rebuilt with the new tables
 	return 1;
 }

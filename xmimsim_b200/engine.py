@@ -68,6 +68,29 @@ def tube_ebel(anode, voltage, current=1.0, angle_electron=60.0, angle_xray=60.0,
     return cont, disc
 
 
+class Comm:
+    """NCCL communicator of the engine, one rank per GPU.  Rank 0 creates the id (Comm.unique_id()), the launcher's own
+    channel carries the 128 bytes to the other ranks (torch.distributed / MPI), every rank builds Comm(id, rank, n)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        if not abi.lib().xmb_comm_unique_id(buf):
+            raise RuntimeError("xmb_comm_unique_id: " + abi.last_error())
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, n_ranks: int, device: int = -1):
+        assert len(unique_id) == abi.COMM_ID_BYTES
+        self.handle = C.c_void_p()
+        if not abi.lib().xmb_comm_init_rank(unique_id, rank, n_ranks, device, C.byref(self.handle)):
+            raise RuntimeError("xmb_comm_init_rank: " + abi.last_error())
+        self.rank, self.n_ranks = rank, n_ranks
+
+    def close(self):
+        if self.handle:
+            abi.lib().xmb_comm_free(C.byref(self.handle))
+
+
 class Simulation:
     """Owns the two opaque handles (input + tables) of one simulation."""
 
@@ -195,6 +218,37 @@ class Simulation:
                                         C.byref(acc), C.byref(n)):
             raise RuntimeError("xmb_main_msim_raw: " + abi.last_error())
         return ex
+
+    # -- multi-GPU (multi_gpu.cu): shards + one NCCL all-reduce of the integer histograms -----------------------
+    def main_msim_multi(self, comm, options=None, sa=None):
+        """xmi_main_msim over a communicator (Comm): the three output arrays, summed over all ranks, on every rank."""
+        options = options or main_options()
+        ch, br, vr = abi.c_double_p(), abi.c_double_p(), abi.c_double_p()
+        if not self.L.xmb_main_msim_multi(self.inputF, self.hdf5F, comm.handle, C.byref(ch), C.byref(options), C.byref(br),
+                                          C.byref(vr), self._sa_arg(sa, options)):
+            raise RuntimeError("xmb_main_msim_multi: " + abi.last_error())
+        return self._take(ch, br, vr)
+
+    def main_msim_multi_device(self, comm, options=None, sa=None, seed=0):
+        """History kernel -> limbs -> ncclAllReduce on one stream, the reduced limbs left in HBM (device_limbs());
+        the solid-angle grid is uploaded only when its content changed.  Returns MsimEx (this rank's counters)."""
+        options = options or main_options()
+        ex = abi.MsimEx(0, 1, seed, -1, 1, 0, 0.0, 0, 0)
+        if not self.L.xmb_main_msim_multi_raw(self.inputF, self.hdf5F, C.byref(options), self._sa_arg(sa, options),
+                                              comm.handle, C.byref(ex)):
+            raise RuntimeError("xmb_main_msim_multi_raw: " + abi.last_error())
+        return ex
+
+    def main_msim_all_devices(self, n_devices=0, options=None, sa=None, seed=0, devices=None):
+        """One process, n_devices GPUs (0: all visible).  Returns (channels, brute_history, var_red_history, MsimEx)."""
+        options = options or main_options()
+        ch, br, vr = abi.c_double_p(), abi.c_double_p(), abi.c_double_p()
+        ex = abi.MsimEx(0, 1, seed, -1, 0, 0, 0.0, 0, 0)
+        dv = (C.c_int * len(devices))(*devices) if devices else None
+        if not self.L.xmb_main_msim_all_devices(self.inputF, self.hdf5F, len(devices) if devices else n_devices, dv, C.byref(ch),
+                                                C.byref(options), C.byref(br), C.byref(vr), self._sa_arg(sa, options), C.byref(ex)):
+            raise RuntimeError("xmb_main_msim_all_devices: " + abi.last_error())
+        return self._take(ch, br, vr) + (ex,)
 
     def device_limbs(self):
         """(device pointer, n_words) of the last run's uint64 limbs."""

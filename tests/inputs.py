@@ -44,56 +44,7 @@ def caso4():
         crystal_layers=[x.LayerD([14], [1.0], 2.33, 0.5)])
 
 
-def synthetic_layers(n_photons=30000, n_int=8, n_lines=1):
-    """BASELINE config 4: 10 parallel layers, 3-6 elements each from a Z = 8..82 pool, Dirichlet(1)
-    weights, rho ~ U(1,10), thickness ~ logU(1e-4, 1e-1), numpy default_rng(20260101); geometry/detector as
-    srm1155; one 28 keV line (or n_lines lines on 20..40 keV)."""
-    import numpy as np
-    rng = np.random.default_rng(20260101)
-    pool = [8, 13, 14, 20, 22, 26, 29, 30, 38, 42, 47, 50, 56, 74, 79, 82]
-    base = example("srm1155")
-    layers = []
-    for _ in range(10):
-        k = int(rng.integers(3, 7))
-        zs = sorted(int(z) for z in rng.choice(pool, size=k, replace=False))
-        w = rng.dirichlet(np.ones(k))
-        layers.append(x.LayerD(zs, [float(v) for v in w], float(rng.uniform(1, 10)),
-                               float(10 ** rng.uniform(-4, -1))))
-    d = copy.deepcopy(base)
-    d.layers = layers
-    d.reference_layer = 1
-    d.n_interactions_trajectory = n_int
-    d.n_photons_line = n_photons
-    if n_lines == 1:
-        d.discrete = [x.DiscreteD(28.0, 1e12, 1e9)]
-    else:
-        d.discrete = [x.DiscreteD(float(e), 1e10, 1e9) for e in np.linspace(20.0, 40.0, n_lines)]
-    d.gain = 0.02
-    d.zero = 0.0
-    return d
-
-
-def ebel_like(n_intervals=1000, n_photons_interval=10000, n_photons_line=10000, e_max=40.0):
-    """BASELINE config 5 shape: a tube-like continuum of n_intervals trapezoid intervals from 1 keV to
-    e_max (Kramers shape, unpolarised) plus Ag K/L characteristic lines, two of them broadened (Gaussian /
-    Lorentzian) to exercise those samplers.  Authored synthetically: xmi_tube_ebel needs xraylib."""
-    import numpy as np
-    d = copy.deepcopy(example("srm1155"))
-    es = np.linspace(1.0, e_max, n_intervals + 1)
-    cont = []
-    for e in es:
-        inten = 1e8 * max(e_max / e - 1.0, 0.0) * np.exp(-2.0 / e)
-        cont.append(x.ContinuousD(float(e), float(inten / 2), float(inten / 2)))
-    d.continuous = cont
-    d.discrete = [x.DiscreteD(2.984, 2e8, 2e8), x.DiscreteD(3.151, 1e8, 1e8),
-                  x.DiscreteD(21.990, 4e8, 4e8, distribution_type=1, scale_parameter=0.05),
-                  x.DiscreteD(22.163, 8e8, 8e8),
-                  x.DiscreteD(24.942, 2e8, 2e8, distribution_type=2, scale_parameter=0.02)]
-    d.n_photons_interval = n_photons_interval
-    d.n_photons_line = n_photons_line
-    d.gain = 0.025
-    d.zero = 0.0
-    return d
+from xmimsim_b200.workloads import synthetic_layers, ebel_like   # noqa: E402,F401  (BASELINE configs[3] / configs[4])
 
 
 def close_detector(n_photons=200000, n_int=2):

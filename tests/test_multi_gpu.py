@@ -79,6 +79,10 @@ def test_cli_gpus_option_writes_the_same_xmso(tmp_path):
         r = subprocess.run([exe, "--surrogate-cross-sections", "--table-quality=0", "--gpus=%d" % n, "--disable-escape-peaks", xmsi],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
-        txt = open(inp.outputfile).read()
-        outs.append(txt[txt.index("<spectrum_conv>"):txt.index("</brute_force_history>") if "</brute_force_history>" in txt else len(txt)])
-    assert all(o == outs[0] for o in outs)
+        outs.append(x.read_xmso(inp.outputfile))
+    for o in outs[1:]:
+        assert np.array_equal(o["conv"], outs[0]["conv"]), float(np.abs(o["conv"] - outs[0]["conv"]).max())
+        assert np.array_equal(o["unconv"], outs[0]["unconv"]), float(np.abs(o["unconv"] - outs[0]["unconv"]).max())
+        assert o["history"].keys() == outs[0]["history"].keys()
+        for k, v in o["history"].items():
+            assert v["counts"] == outs[0]["history"][k]["counts"], k

@@ -22,9 +22,11 @@ ORC_LIB   := oracle/_build/liborc.so
 PLUGIN    := xmimsim_b200/lib/xmimsim-cl.so
 
 CLI       := bin/xmimsim-b200
+INTERPOSE := xmimsim_b200/lib/libxmimsim-b200-interpose.so
+HARNESS   := xmimsim_b200/lib/plugin_harness
 
-all: $(LIB) $(PLUGIN) $(ORC_LIB) $(CLI) oracle_ref
-lib: $(LIB) $(PLUGIN) $(CLI)
+all: $(LIB) $(PLUGIN) $(INTERPOSE) $(HARNESS) $(ORC_LIB) $(CLI) oracle_ref
+lib: $(LIB) $(PLUGIN) $(INTERPOSE) $(HARNESS) $(CLI)
 oracle: $(ORC_LIB)
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(HDRS)
@@ -48,6 +50,16 @@ $(LIB): $(OBJS)
 # the same symbols are inside $(LIB); this is that library under the expected name (a relative symlink).
 $(PLUGIN): $(LIB)
 	ln -sf $(notdir $(LIB)) $(PLUGIN)
+
+# The reference-named history entry point xmi_main_msim (include/xmi_main.h:29) lives in its own file: LD_PRELOAD it into
+# the reference's host to route its xmi_main_msim calls to the GPU; inside the plugin file the name
+# would clash with libxmimsim's own.
+$(INTERPOSE): $(SRC)/plugin_shim.cpp $(LIB) $(HDRS)
+	$(CXX) $(CXXFLAGS) -DXMB_EXPORT_XMI_MAIN_MSIM -DXMB_INTERPOSE_ONLY -shared -o $@ $(SRC)/plugin_shim.cpp -Lxmimsim_b200/lib -lxmimsim_b200 -ldl -Wl,-rpath,'$$ORIGIN'
+
+# C harness that calls the reference-named symbols the way bin/xmimsim.c does (tests/test_plugin_harness_gpu.py runs it)
+$(HARNESS): tests/c/plugin_harness.c $(LIB) $(INTERPOSE) include/xmimsim_b200.h
+	$(CC) -O1 -std=gnu99 -Wall -Iinclude -rdynamic -o $@ tests/c/plugin_harness.c -Lxmimsim_b200/lib -lxmimsim_b200 -ldl -Wl,-rpath,'$$ORIGIN'
 
 # Command-line driver with the reference's options (bin/xmimsim.c); finds the library next to the package.
 $(CLI): bin/xmimsim_main.cpp $(LIB) include/xmimsim_b200.h

@@ -291,9 +291,15 @@ def run_ours(args):
         return max_over_ranks(max(wall, ev0.elapsed_time(ev1) / 1e3)), outs
 
     def limbs_digest(sim):
+        """SHA-256 of the reduced 128-bit histogram integers.  A slot is two limbs (low 48 bits, the rest); after the sum over
+        ranks the low limb carries up to log2(N) extra bits, so the VALUE lo + (hi << 48) is hashed, not the limb pair."""
         ptr, n = sim.device_limbs()
         holder = type("H", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}})()
-        return hashlib.sha256(torch.as_tensor(holder, device="cuda").cpu().numpy().tobytes()).hexdigest()[:16]
+        a = torch.as_tensor(holder, device="cuda").cpu().numpy().view(np.uint64).reshape(-1, 2)
+        lo, hi = a[:, 0], a[:, 1]
+        hi = hi + (lo >> np.uint64(48))                       # carry of the low limb (hi < 2^63 here)
+        lo = lo & np.uint64(0xFFFFFFFFFFFF)
+        return hashlib.sha256(np.stack([lo, hi], axis=1).tobytes()).hexdigest()[:16]
 
     # ================= headline: BASELINE configs[1] ============================================================
     inp = load_workload(args.workload, n_gpus, args.photons_per_line)

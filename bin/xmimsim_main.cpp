@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
 			return 1;
 		}
 	}
+	xmb_plugin_set_provider(xrl);   // a --custom-detector-response plugin that is this library computes with the same cross sections
 	xmb_input *input = nullptr;
 	if (!xmb_input_read_from_xml_file(infile.c_str(), &input)) { fprintf(stderr, "Could not read %s: %s\n", infile.c_str(), xmb_last_error()); return 1; }
 	if (opt.verbose) printf("Inputfile %s successfully parsed\n", infile.c_str());

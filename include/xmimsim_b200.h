@@ -620,6 +620,13 @@ void xmi_detector_convolute_all_custom(void *inputFPtr, double **channels_noconv
                                        int n_interactions_all, int zero_interaction);
 /* Cross-section provider used by the two plugin symbols (NULL: analytic surrogate). */
 void xmb_plugin_set_provider(const xmb_xrl_provider *provider);
+/* The provider the plugin symbols use: the registered one, else xraylib bound at run time, else -- only with
+ * XMB_ALLOW_SURROGATE=1 -- the analytic stand-in; NULL + xmb_last_error otherwise. */
+const xmb_xrl_provider *xmb_plugin_provider(void);
+/* Turns the handle a reference host passes (its opaque Fortran xmi_inputFPtr, converted with the host's own
+ * xmi_input_F2C, src/xmi_aux_f.F90:766-776) or one of this library's handles into an xmb_inputFPtr; *owned = 1 when
+ * a temporary handle was created (free it with xmb_free_input_F).  Used by libxmimsim-b200-interpose.so. */
+int xmb_plugin_resolve_input(void *inputFPtr, xmb_inputFPtr *out, int *owned);
 
 /* xmi_main_options_new defaults (src/xmi_data_structs.c:2531-2565). */
 void xmb_main_options_defaults(xmb_main_options *options);

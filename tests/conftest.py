@@ -35,3 +35,14 @@ def golden_dir():
 def srm1155():
     import xmimsim_b200 as x
     return x.read_xmsi(os.path.join(GOLDEN, "srm1155.xmsi"))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _plugin_provider():
+    """The plugin symbols (xmi_solid_angle_calculation_cl, ...) refuse to fall back to the analytic stand-in on their
+    own; the image has no xraylib, so the test process registers the stand-in explicitly, as a host would register its
+    provider (tests/test_plugin_harness_gpu.py covers the refusal in fresh processes)."""
+    from xmimsim_b200 import abi
+    L = abi.lib()
+    L.xmb_plugin_set_provider(L.xmb_xrl_surrogate())
+    yield

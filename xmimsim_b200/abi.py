@@ -296,6 +296,9 @@ def lib():
     L.xmb_main_msim_all_devices.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(c_double_p), C.POINTER(MainOptions),
                                             C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(SolidAngle), C.POINTER(MsimEx)]
     L.xmb_main_msim_all_devices.restype = C.c_int
+    L.xmb_plugin_set_provider.argtypes = [C.POINTER(XrlProvider)]; L.xmb_plugin_set_provider.restype = None
+    L.xmb_plugin_provider.restype = C.POINTER(XrlProvider)
+    L.xmb_plugin_resolve_input.argtypes = [vp, vpp, C.POINTER(C.c_int)]; L.xmb_plugin_resolve_input.restype = C.c_int
     L.xmb_version.restype = C.c_char_p
     L.xmb_last_error.restype = C.c_char_p
     L.xmb_cuda_device_count.restype = C.c_int

@@ -131,7 +131,7 @@ __device__ void cascade_emit(const XmbHistParams &P, Photon &q, double *mus, int
 	const int nL = NL > 0 ? NL : P.nL;
 	q.energy = P.line_energy[(size_t)zi * 384 + line];
 	const NodePos lp = node_find(P, q.energy);
-	for (int i = 0; i < nL; i++) mus[i] = row_lerp(P, lp, i);
+	for (int i = 0; i < nL; i++) mus[i] = mu_lerp(P, lp, i);
 	q.theta = acos(2.0 * xs.uniform() - 1.0);
 	q.phi = 2.0 * M_PI * xs.uniform();
 	q.dx = sin(q.theta) * cos(q.phi); q.dy = sin(q.theta) * sin(q.phi); q.dz = cos(q.theta);

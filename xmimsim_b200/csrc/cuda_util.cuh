@@ -18,6 +18,29 @@
 #define XMB_TAG_HISTORY 0x48u
 #define XMB_TAG_DETECTOR 0x44u
 
+// ---- bulk asynchronous copy global -> shared with an mbarrier (the TMA engine's 1-D path: UBLKCP in SASS) -----------
+// One thread arms the barrier with the byte count and issues the copy; every consumer waits on the barrier's phase
+// parity.  Addresses are shared-window addresses (__cvta_generic_to_shared); src / dst 16-byte aligned, bytes % 16 == 0.
+#ifdef __CUDACC__
+__device__ __forceinline__ void xmb_mbar_init(unsigned mbar_s32, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s32), "r"(count) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void xmb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void xmb_bulk_g2s(unsigned dst_s32, const void *src, unsigned bytes, unsigned mbar_s32) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s32), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(dst_s32), "l"(src), "r"(bytes), "r"(mbar_s32) : "memory");
+}
+__device__ __forceinline__ void xmb_mbar_wait(unsigned mbar_s32, unsigned parity) {
+	unsigned done;
+	do {
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+		             : "=r"(done) : "r"(mbar_s32), "r"(parity) : "memory");
+	} while (!done);
+}
+#endif
+
 // Philox4x32-10 (Random123): one call = 4 x 32 random bits from (counter[4], key[2]).
 __host__ __device__ __forceinline__ uint4 xmb_philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

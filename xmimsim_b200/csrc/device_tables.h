@@ -14,6 +14,7 @@ struct XmbDeviceTables {
 	// host metadata for the epilogue
 	std::vector<int> rec_slot, rec_channel, rec_line, rec_zi, hist_base;
 	int n_rec = 0, n_hist_slots = 0, max_nE = 1;
+	size_t n_line_tiles_bytes = 0;     // all line-tile blobs (history.cuh)
 	double W_max = 0.0;
 	uint64_t n_total = 0;
 	// solid-angle grid + accumulators (re-used across calls)

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256, XMB_ESC_MINB) xmb_escape_kernel(const __g
 	double mus0[NLA];
 	{
 		const NodePos np = node_find(P, E0);
-		for (int i = 0; i < nL; i++) mus0[i] = row_lerp(P, np, i);
+		for (int i = 0; i < nL; i++) mus0[i] = mu_lerp(P, np, i);
 	}
 	unsigned long long interacted = 0;
 	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < R.n_photons; j += (uint64_t)gridDim.x * blockDim.x) {

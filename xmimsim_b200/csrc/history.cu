@@ -41,6 +41,24 @@
 #ifndef XMB_CONV_TAIL
 #define XMB_CONV_TAIL 1
 #endif
+// -DXMB_PHASE_CLOCKS=1 (experiment builds): lane 0 of every warp accumulates the SM clock per phase of the batch loop,
+// the sums land in counters[40 + phase] (XMB_PHASES=1 prints them after a run)
+#ifndef XMB_COMPTON_EXP_F32
+#define XMB_COMPTON_EXP_F32 0
+#endif
+#ifndef XMB_PHASE_CLOCKS
+#define XMB_PHASE_CLOCKS 0
+#endif
+#if XMB_PHASE_CLOCKS
+// a barrier whose result is consumed: the clock read behind it cannot be issued before the barrier completes (BAR.SYNC.DEFER_BLOCKING lets a warp run on)
+#define XMB_SYNC_TIMED() do { if (__syncthreads_or(0)) ph_last_ = 0; } while (0)
+#define XMB_PHW(i) do { __syncwarp(); XMB_PH(i); } while (0)
+#define XMB_PH(i) do { if (lane == 0) { const long long c_ = clock64(); ph_[i] += c_ - ph_last_; ph_last_ = c_; } } while (0)
+#else
+#define XMB_SYNC_TIMED() __syncthreads()
+#define XMB_PH(i) do { } while (0)
+#define XMB_PHW(i) do { } while (0)
+#endif
 #ifndef XMB_BARRIERS
 #define XMB_BARRIERS 5   // phase barriers kept: 1 before the scatter deposits, 2 before the line deposits, 4 before selection + scattering
 #endif
@@ -49,12 +67,16 @@
 template <int NL, bool ADV = false>
 __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
 	const int nL = NL > 0 ? NL : P.nL;
-	extern __shared__ double smem[];
+	extern __shared__ __align__(16) double smem[];
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
 	double *mus = smem + tid;                 // mus[j*T]   : mu of layer j at the photon energy
 	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
 	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] pieces
-	constexpr bool P20 = !ADV;   // 20-bit pieces for history slots (one addend per photon and batch; ADV adds one per subshell)
+	// line phase (lane = record): per-warp scratch of the photons' factors per shell group, and the staged line tiles
+	const int wscr = xmb_warp_scratch_doubles(nL);
+	float *wpre_w = reinterpret_cast<float *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(tid >> 5) * wscr);
+	const char *sblob = reinterpret_cast<const char *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(T >> 5) * wscr);
+	constexpr bool P20 = false;   // every staged slot holds four 16-bit pieces (a line slot receives one per-lane sum per tile and warp)
 	const uint64_t n_total = P.n_local_span;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
 	const size_t acc_row = (size_t)P.nch + P.n_hist_slots;
@@ -91,7 +113,21 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
 	for (int i = tid; i < XMB_MAX_QL; i += T) s_qcl[i] = 0;
 	for (int i = tid; i < 4 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0u;
+	// Line tiles of ONE layer are staged in shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, UBLKCP): the
+	// layer of the batch when batches are formed per layer (the copy is issued when the batch is chosen and lands during the
+	// geometry and scatter-deposit phases), else the layer with the most records, once.  Other layers are read in place.
+	__shared__ __align__(8) unsigned long long s_mbar;
+	const unsigned mbar_s32 = smem_u32(&s_mbar), sblob_s32 = smem_u32(sblob);
+	int staged_layer = -1;
+	unsigned stage_parity = 0;
+	bool stage_pending = false;
+	if (tid == 0) { xmb_mbar_init(mbar_s32, 1); xmb_fence_proxy_async(); }
 	__syncthreads();
+	auto stage_layer = [&](int L) {   // block-uniform; callers guarantee that no thread still reads the staged blob
+		const unsigned bytes = (unsigned)(P.lblob_off[L + 1] - P.lblob_off[L]);
+		if (tid == 0) { xmb_fence_proxy_async(); xmb_bulk_g2s(sblob_s32, P.lblob + P.lblob_off[L], bytes, mbar_s32); }
+		staged_layer = L; stage_pending = true;
+	};
 	const int NF = XMB_STATE_FIELDS + nL;
 	const size_t qcap = 2 * (size_t)T;
 	const bool per_layer = NL != 1 && P.layer_sort == 2;   // one queue per (order, layer): see the scheduler below
@@ -158,13 +194,14 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			wbase = __shfl_sync(0xffffffffu, wbase, leader);
 			if (surv) {
 				double *q = qbase + (size_t)(order * nL + myL) * NF * qcap + wbase + __popc(peers & ((1u << lane) - 1u));
-				q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
-				q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
-				q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
-				q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
-				q[13 * qcap] = __longlong_as_double((long long)g);
-				q[14 * qcap] = __longlong_as_double((long long)p.layer);
-				for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+				// (streaming stores / loads: 28 GB of queue traffic per 5e7 histories must not evict the tables and the grid from L2)
+				__stcs(&q[0 * qcap], p.cx); __stcs(&q[1 * qcap], p.cy); __stcs(&q[2 * qcap], p.cz);
+				__stcs(&q[3 * qcap], p.dx); __stcs(&q[4 * qcap], p.dy); __stcs(&q[5 * qcap], p.dz);
+				__stcs(&q[6 * qcap], p.ex); __stcs(&q[7 * qcap], p.ey); __stcs(&q[8 * qcap], p.ez);
+				__stcs(&q[9 * qcap], p.energy); __stcs(&q[10 * qcap], p.weight); __stcs(&q[11 * qcap], p.theta); __stcs(&q[12 * qcap], p.phi);
+				__stcs(&q[13 * qcap], __longlong_as_double((long long)g));
+				__stcs(&q[14 * qcap], __longlong_as_double((long long)p.layer));
+				for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 			}
 			return;   // the caller's __syncthreads() publishes the counts
 		}
@@ -185,14 +222,14 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 #endif
 		if (surv) {
 			double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
-			q[0 * qcap] = p.cx; q[1 * qcap] = p.cy; q[2 * qcap] = p.cz;
-			q[3 * qcap] = p.dx; q[4 * qcap] = p.dy; q[5 * qcap] = p.dz;
-			q[6 * qcap] = p.ex; q[7 * qcap] = p.ey; q[8 * qcap] = p.ez;
-			q[9 * qcap] = p.energy; q[10 * qcap] = p.weight; q[11 * qcap] = p.theta; q[12 * qcap] = p.phi;
-			q[13 * qcap] = __longlong_as_double((long long)g);
-			q[14 * qcap] = __longlong_as_double((long long)p.layer);
+			__stcs(&q[0 * qcap], p.cx); __stcs(&q[1 * qcap], p.cy); __stcs(&q[2 * qcap], p.cz);
+			__stcs(&q[3 * qcap], p.dx); __stcs(&q[4 * qcap], p.dy); __stcs(&q[5 * qcap], p.dz);
+			__stcs(&q[6 * qcap], p.ex); __stcs(&q[7 * qcap], p.ey); __stcs(&q[8 * qcap], p.ez);
+			__stcs(&q[9 * qcap], p.energy); __stcs(&q[10 * qcap], p.weight); __stcs(&q[11 * qcap], p.theta); __stcs(&q[12 * qcap], p.phi);
+			__stcs(&q[13 * qcap], __longlong_as_double((long long)g));
+			__stcs(&q[14 * qcap], __longlong_as_double((long long)p.layer));
 			XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
+for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 		}
 #if !XMB_PUSH_ATOMIC
 		__syncthreads();
@@ -226,6 +263,11 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 		__syncthreads();
 		return (int)s_perm[tid];
 	};
+	if (!per_layer) stage_layer(P.lblob_main_layer);
+#if XMB_PHASE_CLOCKS
+	long long ph_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	long long ph_last_ = clock64();
+#endif
 	for (;;) {
 		// ---- scheduler (block-uniform) ---------------------------------------------------------------
 		int k = -1, Lsel = -1;
@@ -252,6 +294,9 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			__syncthreads();
 			k = s_sched[0]; Lsel = s_sched[1]; from_source = s_sched[2] != 0;
 			if (k < 0 && !from_source) break;
+			// a batch of one layer: its line tiles are copied to shared memory while the batch runs its first phases (every
+			// thread is behind the barrier that ended the previous batch: nobody reads the blob staged before)
+			if (!from_source && Lsel >= 0 && Lsel != staged_layer) stage_layer(Lsel);
 		} else {
 			for (int kk = P.n_int - 1; kk >= 0; kk--) if (s_qcount[kk] >= T) { k = kk; break; }
 			if (k < 0) {
@@ -301,13 +346,13 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			}
 			if (myL >= 0) {
 				const double *q = qbase + (size_t)(k * nL + myL) * NF * qcap + at;
-				p.cx = q[0 * qcap]; p.cy = q[1 * qcap]; p.cz = q[2 * qcap];
-				p.dx = q[3 * qcap]; p.dy = q[4 * qcap]; p.dz = q[5 * qcap];
-				p.ex = q[6 * qcap]; p.ey = q[7 * qcap]; p.ez = q[8 * qcap];
-				p.energy = q[9 * qcap]; p.weight = q[10 * qcap]; p.theta = q[11 * qcap]; p.phi = q[12 * qcap];
-				g = (uint64_t)__double_as_longlong(q[13 * qcap]);
+				p.cx = __ldcs(&q[0 * qcap]); p.cy = __ldcs(&q[1 * qcap]); p.cz = __ldcs(&q[2 * qcap]);
+				p.dx = __ldcs(&q[3 * qcap]); p.dy = __ldcs(&q[4 * qcap]); p.dz = __ldcs(&q[5 * qcap]);
+				p.ex = __ldcs(&q[6 * qcap]); p.ey = __ldcs(&q[7 * qcap]); p.ez = __ldcs(&q[8 * qcap]);
+				p.energy = __ldcs(&q[9 * qcap]); p.weight = __ldcs(&q[10 * qcap]); p.theta = __ldcs(&q[11 * qcap]); p.phi = __ldcs(&q[12 * qcap]);
+				g = (uint64_t)__double_as_longlong(__ldcs(&q[13 * qcap]));
 				p.layer = myL;
-				for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
+				for (int j = 0; j < nL; j++) mus[j * T] = __ldcs(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;
 				p.alive = true;
 			}
@@ -335,20 +380,21 @@ for (int j = 0; j < nL; j++) q[(XMB_STATE_FIELDS + j) * qcap] = mus[j * T];
 			}
 			if (tid < n) {
 				const double *q = qk + src;
-				p.cx = q[0 * qcap]; p.cy = q[1 * qcap]; p.cz = q[2 * qcap];
-				p.dx = q[3 * qcap]; p.dy = q[4 * qcap]; p.dz = q[5 * qcap];
-				p.ex = q[6 * qcap]; p.ey = q[7 * qcap]; p.ez = q[8 * qcap];
-				p.energy = q[9 * qcap]; p.weight = q[10 * qcap]; p.theta = q[11 * qcap]; p.phi = q[12 * qcap];
-				g = (uint64_t)__double_as_longlong(q[13 * qcap]);
-				p.layer = (int)__double_as_longlong(q[14 * qcap]);
+				p.cx = __ldcs(&q[0 * qcap]); p.cy = __ldcs(&q[1 * qcap]); p.cz = __ldcs(&q[2 * qcap]);
+				p.dx = __ldcs(&q[3 * qcap]); p.dy = __ldcs(&q[4 * qcap]); p.dz = __ldcs(&q[5 * qcap]);
+				p.ex = __ldcs(&q[6 * qcap]); p.ey = __ldcs(&q[7 * qcap]); p.ez = __ldcs(&q[8 * qcap]);
+				p.energy = __ldcs(&q[9 * qcap]); p.weight = __ldcs(&q[10 * qcap]); p.theta = __ldcs(&q[11 * qcap]); p.phi = __ldcs(&q[12 * qcap]);
+				g = (uint64_t)__double_as_longlong(__ldcs(&q[13 * qcap]));
+				p.layer = (int)__double_as_longlong(__ldcs(&q[14 * qcap]));
 				XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
+for (int j = 0; j < nL; j++) mus[j * T] = __ldcs(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;
 				p.alive = true;
 			}
 			__syncthreads();
 			if (tid == 0) s_qcount[k] = base;
 		}
+		XMB_PH(0);   // scheduler + batch formation
 		{
 			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length (used when the photon was moved), detector r, detector phi, atom}
 			const int n_ia = order;   // == p.n_interactions for every live lane
@@ -360,6 +406,7 @@ for (int j = 0; j < nL; j++) mus[j * T] = q[(XMB_STATE_FIELDS + j) * qcap];
 			double theta = 0.0, phi = 0.0, Pesc_rayl = 0.0, omega = 0.0;
 			NodePos np;
 			np.pos = 0; np.f = 0.0;
+			if (p.alive) np = node_find(P, p.energy);   // bracket of the photon energy: line phase and selection
 			int pj_lo = nL, pj_hi = -1;   // layers the path to the detector crosses (rd[] is zero outside)
 			bool sa_pending = false;      // interaction point beyond the solid-angle grid
 			double sa_r = 0.0, sa_theta = 0.0;
@@ -409,7 +456,6 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					}
 					Pesc_rayl = exp(-temp_murhod);
 					omega = get_solid_angle(P, p, sa_pending, sa_r, sa_theta);
-					np = node_find(P, p.energy);
 				}
 			}
 			// Points beyond the grid: the reference computes their solid angle on the spot with hits_per_single rays
@@ -417,6 +463,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 			// window), and 5000 rays by one lane would stall the whole CTA: the CTA collects the points of the batch (32
 			// per round) and all its threads share their rays (Philox address: photon id, (order << 20) | ray pair,
 			// XMB_TAG_SA_FALLBACK -- fixed per photon, so the result does not depend on the batch either).
+			XMB_PH(1);   // detector geometry, solid-angle lookup
 			while (__syncthreads_or(sa_pending)) {
 				if (tid == 0) s_sa_n = 0;
 				if (tid < XMB_SA_ROUND) s_sa_hits[tid] = 0;
@@ -453,11 +500,13 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 			}
 			// generic layer count: the optical-depth sums below skip the layers no lane of the warp crosses (terms that
 			// are exactly zero); with a compile-time layer count the loops are unrolled over all layers
+			XMB_PH(2);   // off-grid solid angles (and the barrier that closes the geometry phase)
 			const int jlo = NL > 0 ? 0 : __reduce_min_sync(0xffffffffu, pj_lo);
 			const int jhi = NL > 0 ? nL - 1 : __reduce_max_sync(0xffffffffu, pj_hi);
 #if XMB_BARRIERS & 1
-			__syncthreads();   // phase: scatter deposits of every element
+			XMB_SYNC_TIMED();   // phase: scatter deposits of every element
 #endif
+			XMB_PH(3);
 			// warp-uniform loops over layers / elements / shells / line records
 			for (int L = 0; L < nL; L++) {
 				const bool mine = vr && p.layer == L;
@@ -506,6 +555,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					}
 					deposit_uniform<P20>(acc_k, hbase + 0, fx, lane);
 					fx_rayl += fx;
+					XMB_PHW(11);   // (element phase, per element) prefetch + Rayleigh deposit
 					if (ADV) {
 						// shell-resolved Compton (xmi_compton_varred, :752-947): one deposit per occupied subshell
 						const int r0 = P.adv_off[zi], r1 = P.adv_off[zi + 1];
@@ -529,7 +579,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 									if (e_c != 0.0) {
 										const NodePos cp = node_find(P, e_c);
 										double tm = 0.0;
-										for (int j = 0; j < nL; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+										for (int j = 0; j < nL; j++) tm += mu_lerp(P, cp, j) * rd[j * T];
 										fx = to_fixed(Pconv * Pdir * exp(-tm) * p.weight * shell_weight, P.counters);
 										const int ch = (int)((e_c - P.zero) / P.gain);
 										if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
@@ -544,77 +594,126 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					// Compton (xmi_compton_varred2, :949-1008)
 					fx = 0ULL;
 					int ch_c = -1;
+#if XMB_PHASE_CLOCKS
+					double e_c_keep = 0.0;
+#endif
 					if (mine) {
 						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true, &pf);
+#if XMB_PHASE_CLOCKS
+						e_c_keep = e_c;
+					}
+					XMB_PHW(12);   // Doppler trials
+					if (mine) {
+						const double e_c = e_c_keep;
+#endif
 						const NodePos cp = node_find(P, e_c);
 						double tm = 0.0;
 						XMB_UNROLL_NL
-for (int j = jlo; j <= jhi; j++) tm += row_lerp(P, cp, j) * rd[j * T];
+for (int j = jlo; j <= jhi; j++) tm += mu_lerp(P, cp, j) * rd[j * T];
 						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
 						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
-						fx = to_fixed(Pconv * Pdir * exp_neg(tm, tab_s32) * p.weight, P.counters);
+						fx = to_fixed(Pconv * Pdir * (XMB_COMPTON_EXP_F32 ? exp_neg_f32(tm) : exp_neg(tm, tab_s32)) * p.weight, P.counters);
 						const int ch = (int)((e_c - P.zero) / P.gain);
 						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
 					}
+					XMB_PHW(13);   // bracket, mu, exp, fixed point
 					deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
 					deposit_varying(acc_k, ch_c, fx, lane);
+					XMB_PHW(14);   // staged adds
 				}
 				deposit_varying(acc_k, ch_rayl, fx_rayl, lane);
 			}
+			XMB_PH(4);   // Rayleigh / Compton deposits per element
 #if XMB_BARRIERS & 2
-			__syncthreads();   // phase: fluorescence-line deposits (small loop body: exp + exact warp sum + RED)
+			__syncthreads();   // phase: fluorescence-line deposits
 #endif
-			for (int L = 0; L < nL; L++) {
-				const bool mine = vr && p.layer == L;
-				if (!__any_sync(0xffffffffu, mine)) continue;
-				const double inv_mu = mine ? 1.0 / mus[L * T] : 0.0;
-				double rdv[NL > 0 ? NL : 1];   // rho d of the path to the detector, in registers for the record loop
+			// ---- fluorescence lines (src/xmi_variance_reduction.F90:391-709) -----------------------------------------
+			// deposit(photon, record) = [w_layer / mu * Omega / 4 pi * weight](photon) * P_shell(photon energy)
+			//                           * [w_element * yield * rate](record) * exp(-sum_j mu_j(E_line) rho_j d_j(photon))
+			// In a tile a LANE owns a RECORD: the photons' factors per shell group go through a per-warp scratch, the warp walks
+			// its photons, and the deposits of the warp on a record are one 64-bit integer sum in a register, staged once per
+			// tile (v15: one exact warp sum -- 3 REDUX -- and one staged add per record and interaction).
+			if (stage_pending) { xmb_mbar_wait(mbar_s32, stage_parity); stage_parity ^= 1u; stage_pending = false; }
+			// The attenuation factor exp(-sum_j mu_j rho_j d_j) and the products of a deposit are evaluated in SINGLE precision
+			// ("geometry/angles can be fp32 after validation against the fp64 oracle"): a deposit carries a relative
+			// rounding error of ~1e-7, independent from photon to photon -- five orders below the Monte Carlo error of a line --
+			// and the phase leaves the half-rate fp64 pipe, which bounded it (19 fp64 operations per photon and record;
+			// profiles/r2_history_kernel_v16_*).  Sums stay exact 64-bit integers, so GPU-count independence is untouched.
+			{
+				float *wpref = wpre_w;                                                  // [XMB_TILE_GROUPS][XMB_WPRE_STRIDE]
+				// rho d of the path to the detector is dead in double once the scatter deposits are made: every photon lane
+				// rewrites its slots in place as floats, which the record lanes of its warp read (rdf[2 * (j * T + q)])
 				if (NL > 0) {
 					XMB_UNROLL_NL
-for (int j = 0; j < (NL > 0 ? NL : 1); j++) rdv[j] = rd[j * T];
+for (int j = 0; j < (NL > 0 ? NL : 1); j++) { const float f = vr ? (float)rd[j * T] : 0.f; *reinterpret_cast<float *>(&rd[j * T]) = f; }
+				} else {
+					for (int j = jlo; j <= jhi; j++) { const float f = vr ? (float)rd[j * T] : 0.f; *reinterpret_cast<float *>(&rd[j * T]) = f; }
 				}
-				// fluorescence lines (:391-709): per shell, vacancy cross section at the photon energy (after a
-				// fluorescence interaction that energy is a node of the grid: the reference's precalc_xrf_cs)
-				const double oc = omega / 4.0 / M_PI;
-				const double e_mine = mine ? p.energy : -1.0;   // below every group's edge value: no deposit
-				const int g0 = P.grp_begin[L], g1 = P.grp_begin[L + 1];
-				for (int gi = g0; gi < g1; gi++) {
-					const int4 gh = __ldg(reinterpret_cast<const int4 *>(P.grp + gi));
-					const double2 gw = __ldg(reinterpret_cast<const double2 *>(P.grp + gi) + 1);   // {weight fraction, edge}
-					const int r0 = gh.x, r1 = gh.y;
-					double Ps = 0.0;
-					if (e_mine >= gw.y) Ps = row_lerp(P, np, gh.z);
-					if (!__any_sync(0xffffffffu, Ps != 0.0)) continue;
-					// deposit = pre * (yield * rate) * exp(-tm) with yield * rate <= rec_yr_max and exp <= 1: the
-					// fixed-point scale 2^56 and the range check are taken out of the record loop (a power of two
-					// commutes with the roundings; lanes that do not take part carry pre56 = 0)
-					const double common = mine ? gw.x * inv_mu * oc * p.weight : 0.0;
-					const double pre56 = common * Ps * 72057594037927936.0;
-					bad_fixed |= !(pre56 * P.rec_yr_max < 2.8e17);
-					const double *rp = P.rec_pack + (size_t)r0 * (nL + 2);   // record: {yield * rate, history slot, mu[nL]}
-XMB_UNROLL((NL > 0 ? XMB_REC_UNROLL : 2))   // generic layer count: records of 2 + nL doubles, deeper unrolling spills
-					for (int r = r0; r < r1; r++, rp += nL + 2) {
-						double yr, tm = 0.0;
-						unsigned slot;
-						if (NL == 2) {
-							const double2 a = __ldg(reinterpret_cast<const double2 *>(rp)), m = __ldg(reinterpret_cast<const double2 *>(rp) + 1);
-							yr = a.x; slot = (unsigned)__double2loint(a.y);
-							tm = __fma_rn(m.y, rdv[1], __dmul_rn(m.x, rdv[0]));   // the rounding order of the generic loop below
-						} else {
-							yr = rp[0]; slot = (unsigned)__double2loint(rp[1]);
-							XMB_UNROLL_NL
-for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0] : rd[j * T]);
+				__syncwarp();
+				const float *rdf = reinterpret_cast<const float *>(smem + (size_t)nL * T + (tid & ~31));
+				for (int L = 0; L < nL; L++) {
+					const bool mine = vr && p.layer == L;
+					if (!__any_sync(0xffffffffu, mine)) continue;
+					const char *blob = L == staged_layer ? sblob : P.lblob + P.lblob_off[L];
+					const int4 bh = *reinterpret_cast<const int4 *>(blob);   // {n_tiles, n_groups, lanes_off, tile_bytes}
+					// (after a fluorescence interaction the photon energy is a node of the grid: the reference's precalc_xrf_cs)
+					const double commonp = mine ? (1.0 / mus[L * T]) * (omega / 4.0 / M_PI) * p.weight : 0.0;
+					const double e_mine = mine ? p.energy : -1.0;
+					const XmbLineGroup *G = reinterpret_cast<const XmbLineGroup *>(blob + 16 + 16 * bh.x);
+					for (int t = 0; t < bh.x; t++) {
+						const XmbLineTile th = *reinterpret_cast<const XmbLineTile *>(blob + 16 + 16 * t);
+						const unsigned pmask = __ballot_sync(0xffffffffu, e_mine >= th.min_edge);
+						if (!pmask) continue;   // no photon of the warp can ionise a shell of this tile
+						for (int gi = 0; gi < th.n_groups; gi++) {
+							const XmbLineGroup g = G[th.g_begin + gi];
+							double pre = 0.0;
+							if (e_mine >= th.min_edge && e_mine >= g.edgeK) pre = commonp * row_lerp(P, np, g.row_off);
+							bad_fixed |= !(pre * P.rec_wy_max < 1.4e17);   // a deposit is < 2^57: 32 of them fit the lane's 64-bit sum
+							wpref[gi * XMB_WPRE_STRIDE + lane] = (float)pre;
 						}
-						const double tw = pre56 * yr * exp_neg(tm, tab_s32);
-						deposit_uniform<P20>(acc_k, hist0 + slot, fixed_from_scaled(tw), lane);
+						__syncwarp();
+						const char *lt = blob + bh.z + (size_t)t * bh.w;
+						const float wyf = reinterpret_cast<const float *>(lt)[lane];
+						const float *mulf = reinterpret_cast<const float *>(lt) + 32 + lane;
+						const int2 sg = make_int2(reinterpret_cast<const int *>(lt + 128 * (1 + nL))[lane], reinterpret_cast<const int *>(lt + 128 * (2 + nL))[lane]);   // mulf[j * 32] = -mu_j log2(e)
+						const float *prow = wpref + sg.y * XMB_WPRE_STRIDE;
+						float muv[NL > 0 ? NL : 1];
+						if (NL > 0) {
+							XMB_UNROLL_NL
+for (int j = 0; j < (NL > 0 ? NL : 1); j++) muv[j] = mulf[j * 32];
+						}
+						unsigned long long acc = 0ULL;
+						const int p_lo = __ffs(pmask) - 1, p_hi = 31 - __clz(pmask);
+XMB_UNROLL(4)
+						for (int q = p_lo; q <= p_hi; q++) {
+							float t2 = 0.f;
+							if (NL > 0) {
+								XMB_UNROLL_NL
+for (int j = 0; j < (NL > 0 ? NL : 1); j++) t2 = __fmaf_rn(muv[j], rdf[2 * (j * T + q)], t2);
+							} else {
+								for (int j = jlo; j <= jhi; j++) t2 = __fmaf_rn(mulf[j * 32], rdf[2 * (j * T + q)], t2);
+							}
+							float ex;
+							asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t2));
+							acc += __float2ull_rn(prow[q] * wyf * ex);
+						}
+						__syncwarp();   // the scratch is rewritten by the next tile
+						if (acc) {
+							const unsigned a = acc_k + (hist0 + (unsigned)sg.x) * 16u;
+							const unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
+							stage_red(a, lo & 0xFFFFu); stage_red(a + 4u, lo >> 16); stage_red(a + 8u, hi & 0xFFFFu); stage_red(a + 12u, hi >> 16);
+						}
 					}
 				}
 			}
 
+			XMB_PH(5);   // line deposits
 			// ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ----------------
 #if XMB_BARRIERS & 4
-			__syncthreads();   // phase: selection + scattering (and: every deposit of the batch is staged)
-			flush_staged<P20>(stage, P.acc + 2 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+			XMB_SYNC_TIMED();   // phase: selection + scattering (and: every deposit of the batch is staged)
+			XMB_PH(6);   // waiting for the slowest warp's deposits
+			flush_staged<P20>(stage, P.acc + 4 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+			XMB_PH(7);
 #endif
 			// (the interaction of the last order is scored above; what it does to the photon is never used)
 			const bool do_sel = p.alive && (!XMB_SKIP_LAST || order < P.n_int);
@@ -622,22 +721,28 @@ for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0]
 			if (do_sel) {
 				double we_unused = 0.0;
 				int t_unused, z_unused, l_unused, s_unused;
-				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused, XMB_CONV_TAIL ? sel_mask : 0u);
+				select_and_scatter<NL, 0, ADV>(P, p, g, order, mus, T, b0.w, we_unused, t_unused, z_unused, l_unused, s_unused, XMB_CONV_TAIL ? sel_mask : 0u, &np);
 			}
 			__syncwarp();
+			XMB_PH(8);   // selection + scattering
 		}
 		// ---- move to the next interaction point and queue there --------------------------------------------
 		if (order < P.n_int) {
 			transport(p, g, order);
 			push(p, g, order);
 		}
-		__syncthreads();
+		XMB_PH(9);   // forced move + queue
+		XMB_SYNC_TIMED();
+		XMB_PH(10);
 #if !(XMB_BARRIERS & 4)
 		// every deposit of the batch is staged (barrier above); the next batch's first deposit comes behind the barriers of
 		// its formation and of the off-grid solid-angle round
-		flush_staged<P20>(stage, P.acc + 2 * (size_t)(order - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+		flush_staged<P20>(stage, P.acc + 4 * (size_t)(order - 1) * acc_row, (int)acc_row, P.nch, tid, T);
 #endif
 	}
+#if XMB_PHASE_CLOCKS
+	if (lane == 0) for (int i = 0; i < 16; i++) atomicAdd(&P.counters[40 + i], (unsigned long long)ph_[i]);
+#endif
 	n_inter_local = warp_sum_u64(n_inter_local);
 	if (lane == 0 && n_inter_local) atomicAdd(&P.counters[1], n_inter_local);
 	if (bad_fixed) atomicAdd(&P.counters[2], 1ULL);
@@ -645,12 +750,21 @@ for (int j = jlo; j <= jhi; j++) tm += rp[2 + j] * (NL > 0 ? rdv[NL > 0 ? j : 0]
 	if (tid < nL && s_layer_cnt[tid]) atomicAdd(&P.counters[8 + tid], (unsigned long long)s_layer_cnt[tid]);
 }
 
-// raw (lo, hi) accumulators -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
+// raw (lo, hi) accumulators (brute-force kernel) -> two 48-bit-split words per slot (safe to sum over ranks in 64-bit integers)
 __global__ void xmb_limbs_kernel(const unsigned long long *__restrict__ acc, unsigned long long *__restrict__ limbs, size_t n_slots) {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
 		const unsigned long long lo = acc[2 * i], hi = acc[2 * i + 1];   // 128-bit total
 		limbs[2 * i] = lo & 0xFFFFFFFFFFFFULL;
 		limbs[2 * i + 1] = (lo >> 48) | (hi << 16);
+	}
+}
+// four-word accumulators of the history kernel (w0 + w1 2^16 + w2 2^32 + w3 2^48, see flush_staged) -> the same limbs
+__global__ void xmb_limbs4_kernel(const unsigned long long *__restrict__ acc, unsigned long long *__restrict__ limbs, size_t n_slots) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned __int128 v = (unsigned __int128)acc[4 * i] + ((unsigned __int128)acc[4 * i + 1] << 16) + ((unsigned __int128)acc[4 * i + 2] << 32) +
+		                            ((unsigned __int128)acc[4 * i + 3] << 48);
+		limbs[2 * i] = (unsigned long long)v & 0xFFFFFFFFFFFFULL;
+		limbs[2 * i + 1] = (unsigned long long)(v >> 48);
 	}
 }
 
@@ -737,6 +851,11 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 		}
 	}
 	P.rows = upload(D, rows.data(), rows.size(), ok);
+	{
+		std::vector<double> mt((size_t)nN * nL);
+		for (int n = 0; n < nN; n++) for (int k = 0; k < nL; k++) mt[(size_t)n * nL + k] = T.mu_layer[(size_t)k * nN + n];
+		P.mu_tab = upload(D, mt.data(), mt.size(), ok);
+	}
 	P.n_nodes = nN;
 	P.node_E = upload(D, T.node_E, nN, ok);
 	{
@@ -755,7 +874,8 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			while (i + 1 < nN && T.node_E[i + 1] <= lo + 1e-9) i++;
 			const int start = std::min(i, std::max(nN - 2, 0));
 			bs[b] = start;
-			if (start + 1 < nN && T.node_E[start] <= lo + 1e-9 && T.node_E[start + 1] >= hi - 1e-9) bs[b] = start | (int)0x80000000;
+			// strictly inside the bracket, with a margin far above the rounding of the device's bucket arithmetic
+			if (start + 1 < nN && T.node_E[start] <= lo - 1e-9 && T.node_E[start + 1] >= hi + 1e-9) bs[b] = start | (int)0x80000000;
 		}
 		bs[nBf] = std::max(nN - 2, 0);
 		P.n_buckets = nBf; P.bucket_E0 = T.bucket_E0; P.bucket_inv_dE = inv_dE;
@@ -852,55 +972,94 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	D->n_rec = (int)rec_yr.size();
 	D->n_hist_slots = slot;
 	P.n_hist_slots = slot;
-	P.rec_begin = upload(D, rec_begin.data(), rec_begin.size(), ok);
 	{
-		// one packed record per active line: a 32-byte record is two 128-bit loads for the two-layer kernel
-		std::vector<double> pack((size_t)D->n_rec * (nL + 2));
-		P.rec_yr_max = 0.0;
-		for (int r = 0; r < D->n_rec; r++) {
-			double *q = &pack[(size_t)r * (nL + 2)];
-			q[0] = rec_yr[r];
-			const long long bits = (long long)D->rec_slot[r];
-			memcpy(&q[1], &bits, sizeof(double));
-			for (int k = 0; k < nL; k++) q[2 + k] = rec_mu[(size_t)r * nL + k];
-			P.rec_yr_max = std::max(P.rec_yr_max, rec_yr[r]);
-		}
-		P.rec_pack = upload(D, pack.data(), pack.size(), ok);
-	}
-	{
-		// the line-deposit phase walks the non-empty (element, shell) groups of the photon's layer: with the surrogate line
-		// set 40-odd of the 9 x 15 shells of the glass layer have an active line, and the empty ones cost 18 instructions
-		// each (7 % of the kernel, profiles/r1_history_kernel_v11_hot_lines.txt)
-		std::vector<XmbShellGroup> grp;
-		std::vector<int> grp_begin(nL + 1, 0);
+		// Line tiles (history.cuh): per layer the non-empty (element, shell) groups in the order of their shell edges, their
+		// records cut into tiles of 32 (one record per lane), a tile spanning at most XMB_TILE_GROUPS groups.  A photon
+		// below a tile's lowest edge deposits exactly zero on all of its records (no vacancy cross section below the shell's
+		// own edge; the lower node of the edge doublet lies 1e-5 keV below it), so the tile is skipped for it.
+		struct Grp { int zi, s, r0, r1, row_off; double wfrac, edge, edgeK; };
 		const int n_sh = opt->use_M_lines ? 9 : 4;
+		std::vector<char> blob;
+		std::vector<std::pair<double, int>> edges;   // (shell edge, records) of every group of every layer: energy classes below
+		P.rec_wy_max = 0.0;
+		P.lblob_stage_bytes = 16;
+		int most = -1;
+		P.lblob_main_layer = 0;
 		for (int k = 0; k < nL; k++) {
-			grp_begin[k] = (int)grp.size();
+			std::vector<Grp> grp;
 			for (int e = 0; e < layers[k].n_elements; e++) {
 				const int z = elem_zi[layers[k].elem_begin + e];
-				for (int s = 0; s < n_sh; s++) {
-					XmbShellGroup g;
-					g.r0 = rec_begin[z * 10 + s]; g.r1 = rec_begin[z * 10 + s + 1];
+				for (int sh = 0; sh < n_sh; sh++) {
+					Grp g;
+					g.r0 = rec_begin[z * 10 + sh]; g.r1 = rec_begin[z * 10 + sh + 1];
 					if (g.r0 == g.r1) continue;
-					g.row_off = P.off_elem + z * XMB_ELEM_STRIDE + XMB_EO_VACANCY + s;
-					g.zi = z;
+					g.zi = z; g.s = sh;
+					g.row_off = P.off_elem + z * XMB_ELEM_STRIDE + XMB_EO_VACANCY + sh;
 					g.wfrac = elem_w[layers[k].elem_begin + e];
-					g.edge = s == 0 ? edgeK[z] : 0.0;
+					g.edge = T.edge_energy[z * 9 + sh];
+					g.edgeK = sh == 0 ? edgeK[z] : 0.0;
 					grp.push_back(g);
 				}
 			}
+			std::stable_sort(grp.begin(), grp.end(), [](const Grp &a, const Grp &b) { return a.edge < b.edge; });
+			int n_rec_layer = 0;
+			for (const Grp &g : grp) { edges.push_back(std::make_pair(g.edge, g.r1 - g.r0)); n_rec_layer += g.r1 - g.r0; }
+			if (n_rec_layer > most) { most = n_rec_layer; P.lblob_main_layer = k; }
+			// tiles: (group, record) pairs in order; a tile closes at 32 records or XMB_TILE_GROUPS groups
+			struct Lane { int g, r; };
+			std::vector<std::vector<Lane>> tiles;
+			std::vector<int> tile_g0;
+			for (int g = 0; g < (int)grp.size(); g++)
+				for (int r = grp[g].r0; r < grp[g].r1; r++) {
+					if (tiles.empty() || tiles.back().size() == 32 || g - tile_g0.back() >= XMB_TILE_GROUPS) { tiles.push_back({}); tile_g0.push_back(g); }
+					tiles.back().push_back(Lane{g, r});
+				}
+			const int n_tiles = (int)tiles.size(), n_grp = (int)grp.size();
+			const int tile_bytes = 128 * (3 + nL);
+			const int lanes_off = 16 + 16 * n_tiles + 16 * n_grp;
+			const size_t base = blob.size();
+			blob.resize(base + lanes_off + (size_t)n_tiles * tile_bytes, 0);
+			char *bp = blob.data() + base;
+			const int hdr[4] = {n_tiles, n_grp, lanes_off, tile_bytes};
+			memcpy(bp, hdr, 16);
+			for (int t = 0; t < n_tiles; t++) {
+				XmbLineTile th;
+				th.g_begin = tile_g0[t];
+				th.n_groups = tiles[t].back().g - tile_g0[t] + 1;
+				th.min_edge = grp[tile_g0[t]].edge - 1.5e-5;
+				memcpy(bp + 16 + 16 * t, &th, 16);
+				char *lt = bp + lanes_off + (size_t)t * tile_bytes;
+				float *wyf = (float *)lt, *muf = wyf + 32;
+				int *slot = (int *)(lt + 128 * (1 + nL)), *gs = slot + 32;
+				for (int l = 0; l < 32; l++) {
+					wyf[l] = 0.f; slot[l] = 0; gs[l] = 0;                 // padding lane: deposits nothing
+					for (int j = 0; j < nL; j++) muf[j * 32 + l] = 0.f;
+					if (l >= (int)tiles[t].size()) continue;
+					const Lane &ln = tiles[t][l];
+					const double wy = grp[ln.g].wfrac * rec_yr[ln.r] * 72057594037927936.0;
+					wyf[l] = (float)wy;
+					P.rec_wy_max = std::max(P.rec_wy_max, wy * (1.0 + 1e-6));
+					for (int j = 0; j < nL; j++) muf[j * 32 + l] = (float)(-rec_mu[(size_t)ln.r * nL + j] * 1.4426950408889634074);
+					slot[l] = D->rec_slot[ln.r];
+					gs[l] = ln.g - tile_g0[t];
+				}
+			}
+			for (int g = 0; g < n_grp; g++) {
+				XmbLineGroup lg;
+				lg.row_off = grp[g].row_off; lg.zi = grp[g].zi; lg.edgeK = grp[g].edgeK;
+				memcpy(bp + 16 + 16 * n_tiles + 16 * g, &lg, 16);
+			}
+			P.lblob_off[k] = (int)base;
+			P.lblob_stage_bytes = std::max(P.lblob_stage_bytes, (int)(blob.size() - base));
 		}
-		grp_begin[nL] = (int)grp.size();
+		P.lblob_off[nL] = (int)blob.size();
+		P.lblob = upload(D, blob.data(), blob.size(), ok);
+		D->n_line_tiles_bytes = blob.size();
 		// energy classes for batches sorted by photon energy (layer_sort 3): shell edges that split the records of all
 		// groups into (nearly) equal shares
 		{
-			std::vector<std::pair<double, int>> edges;
 			int n_all = 0;
-			for (const XmbShellGroup &g : grp) {
-				const int s = g.row_off - (P.off_elem + g.zi * XMB_ELEM_STRIDE + XMB_EO_VACANCY);
-				edges.push_back(std::make_pair(T.edge_energy[g.zi * 9 + s], g.r1 - g.r0));
-				n_all += g.r1 - g.r0;
-			}
+			for (const auto &e : edges) n_all += e.second;
 			std::sort(edges.begin(), edges.end());
 			int max_thr = (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0]));
 			if (const char *e = getenv("XMB_ECLS_MAX")) max_thr = std::max(0, std::min(max_thr, atoi(e)));   // experiments
@@ -914,8 +1073,6 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			}
 			for (int i = P.n_ecls; i < (int)(sizeof(P.ecls_thr) / sizeof(P.ecls_thr[0])); i++) P.ecls_thr[i] = 1e300;
 		}
-		P.grp = upload(D, grp.data(), grp.size(), ok);
-		P.grp_begin = upload(D, grp_begin.data(), grp_begin.size(), ok);
 	}
 	P.hist_base = upload(D, D->hist_base.data(), nZ, ok);
 	{
@@ -1091,13 +1248,13 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	if (D->acc_slots != slots) {
 		cudaFree(D->acc); cudaFree(D->limbs); cudaFree(D->counters);
 		D->acc = D->limbs = D->counters = nullptr; D->acc_slots = 0;
-		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 2 * slots));
+		XMB_CUDA_OK(cudaMalloc(&D->acc, sizeof(unsigned long long) * 4 * slots));   // history kernel: 4 words per slot; brute force: (lo, hi)
 		XMB_CUDA_OK(cudaMalloc(&D->limbs, sizeof(unsigned long long) * 2 * slots));
-		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * (8 + XMB_MAX_LAYERS)));
+		XMB_CUDA_OK(cudaMalloc(&D->counters, sizeof(unsigned long long) * XMB_N_COUNTERS));
 		D->acc_slots = slots;
 	}
-	XMB_CUDA_OK(cudaMemsetAsync(D->acc, 0, sizeof(unsigned long long) * 2 * slots));
-	XMB_CUDA_OK(cudaMemsetAsync(D->counters, 0, sizeof(unsigned long long) * (8 + XMB_MAX_LAYERS)));
+	XMB_CUDA_OK(cudaMemsetAsync(D->acc, 0, sizeof(unsigned long long) * (brute ? 2 : 4) * slots));
+	XMB_CUDA_OK(cudaMemsetAsync(D->counters, 0, sizeof(unsigned long long) * XMB_N_COUNTERS));
 	P.acc = D->acc; P.counters = D->counters;
 	// shard of global photon ids
 	const int nr = ex->n_ranks > 0 ? ex->n_ranks : 1, rk = ex->rank;
@@ -1132,14 +1289,18 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	int threads = HIST_THREADS;
 	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
 	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
-	while (threads > 64 && stage_bytes + sizeof(double) * 2 * P.nL * threads > 200 * 1024) threads -= 32;
+	// + the line phase: XMB_TILE_GROUPS x XMB_WPRE_STRIDE doubles of scratch per warp and one staged line-tile blob
+	const size_t fixed_bytes = stage_bytes + (size_t)P.lblob_stage_bytes;
+	auto per_cta = [&](int t) { return fixed_bytes + sizeof(double) * 2 * P.nL * t + sizeof(double) * xmb_warp_scratch_doubles(P.nL) * (t / 32); };
+	if (fixed_bytes > 180 * 1024) { xmb_set_error("channels, history slots and line tiles do not fit the shared memory of an SM"); return 0; }
+	while (threads > 64 && per_cta(threads) > 216 * 1024) threads -= 32;
 	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch; a photon
 	// adds to a channel slot once per element (Compton) plus once for the summed Rayleigh deposits
 	const size_t per_photon = ((size_t)std::max(1, D->max_nE) + 1) * (options->use_advanced_compton ? 32 : 1);   // + one addend per subshell
 	while (threads > 64 && (size_t)threads * per_photon > 60000) threads -= 32;
 	// experiments / tests: force a smaller CTA (the sums do not depend on the launch shape: test_history_gpu.py)
 	if (const char *e = getenv("XMB_HIST_THREADS")) { const int t = atoi(e) & ~31; if (t >= 32 && t < threads) threads = t; }
-	const size_t smem = stage_bytes + sizeof(double) * 2 * P.nL * threads;
+	const size_t smem = per_cta(threads);
 	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
 	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation
@@ -1167,7 +1328,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	cudaEventRecord(D->ev0);
 	if (ex->n_histories > 0) { kernel<<<(unsigned)blocks, threads, smem>>>(P); D->run_launches++; }
 	cudaEventRecord(D->ev1);
-	xmb_limbs_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
+	xmb_limbs4_kernel<<<sms, 256>>>(D->acc, D->limbs, slots);
 	XMB_CUDA_OK(cudaGetLastError());
 	return 1;
 }
@@ -1181,7 +1342,7 @@ int xmb_msim_collect(XmbDeviceTables *D, const xmb_main_options *options, xmb_ms
 	cudaEventElapsedTime(&ms, D->ev0, D->ev1);
 	ex->kernel_ms = ms;
 	ex->n_launches = D->run_launches;
-	unsigned long long cnt[8 + XMB_MAX_LAYERS];
+	unsigned long long cnt[XMB_N_COUNTERS];
 	XMB_CUDA_OK(cudaMemcpy(cnt, D->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
 	ex->n_interactions = cnt[1];
 	if (D->run_brute) {
@@ -1190,6 +1351,14 @@ int xmb_msim_collect(XmbDeviceTables *D, const xmb_main_options *options, xmb_ms
 	} else {
 		for (int i = 0; i < XMB_MAX_LAYERS; i++) D->layer_interactions[i] = cnt[8 + i];
 		if (cnt[0] && options->verbose) fprintf(stderr, "detector_solid_angle_not_found: %llu\n", cnt[0]);
+	}
+	if (getenv("XMB_PHASES")) {   // experiment builds (-DXMB_PHASE_CLOCKS=1): share of the warps' time per phase of the batch loop
+		static const char *nm[16] = {"scheduler+batch", "geometry", "off-grid+barrier", "barrier 1", "element: rest", "line deposits", "barrier 4", "flush",
+		                             "select+scatter", "move+queue", "end barrier", "element: prefetch+Rayleigh", "element: Doppler trials",
+		                             "element: bracket..fixed", "element: staged adds", "-"};
+		double tot = 0.0;
+		for (int i = 0; i < 16; i++) tot += (double)cnt[40 + i];
+		if (tot > 0.0) for (int i = 0; i < 16; i++) fprintf(stderr, "phase %-18s %5.1f %%\n", nm[i], 100.0 * (double)cnt[40 + i] / tot);
 	}
 	if (cnt[2]) { xmb_set_error("%llu deposits fell outside the fixed-point range", cnt[2]); return 0; }
 	return 1;

@@ -4,6 +4,7 @@
 #include "solid_angle_device.cuh"
 
 #define XMB_MAX_LAYERS 32
+#define XMB_N_COUNTERS (8 + XMB_MAX_LAYERS + 16)   // [0..7] see below, [8 + L] interactions in layer L, [40 + i] phase clocks (experiment builds)
 #define XMB_SHARD_BLOCK 1024
 #define XMB_SHARD_SHIFT 10
 #define XMB_ELEM_STRIDE 22         // per-element doubles in a node row
@@ -30,13 +31,29 @@ struct XmbLayerDev {
 	double density, Z_begin, Z_end;
 };
 
-// forced-detection line deposits: the non-empty (element, shell) record ranges of one layer, in (element, shell) order
-struct __align__(16) XmbShellGroup {
-	int r0, r1;                              // records [r0, r1) of rec_pack
+// Forced-detection line deposits ("line tiles").  The active line records of a layer -- (element, shell, line) with
+// yield * rate > 0, E_line >= 1 keV -- are sorted by the edge energy of their shell and cut into tiles of 32 records:
+// in the line phase a LANE owns a RECORD of the tile and the warp walks its 32 photons, so a record's deposits of the
+// warp are summed in a register and leave as one staged add per tile (history.cu).  One blob per layer, 16-byte aligned,
+// staged in shared memory by a bulk copy (cp.async.bulk + mbarrier):
+//   int4 {n_tiles, n_groups, lanes_off, tile_bytes}
+//   XmbLineTile  tiles[n_tiles]
+//   XmbLineGroup groups[n_groups]            the (element, shell) groups in edge order; a tile spans <= XMB_TILE_GROUPS of them
+//   per tile: float wy[32]                   weight fraction * fluorescence yield * radiative rate * 2^56 (0: padding lane)
+//             float mu[nL][32]               -mu log2(e) of every layer at the line energy
+//             int slot[32], gs[32]           history slot of the line; group of the record, relative to the tile's first group
+#define XMB_TILE_GROUPS 8
+#define XMB_WPRE_STRIDE 33                   // doubles per group row of the per-warp scratch (33: lanes of different groups read different banks)
+// doubles of per-warp scratch in the line phase: the photons' factors per shell group of a tile, float [XMB_TILE_GROUPS][XMB_WPRE_STRIDE]
+__host__ __device__ inline int xmb_warp_scratch_doubles(int) { return (4 * XMB_TILE_GROUPS * XMB_WPRE_STRIDE + 15) / 16 * 2; }
+struct __align__(16) XmbLineTile {
+	int g_begin, n_groups;                   // groups [g_begin, g_begin + n_groups) of the layer
+	double min_edge;                         // lowest shell edge of the tile minus the edge-doublet half width: photons below it deposit exactly 0
+};
+struct __align__(16) XmbLineGroup {
 	int row_off;                             // vacancy cross section of the shell in a node row
 	int zi;
-	double wfrac;                            // weight fraction of the element in the layer
-	double edge;                             // K shell: K edge (the reference skips the K lines below it), other shells: 0
+	double edgeK;                            // K shell: K edge (the reference skips the K lines below it), other shells: 0
 };
 
 struct XmbHistParams {
@@ -67,6 +84,7 @@ struct XmbHistParams {
 	const double *node_E;
 	const int *bucket_start;
 	const double *rows;                      // [n_nodes][row_stride]
+	const double *mu_tab;                    // [n_nodes][nL]: mu of the layers, compact (also the first nL entries of a row)
 	// inverse CDFs
 	int n_icdf_E, n_icdf_R, n_phi_T, n_cp, n_q;
 	double cp_dR, cp_inv_dR, q_max;
@@ -86,12 +104,12 @@ struct XmbHistParams {
 	const double *cos_kron;                  // [nZ][13]
 	const double *rad_rate;                  // [nZ][384]
 	const double *line_energy;               // [nZ][384]
-	// forced-detection line records (active lines only), grouped by (element, shell)
-	const int *rec_begin;                    // [nZ][10] record range of (zi, shell) = [rec_begin[zi*10+s], rec_begin[zi*10+s+1])
-	const double *rec_pack;                  // [n_rec][2 + nL]: FluorYield(shell) * RadRate(line), history slot (low word), mu of each layer at the line energy
-	const XmbShellGroup *grp;                // shell groups of layer L: [grp_begin[L], grp_begin[L + 1])
-	const int *grp_begin;                    // [nL + 1]
-	double rec_yr_max;                       // largest yield * rate of the records (range check of the line deposits)
+	// forced-detection line tiles (see XmbLineTile): one blob per layer
+	const char *lblob;                       // all blobs, layer L at lblob + lblob_off[L]
+	int lblob_off[XMB_MAX_LAYERS + 1];
+	int lblob_stage_bytes;                   // shared memory reserved for one staged blob (largest layer)
+	int lblob_main_layer;                    // the layer with the most records (staged once when batches mix layers)
+	double rec_wy_max;                       // largest wy of the records (range check of the line deposits)
 	const int *hist_base;                    // [nZ] first history slot of the element (+0 Rayleigh, +1 Compton)
 	int n_hist_slots;
 	// solid-angle grid

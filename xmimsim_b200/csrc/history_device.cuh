@@ -40,14 +40,19 @@ struct NodePos { int pos; double f; };
 __device__ __forceinline__ NodePos node_find(const XmbHistParams &P, double E) {
 	int b = (int)floor((E - P.bucket_E0) * P.bucket_inv_dE);
 	b = max(0, min(b, P.n_buckets - 1));
-	// bucket_start = the last node at or below the bucket's lower bound; bit 31 marks a bucket without a node inside:
-	// the bracket is known without scanning (build_device_tables: buckets 8 x finer than the uniform node spacing)
+	// bucket_start = the last node at or below the bucket's lower bound.  Bit 31: no node lies inside the bucket or within
+	// 1e-9 keV of its bounds, so every energy that maps to the bucket has this bracket and the node energies need not be
+	// compared first -- the gathers that depend on the position start one memory round trip earlier (build_device_tables:
+	// buckets 16 x finer than the uniform node spacing; the first bucket of a cell and those around edge doublets and
+	// line energies take the checked path).
 	const int bs = P.bucket_start[b];
 	int i = bs & 0x7FFFFFFF;
-	if (bs >= 0 || E < P.node_E[i] || E >= P.node_E[i + 1]) {
-		while (i > 0 && P.node_E[i] > E) i--;
-		while (i + 1 < P.n_nodes - 1 && P.node_E[i + 1] <= E) i++;
-		i = min(i, P.n_nodes - 2);
+	if (bs >= 0) {
+		if (E < P.node_E[i] || E >= P.node_E[i + 1]) {
+			while (i > 0 && P.node_E[i] > E) i--;
+			while (i + 1 < P.n_nodes - 1 && P.node_E[i + 1] <= E) i++;
+			i = min(i, P.n_nodes - 2);
+		}
 	}
 	NodePos p;
 	p.pos = i;
@@ -58,6 +63,13 @@ __device__ __forceinline__ NodePos node_find(const XmbHistParams &P, double E) {
 __device__ __forceinline__ double row_lerp(const XmbHistParams &P, NodePos np, int off) {
 	const double *r0 = P.rows + (size_t)np.pos * P.row_stride + off;
 	const double a = r0[0], b = r0[P.row_stride];
+	return a + (b - a) * np.f;
+}
+// mu of layer j: the same interpolation on the compact table mu_tab[node][nL] (the two nodes of a bracket are adjacent
+// in memory and the nodes a Compton line scatters into fill a few KB, instead of one 32-byte sector per 3 KB node row)
+__device__ __forceinline__ double mu_lerp(const XmbHistParams &P, NodePos np, int j) {
+	const double *r0 = P.mu_tab + (size_t)np.pos * P.nL + j;
+	const double a = r0[0], b = r0[P.nL];
 	return a + (b - a) * np.f;
 }
 
@@ -158,34 +170,27 @@ __device__ __forceinline__ void deposit_varying(unsigned stage_s32, int slot, un
 		stage_red(a, lo & 0xFFFFu); stage_red(a + 4u, lo >> 16); stage_red(a + 8u, hi & 0xFFFFu); stage_red(a + 12u, hi >> 16);
 	}
 }
-// fold the CTA's staged slots into the global (lo, hi) accumulators of one interaction order and clear them;
-// slots below n_ch hold 16-bit pieces, the others 20-bit pieces when P20
+// Fold the CTA's staged slots into the global accumulators of one interaction order and clear them.  A global slot is
+// FOUR 64-bit words, one per 16-bit piece position (value = w0 + w1 2^16 + w2 2^32 + w3 2^48): each staged word is added to
+// its own global word with a fire-and-forget RED -- no carry between words, so no atomic has to return a value (v15 added
+// (lo, hi) pairs with a returning atomic for the carry: the flush waited a round trip to L2 per slot, 8 % of the kernel
+// time on srm1412 and 13 % on the 10-layer sample, profiles/r2_history_phase_clocks.txt).  A staged word is < 2^32, so a
+// global word takes 2^32 flushes; xmb_limbs4_kernel normalises the four words into limbs.
+__device__ __forceinline__ void red_global_u64(unsigned long long *addr, unsigned long long v) {
+	asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
 template <bool P20>
 __device__ __forceinline__ void flush_staged(unsigned int *stage, unsigned long long *global_row, int n_slots, int n_ch, int tid, int T) {
+	static_assert(!P20, "the history kernel stages 16-bit pieces in every slot");
 	for (int i = tid; i < n_slots; i += T) {
 		const uint4 w = *reinterpret_cast<uint4 *>(stage + 4 * i);
 		if ((w.x | w.y | w.z | w.w) == 0u) continue;
 		*reinterpret_cast<uint4 *>(stage + 4 * i) = make_uint4(0u, 0u, 0u, 0u);
-		unsigned long long lo, hi;
-		if (P20 && i >= n_ch) {
-			// total = w0 + w1 2^20 + w2 2^40 (w.w unused)
-			const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 20);   // < 2^53
-			const unsigned long long t2 = (unsigned long long)w.z << 40;
-			lo = t01 + t2;
-			hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.z >> 24);
-		} else {
-			// total = w0 + w1 2^16 + w2 2^32 + w3 2^48 as a 128-bit integer
-			const unsigned long long t01 = (unsigned long long)w.x + ((unsigned long long)w.y << 16);     // < 2^49
-			const unsigned long long t2 = (unsigned long long)w.z << 32, t3 = (unsigned long long)w.w << 48;
-			lo = t01 + t2;
-			hi = (lo < t2 ? 1ULL : 0ULL) + ((unsigned long long)w.w >> 16);
-			const unsigned long long lo2 = lo + t3;
-			if (lo2 < lo) hi++;
-			lo = lo2;
-		}
-		const unsigned long long old = atomicAdd(&global_row[2 * i], lo);
-		if (old + lo < old) hi++;
-		if (hi) atomicAdd(&global_row[2 * i + 1], hi);
+		unsigned long long *gs = global_row + 4 * (size_t)i;
+		if (w.x) red_global_u64(gs + 0, w.x);
+		if (w.y) red_global_u64(gs + 1, w.y);
+		if (w.z) red_global_u64(gs + 2, w.z);
+		if (w.w) red_global_u64(gs + 3, w.w);
 	}
 }
 
@@ -388,7 +393,7 @@ __device__ void start_photon(const XmbHistParams &P, Photon &p, XmbRng &rng, uin
 		const NodePos np = node_find(P, p.energy);
 		p.weight = S.total_rel * exp(-row_lerp(P, np, P.off_exc));
 		XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, np, i);
+for (int i = 0; i < nL; i++) mus[i * T] = mu_lerp(P, np, i);
 	} else {
 		hor_ver_ratio = S.hor_ver_ratio;
 		p.weight = S.weight_rel;
@@ -398,7 +403,7 @@ for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, np, i);
 		if (p.energy <= ENERGY_THRESHOLD || p.energy > ENERGY_MAX) { p.alive = false; return; }
 		const NodePos np = node_find(P, p.energy);
 		XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, np, i);
+for (int i = 0; i < nL; i++) mus[i * T] = mu_lerp(P, np, i);
 	}
 	double x1, y1;
 	if (fabs(S.sigma_x * S.sigma_y) < 1.0E-20) {
@@ -546,6 +551,13 @@ __device__ __forceinline__ double exp_neg(double t, unsigned tab_s32) {
 	return y < 64.0 * 1000.0 ? r : 0.0;
 }
 
+// exp(-t) through the SFU in single precision (relative error ~2e-7): for attenuation factors of forced-detection deposits
+__device__ __forceinline__ double exp_neg_f32(double t) {
+	float ex;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((float)(t * -1.4426950408889634074)));
+	return (double)ex;
+}
+
 // ---- atom and interaction selection, scattering (src/xmi_main.F90:1558-1652) ------------------------------
 // MODE 0: forced detection (the fluorescence yield multiplies the weight); 1: escape-ratio mode (it goes to
 // weight_escape, src/xmi_variance_reduction.F90:697-750); 2: brute force (analogue yield check, :2297-2319 / :5325-5350:
@@ -555,12 +567,12 @@ __device__ __forceinline__ double exp_neg(double t, unsigned tab_s32) {
 template <int NL, int MODE, bool ADV = false>
 __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photon &p, uint64_t g, int order, double *mus, int T,
                                                    uint32_t atom_word, double &weight_escape, int &out_type, int &out_zi, int &out_line,
-                                                   int &out_shell, unsigned conv_mask = 0u) {
+                                                   int &out_shell, unsigned conv_mask = 0u, const NodePos *ep_known = nullptr) {
 	const int nL = NL > 0 ? NL : P.nL;
 	out_line = 0;
 	out_shell = -1;
 	const XmbLayerDev lay = P.layers[p.layer];
-	const NodePos ep = node_find(P, p.energy);
+	const NodePos ep = ep_known ? *ep_known : node_find(P, p.energy);   // the history kernel has looked the photon energy up already
 	const uint4 b1 = draw_block(P.seed, g, order, 1, 0, 1);   // {interaction type, s0, s1, s2}
 	double R2 = xmb_u01(atom_word);
 	double thr = 0.0;
@@ -670,7 +682,7 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 	if (new_energy) {
 		const NodePos cp = node_find(P, p.energy);
 		XMB_UNROLL_NL
-for (int i = 0; i < nL; i++) mus[i * T] = row_lerp(P, cp, i);
+for (int i = 0; i < nL; i++) mus[i * T] = mu_lerp(P, cp, i);
 	}
 	if (rotate) {
 		update_dirv(p, theta_i, phi_rot);

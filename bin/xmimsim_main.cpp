@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
 			return 1;
 		}
 	}
+	xmb_cache_set_provider(xrl);    // cache entries carry the provider's name: stand-in grids never serve an xraylib run
 	xmb_plugin_set_provider(xrl);   // a --custom-detector-response plugin that is this library computes with the same cross sections
 	xmb_input *input = nullptr;
 	if (!xmb_input_read_from_xml_file(infile.c_str(), &input)) { fprintf(stderr, "Could not read %s: %s\n", infile.c_str(), xmb_last_error()); return 1; }

@@ -213,6 +213,9 @@ typedef struct xmb_xrl_provider {
 } xmb_xrl_provider;
 
 const xmb_xrl_provider *xmb_xrl_surrogate(void);
+/* The same stand-in with the line density of real data: every transition of xraylib's enumeration whose subshells exist
+ * carries a rate (forbidden satellites ~1e-3), ~320 instead of ~150 active forced-detection lines for srm1155. */
+const xmb_xrl_provider *xmb_xrl_surrogate_dense(void);
 /* Provider backed by a libxrl loaded at run time (dlopen of `path`, or of libxrl.so.11 / .7 / libxrl.so when NULL):
  * the functions the reference links from xraylib >= 3.99 (configure.ac:115-116).  AugerRate is left NULL.
  * Returns NULL (xmb_last_error says why) when the library or one of its symbols is missing. */
@@ -541,6 +544,9 @@ int xmb_input_write_to_xml_string(const xmb_input *input, char **xmlstring);
  * (creating the file); the struct must carry its xmi_input_string. */
 int xmb_check_solid_angle_match(const xmb_input *cached, const xmb_input *fresh, const xmb_xrl_provider *xrl);
 int xmb_check_escape_ratios_match(const xmb_input *cached, const xmb_input *fresh);
+/* The cross-section provider whose name is stamped into new cache entries and required of matching ones (the axes of a
+ * solid-angle grid and the escape ratios depend on the cross sections).  Call once before using the cache functions. */
+void xmb_cache_set_provider(const xmb_xrl_provider *xrl);
 int xmb_find_solid_angle_match(const char *cache_file, const xmb_input *input, const xmb_xrl_provider *xrl,
                                xmb_solid_angle **rv, const xmb_main_options *options);
 int xmb_update_solid_angle_cache_file(const char *cache_file, const xmb_solid_angle *solid_angle);

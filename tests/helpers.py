@@ -11,9 +11,9 @@ DEFAULT_SEED = 0x584D494D53494D      # "XMIMSIM" 
 
 
 class Pair:
-    def __init__(self, inp, quality=0):
+    def __init__(self, inp, quality=0, provider=None):
         self.inp = inp
-        self.sim = x.Simulation(inp, quality=quality)
+        self.sim = x.Simulation(inp, quality=quality, provider=provider)
         self.ci = x.CInput(inp)
         self.od = orc.init_input(C.pointer(self.ci.input))
         self.n_total = orc.lib().orc_total_histories(C.cast(C.pointer(self.ci.input), C.c_void_p))

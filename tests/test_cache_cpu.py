@@ -119,3 +119,30 @@ def test_escape_ratio_cache_file(tmp_path):
     rv = C.POINTER(abi.EscapeRatios)()
     assert L.xmb_find_escape_ratios_match(path, C.byref(x.CInput(thick).input), C.byref(rv), None) == 1 and not rv
     sim.close()
+
+
+def test_cache_entries_are_bound_to_their_cross_section_provider(tmp_path):
+    """An entry computed with one provider never serves a run on another: the grid axes and the escape ratios depend on
+    the cross sections (the reference has a single provider, xraylib; here the analytic stand-in exists beside it)."""
+    L = abi.lib()
+    path = str(tmp_path / "sa.cache").encode()
+    c = x.CInput(example("srm1155"))
+    g = np.ones((6, 5)); r = np.linspace(0.1, 2, 5); t = np.linspace(1e-5, 1.57, 6)
+    sa = abi.SolidAngle(g.ctypes.data_as(abi.c_double_p), 5, 6, r.ctypes.data_as(abi.c_double_p), t.ctypes.data_as(abi.c_double_p), _xml(c))
+    surrogate = L.xmb_xrl_surrogate()
+    other = abi.XrlProvider.from_buffer_copy(surrogate.contents)      # same functions under another name
+    other.name = b"some other provider"
+    try:
+        L.xmb_cache_set_provider(surrogate)
+        assert L.xmb_update_solid_angle_cache_file(path, C.byref(sa)) == 1, abi.last_error()
+        rv = C.POINTER(abi.SolidAngle)()
+        assert L.xmb_find_solid_angle_match(path, C.byref(c.input), None, C.byref(rv), None) == 1 and rv
+        L.xmb_free_solid_angle(rv)
+        L.xmb_cache_set_provider(C.byref(other))
+        rv = C.POINTER(abi.SolidAngle)()
+        assert L.xmb_find_solid_angle_match(path, C.byref(c.input), None, C.byref(rv), None) == 1 and not rv
+        assert L.xmb_update_solid_angle_cache_file(path, C.byref(sa)) == 1
+        assert L.xmb_find_solid_angle_match(path, C.byref(c.input), None, C.byref(rv), None) == 1 and rv      # its own entry, behind the first
+        L.xmb_free_solid_angle(rv)
+    finally:
+        L.xmb_cache_set_provider(None)

@@ -20,12 +20,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 2e-6
 
 
-def run_both(inp, options=None, seed=11, grid_n=None, hits=400):
+def run_both(inp, options=None, seed=11, grid_n=None, hits=400, provider=None):
     """Engine and oracle once each on the same input, tables, grid and Philox key.  No repetition: a comparison that
     differs is a failure; helpers.diagnose_mismatch records what attributes it (both sides' per-order sums, digests,
     a second engine run, a single-thread oracle run, a fresh Pair) in gpurun_out/ and in the assertion message."""
     options = options or x.main_options()
-    P = Pair(inp)
+    P = Pair(inp, provider=provider)
     sa = P.grid(hits_per_single=hits, n=grid_n)
     ch, br, vr = P.sim.main_msim(options, sa)
     ch_o, vr_o, cnt = P.oracle(options, sa, 0)   # seed 0 -> default key on both sides
@@ -58,6 +58,19 @@ def test_examples_match_oracle(name, n_line):
     assert np.all(np.abs(a - b) <= 1e-6 * b)
     # rows are cumulative over interaction order
     assert np.all(np.diff(ch, axis=0) >= 0)
+
+
+@pytest.mark.parametrize("name", ["srm1155", "srm1412"])
+def test_dense_line_set_matches_oracle(name):
+    """The stand-in provider with xraylib's line density (~320 active forced-detection lines for srm1155 instead of ~150):
+    more and longer line tiles per layer, more groups per tile."""
+    from xmimsim_b200 import abi
+    inp = example(name)
+    inp.n_photons_line = 1200
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128, provider=abi.lib().xmb_xrl_surrogate_dense())
+    assert_spectra_close(ch, ch_o, RTOL, name + " dense channels")
+    assert_spectra_close(vr, vr_o, RTOL, name + " dense history")
+    assert np.count_nonzero(vr.sum(axis=2)) > 250
 
 
 def test_caso4_single_interaction():

@@ -119,7 +119,7 @@ def test_xmso_writer_follows_the_reference_layout(tmp_path):
     assert "<variance_reduction_history/>" in open(out + "2").read()
     txt = open(out).read()
     assert txt.startswith('<?xml version="1.0"?>\n<!DOCTYPE xmimsim-results SYSTEM "http://www.xmi.UGent.be/xml/xmimsim-1.0.dtd">')
-    assert "<brute_force_history/>" in txt and '<xmimsim-results version="1.0">' in txt
+    assert "<brute_force_history/>" in txt and '<xmimsim-results version="8.1">' in txt      # VERSION of the reference (src/xmi_xml.c:1465)
     import xml.etree.ElementTree as ET
     root = ET.parse(out).getroot()
     assert [c.tag for c in root] == ["inputfile", "spectrum_conv", "spectrum_unconv", "brute_force_history",
@@ -167,3 +167,13 @@ def test_spe_and_csv_files(tmp_path):
     assert first[0] == "0" and len(first) == 2 + n_int
     tab = np.loadtxt(csv, delimiter=",")
     assert tab.shape == (nch, 2 + n_int) and np.allclose(tab[:, 2:], rows_np[1:].T, rtol=1e-5)
+
+
+@pytest.mark.parametrize("broken", ["<xmimsim><general version=1.0></general></xmimsim>", "<xmimsim><a><![CDATA[never closed</a></xmimsim>",
+                                    "<xmimsim><general version=\"1.0></general>", "<xmimsim><a>text</a", "<x>" * 200])
+def test_malformed_xml_is_an_error_not_a_hang(broken):
+    """Unquoted or unterminated attribute values, an unterminated CDATA section or end tag, runaway nesting: the built-in
+    parser reports them (the reference leaves this to libxml2)."""
+    inp = C.POINTER(abi.Input)()
+    assert abi.lib().xmb_input_read_from_xml_string(broken.encode(), C.byref(inp)) == 0
+    assert abi.last_error()

@@ -185,6 +185,7 @@ def lib():
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
     L.xmb_xrl_surrogate.restype = C.POINTER(XrlProvider)
+    L.xmb_xrl_surrogate_dense.restype = C.POINTER(XrlProvider)
     L.xmb_xrl_from_library.argtypes = [C.c_char_p]; L.xmb_xrl_from_library.restype = C.POINTER(XrlProvider)
     L.xmb_input_C2F.argtypes = [C.POINTER(Input), vpp]; L.xmb_input_C2F.restype = C.c_int
     L.xmb_input_F2C.argtypes = [vp]; L.xmb_input_F2C.restype = C.POINTER(Input)
@@ -248,6 +249,7 @@ def lib():
     L.xmb_input_write_to_xml_string.argtypes = [C.POINTER(Input), C.POINTER(C.c_void_p)]; L.xmb_input_write_to_xml_string.restype = C.c_int
     L.xmb_check_solid_angle_match.argtypes = [C.POINTER(Input), C.POINTER(Input), C.POINTER(XrlProvider)]; L.xmb_check_solid_angle_match.restype = C.c_int
     L.xmb_check_escape_ratios_match.argtypes = [C.POINTER(Input), C.POINTER(Input)]; L.xmb_check_escape_ratios_match.restype = C.c_int
+    L.xmb_cache_set_provider.argtypes = [C.POINTER(XrlProvider)]; L.xmb_cache_set_provider.restype = None
     L.xmb_find_solid_angle_match.argtypes = [C.c_char_p, C.POINTER(Input), C.POINTER(XrlProvider), C.POINTER(C.POINTER(SolidAngle)), C.POINTER(MainOptions)]
     L.xmb_find_solid_angle_match.restype = C.c_int
     L.xmb_update_solid_angle_cache_file.argtypes = [C.c_char_p, C.POINTER(SolidAngle)]; L.xmb_update_solid_angle_cache_file.restype = C.c_int

@@ -140,46 +140,53 @@ __global__ void __launch_bounds__(DET_THREADS) escape_apply_kernel(DetParams P, 
 }
 
 // ---- pile-up -------------------------------------------------------------------------------------------
-// cdf[k][nch] inclusive prefix sums of max(counts,0); one thread = one independent pulse-train share
+// cdf[k][nch] inclusive prefix sums of max(counts,0); one thread = one independent pulse-train share.  A block counts into a
+// histogram in shared memory and adds it to the global row once at the end: with per-pulse global atomics the strongest
+// channels (a few percent of 8e8 pulses each) serialised in L2 and set the kernel time (50.8 ms for BASELINE configs[4],
+// profiles/r2_detector_kernels_ncu.json; the sums are integers, so the result is the same).
 __global__ void pileup_kernel(DetParams P, const double *__restrict__ cdf, unsigned long long *__restrict__ counts, uint64_t seed, int row_first) {
+	extern __shared__ unsigned int pu_hist[];   // [nch]
 	const int k = blockIdx.y, nch = P.nch;
+	for (int i = threadIdx.x; i < nch; i += blockDim.x) pu_hist[i] = 0u;
+	__syncthreads();
 	const int sid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (sid >= PILEUP_STREAMS) return;
 	const double *c = cdf + (size_t)k * nch;
 	const double total = c[nch - 1];
 	const long long Nt_long = (long long)total;
-	if (Nt_long <= 0) return;
-	const long long quota = Nt_long / PILEUP_STREAMS + (sid < Nt_long % PILEUP_STREAMS ? 1 : 0);
-	if (quota <= 0) return;
-	const double mu = 1.0 / (total / P.live_time);
-	XmbRng rng;
-	rng.init(seed, ((uint64_t)(row_first + k) << 32) | (uint64_t)sid, XMB_TAG_DETECTOR);
-	unsigned long long *out = counts + (size_t)k * nch;
-	long long done = 0;
-	int npulses = 0;
-	long long psum = 0;   // sum of 1-based pulse channels of the open group
-	int first = 0;
-	for (;;) {
-		npulses++; done++;
-		if (npulses > 100) break;   // reference: "pulsetrain maximum reached" (aborts the run)
-		const double u = rng.uniform() * total;
-		int lo = 0, hi = nch - 1;
-		while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] > u) hi = mid; else lo = mid + 1; }
-		if (npulses == 1) first = lo + 1;
-		psum += lo + 1;
-		const double deltaT = -mu * log(1.0 - rng.uniform());
-		if (deltaT > P.pulse_width) {
-			if (npulses == 1) atomicAdd(&out[first - 1], 1ULL);
-			else {
-				// energies_sum = sum(p*gain + zero); pulses_sum = (energies_sum - zero)/gain   (:187-191)
-				const double energies_sum = (double)psum * P.gain + (double)npulses * P.zero;
-				const long long pulses_sum = (long long)((energies_sum - P.zero) / P.gain);
-				if (pulses_sum > 0 && pulses_sum <= nch) atomicAdd(&out[pulses_sum - 1], 1ULL);
+	const long long quota = Nt_long <= 0 || sid >= PILEUP_STREAMS ? 0 : Nt_long / PILEUP_STREAMS + (sid < Nt_long % PILEUP_STREAMS ? 1 : 0);
+	if (quota > 0) {
+		const double mu = 1.0 / (total / P.live_time);
+		XmbRng rng;
+		rng.init(seed, ((uint64_t)(row_first + k) << 32) | (uint64_t)sid, XMB_TAG_DETECTOR);
+		long long done = 0;
+		int npulses = 0;
+		long long psum = 0;   // sum of 1-based pulse channels of the open group
+		int first = 0;
+		for (;;) {
+			npulses++; done++;
+			if (npulses > 100) break;   // reference: "pulsetrain maximum reached" (aborts the run)
+			const double u = rng.uniform() * total;
+			int lo = 0, hi = nch - 1;
+			while (lo < hi) { const int mid = (lo + hi) >> 1; if (c[mid] > u) hi = mid; else lo = mid + 1; }
+			if (npulses == 1) first = lo + 1;
+			psum += lo + 1;
+			const double deltaT = -mu * log(1.0 - rng.uniform());
+			if (deltaT > P.pulse_width) {
+				if (npulses == 1) atomicAdd(&pu_hist[first - 1], 1u);
+				else {
+					// energies_sum = sum(p*gain + zero); pulses_sum = (energies_sum - zero)/gain   (:187-191)
+					const double energies_sum = (double)psum * P.gain + (double)npulses * P.zero;
+					const long long pulses_sum = (long long)((energies_sum - P.zero) / P.gain);
+					if (pulses_sum > 0 && pulses_sum <= nch) atomicAdd(&pu_hist[pulses_sum - 1], 1u);
+				}
+				if (done >= quota) break;
+				npulses = 0; psum = 0;
 			}
-			if (done >= quota) break;
-			npulses = 0; psum = 0;
 		}
 	}
+	__syncthreads();
+	unsigned long long *out = counts + (size_t)k * nch;
+	for (int i = threadIdx.x; i < nch; i += blockDim.x) if (pu_hist[i]) atomicAdd(&out[i], (unsigned long long)pu_hist[i]);
 }
 
 __global__ void prefix_kernel(DetParams P, const double *__restrict__ spec, double *__restrict__ cdf) {
@@ -361,7 +368,7 @@ static int convolute_rows(XmbInputF *in, const xmb_xrl_provider *xrl, double *ro
 		if (!d_cnt) { xmb_set_error("detector: device allocation failed"); return 0; }
 		cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * tot);
 		prefix_kernel<<<1, 32>>>(P, d_spec, d_tmp); launches++;
-		pileup_kernel<<<dim3(PILEUP_STREAMS / 128, n_rows), 128>>>(P, d_tmp, d_cnt, seed ? seed : XMB_DEFAULT_SEED, row_first); launches++;
+		pileup_kernel<<<dim3(PILEUP_STREAMS / 128, n_rows), 128, sizeof(unsigned int) * nch>>>(P, d_tmp, d_cnt, seed ? seed : XMB_DEFAULT_SEED, row_first); launches++;
 		counts_to_double_kernel<<<(tot + 255) / 256, 256>>>(tot, d_cnt, d_spec); launches++;
 	}
 	response_norm_kernel<<<nch, DET_THREADS>>>(P, d_inv); launches++;

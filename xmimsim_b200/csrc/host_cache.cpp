@@ -5,8 +5,11 @@
 // of the input that produced it (dataset xmi_input_string) and the same datasets with the same dimensions.  The match
 // rules that decide whether an entry can be re-used are the reference's.
 //
-//   file   := "XMBCACHE" u32 version(1) u32 kind        kind 1 = XMI_HDF5_SOLID_ANGLES, 2 = XMI_HDF5_ESCAPE_RATIOS
-//   entry  := u64 payload_bytes, u32 xml_len, xml, datasets
+//   file   := "XMBCACHE" u32 version(2) u32 kind        kind 1 = XMI_HDF5_SOLID_ANGLES, 2 = XMI_HDF5_ESCAPE_RATIOS
+//   entry  := u64 payload_bytes, u32 xml_len, xml, u32 tag_len, tag, datasets
+// `tag` names the cross-section provider the entry was computed with (xmb_cache_set_provider; the reference has one
+// provider, xraylib, and needs no such field): the axes of a solid-angle grid and every escape ratio depend on it, so an
+// entry made with the analytic stand-in is never handed to a run on xraylib data, and the other way round.
 //   kind 1 := i64 n_theta, i64 n_r, f64 solid_angles[n_theta][n_r], f64 grid_dims_r_vals[n_r], f64 grid_dims_theta_vals[n_theta]
 //   kind 2 := i32 n_elements, n_fluo_input_energies, n_compton_input_energies, n_compton_output_energies, i32 Z[],
 //             f64 fluo_escape_ratios[n_fluo_in][109][n_elements], f64 fluo_escape_input_energies[], f64 compton_escape_ratios
@@ -28,12 +31,27 @@ struct Reader {
 	template <typename T> void arr(T *p, size_t n) { if (n && fread(p, sizeof(T), n, f) != n) ok = false; }
 };
 
+std::string g_cache_tag;   // provider name stamped into new entries and required of matches
+
+// reads the tag of an entry; false when it differs from the current one (the caller skips the entry)
+bool read_tag_matches(Reader &r) {
+	const unsigned n = r.get<unsigned>();
+	if (!r.ok || n > 4096) { r.ok = false; return false; }
+	std::string tag(n, '\0');
+	r.arr(&tag[0], n);
+	return r.ok && tag == g_cache_tag;
+}
+void write_tag(FILE *f) {
+	const unsigned n = (unsigned)g_cache_tag.size();
+	fwrite(&n, 4, 1, f); fwrite(g_cache_tag.data(), 1, n, f);
+}
+
 FILE *open_cache(const char *file, unsigned kind, bool create, const char *mode) {
 	FILE *f = fopen(file, mode);
 	if (!f && create) {
 		f = fopen(file, "wb+");
 		if (!f) { xmb_set_error("Cannot create cache file %s", file); return nullptr; }
-		const unsigned version = 1;
+		const unsigned version = 2;
 		fwrite(MAGIC, 1, 8, f); fwrite(&version, 4, 1, f); fwrite(&kind, 4, 1, f);
 		fflush(f);
 		return f;
@@ -41,8 +59,8 @@ FILE *open_cache(const char *file, unsigned kind, bool create, const char *mode)
 	if (!f) { xmb_set_error("Cannot open file %s for reading", file); return nullptr; }
 	char m[8];
 	unsigned version = 0, k = 0;
-	if (fread(m, 1, 8, f) != 8 || memcmp(m, MAGIC, 8) != 0 || fread(&version, 4, 1, f) != 1 || fread(&k, 4, 1, f) != 1 || version != 1) {
-		xmb_set_error("%s is not a cache file of this library", file); fclose(f); return nullptr;
+	if (fread(m, 1, 8, f) != 8 || memcmp(m, MAGIC, 8) != 0 || fread(&version, 4, 1, f) != 1 || fread(&k, 4, 1, f) != 1 || version != 2) {
+		xmb_set_error("%s is not a cache file of this library (or of an earlier format without the provider tag)", file); fclose(f); return nullptr;
 	}
 	if (k != kind) { xmb_set_error("%s has kind %u, expected %u", file, k, kind); fclose(f); return nullptr; }   // the reference's kind attribute check
 	return f;
@@ -93,6 +111,8 @@ void extremes(const xmb_input *A, const xmb_xrl_provider *xrl, double *S1, doubl
 
 // xmi_check_solid_angle_match (src/xmi_solid_angle.c:420-670): A = cached (old), B = new input.  The cached grid can be
 // re-used when it covers the depth range the new sample can be excited in and the detector geometry is the same.
+extern "C" void xmb_cache_set_provider(const xmb_xrl_provider *xrl) { g_cache_tag = xrl && xrl->name ? xrl->name : ""; }
+
 extern "C" int xmb_check_solid_angle_match(const xmb_input *A, const xmb_input *B, const xmb_xrl_provider *xrl) {
 	if (!xrl) xrl = xmb_xrl_surrogate();
 	double S1a, S2a, S1b, S2b;
@@ -151,7 +171,9 @@ extern "C" int xmb_find_solid_angle_match(const char *file, const xmb_input *A, 
 		r.arr(&xml[0], xml_len);
 		xmb_input *cached = nullptr;
 		if (!r.ok || !xmb_input_read_from_xml_string(xml.c_str(), &cached)) { fclose(f); xmb_set_error("%s: corrupt entry", file); return 0; }
-		const int match = xmb_check_solid_angle_match(cached, A, xrl);
+		const bool same_provider = read_tag_matches(r);
+		if (!r.ok) { xmb_input_free(&cached); fclose(f); xmb_set_error("%s: corrupt entry", file); return 0; }
+		const int match = same_provider && xmb_check_solid_angle_match(cached, A, xrl);
 		xmb_input_free(&cached);
 		if (options && options->extra_verbose) printf(match ? "Match in solid angle grid\n" : "No match in solid angle grid\n");
 		if (!match) { fseek(f, start + (long)bytes, SEEK_SET); continue; }
@@ -181,8 +203,9 @@ extern "C" int xmb_update_solid_angle_cache_file(const char *file, const xmb_sol
 	fseek(f, 0, SEEK_END);
 	const unsigned xml_len = (unsigned)strlen(sa->xmi_input_string);
 	const long long nt = sa->grid_dims_theta_n, nr = sa->grid_dims_r_n;
-	const unsigned long long bytes = 4 + xml_len + 16 + sizeof(double) * ((size_t)nt * nr + nt + nr);
+	const unsigned long long bytes = 4 + xml_len + 4 + g_cache_tag.size() + 16 + sizeof(double) * ((size_t)nt * nr + nt + nr);
 	fwrite(&bytes, 8, 1, f); fwrite(&xml_len, 4, 1, f); fwrite(sa->xmi_input_string, 1, xml_len, f);
+	write_tag(f);
 	fwrite(&nt, 8, 1, f); fwrite(&nr, 8, 1, f);
 	fwrite(sa->solid_angles, sizeof(double), (size_t)nt * nr, f);
 	fwrite(sa->grid_dims_r_vals, sizeof(double), nr, f);
@@ -211,7 +234,9 @@ extern "C" int xmb_find_escape_ratios_match(const char *file, const xmb_input *A
 		r.arr(&xml[0], xml_len);
 		xmb_input *cached = nullptr;
 		if (!r.ok || !xmb_input_read_from_xml_string(xml.c_str(), &cached)) { fclose(f); xmb_set_error("%s: corrupt entry", file); return 0; }
-		const int match = xmb_check_escape_ratios_match(cached, A);
+		const bool same_provider = read_tag_matches(r);
+		if (!r.ok) { xmb_input_free(&cached); fclose(f); xmb_set_error("%s: corrupt entry", file); return 0; }
+		const int match = same_provider && xmb_check_escape_ratios_match(cached, A);
 		xmb_input_free(&cached);
 		if (options && options->extra_verbose) printf(match ? "Match in escape ratios\n" : "No match in escape ratios\n");
 		if (!match) { fseek(f, start + (long)bytes, SEEK_SET); continue; }
@@ -247,9 +272,10 @@ extern "C" int xmb_update_escape_ratios_cache_file(const char *file, const xmb_e
 	fseek(f, 0, SEEK_END);
 	const unsigned xml_len = (unsigned)strlen(e->xmi_input_string);
 	const size_t nf = (size_t)e->n_fluo_input_energies * 109 * e->n_elements, nc = (size_t)e->n_compton_input_energies * e->n_compton_output_energies;
-	const unsigned long long bytes = 4 + xml_len + 16 + 4ULL * e->n_elements +
+	const unsigned long long bytes = 4 + xml_len + 4 + g_cache_tag.size() + 16 + 4ULL * e->n_elements +
 	                                 sizeof(double) * (nf + e->n_fluo_input_energies + nc + e->n_compton_input_energies + e->n_compton_output_energies);
 	fwrite(&bytes, 8, 1, f); fwrite(&xml_len, 4, 1, f); fwrite(e->xmi_input_string, 1, xml_len, f);
+	write_tag(f);
 	fwrite(&e->n_elements, 4, 1, f); fwrite(&e->n_fluo_input_energies, 4, 1, f); fwrite(&e->n_compton_input_energies, 4, 1, f); fwrite(&e->n_compton_output_energies, 4, 1, f);
 	fwrite(e->Z, 4, e->n_elements, f);
 	fwrite(e->fluo_escape_ratios, sizeof(double), nf, f);

@@ -60,9 +60,13 @@ std::string escape(const char *s) {
 	return o;
 }
 
+// the version string the reference writes into <general version=...> and <xmimsim-results version=...> (VERSION of configure.ac:16; src/xmi_xml.c:1465,1687)
+#define XMB_REFERENCE_VERSION "8.1"
+
 struct Parser {
 	const std::string &s;
 	size_t i = 0;
+	int depth = 0;
 	std::string err;
 	explicit Parser(const std::string &src) : s(src) {}
 	bool starts(const char *t) const { return s.compare(i, strlen(t), t) == 0; }
@@ -90,17 +94,33 @@ struct Parser {
 			std::string an, av;
 			while (i < s.size() && s[i] != '=' && !isspace((unsigned char)s[i])) an += s[i++];
 			while (i < s.size() && (isspace((unsigned char)s[i]) || s[i] == '=')) i++;
+			if (i >= s.size() || (s[i] != '"' && s[i] != '\'')) { err = "attribute " + an + " of " + n->name + " without a quoted value"; return nullptr; }
 			const char q = s[i++];
 			while (i < s.size() && s[i] != q) av += s[i++];
+			if (i >= s.size()) { err = "unterminated attribute value in " + n->name; return nullptr; }
 			i++;
 			n->attrs.emplace_back(an, unescape(av));
 		}
 		for (;;) {
 			if (i >= s.size()) { err = "unterminated element " + n->name; return nullptr; }
 			if (starts("<!--")) { const size_t e = s.find("-->", i); i = e == std::string::npos ? s.size() : e + 3; continue; }
-			if (starts("<![CDATA[")) { const size_t e = s.find("]]>", i); n->text += s.substr(i + 9, e - i - 9); i = e + 3; continue; }
-			if (starts("</")) { const size_t e = s.find('>', i); i = e + 1; break; }
-			if (s[i] == '<') { auto k = element(); if (!k) return nullptr; n->kids.push_back(std::move(k)); continue; }
+			if (starts("<![CDATA[")) {
+				const size_t e = s.find("]]>", i);
+				if (e == std::string::npos) { err = "unterminated CDATA section in " + n->name; return nullptr; }
+				n->text += s.substr(i + 9, e - i - 9); i = e + 3; continue;
+			}
+			if (starts("</")) {
+				const size_t e = s.find('>', i);
+				if (e == std::string::npos) { err = "unterminated end tag of " + n->name; return nullptr; }
+				i = e + 1; break;
+			}
+			if (s[i] == '<') {
+				if (++depth > 64) { err = "elements nested deeper than 64 levels"; return nullptr; }
+				auto k = element();
+				depth--;
+				if (!k) return nullptr;
+				n->kids.push_back(std::move(k)); continue;
+			}
 			const size_t e = s.find('<', i);
 			n->text += unescape(s.substr(i, e - i));
 			i = e;
@@ -272,7 +292,7 @@ void write_vec(Out &o, int d, const char *tag, const double *v) {
 	o.open(d, tag); o.g(d + 1, "x", v[0]); o.g(d + 1, "y", v[1]); o.g(d + 1, "z", v[2]); o.close(d, tag);
 }
 void write_input_body(Out &o, int d, const xmb_input *in) {                           // xmi_write_input_xml_body, :1679-1801
-	fprintf(o.f, "%*s<general version=\"%s\">\n", d, "", "1.0");
+	fprintf(o.f, "%*s<general version=\"%s\">\n", d, "", XMB_REFERENCE_VERSION);
 	o.s(d + 1, "outputfile", in->general->outputfile);
 	o.i(d + 1, "n_photons_interval", in->general->n_photons_interval);
 	o.i(d + 1, "n_photons_line", in->general->n_photons_line);
@@ -551,7 +571,7 @@ extern "C" int xmb_output_write_to_xml_file(const xmb_input *input, const char *
 	if (!f) { xmb_set_error("could not write to %s", xmsofile); return 0; }
 	const int n_int = input->general->n_interactions_trajectory, nch = input->detector->nchannels, i0 = use_zero_interactions ? 0 : 1;
 	write_header(f, "xmimsim-results");
-	fputs("<xmimsim-results version=\"1.0\">\n", f);
+	fputs("<xmimsim-results version=\"" XMB_REFERENCE_VERSION "\">\n", f);
 	Out o{f};
 	o.s(1, "inputfile", inputfile ? inputfile : "");
 	for (int pass = 0; pass < 2; pass++) {

@@ -43,6 +43,17 @@
 #endif
 // -DXMB_PHASE_CLOCKS=1 (experiment builds): lane 0 of every warp accumulates the SM clock per phase of the batch loop,
 // the sums land in counters[40 + phase] (XMB_PHASES=1 prints them after a run)
+// queue traffic with the streaming (evict-first) cache operator, or plain
+#ifndef XMB_QUEUE_STREAMING
+#define XMB_QUEUE_STREAMING 0
+#endif
+#if XMB_QUEUE_STREAMING
+#define XMB_QST(p, v) __stcs((p), (v))
+#define XMB_QLD(p) __ldcs(p)
+#else
+#define XMB_QST(p, v) (*(p) = (v))
+#define XMB_QLD(p) (*(p))
+#endif
 #ifndef XMB_COMPTON_EXP_F32
 #define XMB_COMPTON_EXP_F32 0
 #endif
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	double *rd = smem + (size_t)nL * T + tid;   // rd[j*T]    : distances, then rho_j * d_j towards the detector
 	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] pieces
 	// line phase (lane = record): per-warp scratch of the photons' factors per shell group, and the staged line tiles
-	const int wscr = xmb_warp_scratch_doubles(nL);
+	const int wscr = xmb_warp_scratch_doubles(P.tile_groups);
 	float *wpre_w = reinterpret_cast<float *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(tid >> 5) * wscr);
 	const char *sblob = reinterpret_cast<const char *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(T >> 5) * wscr);
 	constexpr bool P20 = false;   // every staged slot holds four 16-bit pieces (a line slot receives one per-lane sum per tile and warp)
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	if (tid == 0) { xmb_mbar_init(mbar_s32, 1); xmb_fence_proxy_async(); }
 	__syncthreads();
 	auto stage_layer = [&](int L) {   // block-uniform; callers guarantee that no thread still reads the staged blob
+		if (P.lblob_stage_bytes == 0) return;   // no room in shared memory (many layers): the tiles are read in place
 		const unsigned bytes = (unsigned)(P.lblob_off[L + 1] - P.lblob_off[L]);
 		if (tid == 0) { xmb_fence_proxy_async(); xmb_bulk_g2s(sblob_s32, P.lblob + P.lblob_off[L], bytes, mbar_s32); }
 		staged_layer = L; stage_pending = true;
@@ -195,13 +207,13 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			if (surv) {
 				double *q = qbase + (size_t)(order * nL + myL) * NF * qcap + wbase + __popc(peers & ((1u << lane) - 1u));
 				// (streaming stores / loads: 28 GB of queue traffic per 5e7 histories must not evict the tables and the grid from L2)
-				__stcs(&q[0 * qcap], p.cx); __stcs(&q[1 * qcap], p.cy); __stcs(&q[2 * qcap], p.cz);
-				__stcs(&q[3 * qcap], p.dx); __stcs(&q[4 * qcap], p.dy); __stcs(&q[5 * qcap], p.dz);
-				__stcs(&q[6 * qcap], p.ex); __stcs(&q[7 * qcap], p.ey); __stcs(&q[8 * qcap], p.ez);
-				__stcs(&q[9 * qcap], p.energy); __stcs(&q[10 * qcap], p.weight); __stcs(&q[11 * qcap], p.theta); __stcs(&q[12 * qcap], p.phi);
-				__stcs(&q[13 * qcap], __longlong_as_double((long long)g));
-				__stcs(&q[14 * qcap], __longlong_as_double((long long)p.layer));
-				for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
+				XMB_QST(&q[0 * qcap], p.cx); XMB_QST(&q[1 * qcap], p.cy); XMB_QST(&q[2 * qcap], p.cz);
+				XMB_QST(&q[3 * qcap], p.dx); XMB_QST(&q[4 * qcap], p.dy); XMB_QST(&q[5 * qcap], p.dz);
+				XMB_QST(&q[6 * qcap], p.ex); XMB_QST(&q[7 * qcap], p.ey); XMB_QST(&q[8 * qcap], p.ez);
+				XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight); XMB_QST(&q[11 * qcap], p.theta); XMB_QST(&q[12 * qcap], p.phi);
+				XMB_QST(&q[13 * qcap], __longlong_as_double((long long)g));
+				XMB_QST(&q[14 * qcap], __longlong_as_double((long long)p.layer));
+				for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 			}
 			return;   // the caller's __syncthreads() publishes the counts
 		}
@@ -222,14 +234,14 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 #endif
 		if (surv) {
 			double *q = qbase + (size_t)order * NF * qcap + have + off + __popc(bal & ((1u << lane) - 1u));
-			__stcs(&q[0 * qcap], p.cx); __stcs(&q[1 * qcap], p.cy); __stcs(&q[2 * qcap], p.cz);
-			__stcs(&q[3 * qcap], p.dx); __stcs(&q[4 * qcap], p.dy); __stcs(&q[5 * qcap], p.dz);
-			__stcs(&q[6 * qcap], p.ex); __stcs(&q[7 * qcap], p.ey); __stcs(&q[8 * qcap], p.ez);
-			__stcs(&q[9 * qcap], p.energy); __stcs(&q[10 * qcap], p.weight); __stcs(&q[11 * qcap], p.theta); __stcs(&q[12 * qcap], p.phi);
-			__stcs(&q[13 * qcap], __longlong_as_double((long long)g));
-			__stcs(&q[14 * qcap], __longlong_as_double((long long)p.layer));
+			XMB_QST(&q[0 * qcap], p.cx); XMB_QST(&q[1 * qcap], p.cy); XMB_QST(&q[2 * qcap], p.cz);
+			XMB_QST(&q[3 * qcap], p.dx); XMB_QST(&q[4 * qcap], p.dy); XMB_QST(&q[5 * qcap], p.dz);
+			XMB_QST(&q[6 * qcap], p.ex); XMB_QST(&q[7 * qcap], p.ey); XMB_QST(&q[8 * qcap], p.ez);
+			XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight); XMB_QST(&q[11 * qcap], p.theta); XMB_QST(&q[12 * qcap], p.phi);
+			XMB_QST(&q[13 * qcap], __longlong_as_double((long long)g));
+			XMB_QST(&q[14 * qcap], __longlong_as_double((long long)p.layer));
 			XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
+for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 		}
 #if !XMB_PUSH_ATOMIC
 		__syncthreads();
@@ -346,13 +358,13 @@ for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T
 			}
 			if (myL >= 0) {
 				const double *q = qbase + (size_t)(k * nL + myL) * NF * qcap + at;
-				p.cx = __ldcs(&q[0 * qcap]); p.cy = __ldcs(&q[1 * qcap]); p.cz = __ldcs(&q[2 * qcap]);
-				p.dx = __ldcs(&q[3 * qcap]); p.dy = __ldcs(&q[4 * qcap]); p.dz = __ldcs(&q[5 * qcap]);
-				p.ex = __ldcs(&q[6 * qcap]); p.ey = __ldcs(&q[7 * qcap]); p.ez = __ldcs(&q[8 * qcap]);
-				p.energy = __ldcs(&q[9 * qcap]); p.weight = __ldcs(&q[10 * qcap]); p.theta = __ldcs(&q[11 * qcap]); p.phi = __ldcs(&q[12 * qcap]);
-				g = (uint64_t)__double_as_longlong(__ldcs(&q[13 * qcap]));
+				p.cx = XMB_QLD(&q[0 * qcap]); p.cy = XMB_QLD(&q[1 * qcap]); p.cz = XMB_QLD(&q[2 * qcap]);
+				p.dx = XMB_QLD(&q[3 * qcap]); p.dy = XMB_QLD(&q[4 * qcap]); p.dz = XMB_QLD(&q[5 * qcap]);
+				p.ex = XMB_QLD(&q[6 * qcap]); p.ey = XMB_QLD(&q[7 * qcap]); p.ez = XMB_QLD(&q[8 * qcap]);
+				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]); p.theta = XMB_QLD(&q[11 * qcap]); p.phi = XMB_QLD(&q[12 * qcap]);
+				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[13 * qcap]));
 				p.layer = myL;
-				for (int j = 0; j < nL; j++) mus[j * T] = __ldcs(&q[(XMB_STATE_FIELDS + j) * qcap]);
+				for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;
 				p.alive = true;
 			}
@@ -380,14 +392,14 @@ for (int j = 0; j < nL; j++) __stcs(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T
 			}
 			if (tid < n) {
 				const double *q = qk + src;
-				p.cx = __ldcs(&q[0 * qcap]); p.cy = __ldcs(&q[1 * qcap]); p.cz = __ldcs(&q[2 * qcap]);
-				p.dx = __ldcs(&q[3 * qcap]); p.dy = __ldcs(&q[4 * qcap]); p.dz = __ldcs(&q[5 * qcap]);
-				p.ex = __ldcs(&q[6 * qcap]); p.ey = __ldcs(&q[7 * qcap]); p.ez = __ldcs(&q[8 * qcap]);
-				p.energy = __ldcs(&q[9 * qcap]); p.weight = __ldcs(&q[10 * qcap]); p.theta = __ldcs(&q[11 * qcap]); p.phi = __ldcs(&q[12 * qcap]);
-				g = (uint64_t)__double_as_longlong(__ldcs(&q[13 * qcap]));
-				p.layer = (int)__double_as_longlong(__ldcs(&q[14 * qcap]));
+				p.cx = XMB_QLD(&q[0 * qcap]); p.cy = XMB_QLD(&q[1 * qcap]); p.cz = XMB_QLD(&q[2 * qcap]);
+				p.dx = XMB_QLD(&q[3 * qcap]); p.dy = XMB_QLD(&q[4 * qcap]); p.dz = XMB_QLD(&q[5 * qcap]);
+				p.ex = XMB_QLD(&q[6 * qcap]); p.ey = XMB_QLD(&q[7 * qcap]); p.ez = XMB_QLD(&q[8 * qcap]);
+				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]); p.theta = XMB_QLD(&q[11 * qcap]); p.phi = XMB_QLD(&q[12 * qcap]);
+				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[13 * qcap]));
+				p.layer = (int)__double_as_longlong(XMB_QLD(&q[14 * qcap]));
 				XMB_UNROLL_NL
-for (int j = 0; j < nL; j++) mus[j * T] = __ldcs(&q[(XMB_STATE_FIELDS + j) * qcap]);
+for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;
 				p.alive = true;
 			}
@@ -982,6 +994,11 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 		std::vector<char> blob;
 		std::vector<std::pair<double, int>> edges;   // (shell edge, records) of every group of every layer: energy classes below
 		P.rec_wy_max = 0.0;
+		// (With many layers the per-thread arrays mus[nL], rd[nL] leave little shared memory and the CTA runs fewer threads: 864
+		// on the 10-layer sample.  Halving the per-warp scratch -- tiles of 4 groups -- and reading the tiles in place keeps 1024
+		// threads but measured 2 % slower, profiles/r2_history_ablation.txt.)
+		const bool short_smem = false;
+		P.tile_groups = XMB_TILE_GROUPS;
 		P.lblob_stage_bytes = 16;
 		int most = -1;
 		P.lblob_main_layer = 0;
@@ -1011,7 +1028,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			std::vector<int> tile_g0;
 			for (int g = 0; g < (int)grp.size(); g++)
 				for (int r = grp[g].r0; r < grp[g].r1; r++) {
-					if (tiles.empty() || tiles.back().size() == 32 || g - tile_g0.back() >= XMB_TILE_GROUPS) { tiles.push_back({}); tile_g0.push_back(g); }
+					if (tiles.empty() || tiles.back().size() == 32 || g - tile_g0.back() >= P.tile_groups) { tiles.push_back({}); tile_g0.push_back(g); }
 					tiles.back().push_back(Lane{g, r});
 				}
 			const int n_tiles = (int)tiles.size(), n_grp = (int)grp.size();
@@ -1052,6 +1069,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			P.lblob_off[k] = (int)base;
 			P.lblob_stage_bytes = std::max(P.lblob_stage_bytes, (int)(blob.size() - base));
 		}
+		if (short_smem) P.lblob_stage_bytes = 0;
 		P.lblob_off[nL] = (int)blob.size();
 		P.lblob = upload(D, blob.data(), blob.size(), ok);
 		D->n_line_tiles_bytes = blob.size();
@@ -1291,7 +1309,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
 	// + the line phase: XMB_TILE_GROUPS x XMB_WPRE_STRIDE doubles of scratch per warp and one staged line-tile blob
 	const size_t fixed_bytes = stage_bytes + (size_t)P.lblob_stage_bytes;
-	auto per_cta = [&](int t) { return fixed_bytes + sizeof(double) * 2 * P.nL * t + sizeof(double) * xmb_warp_scratch_doubles(P.nL) * (t / 32); };
+	auto per_cta = [&](int t) { return fixed_bytes + sizeof(double) * 2 * P.nL * t + sizeof(double) * xmb_warp_scratch_doubles(P.tile_groups) * (t / 32); };
 	if (fixed_bytes > 180 * 1024) { xmb_set_error("channels, history slots and line tiles do not fit the shared memory of an SM"); return 0; }
 	while (threads > 64 && per_cta(threads) > 216 * 1024) threads -= 32;
 	// a staged 16-bit piece holds < 2^16 per addend and the word 2^32: at most 2^16 addends per slot and batch; a photon

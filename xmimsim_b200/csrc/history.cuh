@@ -44,8 +44,8 @@ struct XmbLayerDev {
 //             int slot[32], gs[32]           history slot of the line; group of the record, relative to the tile's first group
 #define XMB_TILE_GROUPS 8
 #define XMB_WPRE_STRIDE 33                   // doubles per group row of the per-warp scratch (33: lanes of different groups read different banks)
-// doubles of per-warp scratch in the line phase: the photons' factors per shell group of a tile, float [XMB_TILE_GROUPS][XMB_WPRE_STRIDE]
-__host__ __device__ inline int xmb_warp_scratch_doubles(int) { return (4 * XMB_TILE_GROUPS * XMB_WPRE_STRIDE + 15) / 16 * 2; }
+// doubles of per-warp scratch in the line phase: the photons' factors per shell group of a tile, float [tile_groups][XMB_WPRE_STRIDE]
+__host__ __device__ inline int xmb_warp_scratch_doubles(int tile_groups) { return (4 * tile_groups * XMB_WPRE_STRIDE + 15) / 16 * 2; }
 struct __align__(16) XmbLineTile {
 	int g_begin, n_groups;                   // groups [g_begin, g_begin + n_groups) of the layer
 	double min_edge;                         // lowest shell edge of the tile minus the edge-doublet half width: photons below it deposit exactly 0
@@ -107,7 +107,8 @@ struct XmbHistParams {
 	// forced-detection line tiles (see XmbLineTile): one blob per layer
 	const char *lblob;                       // all blobs, layer L at lblob + lblob_off[L]
 	int lblob_off[XMB_MAX_LAYERS + 1];
-	int lblob_stage_bytes;                   // shared memory reserved for one staged blob (largest layer)
+	int lblob_stage_bytes;                   // shared memory reserved for one staged blob (largest layer); 0: tiles are read in place
+	int tile_groups;                         // shell groups a tile may span (XMB_TILE_GROUPS, or half of it when shared memory is short)
 	int lblob_main_layer;                    // the layer with the most records (staged once when batches mix layers)
 	double rec_wy_max;                       // largest wy of the records (range check of the line deposits)
 	const int *hist_base;                    // [nZ] first history slot of the element (+0 Rayleigh, +1 Compton)

@@ -28,20 +28,72 @@ for r in csv.reader(src.splitlines()):
             pass
 
 
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "xmimsim_b200", "csrc")
+# regions of history.cu: (first line matching the marker text, name), found in the source as it is now (run the tool on a
+# capture of the same tree)
+HIST_MARKERS = [("template <int NL, bool ADV", "setup"), ("auto transport = ", "transport"), ("auto push = ", "push"),
+                ("auto energy_class = ", "sort_batch"), ("// ---- scheduler (block-uniform)", "scheduler"), ("Photon p;", "pop / source"),
+                ("// ---- forced detection (src/xmi_variance_reduction", "detector geometry"), ("while (__syncthreads_or(sa_pending))", "off-grid SA"),
+                ("// warp-uniform loops over layers / elements", "element loop: per-layer setup"), ("// Rayleigh (:342-369)", "element loop: Rayleigh"),
+                ("// shell-resolved Compton (xmi_compton_varred,", "element loop: ADV"), ("// Compton (xmi_compton_varred2", "element loop: Compton"),
+                ("// ---- fluorescence lines (src/xmi_variance_reduction", "line phase"), ("// ---- atom and interaction selection, scattering", "selection/flush glue"),
+                ("// ---- move to the next interaction point and queue there", "move + queue glue"), ("n_inter_local = warp_sum_u64(n_inter_local);", "epilogue")]
+
+
+def _marks(path, markers):
+    out = []
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        return out
+    for text, name in markers:
+        for i, ln in enumerate(lines, 1):
+            if text in ln:
+                out.append((i, name))
+                break
+    return sorted(out)
+
+
+def _functions(path):
+    out = []
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        return out
+    for i, ln in enumerate(lines, 1):
+        m = re.match(r"^(?:static )?(?:template <[^>]*>\s*)?__device__ (?:__forceinline__ )?[\w:<> ]+?[ *&](\w+)\(", ln)
+        if m:
+            out.append((i, m.group(1)))
+    return out
+
+
+_H = _marks(os.path.join(CSRC, "history.cu"), HIST_MARKERS)
+_D = _functions(os.path.join(CSRC, "history_device.cuh"))
+_GROUP = {"findpos_uniform": "bilinear", "to_fixed": "to_fixed", "fixed_from_scaled": "to_fixed", "warp_sum_u64": "deposit", "smem_u32": "deposit", "stage_red": "deposit",
+          "deposit_uniform20": "deposit", "deposit_uniform16": "deposit", "deposit_uniform": "deposit", "deposit_varying": "deposit", "red_global_u64": "flush_staged",
+          "normalize3": "dirv/elecv", "update_dirv": "dirv/elecv", "update_elecv": "dirv/elecv", "elec_phi0": "dirv/elecv", "compton_prefetch": "compton_energy",
+          "get_solid_angle": "solid-angle lookup", "ran_gaussian": "start_photon", "shard_global_id": "start_photon", "adv_q_from_energy": "advanced compton",
+          "adv_energy_from_q": "advanced compton", "adv_shell_cdf": "advanced compton", "adv_sample_q": "advanced compton", "compton_energy_adv": "advanced compton",
+          "exp_neg_f32": "exp_neg", "mu_lerp": "row_lerp"}
+
+
 def region(f, l, srcline):
     if f == "history.cu":
-        for hi, name in ((101, "setup"), (146, "transport"), (201, "push"), (228, "sort_batch"), (264, "scheduler"), (351, "pop"), (414, "detector geometry"),
-                         (457, "off-grid SA"), (488, "element loop: per-layer setup"), (508, "element loop: Rayleigh"), (543, "element loop: ADV"),
-                         (563, "element loop: Compton"), (612, "line loop"), (640, "selection/flush glue")):
-            if l <= hi:
-                return name
-        return "epilogue"
+        name = "setup"
+        for i, n in _H:
+            if i <= l:
+                name = n
+        return name
     if f == "history_device.cuh":
-        for hi, name in ((57, "node_find"), (62, "row_lerp"), (84, "bilinear"), (100, "to_fixed"), (160, "deposit"), (190, "flush_staged"), (214, "draw_block"),
-                         (270, "dirv/elecv"), (325, "compton_energy"), (347, "solid-angle lookup"), (438, "start_photon"), (450, "step_to_plane"),
-                         (520, "advanced compton"), (547, "exp_neg"), (700, "select_and_scatter")):
-            if l <= hi:
-                return name
+        name = "history_device.cuh"
+        for i, n in _D:
+            if i <= l:
+                name = _GROUP.get(n, n)
+        return name
     if f == "cuda_util.cuh":
         return "philox / u01"
     return f

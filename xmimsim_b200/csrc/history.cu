@@ -703,7 +703,9 @@ XMB_UNROLL(4)
 								XMB_UNROLL_NL
 for (int j = 0; j < (NL > 0 ? NL : 1); j++) t2 = __fmaf_rn(muv[j], rdf[2 * (j * T + q)], t2);
 							} else {
-								for (int j = jlo; j <= jhi; j++) t2 = __fmaf_rn(mulf[j * 32], rdf[2 * (j * T + q)], t2);
+								const float *mj = mulf + jlo * 32, *rj = rdf + 2 * (jlo * T + q);   // pointer walk: the strides fold into the loads
+XMB_UNROLL(4)
+								for (int n = jhi - jlo + 1; n > 0; n--, mj += 32, rj += 2 * T) t2 = __fmaf_rn(*mj, *rj, t2);
 							}
 							float ex;
 							asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t2));

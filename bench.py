@@ -48,7 +48,8 @@ def workload_config(name, inp, photons_per_line):
     """The `config` object both arms print (same workload string: the driver compares the two lines)."""
     return {"workload": "%s.xmsi (BASELINE configs[1]): %d lines x %.0e photons/line per GPU, %d interactions, variance reduction on, "
                         "M-lines + full cascade" % (name, len(inp.discrete), photons_per_line, inp.n_interactions_trajectory),
-            "cross_sections": "analytic surrogate provider (xraylib unavailable offline)"}
+            "cross_sections": "analytic surrogate provider (xraylib unavailable offline)",
+            "arithmetic": "f64 throughout; the attenuation factor and products of the fluorescence-line deposits in f32 (sums: exact 64-bit integers)"}
 
 
 def peaks():

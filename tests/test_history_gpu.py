@@ -102,6 +102,43 @@ def test_synthetic_ten_layers_eight_interactions():
     assert_spectra_close(vr, vr_o, RTOL, "synthetic history")
 
 
+@pytest.mark.parametrize("n_layers", [1, 2, 3, 4, 5, 7])
+def test_every_layer_count_instantiation_matches_oracle(n_layers):
+    """The kernel is compiled for 1, 2, 3 and 4 layers (loops over layers unrolled) and in a generic form: the first
+    n layers of the 10-layer sample exercise each instantiation, with three or more layers also the per-layer queues."""
+    inp = synthetic_layers(n_photons=12000, n_int=5)
+    inp.layers = inp.layers[:n_layers]
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert ch[-1].sum() > 0
+    assert_spectra_close(ch, ch_o, RTOL, "%d layers channels" % n_layers)
+    assert_spectra_close(vr, vr_o, RTOL, "%d layers history" % n_layers)
+
+
+@pytest.mark.parametrize("n_photons,n_int", [(1, 1), (1, 4), (31, 3), (1025, 2), (3, 12)])
+def test_tiny_and_ragged_sizes(n_photons, n_int):
+    """One photon, fewer photons than a warp, one more than a CTA, more interactions than photons: partial batches only."""
+    inp = example("srm1155")
+    inp.n_photons_line = n_photons
+    inp.n_interactions_trajectory = n_int
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=64)
+    assert ch.shape == (n_int + 1, inp.nchannels)
+    assert_spectra_close(ch, ch_o, RTOL, "tiny channels")
+    assert_spectra_close(vr, vr_o, RTOL, "tiny history")
+
+
+def test_small_detector_and_many_elements_per_layer():
+    """Few channels (most deposits fall outside and are dropped, src/xmi_variance_reduction.F90:370-389) and a layer
+    with 16 elements (the widest element loop of the pool)."""
+    inp = synthetic_layers(n_photons=8000, n_int=3)
+    pool = [8, 13, 14, 20, 22, 26, 29, 30, 38, 42, 47, 50, 56, 74, 79, 82]
+    inp.layers = [x.LayerD(pool, [1.0 / len(pool)] * len(pool), 4.0, 0.02), inp.layers[1]]
+    inp.nchannels = 256
+    inp.gain = 0.05
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=96)
+    assert_spectra_close(ch, ch_o, RTOL, "few channels")
+    assert_spectra_close(vr, vr_o, RTOL, "few channels history")
+
+
 def test_continuous_and_broadened_sources():
     inp = ebel_like(n_intervals=40, n_photons_interval=600, n_photons_line=1500)
     ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)

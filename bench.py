@@ -170,7 +170,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def ncu_counters(workload, n, timeout=240):
+def ncu_counters(workload, n, timeout=180):
     """Warp instructions and DRAM bytes of the history kernel, MEASURED in this run: a sub-process runs a bounded sample
     of the workload under ncu (outside every timed region).  Returns a dict, or {"unavailable": why}."""
     import csv
@@ -178,6 +178,8 @@ def ncu_counters(workload, n, timeout=240):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return {"unavailable": "ncu not found"}
+    if any(("NSIGHT" in k or k.startswith("CUDA_INJECTION") or k.startswith("NV_COMPUTE_PROFILER")) for k in os.environ):
+        return {"unavailable": "this process runs under a profiler already: no nested ncu"}
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     log = os.path.join(out_dir, "bench_ncu_%s_%d.csv" % (workload, os.getpid()))

@@ -178,7 +178,7 @@ def ncu_counters(workload, n, timeout=180):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
         return {"unavailable": "ncu not found"}
-    if any(("NSIGHT" in k or k.startswith("CUDA_INJECTION") or k.startswith("NV_COMPUTE_PROFILER")) for k in os.environ):
+    if any(k.startswith(("CUDA_INJECTION", "NVTX_INJECTION", "NV_NSIGHT_INJECTION")) for k in os.environ):
         return {"unavailable": "this process runs under a profiler already: no nested ncu"}
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)

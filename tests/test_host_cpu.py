@@ -145,6 +145,57 @@ def test_tables_sanity():
     sim.close()
 
 
+@pytest.mark.parametrize("name", ["srm1412", "srm1155"])
+def test_node_tables_equal_the_provider_at_every_sampled_node(name):
+    """Every energy-dependent table holds the provider's value AT its nodes (interpolation happens between them): cross
+    sections, branching ratios, partial and vacancy cross sections for the four cascade modes, mu of the layers, the exciter
+    absorbers' optical depth -- checked entry by entry on a random sample of nodes, against calls of the provider's own
+    functions.  Engine and oracle read the same bundle, so only this kind of test sees an error of the generator."""
+    inp = example(name)
+    sim = x.Simulation(inp, quality=0)
+    T, P = sim.tables, sim.provider.contents
+    nZ, nN, nL = T.nZ, T.n_nodes, T.n_layers
+    Z = [T.Z[i] for i in range(nZ)]
+    E = np.ctypeslib.as_array(T.node_E, shape=(nN,))
+    arr = lambda ptr, shape: np.ctypeslib.as_array(ptr, shape=shape)
+    cs, ph = arr(T.cs_total, (nZ, nN)), arr(T.cs_photo_total, (nZ, nN))
+    pr, prc = arr(T.p_rayl, (nZ, nN)), arr(T.p_rayl_compt, (nZ, nN))
+    part, vac = arr(T.cs_photo_partial, (nZ, 9, nN)), arr(T.cs_vacancy, (4, nZ, 9, nN))
+    mu, exc = arr(T.mu_layer, (nL, nN)), arr(T.exc_murhod, (nN,))
+    rng = np.random.default_rng(7)
+    nodes = np.unique(np.concatenate([rng.integers(0, nN, 60), [0, nN - 1]]))
+    buf = (C.c_double * 9)()
+    for n in nodes:
+        e = float(E[n])
+        for iz, z in enumerate(Z):
+            tot = P.CS_Total_Kissel(z, e)
+            assert cs[iz, n] == tot and ph[iz, n] == P.CS_Photo_Total(z, e)
+            assert pr[iz, n] == P.CS_Rayl(z, e) / tot
+            assert prc[iz, n] == P.CS_Compt(z, e) / tot + P.CS_Rayl(z, e) / tot
+            for sh in range(9):
+                assert part[iz, sh, n] == P.CS_Photo_Partial(z, sh, e)
+            for mode in (1, 2, 3, 4):
+                for sh in range(9):
+                    buf[sh] = P.VacancyCS(z, sh, e, mode, buf)
+                    assert vac[mode - 1, iz, sh, n] == buf[sh], (z, mode, sh, e)
+        for k, lay in enumerate(inp.layers):
+            w = np.array(lay.weight) / np.sum(lay.weight)
+            want = sum(wi * P.CS_Total_Kissel(int(zz), e) for zz, wi in zip(lay.Z, w))
+            assert abs(mu[k, n] - want) <= 4e-16 * want, (k, e)
+        want = sum(l.density * l.thickness * sum(wi * P.CS_Total_Kissel(int(zz), e) for zz, wi in zip(l.Z, np.array(l.weight) / np.sum(l.weight)))
+                   for l in inp.exc_layers)
+        assert abs(exc[n] - want) <= 1e-15 * max(want, 1e-300)
+    # every fluorescence line of every element and every source line is a node (exact lookups: precalc_mu_cs, precalc_xrf_cs)
+    le = arr(T.line_energy, (nZ, 384))
+    for iz in range(nZ):
+        for l in range(1, 220):
+            if 0.1 <= le[iz, l] < E[-1]:
+                assert le[iz, l] in E
+    for d in inp.discrete:
+        assert d.energy in E
+    sim.close()
+
+
 def test_plugin_file_exports_reference_symbol_names():
     """The drop-in plugin file (name the reference's GModule loader opens, src/xmi_solid_angle.c:121-136) exports the
     reference's symbol names (src/xmi_solid_angle_cl.c:118-120; bin/xmimsim.c:513)."""

@@ -54,6 +54,10 @@
 #define XMB_QST(p, v) (*(p) = (v))
 #define XMB_QLD(p) (*(p))
 #endif
+#ifndef XMB_FINE_ENERGY_KEY
+#define XMB_FINE_ENERGY_KEY 1   // batches sorted by 255 uniform energy buckets (0: by the <= 31 shell-edge classes of v14)
+#endif
+#define XMB_FINE_KEYS 255
 #ifndef XMB_COMPTON_EXP_F32
 #define XMB_COMPTON_EXP_F32 0
 #endif
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	__shared__ double s_sa_pt[2 * XMB_SA_ROUND];
 	__shared__ uint64_t s_sa_g[XMB_SA_ROUND];
 	__shared__ SaCone s_sa_cone[XMB_SA_ROUND];
-	__shared__ int s_lcnt[XMB_MAX_LAYERS + 1];    // batch members per layer (counting sort of a batch)
+	__shared__ int s_lcnt[XMB_FINE_KEYS + 1];     // batch members per key (counting sort of a batch by layer or by energy)
 	__shared__ int s_qcl[XMB_MAX_QL];             // layer_sort 2: photons waiting in the queue of (order k, layer L), [k * nL + L]
 	__shared__ int s_sched[3];                    // layer_sort 2: the scheduler's choice {k, L or -1 (mixed batch), source?}
 	__shared__ unsigned short s_perm[HIST_THREADS];
@@ -252,15 +256,23 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 	// A shell group of the line phase is skipped when no lane of the warp can ionise the shell; after the first
 	// interaction the photons are fluorescence lines of every energy, and a warp of one class skips the shells above it.
 	auto energy_class = [&](double e) {
+#if XMB_FINE_ENERGY_KEY
+		// uniform energy buckets between the lowest tracked energy and the top of the table window: photons of one
+		// fluorescence line (the bulk of a batch behind the first interaction) share a bucket, so a warp reads the same
+		// node rows and takes the same branches; monotone in the energy, as the line phase's per-tile photon range needs
+		const int c = (int)((e - ENERGY_THRESHOLD) * P.ekey_scale);
+		return max(0, min(c, XMB_FINE_KEYS - 1));
+#else
 		int c = 0;
 		for (int i = 0; i < P.n_ecls; i++) c += e >= P.ecls_thr[i] ? 1 : 0;
 		return c;
+#endif
 	};
 	// Counting sort of a batch by a small key (0 .. nK-1; -1: idle lane, sorted last): returns the batch position whose
-	// photon this thread takes.  Three CTA barriers.
+	// photon this thread takes.  Four CTA barriers; the first warp turns the counts into start positions.
 	auto sort_batch = [&](int key, int nK) {
 		if (key < 0) key = nK;
-		if (tid <= nK) s_lcnt[tid] = 0;
+		for (int i = tid; i <= nK; i += T) s_lcnt[i] = 0;
 		__syncthreads();
 		const unsigned peers = __match_any_sync(0xffffffffu, key);
 		const int leader = __ffs(peers) - 1;
@@ -269,9 +281,18 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 		wbase = __shfl_sync(0xffffffffu, wbase, leader);
 		const int rank = wbase + __popc(peers & ((1u << lane) - 1u));
 		__syncthreads();
-		int start = 0;
-		for (int l = 0; l < key; l++) start += s_lcnt[l];
-		s_perm[start + rank] = (unsigned short)tid;
+		if (tid < 32) {   // exclusive scan of the nK + 1 counts, in place
+			const int per = (nK + 1 + 31) >> 5, i0 = lane * per, i1 = min(i0 + per, nK + 1);
+			int sum = 0;
+			for (int i = i0; i < i1; i++) sum += s_lcnt[i];
+			int incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+			int run = incl - sum;
+			for (int i = i0; i < i1; i++) { const int c = s_lcnt[i]; s_lcnt[i] = run; run += c; }
+		}
+		__syncthreads();
+		s_perm[s_lcnt[key] + rank] = (unsigned short)tid;
 		__syncthreads();
 		return (int)s_perm[tid];
 	};
@@ -348,7 +369,7 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 			if (Lsel >= 0) {
 				myL = Lsel; at = s_qcl[k * nL + Lsel] - T + tid;
 				if (XMB_ECLS_PER_LAYER && P.n_ecls > 0)   // a batch of one layer: its lanes sorted by energy class
-					at = s_qcl[k * nL + Lsel] - T + sort_batch(energy_class(qbase[(size_t)(k * nL + Lsel) * NF * qcap + 9 * qcap + at]), P.n_ecls + 1);
+					at = s_qcl[k * nL + Lsel] - T + sort_batch(energy_class(qbase[(size_t)(k * nL + Lsel) * NF * qcap + 9 * qcap + at]), XMB_FINE_ENERGY_KEY ? XMB_FINE_KEYS : P.n_ecls + 1);
 			} else {
 				for (int l = 0; l < nL; l++) {
 					const int c = s_qcl[k * nL + l], n_l = min(c, T - taken);
@@ -388,7 +409,7 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				const bool by_energy = P.layer_sort == 3;
 				int key = -1;
 				if (tid < n) key = by_energy ? energy_class(qk[9 * qcap + tid]) : (int)__double_as_longlong(qk[14 * qcap + tid]);
-				src = sort_batch(key, by_energy ? P.n_ecls + 1 : nL);
+				src = sort_batch(key, by_energy ? (XMB_FINE_ENERGY_KEY ? XMB_FINE_KEYS : P.n_ecls + 1) : nL);
 			}
 			if (tid < n) {
 				const double *q = qk + src;
@@ -872,6 +893,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	}
 	P.n_nodes = nN;
 	P.node_E = upload(D, T.node_E, nN, ok);
+	P.ekey_scale = (double)XMB_FINE_KEYS / std::max(T.node_E[nN - 1] - ENERGY_THRESHOLD, 1e-3);
 	{
 		// Device bucket index, XMB_BUCKET_FINE x finer than the host's (whose buckets are the cells of the uniform part of
 		// the node grid): bucket b covers [E0 + b dE, E0 + (b + 1) dE) and stores the last node at or below its lower

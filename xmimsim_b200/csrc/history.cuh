@@ -68,6 +68,7 @@ struct XmbHistParams {
 	int use_M_lines;
 	int layer_sort;                          // batch formation: 0 as queued, 1 counting sort of a batch by layer, 2 one queue per (order, layer), 3 counting sort of a batch by energy class
 	int n_ecls;                              // energy classes (mode 3): class = number of ecls_thr[] at or below the photon energy
+	double ekey_scale;                       // energy buckets of the batch sort: key = (E - 1 keV) * ekey_scale
 	double ecls_thr[30];                     // ascending shell-edge energies that split the line records into equal shares
 	double zero, gain;
 	const XmbSegDev *segs;

@@ -1093,7 +1093,7 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 			P.lblob_off[k] = (int)base;
 			P.lblob_stage_bytes = std::max(P.lblob_stage_bytes, (int)(blob.size() - base));
 		}
-		if (short_smem) P.lblob_stage_bytes = 0;
+		if (short_smem || P.lblob_stage_bytes > 48 * 1024) P.lblob_stage_bytes = 0;   // very large line sets: tiles are read in place
 		P.lblob_off[nL] = (int)blob.size();
 		P.lblob = upload(D, blob.data(), blob.size(), ok);
 		D->n_line_tiles_bytes = blob.size();

@@ -387,17 +387,19 @@ def run_ours(args):
                              "digest_note": "SHA-256 of the reduced integer histograms: identical at every GPU count (bit-exactness)"}
         sim3.close()
         # ============= BASELINE configs[4]: 1000-interval continuum, 1.25e9 histories per GPU + detector response ======
-        per = max(1, int(args.configs4_per_gpu) * world // 1005)
-        inp4 = workloads.ebel_like(n_intervals=1000, n_photons_interval=per, n_photons_line=per)
+        nseg = workloads.n_source_segments(workloads.ebel_tube(1))
+        per = max(1, int(args.configs4_per_gpu) * world // nseg)
+        inp4 = workloads.ebel_tube(n_photons_interval=per)
         sim4 = x.Simulation(inp4, quality=args.table_quality)
         g4, r4, t4 = sim4.solid_angle_calculation(opt, hits_per_single=5000, seed=1)
         sa4 = sim4.make_solid_angle(g4.copy(), r4.copy(), t4.copy())
         opt4 = x.main_options(use_sum_peaks=1, use_escape_peaks=1)
         device_step(sim4, sa4, opt4)
         el4, ex4 = timed(lambda: device_step(sim4, sa4, opt4), 1)
-        total4 = 1005 * per
-        c4 = {"workload": "BASELINE configs[4]: 1000-interval tube-like continuum + 5 lines, %.4g histories (%.3g per GPU), 4 interactions; "
-                          "then escape-ratio Monte Carlo + detector response with escape peaks and pile-up" % (total4, total4 / world),
+        total4 = nseg * per
+        c4 = {"workload": "BASELINE configs[4]: Ebel tube spectrum (Ag anode, 40 kV, dE 0.039 keV: %d source segments from xmb_tube_ebel), %.4g histories "
+                          "(%.3g per GPU), 4 interactions; then escape-ratio Monte Carlo + detector response with escape peaks and pile-up "
+                          "(pulse width 1e-6 s)" % (nseg, total4, total4 / world),
               "scaling": "weak", "histories": total4, "value": total4 / el4, "unit": UNIT, "ms_per_step": 1e3 * el4,
               "per_rank_kernel_ms": gather(ex4[0].kernel_ms), "steps": 1, "warmup": 1}
         # detector response of the full result on rank 0 (the reference convolutes on rank 0 after MPI_Reduce, bin/xmimsim.c:413-526)

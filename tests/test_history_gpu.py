@@ -146,6 +146,17 @@ def test_continuous_and_broadened_sources():
     assert_spectra_close(vr, vr_o, RTOL, "continuous history")
 
 
+def test_ebel_tube_spectrum_matches_oracle():
+    """BASELINE config 5's excitation as the survey specifies it: the product's xmb_tube_ebel spectrum of an Ag anode at 40 kV
+    (1000 continuous intervals + 20 discrete lines, xmimsim_b200/workloads.py::ebel_tube), a few photons per segment."""
+    from xmimsim_b200 import workloads
+    inp = workloads.ebel_tube(n_photons_interval=40)
+    assert workloads.n_source_segments(inp) == 1020
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=128)
+    assert_spectra_close(ch, ch_o, RTOL, "ebel tube channels")
+    assert_spectra_close(vr, vr_o, RTOL, "ebel tube history")
+
+
 def test_gaussian_source_and_excitation_absorber():
     inp = example("srm1412")       # has an Al excitation-path absorber
     inp.n_photons_line = 600

@@ -21,8 +21,8 @@ def build(name, n):
     if name == "configs3":
         return workloads.synthetic_layers(n_photons=n, n_int=8)
     if name == "configs4":
-        per = max(1, n // 1005)
-        return workloads.ebel_like(n_intervals=1000, n_photons_interval=per, n_photons_line=per)
+        per = max(1, n // workloads.n_source_segments(workloads.ebel_tube(1)))
+        return workloads.ebel_tube(n_photons_interval=per)
     inp = workloads.example(name)
     inp.n_photons_line = n
     return inp

@@ -363,7 +363,8 @@ def run_ours(args):
                              "note": "SURVEY.md 8(d) algorithmic bytes; the tables are L2-resident and warps skip the shells their "
                                      "photons cannot ionise, so DRAM carries a few percent of this (traffic) and frac can exceed 1: "
                                      "not the operative bound"},
-            "solid_angle_grid": {"seconds_wall": sa_wall, "kernel_ms": sa_kernel_ms, "rays": 1024 * 1024 * 5000},
+            "solid_angle_grid": {"workload": "headline geometry (set-up of the timed runs)", "seconds_wall": sa_wall, "kernel_ms": sa_kernel_ms,
+                                 "rays": 1024 * 1024 * 5000},
         }
         line["roofline"] = {"kernel": "xmb_history_kernel", "kernel_ms": k_ms, "per_rank_kernel_ms": per_rank_kernel_ms,
                             "mean_interactions_per_history": interactions / max(1, n_hist_rank)}
@@ -475,20 +476,37 @@ def run_ours(args):
                                               "cost linear in photons" % (n, args.reference_sample_per_line, args.photons_per_line)}
             # BASELINE's second metric, "solid-angle grid s": the reference's own OpenCL kernel source compiled for the host
             # (oracle/_ref, fp32, all host threads) on every 8th row and column of the same grid, scaled to the full grid
+            # BASELINE configs[2]: the grid of the examples/srm1132.xmsi geometry (conical collimator), 1024 x 1024 x 5000 rays
+            sim2 = x.Simulation(workloads.example("srm1132"), quality=args.table_quality)
+            sim2.solid_angle_calculation(opt, hits_per_single=5000, seed=1)            # first call: allocations, module load
+            t0 = time.perf_counter()
+            g2, r2, t2 = sim2.solid_angle_calculation(opt, hits_per_single=5000, seed=1)
+            sa2_wall = time.perf_counter() - t0
+            sa2_ms = sim2.L.xmb_solid_angle_last_ms()
+            sg = {"workload": "BASELINE configs[2]: solid-angle grid of the srm1132 geometry, 1024 x 1024 points x 5000 rays",
+                  "seconds_wall": sa2_wall, "kernel_ms": sa2_ms, "rays": 1024 * 1024 * 5000, "rays_per_s": 1024 * 1024 * 5000 / (sa2_ms * 1e-3),
+                  "nonzero_points": int((g2 > 0).sum())}
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import ref
                 if ref.available():
-                    d = sim.derived
+                    d = sim2.derived
                     t0 = time.perf_counter()
-                    ref.solid_angle_grid_cl(r_vals[::8], t_vals[::8], d.collimator_present, d.detector_radius, d.collimator_radius,
+                    ref.solid_angle_grid_cl(r2[::8], t2[::8], d.collimator_present, d.detector_radius, d.collimator_radius,
                                             d.collimator_height, 5000)
                     dt = time.perf_counter() - t0
-                    line["solid_angle_grid"]["cpu_reference"] = {
+                    sg["cpu_reference"] = {
                         "seconds_full_grid": dt * 64.0, "cores": cores, "kind": "reference",
                         "sample": "128 x 128 of the 1024 x 1024 points x 5000 rays, src/xmi_kernels.cl compiled for the host, x 64"}
             except Exception as exc:   # the checker is optional for the bench line
-                line["solid_angle_grid"]["cpu_reference"] = {"unavailable": str(exc)[:120]}
+                sg["cpu_reference"] = {"unavailable": str(exc)[:120]}
+            sim2.close()
+            # issue roofline of the grid kernel: 4.15 warp instructions per ray (8.72e9 per 2.10e9 rays, ncu capture
+            # profiles/r2_solid_angle_kernel_v2_ncu_full.json: issue slots 75 % busy, fp64 pipe 52 %)
+            sg["roofline"] = {"bound": "issue", "unit": "warp-inst/s", "achieved": 4.15 * sg["rays_per_s"], "peak": sms * 4 * clock_hz,
+                              "frac": 4.15 * sg["rays_per_s"] / (sms * 4 * clock_hz), "warp_inst_per_ray": 4.15,
+                              "source": "instruction count from the committed ncu capture of the same kernel; time measured here"}
+            line["solid_angle_configs2"] = sg
         print(json.dumps(line))
     barrier()
     sim.close()

@@ -58,6 +58,9 @@
 #define XMB_FINE_ENERGY_KEY 1   // batches sorted by 255 uniform energy buckets (0: by the <= 31 shell-edge classes of v14)
 #endif
 #define XMB_FINE_KEYS 255
+#ifndef XMB_PREFETCH_EARLY
+#define XMB_PREFETCH_EARLY 0
+#endif
 #ifndef XMB_COMPTON_EXP_F32
 #define XMB_COMPTON_EXP_F32 0
 #endif
@@ -439,7 +442,6 @@ for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qc
 			double theta = 0.0, phi = 0.0, Pesc_rayl = 0.0, omega = 0.0;
 			NodePos np;
 			np.pos = 0; np.f = 0.0;
-			if (p.alive) np = node_find(P, p.energy);   // bracket of the photon energy: line phase and selection
 			int pj_lo = nL, pj_hi = -1;   // layers the path to the detector crosses (rd[] is zero outside)
 			bool sa_pending = false;      // interaction point beyond the solid-angle grid
 			double sa_r = 0.0, sa_theta = 0.0;
@@ -564,6 +566,12 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					const int ch = (int)((p.energy - P.zero) / P.gain);
 					if (p.energy >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_rayl = ch;
 				}
+				// The factors of a deposit that belong to the photon are multiplied once, in front of the element loop -- the loop
+				// then keeps two products alive instead of six factors (it runs at the kernel's register cap):
+				//   Rayleigh deposit = [w_e N_A/A_e] F^2 * Rp,   Rp = 1/mu * Omega * r_e^2 (1 - sin^2 theta cos^2 phi) * P_esc * weight
+				//   Compton  deposit = [w_e N_A/A_e] S * exp(-tau(E')) * Cp,   Cp = 1/mu * Omega * dsigma_KN * weight
+				const double Rp = mine ? inv_mu * omega * (RE2 * (1.0 - sin2cos2)) * Pesc_rayl * p.weight : 0.0;
+				const double Cp = mine ? inv_mu * omega * dcsp_kn * p.weight : 0.0;
 
 				// Rayleigh deposits of all elements go to the channel of the photon's energy: summed here (integers), one
 				// channel deposit after the element loop
@@ -571,20 +579,24 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 				for (int e = 0; e < lay.n_elements; e++) {
 					const int zi = P.elem_zi[lay.elem_begin + e];
 					const double wfrac = P.elem_w[lay.elem_begin + e];
+					const double wa = P.elem_wa[lay.elem_begin + e];   // weight fraction * N_A / A
 					const unsigned hbase = hist0 + (unsigned)P.hist_base[zi];
 					// the element's random block, first inverse-CDF bracket and form factors are requested together, ahead of
 					// the dependent chain Compton energy -> energy bracket -> mu rows -> exp
 					ComptonPrefetch pf;
+#if XMB_PREFETCH_EARLY
 					if (mine && !ADV) compton_prefetch(P, zi, g, order, e, qi, pf);
+#else
+					if (mine && !ADV) { const double *f = P.ff + (size_t)zi * P.n_q + qi; pf.F0 = f[0]; pf.F1 = f[1]; }
+#endif
 					if (mine && ADV) { const double *f = P.ff + (size_t)zi * P.n_q + qi, *sfp = P.sf + (size_t)zi * P.n_q + qi; pf.F0 = f[0]; pf.F1 = f[1]; pf.S0 = sfp[0]; pf.S1 = sfp[1]; }
 					// Rayleigh (:342-369)
 					unsigned long long fx = 0ULL;
 					double Pconv = 0.0;
 					if (mine) {
-						Pconv = wfrac * inv_mu;
+						Pconv = wfrac * inv_mu;   // (shell-resolved Compton below)
 						const double F = pf.F0 * (1.0 - qf) + pf.F1 * qf;
-						const double dcsp = P.avog_over_A[zi] * F * F * RE2 * (1.0 - sin2cos2);
-						fx = to_fixed(Pconv * (omega * dcsp) * Pesc_rayl * p.weight, P.counters);
+						fx = to_fixed(wa * (F * F) * Rp, P.counters);
 					}
 					deposit_uniform<P20>(acc_k, hbase + 0, fx, lane);
 					fx_rayl += fx;
@@ -631,6 +643,11 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					double e_c_keep = 0.0;
 #endif
 					if (mine) {
+#if !XMB_PREFETCH_EARLY
+						// the element's first random block and inverse-CDF bracket are requested here, behind the Rayleigh deposit: ahead
+						// of it they had to survive the Rayleigh arithmetic in spilled registers (seven local stores per element)
+						compton_prefetch(P, zi, g, order, e, qi, pf);
+#endif
 						const double e_c = compton_energy(P, zi, p.energy, c_lamb0, sth2, g, order, 2, e, true, &pf);
 #if XMB_PHASE_CLOCKS
 						e_c_keep = e_c;
@@ -639,13 +656,14 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 					if (mine) {
 						const double e_c = e_c_keep;
 #endif
+						const double *sfp = P.sf + (size_t)zi * P.n_q + qi;
+						const double S0 = sfp[0], S1 = sfp[1];
 						const NodePos cp = node_find(P, e_c);
 						double tm = 0.0;
 						XMB_UNROLL_NL
 for (int j = jlo; j <= jhi; j++) tm += mu_lerp(P, cp, j) * rd[j * T];
-						const double S = pf.S0 * (1.0 - qf) + pf.S1 * qf;
-						const double Pdir = omega * P.avog_over_A[zi] * S * dcsp_kn;
-						fx = to_fixed(Pconv * Pdir * (XMB_COMPTON_EXP_F32 ? exp_neg_f32(tm) : exp_neg(tm, tab_s32)) * p.weight, P.counters);
+						const double S = S0 * (1.0 - qf) + S1 * qf;
+						fx = to_fixed(wa * S * (XMB_COMPTON_EXP_F32 ? exp_neg_f32(tm) : exp_neg(tm, tab_s32)) * Cp, P.counters);
 						const int ch = (int)((e_c - P.zero) / P.gain);
 						if (e_c >= ENERGY_THRESHOLD && ch >= 0 && ch <= P.nch - 1) ch_c = ch;
 					}
@@ -667,6 +685,7 @@ for (int j = jlo; j <= jhi; j++) tm += mu_lerp(P, cp, j) * rd[j * T];
 			// its photons, and the deposits of the warp on a record are one 64-bit integer sum in a register, staged once per
 			// tile (v15: one exact warp sum -- 3 REDUX -- and one staged add per record and interaction).
 			if (stage_pending) { xmb_mbar_wait(mbar_s32, stage_parity); stage_parity ^= 1u; stage_pending = false; }
+			if (p.alive) np = node_find(P, p.energy);   // bracket of the photon energy for the line phase and the selection (looked up here: not alive across the element loop)
 			// The attenuation factor exp(-sum_j mu_j rho_j d_j) and the products of a deposit are evaluated in SINGLE precision
 			// ("geometry/angles can be fp32 after validation against the fp64 oracle"): a deposit carries a relative
 			// rounding error of ~1e-7, independent from photon to photon -- five orders below the Monte Carlo error of a line --
@@ -968,6 +987,11 @@ static XmbDeviceTables *build_device_tables(XmbInputF *in, XmbHdf5F *h, const xm
 	P.layers = upload(D, layers.data(), nL, ok);
 	P.elem_zi = upload(D, elem_zi.data(), elem_zi.size(), ok);
 	P.elem_w = upload(D, elem_w.data(), elem_w.size(), ok);
+	{
+		std::vector<double> wa(elem_w.size());
+		for (size_t i = 0; i < wa.size(); i++) wa[i] = elem_w[i] * (AVOGNUM / T.atomic_weight[elem_zi[i]]);
+		P.elem_wa = upload(D, wa.data(), wa.size(), ok);
+	}
 	// ---- forced-detection line records (active lines only) and history slots --------------------------------
 	const int line_last = opt->use_M_lines ? XMB_M5P5 : XMB_L3Q1;
 	const xmb_detector &det = *I.detector;

@@ -79,6 +79,7 @@ struct XmbHistParams {
 	const XmbLayerDev *layers;
 	const int *elem_zi;                      // unique-element index per (layer, element)
 	const double *elem_w;                    // weight fraction
+	const double *elem_wa;                   // weight fraction * N_A / A of the element (forced-detection scatter deposits)
 	// node grid rows
 	int n_nodes, n_buckets, row_stride, off_exc, off_elem;
 	double bucket_E0, bucket_inv_dE;

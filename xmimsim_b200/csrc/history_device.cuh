@@ -288,8 +288,8 @@ __device__ __forceinline__ void compton_prefetch(const XmbHistParams &P, int zi,
 	const int pos = min((int)(xmb_u01(pf.w.x) * P.cp_inv_dR), P.n_cp - 2);
 	const double *icdf = P.cp_icdf + (size_t)zi * P.n_cp + pos;
 	pf.i0 = icdf[0]; pf.i1 = icdf[1];
-	const double *f = P.ff + (size_t)zi * P.n_q + qi, *sfp = P.sf + (size_t)zi * P.n_q + qi;
-	pf.F0 = f[0]; pf.F1 = f[1]; pf.S0 = sfp[0]; pf.S1 = sfp[1];
+	const double *f = P.ff + (size_t)zi * P.n_q + qi;
+	pf.F0 = f[0]; pf.F1 = f[1];   // (the scattering function is gathered next to the energy bracket: four registers less across the Doppler loop)
 }
 
 __device__ __forceinline__ double compton_energy(const XmbHistParams &P, int zi, double E0, double c_lamb0, double sth2, uint64_t g, int order,

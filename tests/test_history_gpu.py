@@ -324,7 +324,7 @@ def test_unsupported_modes_fail_loudly():
 def test_fixed_point_sums_reproduce_the_recorded_digests():
     """Regression pin of the integer accumulators: seven inputs (two- and ten-layer samples, continuous source, all
     cascade modes off, shell-resolved Compton, a 1-of-3 shard) must reproduce, bit for bit, the digests recorded with
-    kernel v17 (tests/golden/limbs_digest.json, written by tools/limbs_digest.py; v16 evaluates the line attenuation factors in single precision and v17 multiplies the per-photon factors of the scatter deposits first, which moved the sums recorded before) -- kernel rewrites that regroup
+    kernel v18 (tests/golden/limbs_digest.json, written by tools/limbs_digest.py; v16 evaluates the line attenuation factors in single precision, v17 multiplies the per-photon factors of the scatter deposits first and v18 rotates directions from their components instead of stored polar angles, each of which moved the sums recorded before by rounding) -- kernel rewrites that regroup
     photons, restage deposits or change launch shapes must not move a single bit."""
     import json
     import os

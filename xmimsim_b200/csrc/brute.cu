@@ -132,9 +132,9 @@ __device__ void cascade_emit(const XmbHistParams &P, Photon &q, double *mus, int
 	q.energy = P.line_energy[(size_t)zi * 384 + line];
 	const NodePos lp = node_find(P, q.energy);
 	for (int i = 0; i < nL; i++) mus[i] = mu_lerp(P, lp, i);
-	q.theta = acos(2.0 * xs.uniform() - 1.0);
-	q.phi = 2.0 * M_PI * xs.uniform();
-	q.dx = sin(q.theta) * cos(q.phi); q.dy = sin(q.theta) * sin(q.phi); q.dz = cos(q.theta);
+	const double theta = acos(2.0 * xs.uniform() - 1.0);
+	const double phi = 2.0 * M_PI * xs.uniform();
+	q.dx = sin(theta) * cos(phi); q.dy = sin(theta) * sin(phi); q.dz = cos(theta);
 	const double r = 2.0 * M_PI * xs.uniform();
 	q.ex = cos(r); q.ey = sin(r); q.ez = 0.0;
 	const double cosalfa = q.ex * q.dx + q.ey * q.dy + q.ez * q.dz;

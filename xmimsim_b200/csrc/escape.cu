@@ -56,8 +56,6 @@ __global__ void __launch_bounds__(256, XMB_ESC_MINB) xmb_escape_kernel(const __g
 		p.cx = p.cy = p.cz = 0.0;
 		p.dx = tan(x1); p.dy = tan(y1); p.dz = 1.0;
 		normalize3(p.dx, p.dy, p.dz);
-		p.theta = acos(p.dz);
-		p.phi = atan2(p.dy, p.dx);
 		{
 			double se, ce;
 			sincos(rng.uniform() * M_PI * 2.0, &se, &ce);

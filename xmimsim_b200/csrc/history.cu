@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 				XMB_QST(&q[0 * qcap], p.cx); XMB_QST(&q[1 * qcap], p.cy); XMB_QST(&q[2 * qcap], p.cz);
 				XMB_QST(&q[3 * qcap], p.dx); XMB_QST(&q[4 * qcap], p.dy); XMB_QST(&q[5 * qcap], p.dz);
 				XMB_QST(&q[6 * qcap], p.ex); XMB_QST(&q[7 * qcap], p.ey); XMB_QST(&q[8 * qcap], p.ez);
-				XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight); XMB_QST(&q[11 * qcap], p.theta); XMB_QST(&q[12 * qcap], p.phi);
-				XMB_QST(&q[13 * qcap], __longlong_as_double((long long)g));
-				XMB_QST(&q[14 * qcap], __longlong_as_double((long long)p.layer));
+				XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight);
+				XMB_QST(&q[11 * qcap], __longlong_as_double((long long)g));
+				XMB_QST(&q[12 * qcap], __longlong_as_double((long long)p.layer));
 				for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 			}
 			return;   // the caller's __syncthreads() publishes the counts
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 			XMB_QST(&q[0 * qcap], p.cx); XMB_QST(&q[1 * qcap], p.cy); XMB_QST(&q[2 * qcap], p.cz);
 			XMB_QST(&q[3 * qcap], p.dx); XMB_QST(&q[4 * qcap], p.dy); XMB_QST(&q[5 * qcap], p.dz);
 			XMB_QST(&q[6 * qcap], p.ex); XMB_QST(&q[7 * qcap], p.ey); XMB_QST(&q[8 * qcap], p.ez);
-			XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight); XMB_QST(&q[11 * qcap], p.theta); XMB_QST(&q[12 * qcap], p.phi);
-			XMB_QST(&q[13 * qcap], __longlong_as_double((long long)g));
-			XMB_QST(&q[14 * qcap], __longlong_as_double((long long)p.layer));
+			XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight);
+			XMB_QST(&q[11 * qcap], __longlong_as_double((long long)g));
+			XMB_QST(&q[12 * qcap], __longlong_as_double((long long)p.layer));
 			XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
 		}
@@ -385,8 +385,8 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				p.cx = XMB_QLD(&q[0 * qcap]); p.cy = XMB_QLD(&q[1 * qcap]); p.cz = XMB_QLD(&q[2 * qcap]);
 				p.dx = XMB_QLD(&q[3 * qcap]); p.dy = XMB_QLD(&q[4 * qcap]); p.dz = XMB_QLD(&q[5 * qcap]);
 				p.ex = XMB_QLD(&q[6 * qcap]); p.ey = XMB_QLD(&q[7 * qcap]); p.ez = XMB_QLD(&q[8 * qcap]);
-				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]); p.theta = XMB_QLD(&q[11 * qcap]); p.phi = XMB_QLD(&q[12 * qcap]);
-				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[13 * qcap]));
+				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]);
+				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[11 * qcap]));
 				p.layer = myL;
 				for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;
@@ -411,7 +411,7 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				// the loops of its own layer only instead of those of every layer its lanes are in.  Mode 3: energy class.
 				const bool by_energy = P.layer_sort == 3;
 				int key = -1;
-				if (tid < n) key = by_energy ? energy_class(qk[9 * qcap + tid]) : (int)__double_as_longlong(qk[14 * qcap + tid]);
+				if (tid < n) key = by_energy ? energy_class(qk[9 * qcap + tid]) : (int)__double_as_longlong(qk[12 * qcap + tid]);
 				src = sort_batch(key, by_energy ? (XMB_FINE_ENERGY_KEY ? XMB_FINE_KEYS : P.n_ecls + 1) : nL);
 			}
 			if (tid < n) {
@@ -419,9 +419,9 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				p.cx = XMB_QLD(&q[0 * qcap]); p.cy = XMB_QLD(&q[1 * qcap]); p.cz = XMB_QLD(&q[2 * qcap]);
 				p.dx = XMB_QLD(&q[3 * qcap]); p.dy = XMB_QLD(&q[4 * qcap]); p.dz = XMB_QLD(&q[5 * qcap]);
 				p.ex = XMB_QLD(&q[6 * qcap]); p.ey = XMB_QLD(&q[7 * qcap]); p.ez = XMB_QLD(&q[8 * qcap]);
-				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]); p.theta = XMB_QLD(&q[11 * qcap]); p.phi = XMB_QLD(&q[12 * qcap]);
-				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[13 * qcap]));
-				p.layer = (int)__double_as_longlong(XMB_QLD(&q[14 * qcap]));
+				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]);
+				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[11 * qcap]));
+				p.layer = (int)__double_as_longlong(XMB_QLD(&q[12 * qcap]));
 				XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
 				p.n_interactions = order;

@@ -24,7 +24,7 @@
 #endif
 #define XMB_MAX_ORDERS 64
 #define XMB_MAX_QL 1024          // (order, layer) queues of a CTA when batches are formed per layer
-#define XMB_STATE_FIELDS 15      // 13 doubles of photon state + photon id + layer (mus[nL] follow)
+#define XMB_STATE_FIELDS 13      // 11 doubles of photon state + photon id + layer (mus[nL] follow)
 #define XMB_PRAGMA(x) _Pragma(#x)
 #define XMB_UNROLL_NL _Pragma("unroll")
 #define XMB_UNROLL(n) XMB_PRAGMA(unroll n)
@@ -220,7 +220,7 @@ struct SubStream {   // sequential cursor over the blocks of one (order, stage, 
 
 struct Photon {
 	double cx, cy, cz, dx, dy, dz, ex, ey, ez;
-	double energy, weight, theta, phi;
+	double energy, weight;   // (the polar angles of the direction, which the reference keeps beside it, are functions of dx, dy, dz: frame_trig())
 	int layer;
 	int n_interactions;
 	bool alive;
@@ -231,47 +231,47 @@ __device__ __forceinline__ void normalize3(double &x, double &y, double &z) {
 	x /= n; y /= n; z /= n;
 }
 
-// xmi_update_photon_dirv (src/xmi_main.F90:5071-5148)
-__device__ __forceinline__ void update_dirv(Photon &p, double theta_i, double phi_i) {
-	double phi_new = phi_i;
-	if (phi_i > 2.0 * M_PI) phi_new = phi_i - 2.0 * M_PI;
-	else if (phi_i < 0.0) phi_new = phi_i + 2.0 * M_PI;
-	double sph, cph, sth, cth, sti, cti, spn, cpn;
-	sincos(p.phi, &sph, &cph);
-	sincos(p.theta, &sth, &cth);
-	sincos(theta_i, &sti, &cti);
-	sincos(phi_new, &spn, &cpn);
+// Sines and cosines of the polar angles theta = acos(dz), phi = atan2(dy, dx) of the (unit) direction, which the reference stores
+// with the photon and feeds to sin / cos at every scatter (src/xmi_main.F90:5071-5148, :2055-2066): taken from the components
+// themselves -- no acos / atan2 when a direction is set, no two sincos when it is used.  atan2(0, 0) = 0: cos phi = 1, sin phi = 0.
+__device__ __forceinline__ void frame_trig(const Photon &p, double &sth, double &cth, double &sph, double &cph) {
+	cth = p.dz;
+	sth = sqrt(p.dx * p.dx + p.dy * p.dy);
+	if (sth > 0.0) { const double inv = 1.0 / sth; cph = p.dx * inv; sph = p.dy * inv; }
+	else { cph = 1.0; sph = 0.0; }
+}
+// xmi_update_photon_dirv (src/xmi_main.F90:5071-5148): the new direction has polar angle theta_i (sti, cti) and azimuth phi_i
+// (spn, cpn) in the frame of the old one
+__device__ __forceinline__ void update_dirv(Photon &p, double sti, double cti, double spn, double cpn) {
+	double sth, cth, sph, cph;
+	frame_trig(p, sth, cth, sph, cph);
 	const double v0 = sti * cpn, v1 = sti * spn, v2 = cti;
 	p.dx = cth * cph * v0 + (-sph) * v1 + sth * cph * v2;
 	p.dy = cth * sph * v0 + cph * v1 + sth * sph * v2;
 	p.dz = (-sth) * v0 + 0.0 * v1 + cth * v2;
 	normalize3(p.dx, p.dy, p.dz);
-	p.theta = acos(p.dz);
-	p.phi = atan2(p.dy, p.dx);
-	if (p.phi > 2.0 * M_PI) p.phi -= 2.0 * M_PI;
-	else if (p.phi < 0.0) p.phi += 2.0 * M_PI;
 }
-// xmi_update_photon_elecv (:5150-5182)
+// xmi_update_photon_elecv (:5150-5182); sin(acos(c)) = sqrt(1 - c^2)
 __device__ __forceinline__ void update_elecv(Photon &p) {
 	const double cosalfa = p.dx * p.ex + p.dy * p.ey + p.dz * p.ez;
-	const double sinalfa = sin(acos(cosalfa));
+	const double sinalfa = sqrt(fmax(0.0, 1.0 - cosalfa * cosalfa));
 	const double c_ae = 1.0 / sinalfa, c_be = -c_ae * cosalfa;
 	p.ex = c_ae * p.ex + c_be * p.dx;
 	p.ey = c_ae * p.ey + c_be * p.dy;
 	p.ez = c_ae * p.ez + c_be * p.dz;
 	normalize3(p.ex, p.ey, p.ez);
 }
-// phi0 of the electric vector in the photon frame (:2055-2066)
-__device__ __forceinline__ double elec_phi0(const Photon &p) {
-	double sph, cph, sth, cth;
-	sincos(p.phi, &sph, &cph);
-	sincos(p.theta, &sth, &cth);
+// phi0 of the electric vector in the photon frame (:2055-2066): returned as (sin phi0, cos phi0); the reference takes
+// phi0 = acos(cos phi0) and flips its sign when the sine of the projection is positive
+__device__ __forceinline__ void elec_phi0(const Photon &p, double &s0, double &c0) {
+	double sth, cth, sph, cph;
+	frame_trig(p, sth, cth, sph, cph);
 	double cosphi0 = p.ex * (cph * cth) + p.ey * (cth * sph) + p.ez * (-sth);
 	const double sinphi0 = p.ex * sph + p.ey * (-cph) + p.ez * 0.0;
 	if (fabs(cosphi0) > 1.0) cosphi0 = cosphi0 > 0 ? 1.0 : -1.0;
-	double phi0 = acos(cosphi0);
-	if (sinphi0 > 0.0) phi0 = -phi0;
-	return phi0;
+	const double mag = sqrt(fmax(0.0, 1.0 - cosphi0 * cosphi0));   // sin(acos(c)) >= 0
+	c0 = cosphi0;
+	s0 = sinphi0 > 0.0 ? -mag : mag;
 }
 
 // Doppler-broadened Compton energy (src/xmi_main.F90:4985-5067; forced-detection variant
@@ -419,14 +419,12 @@ for (int i = 0; i < nL; i++) mus[i * T] = mu_lerp(P, np, i);
 	}
 	p.dx = tan(x1); p.dy = tan(y1); p.dz = 1.0;
 	normalize3(p.dx, p.dy, p.dz);
-	p.theta = acos(p.dz);
-	p.phi = atan2(p.dy, p.dx);
 	bool horizontal;
 	if (S.is_cont) horizontal = rng.uniform() <= hor_ver_ratio;
 	else horizontal = (double)(j + 1) <= hor_ver_ratio;
 	if (horizontal) { p.ex = 0.0; p.ey = 1.0; p.ez = 0.0; } else { p.ex = 1.0; p.ey = 0.0; p.ez = 0.0; }
 	const double cosalfa = p.ex * p.dx + p.ey * p.dy + p.ez * p.dz;
-	const double c_ae = 1.0 / sin(acos(cosalfa)), c_be = -c_ae * cosalfa;
+	const double c_ae = 1.0 / sqrt(fmax(0.0, 1.0 - cosalfa * cosalfa)), c_be = -c_ae * cosalfa;   // sin(acos(c))
 	p.ex = c_ae * p.ex + c_be * p.dx; p.ey = c_ae * p.ey + c_be * p.dy; p.ez = c_ae * p.ez + c_be * p.dz;
 	// xmi_photon_shift_first_layer (:1140-1186)
 	p.layer = -1;
@@ -592,14 +590,14 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 	// rotation of the direction / polarisation vectors run once, after the branches, with the warp converged
 	// (profiles/r1_history_kernel_v8_*: the rotation code ran at 10 of 32 lanes when it was inlined per branch).
 	const bool is_rayl = R2 < pr, is_compt = !is_rayl && R2 < prc;
-	double theta_i = 0.0, phi_i = 0.0, phi_rot = 0.0;
+	// the scatter: polar angle (sti, cti) and azimuth (srot, crot) of the new direction in the frame of the old one
+	double sti = 0.0, cti = 1.0, srot = 0.0, crot = 1.0, spi = 0.0, cpi = 1.0;
 	bool rotate = false, new_energy = false;
 	if (is_rayl || is_compt) {
 		out_type = is_rayl ? 1 : 2;
 		// Rayleigh (:1986-2101) / Compton (:2103-2229): theta from the element's inverse CDF, phi from the polarisation table
 		const double *icdf = (is_rayl ? P.rayl_icdf : P.compt_icdf) + (size_t)zi * P.n_icdf_E * P.n_icdf_R;
-		theta_i = bilinear(icdf, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
-		double sti, cti;
+		const double theta_i = bilinear(icdf, P.n_icdf_R, P.icdf_E, P.n_icdf_E, P.icdf_R, p.energy, s0);
 		sincos(theta_i, &sti, &cti);
 		double tt = sti * sti;
 		if (is_rayl) tt = tt / (4.0 - 2.0 * tt);
@@ -607,15 +605,20 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 			const double K0K = 1.0 + p.energy * (1.0 - cti) / XMI_MEC2;
 			tt = tt / (K0K + (1.0 / K0K) - tt) / 2.0;
 		}
-		phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
-		phi_rot = phi_i + elec_phi0(p);
+		const double phi_i = bilinear(P.phi_icdf, P.n_icdf_R, P.phi_T, P.n_phi_T, P.icdf_R, tt, s1);
+		sincos(phi_i, &spi, &cpi);
+		{   // azimuth phi_i + phi0 by the addition theorems
+			double s0e, c0e;
+			elec_phi0(p, s0e, c0e);
+			srot = spi * c0e + cpi * s0e; crot = cpi * c0e - spi * s0e;
+		}
 		rotate = true;
 		if (is_compt) {
 			if (ADV) {
 				const uint4 w = draw_block(P.seed, g, order, 3, 0, 0);
 				p.energy = compton_energy_adv(P, zi, p.energy, theta_i, xmb_u01(w.x), xmb_u01(w.y));
 			} else
-				p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sin(theta_i / 2.0), g, order, 3, 0, false);
+				p.energy = compton_energy(P, zi, p.energy, 1.2399E-6 / (p.energy * 1000.0), sqrt(0.5 * (1.0 - cti)), g, order, 3, 0, false);   // sin(theta_i / 2)
 			new_energy = true;
 			rotate = p.energy != 0.0;
 		}
@@ -668,8 +671,9 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 				out_shell = shell;
 				p.energy = P.line_energy[(size_t)zi * 384 + line];
 				new_energy = true;
-				theta_i = acos(-2.0 * s2 + 1.0);
-				phi_rot = 2.0 * M_PI * u_phi;
+				cti = -2.0 * s2 + 1.0;                         // theta_i = acos(1 - 2 s2), isotropic
+				sti = 2.0 * sqrt(fmax(0.0, s2 * (1.0 - s2)));
+				sincospi(2.0 * u_phi, &srot, &crot);
 				rotate = true;
 			}
 		}
@@ -685,13 +689,10 @@ __device__ __forceinline__ void select_and_scatter(const XmbHistParams &P, Photo
 for (int i = 0; i < nL; i++) mus[i * T] = mu_lerp(P, cp, i);
 	}
 	if (rotate) {
-		update_dirv(p, theta_i, phi_rot);
+		update_dirv(p, sti, cti, srot, crot);
 		update_elecv(p);
 		if (is_compt) {
 			// depolarisation of the Compton-scattered photon (:2201-2211)
-			double spi, cpi;
-			sincos(phi_i, &spi, &cpi);
-			const double cti = cos(theta_i);
 			double pp = 2.0 * ((cti * cpi) * (cti * cpi) + spi * spi);
 			const double rat = 1.0 / (1.0 + (1 - cti) * p.energy / 510.998910);
 			const double rk = rat - 2.0 + 1.0 / rat;

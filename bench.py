@@ -139,6 +139,28 @@ def oracle_solid_angle_grid(inp, n=96, hits=400):
     return sa, r, t
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The driver reads ONE JSON line from stdout: libraries that write banners there (NCCL prints its version on
+    file descriptor 1 when the first communicator is created) are sent to stderr; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; the Fortran binary cannot be built
     here) with all host threads, each step a bounded sample of the workload."""
@@ -167,7 +189,7 @@ def run_reference(args):
                                        % (n, sample_per_line, args.photons_per_line)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def ncu_counters(workload, n, timeout=180):
@@ -510,7 +532,7 @@ def run_ours(args):
                               "frac": 4.15 * sg["rays_per_s"] / (sms * 4 * clock_hz), "warp_inst_per_ray": 4.15,
                               "source": "instruction count from the committed ncu capture of the same kernel; time measured here"}
             line["solid_angle_configs2"] = sg
-        print(json.dumps(line))
+        emit(line)
     barrier()
     sim.close()
     if comm is not None:
@@ -537,6 +559,7 @@ def main():
     ap.add_argument("--no-ncu", action="store_true", help="do not start the ncu sub-process that measures instructions / DRAM bytes per history")
     ap.add_argument("--ncu-sample-per-line", type=int, default=400000)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

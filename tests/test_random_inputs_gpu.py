@@ -1,0 +1,25 @@
+"""Randomized parity: engine and oracle on random valid inputs (tests/random_inputs.py: 1 - 8 layers, gas gaps, conical /
+cylindrical / no collimator, broadened lines, Gaussian sources, continuous blocks, absorbers, 1 - 6 interactions, random
+cascade / M-line options).  Same tolerance as the authored cases of tests/test_history_gpu.py.  tools/random_parity_hunt.py
+runs the same comparison over many more seeds (record: profiles/r2_random_parity_hunt.txt)."""
+import numpy as np
+import pytest
+
+import xmimsim_b200 as x
+from helpers import assert_spectra_close
+from random_inputs import random_input
+from test_history_gpu import run_both, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_input_matches_oracle(seed):
+    inp, opts = random_input(seed, n_photons=1500)
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, options=x.main_options(**opts), grid_n=96, hits=300)
+    assert ch.shape == (inp.n_interactions_trajectory + 1, inp.nchannels)
+    assert np.isfinite(ch).all() and np.isfinite(vr).all()
+    assert ch_o[-1].sum() > 0
+    assert_spectra_close(ch, ch_o, RTOL, "random %d channels" % seed)
+    assert_spectra_close(vr, vr_o, RTOL, "random %d history" % seed)
+    assert np.all(np.diff(ch, axis=0) >= 0)

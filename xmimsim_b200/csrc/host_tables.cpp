@@ -96,15 +96,16 @@ int xmb_build_tables(const xmb_xrl_provider *xrl, xmb_inputFPtr inputF, int qual
 			nodes.push_back(e + 0.00001);
 			nodes.push_back(e - 0.00001);
 		}
-	// fluorescence-line energies and monochromatic source lines become nodes: lookups there are exact
+	// fluorescence-line energies and the nominal energies of the discrete source lines become nodes: lookups there are exact
+	// (broadened lines too: the reference evaluates their excitation-absorber correction at the nominal energy,
+	// src/xmi_main.F90:586-592, and a table lookup there must return the provider's value)
 	for (int i = 0; i < nZ; i++)
 		for (int l = 1; l <= XMB_M5P5; l++) {
 			double e = xrl->LineEnergy(h->Z[i], -l);
 			if (e >= LOWE && e < top) nodes.push_back(e);
 		}
 	for (int i = 0; i < exc.n_discrete; i++)
-		if (exc.discrete[i].distribution_type == XMB_DISCRETE_MONOCHROMATIC && exc.discrete[i].energy >= LOWE &&
-		    exc.discrete[i].energy < top)
+		if (exc.discrete[i].energy >= LOWE && exc.discrete[i].energy < top)
 			nodes.push_back(exc.discrete[i].energy);
 	std::sort(nodes.begin(), nodes.end());
 	nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());

@@ -23,3 +23,31 @@ def test_random_input_matches_oracle(seed):
     assert_spectra_close(ch, ch_o, RTOL, "random %d channels" % seed)
     assert_spectra_close(vr, vr_o, RTOL, "random %d history" % seed)
     assert np.all(np.diff(ch, axis=0) >= 0)
+
+
+def _hunt():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import random_kernel_hunt
+    return random_kernel_hunt
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 5, 8])
+def test_random_geometry_solid_angle_hits_match_oracle(seed):
+    """Random detector distance / area / collimator: integer hit counts of a sub-grid of the real axes, point for point."""
+    ok, note = _hunt().hunt_sa(seed)
+    assert ok, note
+
+
+@pytest.mark.parametrize("seed", [1, 2, 5, 7])
+def test_random_input_brute_force_matches_oracle(seed):
+    """Brute-force mode on random samples (detector brought close): the same photons are detected."""
+    ok, note = _hunt().hunt_brute(seed)
+    assert ok, note
+
+
+@pytest.mark.parametrize("seed", [0, 4, 9])
+def test_random_input_advanced_compton_matches_oracle(seed):
+    ok, note = _hunt().hunt_adv(seed)
+    assert ok, note

@@ -51,3 +51,15 @@ def test_random_input_brute_force_matches_oracle(seed):
 def test_random_input_advanced_compton_matches_oracle(seed):
     ok, note = _hunt().hunt_adv(seed)
     assert ok, note
+
+
+@pytest.mark.parametrize("seed", [0, 3, 6])
+def test_random_crystal_escape_ratios_match_oracle(seed):
+    ok, note = _hunt().hunt_esc(seed)
+    assert ok, note
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_detector_response_matches_oracle(seed):
+    ok, note = _hunt().hunt_det(seed)
+    assert ok, note

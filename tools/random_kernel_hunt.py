@@ -3,6 +3,8 @@
   sa    solid-angle sub-grid (32 x 24 points of the real axes, 500 rays): integer hit counts point for point
   brute brute-force mode (detector brought close): hit / interaction / offspring counters, spectra within 2 photon weights
   adv   shell-resolved Compton with forced detection: spectra within the history tolerance (2e-6 of the maximum)
+  esc   escape-ratio Monte Carlo on random detector crystals: same non-zero bins, ratios within 1e-9 of their maximum
+  det   detector response (efficiency, escape peaks, Gaussian + tail convolution) on random detectors and spectra: 1e-11
 usage: tools/random_kernel_hunt.py WHAT FIRST LAST   (needs a GPU)"""
 import ctypes as C
 import os
@@ -81,9 +83,87 @@ def hunt_adv(seed):
     return bool(np.isfinite(ch).all() and e_ch <= 2e-6 and e_vr <= 2e-6), "err channels %.2e  history %.2e" % (e_ch, e_vr)
 
 
+CRYSTALS = [([14], [1.0], 2.33), ([32], [1.0], 5.32), ([31, 33], [0.48, 0.52], 5.32), ([48, 52], [0.47, 0.53], 5.85),
+            ([48, 30, 52], [0.43, 0.03, 0.54], 5.78)]
+
+
+def hunt_esc(seed):
+    from xmimsim_b200.xmsi import LayerD
+    from inputs import example
+    rng = np.random.default_rng(5000 + seed)
+    inp = example("srm1155")
+    layers = []
+    for _ in range(int(rng.integers(1, 3))):
+        z, w, rho = CRYSTALS[int(rng.integers(0, len(CRYSTALS)))]
+        layers.append(LayerD(list(z), list(w), rho, float(10 ** rng.uniform(-3, -0.3))))
+    inp.crystal_layers = layers
+    sim = x.Simulation(inp)
+    ero = sim.escape_ratios_options(n_input_energies=int(rng.integers(6, 14)), n_photons=20000,
+                                    input_energy_min=float(rng.uniform(1.2, 6.0)), input_energy_delta=float(rng.uniform(1.5, 4.0)),
+                                    n_compton_output_energies=int(rng.integers(200, 500)))
+    ein, eh = sim.escape_ratios_handles(ero)
+    L = sim.L
+    cin = L.xmb_input_F2C(ein)
+    od = orc.init_input(cin)
+    T = L.xmb_get_tables(eh)
+    fluo_o, compt_o = orc.escape_ratios(cin, od, T, seed + 3, ero.n_input_energies, T.contents.nZ, ero.n_photons,
+                                        ero.n_compton_output_energies, ero.compton_output_energy_min,
+                                        ero.compton_output_energy_delta, 16)
+    er = sim.escape_ratios_run(ein, eh, ero, seed=seed + 3)
+    Z, fluo, e_in, compt, e_out = sim.escape_ratios_arrays(er)
+    fluo = fluo.copy(); compt = compt.copy()
+    sim.escape_ratios_free(er)
+    same_bins = bool(np.array_equal(fluo > 0, fluo_o > 0) and np.array_equal(compt > 0, compt_o > 0))
+    ef = float(np.abs(fluo - fluo_o).max() / max(fluo_o.max(), 1e-300))
+    ec = float(np.abs(compt - compt_o).max() / max(compt_o.max(), 1e-300))
+    L.xmb_free_hdf5_F(C.byref(eh)); L.xmb_free_input_F(C.byref(ein)); sim.close()
+    ok = same_bins and ef <= 1e-9 and ec <= 1e-9 and fluo_o.sum() > 0
+    return ok, "crystal %s  energies %d  same bins %s  err fluo %.1e  compton %.1e" % (
+        "+".join("".join(str(z) + "." for z in l.Z) for l in layers), ero.n_input_energies, same_bins, ef, ec)
+
+
+def hunt_det(seed):
+    from inputs import example
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_detector_gpu import synthetic_escape_ratios
+    rng = np.random.default_rng(7000 + seed)
+    inp = example("srm1155")
+    inp.detector_type = int(rng.integers(0, 3))
+    inp.nchannels = int(rng.choice([512, 1024, 2048, 4096]))
+    inp.gain = float(40.0 * rng.uniform(0.5, 1.2) / inp.nchannels)
+    inp.zero = float(rng.uniform(-0.05, 0.05))
+    inp.fano = float(rng.uniform(0.08, 0.15)); inp.noise = float(rng.uniform(0.03, 0.2))
+    inp.n_interactions_trajectory = int(rng.integers(1, 5))
+    if rng.random() < 0.5:
+        inp.det_layers = []
+    escape = rng.random() < 0.6
+    sim = x.Simulation(inp, quality=0)
+    ci = x.CInput(inp)
+    n_int = inp.n_interactions_trajectory
+    ch = np.zeros((n_int + 1, inp.nchannels))
+    e = inp.zero + inp.gain * np.arange(inp.nchannels)
+    for k in range(1, n_int + 1):
+        row = 1e3 * np.exp(-e / 10.0) * rng.uniform(0.5, 1.5, inp.nchannels)
+        for _ in range(6):
+            c = int(rng.integers(20, inp.nchannels - 20))
+            row[c] += 10 ** rng.uniform(4, 7)
+        ch[k] = ch[k - 1] + row
+    er = synthetic_escape_ratios(sim) if escape else None
+    o = x.main_options(use_escape_peaks=1 if escape else 0)
+    ch_gpu = ch.copy()
+    conv = sim.detector_convolute_all(ch_gpu, None, None, o, er)
+    worst = 0.0
+    for k in range(1, n_int + 1):
+        row, ref = orc.detector_convolute_spectrum(C.pointer(ci.input), ch[k].copy(), o, er, k)
+        worst = max(worst, float(np.abs(conv[k] - ref).max() / ref.max()), float(np.abs(ch_gpu[k] - row).max() / row.max()))
+    sim.close()
+    return worst <= 1e-11, "type %d  channels %d  gain %.4f  escape %d  rows %d  worst %.1e" % (
+        inp.detector_type, inp.nchannels, inp.gain, escape, n_int, worst)
+
+
 def main():
     what, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    fn = {"sa": hunt_sa, "brute": hunt_brute, "adv": hunt_adv}[what]
+    fn = {"sa": hunt_sa, "brute": hunt_brute, "adv": hunt_adv, "esc": hunt_esc, "det": hunt_det}[what]
     bad = []
     for seed in range(first, last):
         t0 = time.time()

@@ -90,6 +90,17 @@ def random_input(seed, n_photons=1500):
         discrete=disc, continuous=cont, exc_layers=exc, det_layers=det, detector_type=int(rng.integers(0, 3)),
         live_time=float(rng.uniform(0.5, 100.0)), pulse_width=1e-5, gain=gain, zero=float(rng.uniform(-0.05, 0.05)),
         fano=0.12, noise=0.1, nchannels=nch, crystal_layers=[x.LayerD([14], [1.0], 2.33, 0.5)])
+    if seed >= 1000:
+        # seeds from 1000: the sample normal and the detector direction leave the 45 / 90 degree set-up of the examples --
+        # normal (0, sin a, cos a), a in [25, 65] degrees; the detector looks at the beam spot from a direction up to 15 degrees
+        # behind and 30 degrees in front of the perpendicular to the beam, up to 0.2 out of the plane of incidence
+        a = math.radians(float(rng.uniform(25.0, 65.0)))
+        gam = math.radians(float(rng.uniform(-15.0, 30.0)))
+        u = np.array([float(rng.uniform(-0.2, 0.2)), -math.cos(gam), -math.sin(gam)])
+        u /= np.linalg.norm(u)
+        inp.n_sample_orientation = [0.0, math.sin(a), math.cos(a)]
+        inp.p_detector_window = [float(det_d * u[0]), float(det_d * u[1]), float(100.0 + det_d * u[2])]
+        inp.n_detector_orientation = [float(-u[0]), float(-u[1]), float(-u[2])]
     opts = dict(use_M_lines=int(rng.random() < 0.7), use_cascade_auger=int(rng.random() < 0.6),
                 use_cascade_radiative=int(rng.random() < 0.6))
     return inp, opts

@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_ker
 	// Every batch therefore has all lanes alive and one interaction order; exact integer deposits and fixed-address
 	// random numbers make the result independent of this regrouping.
 	__shared__ int s_qcount[XMB_MAX_ORDERS];      // photons waiting to run order k+1
+#if !XMB_PUSH_ATOMIC
+	__shared__ int s_wsum[32];
+#endif
 	// solid angles of interaction points beyond the grid, computed by the whole CTA, XMB_SA_ROUND points at a time
 	__shared__ int s_sa_n, s_sa_hits[XMB_SA_ROUND];
 	__shared__ double s_sa_pt[2 * XMB_SA_ROUND];

@@ -82,8 +82,11 @@
 #endif
 
 // NL > 0: number of layers known at compile time (loops over layers fully unrolled); NL = 0: generic.
-template <int NL, bool ADV = false>
-__global__ void __launch_bounds__(HIST_THREADS, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
+// MAXT: the largest CTA the instantiation is launched with.  One CTA per SM owns the register file, so a launch that cannot use
+// 1024 threads (shared memory: 2 nL doubles per thread; 16-bit pieces: T x max nE addends) takes the instantiation compiled for
+// its size and gets the registers of the absent warps: 72 per thread at 896 threads (the 10-layer sample: 67.6 -> 65.7 ms), 80 at 768.
+template <int NL, bool ADV = false, int MAXT = HIST_THREADS>
+__global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
 	const int nL = NL > 0 ? NL : P.nL;
 	extern __shared__ __align__(16) double smem[];
 	const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -1371,7 +1374,8 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	const size_t smem = per_cta(threads);
 	void (*kernel)(const XmbHistParams) = P.nL == 1 ? xmb_history_kernel<1> : P.nL == 2 ? xmb_history_kernel<2> : P.nL == 3 ? xmb_history_kernel<3>
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
-	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation
+	if (P.nL > 4 && threads <= 896) kernel = threads <= 640 ? xmb_history_kernel<0, false, 640> : threads <= 768 ? xmb_history_kernel<0, false, 768> : xmb_history_kernel<0, false, 896>;
+	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation (compiled for 256 threads and 225 registers it is slower: 79 -> 113 ms on srm1132)
 	XMB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
 	if (occ < 1) occ = 1;

@@ -1377,6 +1377,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	if (P.nL > 4 && threads <= 896) kernel = threads <= 640 ? xmb_history_kernel<0, false, 640> : threads <= 768 ? xmb_history_kernel<0, false, 768> : xmb_history_kernel<0, false, 896>;
 	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation (compiled for 256 threads and 225 registers it is slower: 79 -> 113 ms on srm1132)
 	XMB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	if (const char *e = getenv("XMB_SMEM_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));   // experiments: percent of the SM's L1 + shared array
 	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
 	if (occ < 1) occ = 1;
 	const uint64_t n_chunks = (ex->n_histories + threads - 1) / threads;

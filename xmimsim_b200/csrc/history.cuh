@@ -42,7 +42,9 @@ struct XmbLayerDev {
 //   per tile: float wy[32]                   weight fraction * fluorescence yield * radiative rate * 2^56 (0: padding lane)
 //             float mu[nL][32]               -mu log2(e) of every layer at the line energy
 //             int slot[32], gs[32]           history slot of the line; group of the record, relative to the tile's first group
+#ifndef XMB_TILE_GROUPS
 #define XMB_TILE_GROUPS 8
+#endif
 #define XMB_WPRE_STRIDE 33                   // doubles per group row of the per-warp scratch (33: lanes of different groups read different banks)
 // doubles of per-warp scratch in the line phase: the photons' factors per shell group of a tile, float [tile_groups][XMB_WPRE_STRIDE]
 __host__ __device__ inline int xmb_warp_scratch_doubles(int tile_groups) { return (4 * tile_groups * XMB_WPRE_STRIDE + 15) / 16 * 2; }

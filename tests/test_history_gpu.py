@@ -338,3 +338,49 @@ def test_fixed_point_sums_reproduce_the_recorded_digests():
         g = got[name]
         assert (g["n"], g["inter"]) == (w["n"], w["inter"]), name
         assert (g["sha"], g["sha_shard"]) == (w["sha"], w["sha_shard"]), name
+
+
+def test_resident_grid_follows_the_contents_of_the_host_buffer():
+    """With keep_on_device the solid-angle grid stays in HBM between calls.  Residency is keyed on the CONTENTS of the caller's
+    buffers (a 64-bit hash), not on their address: a caller that refills the same buffer, or a new grid that lands on the address
+    of a freed one, must get the new grid (the round-1 library compared host pointer and size only).  Also a grid with the two
+    axis lengths swapped on the same handle (per-buffer capacities)."""
+    import hashlib
+    import torch
+
+    def limbs(sim):
+        ptr, n = sim.device_limbs()
+        holder = type("H", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}})()
+        return hashlib.sha256(torch.as_tensor(holder, device="cuda").cpu().numpy().tobytes()).hexdigest()
+
+    inp = example("srm1155")
+    inp.n_photons_line = 300
+    sim = x.Simulation(inp, quality=0)
+    r_full, t_full = sim.solid_angle_inputs()
+    r, t = r_full[::16].copy(), t_full[::16].copy()
+    rng = np.random.default_rng(3)
+    g_a = rng.uniform(1e-4, 2e-4, (t.size, r.size))
+    g_b = g_a * 1.5
+    opt = x.main_options()
+    buf = g_a.copy()
+    sa = sim.make_solid_angle(buf, r, t)          # borrows buf's memory
+    host_buf = sa._keep[0]
+    assert host_buf.ctypes.data == buf.ctypes.data
+    sim.main_msim_device(opt, sa); d_a = limbs(sim)
+    sim.main_msim_device(opt, sa); assert limbs(sim) == d_a          # unchanged buffer: resident grid, same sums
+    host_buf[...] = g_b                                              # the SAME buffer refilled in place
+    sim.main_msim_device(opt, sa); d_b = limbs(sim)
+    assert d_b != d_a
+    fresh = x.Simulation(inp, quality=0)                             # what a run that never saw grid A gives for grid B
+    fresh.main_msim_device(opt, fresh.make_solid_angle(g_b.copy(), r, t)); assert limbs(fresh) == d_b
+    fresh.close()
+    host_buf[...] = g_a
+    sim.main_msim_device(opt, sa); assert limbs(sim) == d_a
+    # axis lengths swapped (n_r x n_theta, then n_theta x n_r with n_theta > the old n_r capacity): no overflow, right sums
+    r2, t2 = r_full[::32].copy(), t_full[::8].copy()
+    g2 = rng.uniform(1e-4, 2e-4, (t2.size, r2.size))
+    sim.main_msim_device(opt, sim.make_solid_angle(g2.copy(), r2, t2)); d_2 = limbs(sim)
+    fresh = x.Simulation(inp, quality=0)
+    fresh.main_msim_device(opt, fresh.make_solid_angle(g2.copy(), r2, t2)); assert limbs(fresh) == d_2
+    fresh.close()
+    sim.close()

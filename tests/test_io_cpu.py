@@ -123,7 +123,7 @@ def test_xmso_writer_follows_the_reference_layout(tmp_path):
     import xml.etree.ElementTree as ET
     root = ET.parse(out).getroot()
     assert [c.tag for c in root] == ["inputfile", "spectrum_conv", "spectrum_unconv", "brute_force_history",
-                                     "variance_reduction_history", "xmimsim-input"]
+                                     "variance_reduction_history", "xmimsim-input", "svg_graphs"]
     assert root.find("inputfile").text == "in.xmsi"
     chans = root.find("spectrum_conv").findall("channel")
     assert len(chans) == nch and chans[7].find("channelnr").text == "7"
@@ -177,3 +177,40 @@ def test_malformed_xml_is_an_error_not_a_hang(broken):
     inp = C.POINTER(abi.Input)()
     assert abi.lib().xmb_input_read_from_xml_string(broken.encode(), C.byref(inp)) == 0
     assert abi.last_error()
+
+
+def test_xmso_svg_graphs_reproduce_the_shipped_file(tmp_path):
+    """The <svg_graphs> block (src/xmi_xml.c:1578-1622, :1880-2022) written from the spectra of the reference's shipped
+    examples/srm1155.xmso must reproduce that file's own block: tests/golden/srm1155_svg.npz (tools/make_golden.py) holds its eight
+    graphics.  The spectra in the file are printed with six digits, so the coordinates agree to a few 1e-6 of the box, not to the bit."""
+    inp = example("srm1155")
+    ci = x.CInput(inp)
+    n_int, nch = inp.n_interactions_trajectory, inp.nchannels
+    g = np.load(os.path.join(GOLDEN, "srm1155_xmso.npz"))
+    svg = np.load(os.path.join(GOLDEN, "srm1155_svg.npz"))
+    conv = np.zeros((n_int + 1, nch)); conv[1:] = g["conv"]
+    unconv = np.zeros((n_int + 1, nch)); unconv[1:] = g["unconv"]
+    rows = (abi.c_double_p * (n_int + 1))(*[C.cast(conv.ctypes.data + i * nch * 8, abi.c_double_p) for i in range(n_int + 1)])
+    out = str(tmp_path / "svg.xmso")
+    assert abi.lib().xmb_output_write_to_xml_file(C.byref(ci.input), b"in.xmsi", out.encode(), unconv.ctypes.data_as(abi.c_double_p), rows,
+                                                  None, None, 0, None) == 1, abi.last_error()
+    import xml.etree.ElementTree as ET
+    graphics = ET.parse(out).getroot().find("svg_graphs").findall("graphic")
+    assert len(graphics) == 2 * n_int
+    for gi, gr in enumerate(graphics):
+        kind, order = svg["g%d_id" % gi]
+        assert gr.find("id/name").text == ("convoluted" if kind == 0 else "unconvoluted") and int(gr.find("id/interaction").text) == order
+        size = gr.find("rect/size")
+        assert gr.find("rect/view") is not None
+        box = np.array([float(size.find(k).text) for k in ("width", "height", "min_energy", "max_energy")])
+        assert np.allclose(box, svg["g%d_box" % gi], rtol=1e-5)
+        xt = np.array([[float(i.find("value").text), float(i.find("name").text)] for i in gr.find("rect/x-axis").findall("index")])
+        yt = np.array([[float(i.find("value").text), float(i.find("name").text)] for i in gr.find("rect/y-axis").findall("index")])
+        assert xt.shape == svg["g%d_xt" % gi].shape and np.allclose(xt, svg["g%d_xt" % gi], rtol=1e-5, atol=1e-3)
+        assert yt.shape == svg["g%d_yt" % gi].shape and np.allclose(yt, svg["g%d_yt" % gi], rtol=1e-5, atol=1e-3)
+        assert gr.find("rect/x-axis/name").text == "Energy (keV)" and gr.find("rect/y-axis/name").text == "Intensity (counts)"
+        assert gr.find("points/color").text == "blue"
+        pts = np.array([[float(p.find("x").text), float(p.find("y").text)] for p in gr.find("points").findall("point")])
+        want = svg["g%d_pts" % gi]
+        assert pts.shape == want.shape, (gi, pts.shape, want.shape)
+        assert np.abs(pts - want).max() < 2e-3, (gi, np.abs(pts - want).max())     # of a 500 x 250 box

@@ -26,3 +26,25 @@ for name in ("srm1155", "srm1412", "srm1132", "In"):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + "_xmso.npz"), conv=o["conv"], unconv=o["unconv"],
                         hist_Z=hz, hist_line=hl, hist_energy=he, hist_counts=hc)
     print(name, o["conv"].shape, len(keys), "lines; sum unconv", o["unconv"].sum(axis=1))
+
+
+def svg_fixture(name="srm1155"):
+    """The <svg_graphs> block of a shipped .xmso as arrays (tests/golden/<name>_svg.npz): per graphic its (kind, interaction), the
+    box's min / max energy, the tick positions of both axes and the points -- what tests/test_io_cpu.py asks of the XMSO writer."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(os.path.join(src, name + ".xmso")).getroot()
+    out = {}
+    for gi, g in enumerate(root.find("svg_graphs").findall("graphic")):
+        kind = g.find("id/name").text
+        order = int(g.find("id/interaction").text)
+        size = g.find("rect/size")
+        out["g%d_id" % gi] = np.array([0 if kind == "convoluted" else 1, order])
+        out["g%d_box" % gi] = np.array([float(size.find(k).text) for k in ("width", "height", "min_energy", "max_energy")])
+        out["g%d_xt" % gi] = np.array([[float(i.find("value").text), float(i.find("name").text)] for i in g.find("rect/x-axis").findall("index")])
+        out["g%d_yt" % gi] = np.array([[float(i.find("value").text), float(i.find("name").text)] for i in g.find("rect/y-axis").findall("index")])
+        out["g%d_pts" % gi] = np.array([[float(p.find("x").text), float(p.find("y").text)] for p in g.find("points").findall("point")], np.float32)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + "_svg.npz"), **out)
+    print(name, "svg graphics:", len(out) // 5)
+
+
+svg_fixture()

@@ -558,10 +558,83 @@ extern "C" int xmb_input_write_to_xml_file(const xmb_input *input, const char *x
 	return 1;
 }
 
+// The <svg_graphs> block of a stand-alone XMSO file (src/xmi_xml.c:1578-1622 and xmi_write_input_xml_svg, :1880-2022): per
+// interaction order a "convoluted" and an "unconvoluted" graphic -- a 500 x 250 box, energy ticks every 5 keV, decade ticks of the
+// intensity up to the global maximum of the kind, and one point per channel up to the last channel with at least one count, in
+// box coordinates (x linear in energy, y in log10 of the counts, both clamped to the box; single precision as the reference's
+// e2c / i2c return float).  The reference's XSLT style sheets draw the spectra from it.
+namespace {
+const int SVG_W = 500, SVG_H = 250;
+float svg_e2c(double energy, const double *energies, int n) {   // n = max_channel, as the reference passes it
+	float x = (float)(SVG_W * (energy - energies[0]) / (energies[n - 1] - energies[0]));
+	if (x < 0) x = 0;
+	if (x > SVG_W) x = SVG_W;
+	return x;
+}
+float svg_i2c(double intensity, double max_log, double min_log) {
+	const double ic = intensity < 1 ? 1 : intensity;
+	float v = (float)(SVG_H) * (log10(ic) - min_log) / (max_log - min_log);
+	if (v < 0) v = 0;
+	if (v > SVG_H) v = SVG_H;
+	return v;
+}
+void write_svg_graphic(Out &o, const xmb_input *input, const char *name, int interaction, const double *channels, double maximum) {
+	FILE *f = o.f;
+	const int nch = input->detector->nchannels;
+	const double max_log = log10(maximum), min_log = 0.0;   // minimum = 1
+	int max_channel = 0;
+	for (int i = nch - 1; i >= 0; i--) if (channels[i] >= 1) { max_channel = i; break; }
+	std::vector<double> energies(nch);
+	for (int i = 0; i < nch; i++) energies[i] = i * input->detector->gain + input->detector->zero;
+	o.open(2, "graphic");
+	o.open(3, "id");
+	o.s(4, "name", name);
+	o.i(4, "interaction", interaction);
+	o.close(3, "id");
+	o.open(3, "rect");
+	fputs("    <view/>\n", f);
+	o.open(4, "size");
+	o.i(5, "width", SVG_W);
+	o.i(5, "height", SVG_H);
+	o.g(5, "min_energy", energies[0]);
+	o.g(5, "max_energy", energies[max_channel > 0 ? max_channel - 1 : 0]);
+	o.close(4, "size");
+	o.open(4, "x-axis");
+	o.s(5, "name", "Energy (keV)");
+	for (double energy = 0.0; energy <= energies[max_channel]; energy += 5.0) {
+		o.open(5, "index");
+		o.g(6, "value", max_channel > 1 ? svg_e2c(energy, energies.data(), max_channel) : 0.0);
+		fprintf(f, "      <name>%.1f</name>\n", energy);
+		o.close(5, "index");
+	}
+	o.close(4, "x-axis");
+	o.open(4, "y-axis");
+	o.s(5, "name", "Intensity (counts)");
+	for (double intensity = 1.0; intensity <= maximum; intensity *= 10.0) {
+		o.open(5, "index");
+		o.g(6, "value", svg_i2c(intensity, max_log, min_log));
+		fprintf(f, "      <name>%.0f</name>\n", intensity);
+		o.close(5, "index");
+	}
+	o.close(4, "y-axis");
+	o.close(3, "rect");
+	o.open(3, "points");
+	o.s(4, "color", "blue");
+	for (int i = 0; i <= max_channel; i++) {
+		o.open(4, "point");
+		o.g(5, "x", max_channel > 1 ? svg_e2c(energies[i], energies.data(), max_channel) : 0.0);
+		o.g(5, "y", svg_i2c(channels[i], max_log, min_log));
+		o.close(4, "point");
+	}
+	o.close(3, "points");
+	o.close(2, "graphic");
+}
+}  // namespace
+
 // Replaces xmi_output_new + xmi_output_write_to_xml_file (src/xmi_data_structs.c:1369-1519, src/xmi_xml.c:1453-1700).
 // channels_unconv: the raw [(n_int+1)][nch] array of xmb_main_msim; channels_conv: the rows of the detector response
 // (index 0 may be NULL unless use_zero_interactions); the two histories [100][385][n_int] (either may be NULL).
-// The optional <svg_graphs> block of the reference (with_svg) is not written.
+// With the <svg_graphs> block (with_svg = 1, as xmi_output_write_to_xml_file passes it) unless XMB_XMSO_NO_SVG is set.
 extern "C" int xmb_output_write_to_xml_file(const xmb_input *input, const char *inputfile, const char *xmsofile,
                                             const double *channels_unconv, double *const *channels_conv, const double *brute_history,
                                             const double *var_red_history, int use_zero_interactions, const xmb_xrl_provider *xrl) {
@@ -589,6 +662,20 @@ extern "C" int xmb_output_write_to_xml_file(const xmb_input *input, const char *
 	o.open(1, "xmimsim-input");
 	write_input_body(o, 2, input);
 	o.close(1, "xmimsim-input");
+	if (!getenv("XMB_XMSO_NO_SVG")) {
+		o.open(1, "svg_graphs");
+		double gl_conv = 0.0, gl_unconv = 0.0;   // global maxima over the orders written (maxima[0] = 0 as the reference initialises it)
+		for (int i = i0; i <= n_int; i++)
+			for (int j = 0; j < nch; j++) {
+				gl_conv = std::max(gl_conv, channels_conv[i][j]);
+				gl_unconv = std::max(gl_unconv, channels_unconv[(size_t)i * nch + j]);
+			}
+		for (int i = i0; i <= n_int; i++) {
+			write_svg_graphic(o, input, "convoluted", i, channels_conv[i], gl_conv);
+			write_svg_graphic(o, input, "unconvoluted", i, channels_unconv + (size_t)i * nch, gl_unconv);
+		}
+		o.close(1, "svg_graphs");
+	}
 	fputs("</xmimsim-results>\n", f);
 	fclose(f);
 	return 1;

@@ -61,6 +61,11 @@
 #ifndef XMB_PREFETCH_EARLY
 #define XMB_PREFETCH_EARLY 0
 #endif
+// the layers' mu travel through the compaction queues with the photon when there are one or two layers; with more they are
+// looked up again when the photon is taken from the queue (10-layer sample 65.7 -> 64.2 ms; two layers: 145.6 -> 146.1, kept queued)
+#ifndef XMB_QUEUE_MUS_FOR
+#define XMB_QUEUE_MUS_FOR(nl) ((nl) <= 2)
+#endif
 #ifndef XMB_COMPTON_EXP_F32
 #define XMB_COMPTON_EXP_F32 0
 #endif
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(cons
 		if (tid == 0) { xmb_fence_proxy_async(); xmb_bulk_g2s(sblob_s32, P.lblob + P.lblob_off[L], bytes, mbar_s32); }
 		staged_layer = L; stage_pending = true;
 	};
-	const int NF = XMB_STATE_FIELDS + nL;
+	const int NF = XMB_STATE_FIELDS + (XMB_QUEUE_MUS_FOR(nL) ? nL : 0);
 	const size_t qcap = 2 * (size_t)T;
 	const bool per_layer = NL != 1 && P.layer_sort == 2;   // one queue per (order, layer): see the scheduler below
 	double *qbase = P.queue + (size_t)blockIdx.x * P.n_int * (per_layer ? nL : 1) * NF * qcap;
@@ -225,7 +230,9 @@ __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(cons
 				XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight);
 				XMB_QST(&q[11 * qcap], __longlong_as_double((long long)g));
 				XMB_QST(&q[12 * qcap], __longlong_as_double((long long)p.layer));
-				for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
+				if (XMB_QUEUE_MUS_FOR(nL)) {
+					for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
+				}
 			}
 			return;   // the caller's __syncthreads() publishes the counts
 		}
@@ -252,8 +259,10 @@ __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(cons
 			XMB_QST(&q[9 * qcap], p.energy); XMB_QST(&q[10 * qcap], p.weight);
 			XMB_QST(&q[11 * qcap], __longlong_as_double((long long)g));
 			XMB_QST(&q[12 * qcap], __longlong_as_double((long long)p.layer));
-			XMB_UNROLL_NL
+			if (XMB_QUEUE_MUS_FOR(nL)) {
+				XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * T]);
+			}
 		}
 #if !XMB_PUSH_ATOMIC
 		__syncthreads();
@@ -393,7 +402,11 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]);
 				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[11 * qcap]));
 				p.layer = myL;
-				for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
+				if (XMB_QUEUE_MUS_FOR(nL)) {
+					for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
+				} else {
+					{ const NodePos nq = node_find(P, p.energy); for (int j = 0; j < nL; j++) mus[j * T] = mu_lerp(P, nq, j); }
+				}
 				p.n_interactions = order;
 				p.alive = true;
 			}
@@ -427,8 +440,19 @@ for (int j = 0; j < nL; j++) XMB_QST(&q[(XMB_STATE_FIELDS + j) * qcap], mus[j * 
 				p.energy = XMB_QLD(&q[9 * qcap]); p.weight = XMB_QLD(&q[10 * qcap]);
 				g = (uint64_t)__double_as_longlong(XMB_QLD(&q[11 * qcap]));
 				p.layer = (int)__double_as_longlong(XMB_QLD(&q[12 * qcap]));
-				XMB_UNROLL_NL
+				if (XMB_QUEUE_MUS_FOR(nL)) {
+					XMB_UNROLL_NL
 for (int j = 0; j < nL; j++) mus[j * T] = XMB_QLD(&q[(XMB_STATE_FIELDS + j) * qcap]);
+				} else {
+					{
+						// mu of the layers is a function of the photon energy alone (every writer of mus[] is mu_lerp at node_find(energy)):
+						// looked up again here instead of travelling through the queue -- nL doubles less per photon written and read
+						// (10 of 23 on the 10-layer sample); photons of one fluorescence line share the two table rows
+						const NodePos nq = node_find(P, p.energy);
+						XMB_UNROLL_NL
+for (int j = 0; j < nL; j++) mus[j * T] = mu_lerp(P, nq, j);
+					}
+				}
 				p.n_interactions = order;
 				p.alive = true;
 			}
@@ -1386,7 +1410,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	if (const char *e = getenv("XMB_HIST_BLOCKS")) { const long b = atol(e); if (b >= 1 && (uint64_t)b < blocks) blocks = (uint64_t)b; }
 	if (P.n_int > XMB_MAX_ORDERS) { xmb_set_error("more than %d interactions per trajectory", XMB_MAX_ORDERS); return 0; }
 	// per-CTA compaction queues: n_int orders (x nL layers) x 2T photons x (15 + nL) doubles (structure of arrays)
-	size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + P.nL) * 2 * threads;
+	size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + (XMB_QUEUE_MUS_FOR(P.nL) ? P.nL : 0)) * 2 * threads;
 	if (P.layer_sort == 2) {
 		if (qd * P.nL * sizeof(double) > ((size_t)24 << 30)) P.layer_sort = 1;   // keep the queues within 24 GB of HBM
 		else qd *= P.nL;

@@ -37,3 +37,14 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
     assert not any(ln.strip().startswith("{") for ln in r.stdout.splitlines())      # no bench line from a fallback
+
+
+def test_library_banners_do_not_reach_the_json_line():
+    """NCCL prints its version on file descriptor 1 when the first communicator is created: bench.py sends everything written to
+    fd 1 during the run to stderr and writes its JSON line to the real stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.quiet_stdout(); os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); "
+            "print('a print from a library'); bench.emit({'metric': 'x', 'value': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert r.stdout == '{"metric": "x", "value": 1}\n'
+    assert "NCCL version" in r.stderr and "a print from a library" in r.stderr

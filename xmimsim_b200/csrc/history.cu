@@ -1409,7 +1409,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, n_chunks));
 	if (const char *e = getenv("XMB_HIST_BLOCKS")) { const long b = atol(e); if (b >= 1 && (uint64_t)b < blocks) blocks = (uint64_t)b; }
 	if (P.n_int > XMB_MAX_ORDERS) { xmb_set_error("more than %d interactions per trajectory", XMB_MAX_ORDERS); return 0; }
-	// per-CTA compaction queues: n_int orders (x nL layers) x 2T photons x (15 + nL) doubles (structure of arrays)
+	// per-CTA compaction queues: n_int orders (x nL layers) x 2T photons x 13 doubles, + nL with one or two layers (structure of arrays)
 	size_t qd = (size_t)blocks * P.n_int * (XMB_STATE_FIELDS + (XMB_QUEUE_MUS_FOR(P.nL) ? P.nL : 0)) * 2 * threads;
 	if (P.layer_sort == 2) {
 		if (qd * P.nL * sizeof(double) > ((size_t)24 << 30)) P.layer_sort = 1;   // keep the queues within 24 GB of HBM

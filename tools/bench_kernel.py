@@ -21,6 +21,8 @@ def main():
     else:
         inp = example(which)
         inp.n_photons_line = n_line
+        if os.environ.get("XMB_BENCH_NCH"):   # experiment: fewer channels (a smaller staging area in shared memory)
+            inp.nchannels = int(os.environ["XMB_BENCH_NCH"])
     sim = x.Simulation(inp, quality=0)
     g, r, t = sim.solid_angle_calculation(hits_per_single=5000, seed=1)
     sa = sim.make_solid_angle(g.copy(), r.copy(), t.copy())

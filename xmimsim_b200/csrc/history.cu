@@ -25,7 +25,9 @@
 #include "solid_angle_device.cuh"
 #include "device_tables.h"
 
+#ifndef XMB_SA_ROUND
 #define XMB_SA_ROUND 32
+#endif
 #ifndef XMB_BUCKET_FINE
 #define XMB_BUCKET_FINE 16
 #endif

@@ -23,7 +23,9 @@
 #define XMB_REC_UNROLL 4
 #endif
 #define XMB_MAX_ORDERS 64
+#ifndef XMB_MAX_QL
 #define XMB_MAX_QL 1024          // (order, layer) queues of a CTA when batches are formed per layer
+#endif
 #define XMB_STATE_FIELDS 13      // 11 doubles of photon state + photon id + layer (mus[nL] follow)
 #define XMB_PRAGMA(x) _Pragma(#x)
 #define XMB_UNROLL_NL _Pragma("unroll")

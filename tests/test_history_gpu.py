@@ -384,3 +384,27 @@ def test_resident_grid_follows_the_contents_of_the_host_buffer():
     fresh.main_msim_device(opt, fresh.make_solid_angle(g2.copy(), r2, t2)); assert limbs(fresh) == d_2
     fresh.close()
     sim.close()
+
+
+def test_very_many_channels_and_the_unstaged_channel_path(monkeypatch):
+    """16 384 channels: channels + history slots exceed the shared-memory staging area, the Rayleigh / Compton channel deposits go
+    straight to the global accumulators (history slots stay staged).  The path is also forced on an ordinary input
+    (XMB_STAGE_CHANNELS=0): integer sums, so the raw accumulators must equal the staged run's bit for bit."""
+    inp = example("srm1155")
+    inp.n_photons_line = 600
+    inp.nchannels = 16384
+    inp.gain = 0.0119 / 8
+    ch, br, vr, ch_o, vr_o, cnt = run_both(inp, grid_n=96)
+    assert ch.shape == (inp.n_interactions_trajectory + 1, 16384) and ch[-1].sum() > 0
+    assert_spectra_close(ch, ch_o, RTOL, "16384 channels")
+    assert_spectra_close(vr, vr_o, RTOL, "16384 channels history")
+    b = example("srm1412"); b.n_photons_line = 2000
+    sim = x.Simulation(b, quality=0)
+    r_full, t_full = sim.solid_angle_inputs()
+    r, t = r_full[::8].copy(), t_full[::8].copy()
+    sa = sim.make_solid_angle(np.random.default_rng(5).uniform(1e-4, 2e-4, (t.size, r.size)), r, t)
+    limbs_staged, _ = sim.main_msim_raw(x.main_options(), sa)
+    monkeypatch.setenv("XMB_STAGE_CHANNELS", "0")
+    limbs_direct, _ = sim.main_msim_raw(x.main_options(), sa)
+    sim.close()
+    assert np.array_equal(limbs_staged, limbs_direct)

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(cons
 	unsigned int *stage = reinterpret_cast<unsigned int *>(smem + (size_t)2 * nL * T);   // [nch + n_hist_slots][4] pieces
 	// line phase (lane = record): per-warp scratch of the photons' factors per shell group, and the staged line tiles
 	const int wscr = xmb_warp_scratch_doubles(P.tile_groups);
-	float *wpre_w = reinterpret_cast<float *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(tid >> 5) * wscr);
-	const char *sblob = reinterpret_cast<const char *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.nch + P.n_hist_slots) + (size_t)(T >> 5) * wscr);
+	float *wpre_w = reinterpret_cast<float *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.stage_nch + P.n_hist_slots) + (size_t)(tid >> 5) * wscr);
+	const char *sblob = reinterpret_cast<const char *>(smem + (size_t)2 * nL * T + 2 * ((size_t)P.stage_nch + P.n_hist_slots) + (size_t)(T >> 5) * wscr);
 	constexpr bool P20 = false;   // every staged slot holds four 16-bit pieces (a line slot receives one per-lane sum per tile and warp)
 	const uint64_t n_total = P.n_local_span;
 	const uint64_t n_chunks = (n_total + T - 1) / T;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(cons
 	__shared__ unsigned short s_perm[HIST_THREADS];
 	if (tid < XMB_MAX_ORDERS) s_qcount[tid] = 0;
 	for (int i = tid; i < XMB_MAX_QL; i += T) s_qcl[i] = 0;
-	for (int i = tid; i < 4 * (P.nch + P.n_hist_slots); i += T) stage[i] = 0u;
+	for (int i = tid; i < 4 * (P.stage_nch + P.n_hist_slots); i += T) stage[i] = 0u;
 	// Line tiles of ONE layer are staged in shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, UBLKCP): the
 	// layer of the batch when batches are formed per layer (the copy is issued when the batch is chosen and lands during the
 	// geometry and scatter-deposit phases), else the layer with the most records, once.  Other layers are read in place.
@@ -466,7 +466,15 @@ for (int j = 0; j < nL; j++) mus[j * T] = mu_lerp(P, nq, j);
 			const uint4 b0 = draw_block(P.seed, g, order, 1, 0, 0);   // {path length (used when the photon was moved), detector r, detector phi, atom}
 			const int n_ia = order;   // == p.n_interactions for every live lane
 			const unsigned acc_k = stage_s32;   // deposits of this batch are staged in shared memory, flushed below
-			const unsigned hist0 = (unsigned)P.nch;
+			const unsigned hist0 = (unsigned)P.stage_nch;
+			// channel deposits: staged like every other deposit, or -- very many channels: nch + history slots beyond the shared
+			// memory of an SM -- added straight to the global accumulators of the order (low and high half of the 2^-56
+			// fixed-point value into piece words 0 and 2: each takes 2^32 deposits)
+			unsigned long long *const grow = P.acc + 4 * (size_t)(n_ia - 1) * acc_row;
+			auto deposit_channel = [&](int ch, unsigned long long v) {
+				if (P.stage_nch) deposit_varying(acc_k, ch, v, lane);
+				else if (ch >= 0 && v) { red_global_u64(grow + 4 * (size_t)ch, v & 0xFFFFFFFFULL); red_global_u64(grow + 4 * (size_t)ch + 2, v >> 32); }
+			};
 
 			// ---- forced detection (src/xmi_variance_reduction.F90:29-726) -----------------------------
 			bool vr = p.alive && p.energy > ENERGY_THRESHOLD;
@@ -663,7 +671,7 @@ for (int i = 0; i < nL; i++) rd[i * T] = 0.0;
 								}
 							}
 							deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
-							deposit_varying(acc_k, ch_c, fx, lane);
+							deposit_channel(ch_c, fx);
 						}
 						continue;
 					}
@@ -700,10 +708,10 @@ for (int j = jlo; j <= jhi; j++) tm += mu_lerp(P, cp, j) * rd[j * T];
 					}
 					XMB_PHW(13);   // bracket, mu, exp, fixed point
 					deposit_uniform<P20>(acc_k, hbase + 1, fx, lane);
-					deposit_varying(acc_k, ch_c, fx, lane);
+					deposit_channel(ch_c, fx);
 					XMB_PHW(14);   // staged adds
 				}
-				deposit_varying(acc_k, ch_rayl, fx_rayl, lane);
+				deposit_channel(ch_rayl, fx_rayl);
 			}
 			XMB_PH(4);   // Rayleigh / Compton deposits per element
 #if XMB_BARRIERS & 2
@@ -797,7 +805,7 @@ XMB_UNROLL(4)
 #if XMB_BARRIERS & 4
 			XMB_SYNC_TIMED();   // phase: selection + scattering (and: every deposit of the batch is staged)
 			XMB_PH(6);   // waiting for the slowest warp's deposits
-			flush_staged<P20>(stage, P.acc + 4 * (size_t)(n_ia - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+			flush_staged<P20>(stage, P.acc + 4 * ((size_t)(n_ia - 1) * acc_row + (size_t)(P.nch - P.stage_nch)), P.stage_nch + P.n_hist_slots, P.nch, tid, T);
 			XMB_PH(7);
 #endif
 			// (the interaction of the last order is scored above; what it does to the photon is never used)
@@ -822,7 +830,7 @@ XMB_UNROLL(4)
 #if !(XMB_BARRIERS & 4)
 		// every deposit of the batch is staged (barrier above); the next batch's first deposit comes behind the barriers of
 		// its formation and of the off-grid solid-angle round
-		flush_staged<P20>(stage, P.acc + 4 * (size_t)(order - 1) * acc_row, (int)acc_row, P.nch, tid, T);
+		flush_staged<P20>(stage, P.acc + 4 * ((size_t)(order - 1) * acc_row + (size_t)(P.nch - P.stage_nch)), P.stage_nch + P.n_hist_slots, P.nch, tid, T);
 #endif
 	}
 #if XMB_PHASE_CLOCKS
@@ -1384,8 +1392,13 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	}
 	// threads per CTA: as many as the per-thread shared arrays (2 nL doubles) allow within 200 KB
 	int threads = HIST_THREADS;
-	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots);
-	if (stage_bytes > 160 * 1024) { xmb_set_error("nchannels + history slots do not fit the shared-memory staging area"); return 0; }
+	// staging area: channels + history slots; beyond 160 KB (more than ~10 000 channels) the history slots alone, and the
+	// Rayleigh / Compton channel deposits go straight to the global accumulators (slower: the peak channels serialise in L2)
+	P.stage_nch = P.nch;
+	if (const char *e = getenv("XMB_STAGE_CHANNELS")) { if (atoi(e) == 0) P.stage_nch = 0; }   // tests: force the unstaged path
+	if (sizeof(unsigned long long) * 2 * ((size_t)P.nch + P.n_hist_slots) > 160 * 1024) P.stage_nch = 0;
+	const size_t stage_bytes = sizeof(unsigned long long) * 2 * ((size_t)P.stage_nch + P.n_hist_slots);
+	if (stage_bytes > 160 * 1024) { xmb_set_error("the history slots of the sample's lines do not fit the shared-memory staging area"); return 0; }
 	// + the line phase: XMB_TILE_GROUPS x XMB_WPRE_STRIDE doubles of scratch per warp and one staged line-tile blob
 	const size_t fixed_bytes = stage_bytes + (size_t)P.lblob_stage_bytes;
 	auto per_cta = [&](int t) { return fixed_bytes + sizeof(double) * 2 * P.nL * t + sizeof(double) * xmb_warp_scratch_doubles(P.tile_groups) * (t / 32); };

@@ -111,6 +111,7 @@ struct XmbHistParams {
 	// forced-detection line tiles (see XmbLineTile): one blob per layer
 	const char *lblob;                       // all blobs, layer L at lblob + lblob_off[L]
 	int lblob_off[XMB_MAX_LAYERS + 1];
+	int stage_nch;                           // channel slots of the shared-memory staging area: nch, or 0 when nch + history slots do not fit -- channel deposits then go straight to the global accumulators
 	int lblob_stage_bytes;                   // shared memory reserved for one staged blob (largest layer); 0: tiles are read in place
 	int tile_groups;                         // shell groups a tile may span (XMB_TILE_GROUPS, or half of it when shared memory is short)
 	int lblob_main_layer;                    // the layer with the most records (staged once when batches mix layers)

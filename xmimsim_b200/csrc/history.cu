@@ -92,7 +92,8 @@
 // MAXT: the largest CTA the instantiation is launched with.  One CTA per SM owns the register file, so a launch that cannot use
 // 1024 threads (shared memory: 2 nL doubles per thread; 16-bit pieces: T x max nE addends) takes the instantiation compiled for
 // its size and gets the registers of the absent warps: 72 per thread at 896 threads (the 10-layer sample: 67.6 -> 65.7 ms), 80 at 768.
-template <int NL, bool ADV = false, int MAXT = HIST_THREADS>
+// UNSTAGED: the channel slots are not in the shared-memory staging area (very many channels, P.stage_nch == 0): generic nL only.
+template <int NL, bool ADV = false, int MAXT = HIST_THREADS, bool UNSTAGED = false>
 __global__ void __launch_bounds__(MAXT, HIST_MIN_BLOCKS) xmb_history_kernel(const __grid_constant__ XmbHistParams P) {
 	const int nL = NL > 0 ? NL : P.nL;
 	extern __shared__ __align__(16) double smem[];
@@ -472,7 +473,7 @@ for (int j = 0; j < nL; j++) mus[j * T] = mu_lerp(P, nq, j);
 			// fixed-point value into piece words 0 and 2: each takes 2^32 deposits)
 			unsigned long long *const grow = P.acc + 4 * (size_t)(n_ia - 1) * acc_row;
 			auto deposit_channel = [&](int ch, unsigned long long v) {
-				if (P.stage_nch) deposit_varying(acc_k, ch, v, lane);
+				if (!UNSTAGED) deposit_varying(acc_k, ch, v, lane);
 				else if (ch >= 0 && v) { red_global_u64(grow + 4 * (size_t)ch, v & 0xFFFFFFFFULL); red_global_u64(grow + 4 * (size_t)ch + 2, v >> 32); }
 			};
 
@@ -1415,6 +1416,7 @@ int xmb_msim_launch(XmbInputF *in, XmbHdf5F *h, const xmb_main_options *options,
 	                                     : P.nL == 4 ? xmb_history_kernel<4> : xmb_history_kernel<0>;
 	if (P.nL > 4 && threads <= 896) kernel = threads <= 640 ? xmb_history_kernel<0, false, 640> : threads <= 768 ? xmb_history_kernel<0, false, 768> : xmb_history_kernel<0, false, 896>;
 	if (options->use_advanced_compton) kernel = xmb_history_kernel<0, true>;   // opt-in physics: one generic-nL instantiation (compiled for 256 threads and 225 registers it is slower: 79 -> 113 ms on srm1132)
+	if (P.stage_nch == 0) kernel = options->use_advanced_compton ? xmb_history_kernel<0, true, HIST_THREADS, true> : xmb_history_kernel<0, false, HIST_THREADS, true>;   // channel deposits unstaged
 	XMB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	if (const char *e = getenv("XMB_SMEM_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));   // experiments: percent of the SM's L1 + shared array
 	XMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
